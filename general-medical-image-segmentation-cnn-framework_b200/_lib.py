@@ -1,0 +1,101 @@
+"""ctypes binding of libb200seg.so (the C ABI declared in include/b200seg.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200seg.so")
+
+_P, _I, _L, _F, _D, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
+_CODES = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D, "z": _Z}
+
+
+class ConvGeom(ctypes.Structure):
+    """b200seg_conv_geom"""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("n", "d", "h", "w", "cin", "od", "oh", "ow", "cout", "k", "stride", "pad", "dil")]
+
+
+# name -> argument type codes ('g' = const b200seg_conv_geom*), in header order
+SIGNATURES = {
+    "b200seg_conv3d_uses_tensor_cores": "g",
+    "b200seg_ncdhw_f32_to_ndhwc_bf16": "ppiilp",
+    "b200seg_ndhwc_bf16_to_ncdhw_f32": "ppiilp",
+    "b200seg_pack_conv_weight": "ppiiiiiip",
+    "b200seg_unpack_conv_wgrad": "ppiiiiiip",
+    "b200seg_conv3d_fprop": "gplppplppzp",
+    "b200seg_conv3d_dgrad": "gplpplpzp",
+    "b200seg_conv3d_wgrad": "gplplppzp",
+    "b200seg_pack_convt_weight": "ppiiip",
+    "b200seg_convt_k2s2_fwd": "plpp" + "pl" + "iiiiii" + "p",
+    "b200seg_convt_k2s2_dgrad": "plp" + "pl" + "iiiiii" + "p",
+    "b200seg_convt_k2s2_wgrad": "plpl" + "p" + "iiiiii" + "p",
+    "b200seg_channel_stats": "pllii" + "pp",
+    "b200seg_norm_finalize": "pdii" + "pppp" + "ffi" + "pp",
+    "b200seg_norm_act_fwd": "plp" + "lii" + "if" + "p" + "pl" + "pl" + "p",
+    "b200seg_norm_act_bwd_reduce": "plpl" + "p" + "lii" + "if" + "p" + "pl" + "pp" + "p",
+    "b200seg_norm_act_bwd_apply": "plpl" + "pp" + "d" + "lii" + "if" + "p" + "pl" + "pl" + "pl" + "p",
+    "b200seg_maxpool2_fwd": "plplp" + "iiiii" + "p",
+    "b200seg_maxpool2_bwd": "plp" + "pl" + "iiiii" + "p",
+    "b200seg_maxpool2_idx_to_torch": "pp" + "iiiii" + "p",
+    "b200seg_upsample2_fwd": "plpl" + "iiiii" + "p",
+    "b200seg_upsample2_bwd": "plpl" + "iiiii" + "p",
+    "b200seg_add": "plplpl" + "li" + "p",
+    "b200seg_head_conv1x1_fwd": "plppp" + "ilii" + "p",
+    "b200seg_head_conv1x1_bwd": "ppl" + "p" + "pl" + "pp" + "ilii" + "p",
+    "b200seg_argmax_labels": "pp" + "ili" + "p",
+    "b200seg_loss_reduce": "pp" + "ili" + "pp",
+    "b200seg_loss_grad": "pp" + "ili" + "p" + "ffff" + "p" + "pp",
+    "b200seg_seg_counts": "ppl" + "pp",
+    "b200seg_window_accumulate_crop": "pp" + "iiiiiii" + "p" + "iii" + "p",
+    "b200seg_window_accumulate_average": "pp" + "iiiii" + "pp" + "iii" + "p",
+    "b200seg_window_finalize": "pp" + "il" + "pp",
+    "b200seg_adam_step": "pppp" + "l" + "fffff" + "i" + "f" + "p",
+}
+STRING_FUNCS = ("b200seg_version", "b200seg_last_error")
+SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g"}
+
+
+class B200SegError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the extension; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200SegError("libb200seg.so is missing at %s: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                           "There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+
+    def types(codes):
+        return [ctypes.POINTER(ConvGeom) if c == "g" else _CODES[c] for c in codes]
+
+    for name, codes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = types(codes)
+        fn.restype = ctypes.c_int
+    for name in STRING_FUNCS:
+        getattr(lib, name).restype = ctypes.c_char_p
+        getattr(lib, name).argtypes = []
+    for name, codes in SIZE_FUNCS.items():
+        getattr(lib, name).restype = ctypes.c_size_t
+        getattr(lib, name).argtypes = types(codes)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an ABI function; raise B200SegError with the library's message on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise B200SegError("%s failed (%d): %s" % (name, rc, lib.b200seg_last_error().decode()))
+
+
+def exported_symbols():
+    return list(SIGNATURES) + list(STRING_FUNCS) + list(SIZE_FUNCS)

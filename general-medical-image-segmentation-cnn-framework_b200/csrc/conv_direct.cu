@@ -1,0 +1,383 @@
+// Direct (CUDA-core) convolution path: every geometry the tensor-core path does not take -- C_in = 1 stems, class
+// heads, channel counts that are not multiples of 16, strided (k2s2 / k3s2) convolutions and their transposes.
+// bf16 operands, fp32 accumulation.  Also weight packing / gradient unpacking shared with the tcgen05 path.
+#include "common.cuh"
+#include "conv_impl.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------ packing
+// w [cout][cin][k3] fp32 -> fprop: p[t][co][ci_local] ; dgrad: p[k3-1-t][ci_local][co]   (bf16)
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int cout, int cin,
+                                        int k3, int cin_off, int cin_cnt, int dgrad) {
+  const int64_t total = static_cast<int64_t>(k3) * cout * cin_cnt;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int t, co, ci;
+    if (!dgrad) {
+      ci = static_cast<int>(i % cin_cnt);
+      co = static_cast<int>((i / cin_cnt) % cout);
+      t = static_cast<int>(i / (static_cast<int64_t>(cin_cnt) * cout));
+      p[i] = __float2bfloat16(w[(static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + t]);
+    } else {
+      co = static_cast<int>(i % cout);
+      ci = static_cast<int>((i / cout) % cin_cnt);
+      t = static_cast<int>(i / (static_cast<int64_t>(cin_cnt) * cout));
+      p[i] = __float2bfloat16(w[(static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + (k3 - 1 - t)]);
+    }
+  }
+}
+
+// dw_packed [t][ci_local][co] fp32 -> grad [co][cin][k3] (+=)
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int cout, int cin,
+                                         int k3, int cin_off, int cin_cnt, int accumulate) {
+  const int64_t total = static_cast<int64_t>(k3) * cout * cin_cnt;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // iterate in destination order for coalesced writes
+    const int t = static_cast<int>(i % k3);
+    const int ci = static_cast<int>((i / k3) % cin_cnt);
+    const int co = static_cast<int>(i / (static_cast<int64_t>(k3) * cin_cnt));
+    const float v = dwp[(static_cast<int64_t>(t) * cin_cnt + ci) * cout + co];
+    float* dst = grad + (static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + t;
+    *dst = accumulate ? *dst + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fprop
+// thread = (output voxel, 8 output channels).  wp: [t][co][ci].
+template <bool VEC>
+__global__ void conv_direct_fprop_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                                         const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias,
+                                         __nv_bfloat16* __restrict__ y, int64_t y_pitch, float* __restrict__ stats) {
+  const int cog = (g.cout + 7) / 8;
+  const int64_t total = static_cast<int64_t>(g.n) * g.od * g.oh * g.ow * cog;
+  const int k = g.k;
+  float ssum[8], ssq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
+  int my_cg = -1;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cog);
+    my_cg = cg;  // grid stride is a multiple of cog (host guarantees), so cg is loop-invariant per thread
+    int64_t v = i / cog;
+    const int64_t orow = v;
+    const int xo = static_cast<int>(v % g.ow);
+    v /= g.ow;
+    const int yo = static_cast<int>(v % g.oh);
+    v /= g.oh;
+    const int zo = static_cast<int>(v % g.od);
+    const int nn = static_cast<int>(v / g.od);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int co0 = cg * 8;
+    for (int a = 0; a < k; ++a) {
+      const int zi = zo * g.stride - g.pad + a * g.dil;
+      if (zi < 0 || zi >= g.d) continue;
+      for (int b = 0; b < k; ++b) {
+        const int yi = yo * g.stride - g.pad + b * g.dil;
+        if (yi < 0 || yi >= g.h) continue;
+        for (int e = 0; e < k; ++e) {
+          const int xi = xo * g.stride - g.pad + e * g.dil;
+          if (xi < 0 || xi >= g.w) continue;
+          const int t = (a * k + b) * k + e;
+          const __nv_bfloat16* xr = x + (((static_cast<int64_t>(nn) * g.d + zi) * g.h + yi) * g.w + xi) * x_pitch;
+          const __nv_bfloat16* wt = wp + static_cast<int64_t>(t) * g.cout * g.cin;
+          if constexpr (VEC) {
+            for (int c0 = 0; c0 < g.cin; c0 += 8) {
+              float xf[8];
+              unpack8(ld8(xr + c0), xf);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (co0 + j < g.cout) {
+                  float wf[8];
+                  unpack8(ld8(wt + static_cast<int64_t>(co0 + j) * g.cin + c0), wf);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) acc[j] += xf[q] * wf[q];
+                }
+              }
+            }
+          } else {
+            for (int c = 0; c < g.cin; ++c) {
+              const float xf = __bfloat162float(xr[c]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (co0 + j < g.cout) acc[j] += xf * __bfloat162float(wt[static_cast<int64_t>(co0 + j) * g.cin + c]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (co0 + j < g.cout) {
+        if (bias) acc[j] += bias[co0 + j];
+        ssum[j] += acc[j];
+        ssq[j] += acc[j] * acc[j];
+        y[orow * y_pitch + co0 + j] = __float2bfloat16(acc[j]);
+      }
+    }
+  }
+  if (stats) {
+    // block-level reduction per channel through shared memory, then one atomic per channel per block
+    extern __shared__ float sred[];  // [2][cout]
+    for (int i = threadIdx.x; i < 2 * g.cout; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+    if (my_cg >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (my_cg * 8 + j < g.cout) {
+          atomicAdd(&sred[my_cg * 8 + j], ssum[j]);
+          atomicAdd(&sred[g.cout + my_cg * 8 + j], ssq[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * g.cout; i += blockDim.x) atomicAdd(&stats[i], sred[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dgrad (gather)
+// thread = (input voxel, 8 input channels).  wd: flipped pack [k3-1-t][ci][co].
+template <bool VEC>
+__global__ void conv_direct_dgrad_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
+                                         const __nv_bfloat16* __restrict__ wd, const float* __restrict__ bias,
+                                         __nv_bfloat16* __restrict__ dx, int64_t dx_pitch) {
+  const int cig = (g.cin + 7) / 8;
+  const int64_t total = static_cast<int64_t>(g.n) * g.d * g.h * g.w * cig;
+  const int k = g.k, k3 = k * k * k;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cig);
+    int64_t v = i / cig;
+    const int64_t irow = v;
+    const int xi = static_cast<int>(v % g.w);
+    v /= g.w;
+    const int yi = static_cast<int>(v % g.h);
+    v /= g.h;
+    const int zi = static_cast<int>(v % g.d);
+    const int nn = static_cast<int>(v / g.d);
+    const int ci0 = cg * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a = 0; a < k; ++a) {
+      const int zn = zi + g.pad - a * g.dil;
+      if (zn < 0 || zn % g.stride) continue;
+      const int zo = zn / g.stride;
+      if (zo >= g.od) continue;
+      for (int b = 0; b < k; ++b) {
+        const int yn = yi + g.pad - b * g.dil;
+        if (yn < 0 || yn % g.stride) continue;
+        const int yo = yn / g.stride;
+        if (yo >= g.oh) continue;
+        for (int e = 0; e < k; ++e) {
+          const int xn = xi + g.pad - e * g.dil;
+          if (xn < 0 || xn % g.stride) continue;
+          const int xo = xn / g.stride;
+          if (xo >= g.ow) continue;
+          const int t = (a * k + b) * k + e;
+          const __nv_bfloat16* dr = dy + (((static_cast<int64_t>(nn) * g.od + zo) * g.oh + yo) * g.ow + xo) * dy_pitch;
+          const __nv_bfloat16* wt = wd + static_cast<int64_t>(k3 - 1 - t) * g.cin * g.cout;
+          if constexpr (VEC) {
+            for (int c0 = 0; c0 < g.cout; c0 += 8) {
+              float df[8];
+              unpack8(ld8(dr + c0), df);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (ci0 + j < g.cin) {
+                  float wf[8];
+                  unpack8(ld8(wt + static_cast<int64_t>(ci0 + j) * g.cout + c0), wf);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) acc[j] += df[q] * wf[q];
+                }
+              }
+            }
+          } else {
+            for (int c = 0; c < g.cout; ++c) {
+              const float df = __bfloat162float(dr[c]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (ci0 + j < g.cin) acc[j] += df * __bfloat162float(wt[static_cast<int64_t>(ci0 + j) * g.cout + c]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (ci0 + j < g.cin) dx[irow * dx_pitch + ci0 + j] = __float2bfloat16(acc[j] + (bias ? bias[ci0 + j] : 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// block = one tap, one 32x32 (ci, co) tile, one chunk of output voxels.  256 threads, 4 accumulators each.
+__global__ void __launch_bounds__(256)
+    conv_direct_wgrad_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                             const __nv_bfloat16* __restrict__ dy, int64_t dy_pitch, float* __restrict__ dwp,
+                             int64_t vox_per_block) {
+  __shared__ float xs[32][33];   // [voxel][ci]
+  __shared__ float ds[32][33];   // [voxel][co]
+  const int co_tiles = (g.cout + 31) / 32;
+  const int ci0 = (blockIdx.x / co_tiles) * 32, co0 = (blockIdx.x % co_tiles) * 32;
+  const int t = blockIdx.y, k = g.k;
+  const int a = t / (k * k), b = (t / k) % k, e = t % k;
+  const int64_t total = static_cast<int64_t>(g.n) * g.od * g.oh * g.ow;
+  const int64_t v_begin = static_cast<int64_t>(blockIdx.z) * vox_per_block;
+  const int64_t v_end = v_begin + vox_per_block < total ? v_begin + vox_per_block : total;
+  const int tid = threadIdx.x;
+  const int ci_l = tid >> 3;          // 0..31
+  const int co_l = (tid & 7) * 4;     // 0,4,..28
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t vb = v_begin; vb < v_end; vb += 32) {
+    // stage 32 voxels: thread (vv = tid/8, 4 channels at (tid%8)*4)
+    {
+      const int vv = tid >> 3, c4 = (tid & 7) * 4;
+      const int64_t v = vb + vv;
+      bool ok = v < v_end;
+      int64_t irow = 0;
+      if (ok) {
+        int64_t r = v;
+        const int xo = static_cast<int>(r % g.ow);
+        r /= g.ow;
+        const int yo = static_cast<int>(r % g.oh);
+        r /= g.oh;
+        const int zo = static_cast<int>(r % g.od);
+        const int nn = static_cast<int>(r / g.od);
+        const int zi = zo * g.stride - g.pad + a * g.dil, yi = yo * g.stride - g.pad + b * g.dil,
+                  xi = xo * g.stride - g.pad + e * g.dil;
+        const bool inb = zi >= 0 && zi < g.d && yi >= 0 && yi < g.h && xi >= 0 && xi < g.w;
+        irow = ((static_cast<int64_t>(nn) * g.d + zi) * g.h + yi) * g.w + xi;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ci = ci0 + c4 + q, co = co0 + c4 + q;
+          xs[vv][c4 + q] = (inb && ci < g.cin) ? __bfloat162float(x[irow * x_pitch + ci]) : 0.f;
+          ds[vv][c4 + q] = (co < g.cout) ? __bfloat162float(dy[v * dy_pitch + co]) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xs[vv][c4 + q] = ds[vv][c4 + q] = 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int vv = 0; vv < 32; ++vv) {
+      const float xv = xs[vv][ci_l];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += xv * ds[vv][co_l + q];
+    }
+    __syncthreads();
+  }
+  const int ci = ci0 + ci_l;
+  if (ci < g.cin) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int co = co0 + co_l + q;
+      if (co < g.cout && acc[q] != 0.f) atomicAdd(&dwp[(static_cast<int64_t>(t) * g.cin + ci) * g.cout + co], acc[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int conv_direct_fprop(const ConvGeom& g, const void* x, int64_t x_pitch, const void* wp, const float* bias, void* y,
+                      int64_t y_pitch, float* stats, cudaStream_t st) {
+  const int cog = (g.cout + 7) / 8;
+  const int64_t total = static_cast<int64_t>(g.n) * g.od * g.oh * g.ow * cog;
+  // blockDim * gridDim must be a multiple of cog so each thread keeps one channel group (see kernel)
+  int threads = 256;
+  int blocks = grid_for(total, threads, kNumSMs * 8);
+  if ((static_cast<int64_t>(threads) * blocks) % cog != 0) {
+    threads = cog * (256 / cog > 0 ? 256 / cog : 1);
+    if (threads > 1024 || threads < 1) {
+      set_error("conv_direct_fprop: cout=%d not supported by the direct path", g.cout);
+      return B200SEG_ERR_INVALID;
+    }
+    blocks = grid_for(total, threads, kNumSMs * 8);
+  }
+  const bool vec = (g.cin % 8 == 0) && (x_pitch % 8 == 0);
+  const size_t smem = stats ? 2 * g.cout * sizeof(float) : 0;
+  if (vec)
+    conv_direct_fprop_kernel<true><<<blocks, threads, smem, st>>>(
+        g, static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<const __nv_bfloat16*>(wp), bias,
+        static_cast<__nv_bfloat16*>(y), y_pitch, stats);
+  else
+    conv_direct_fprop_kernel<false><<<blocks, threads, smem, st>>>(
+        g, static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<const __nv_bfloat16*>(wp), bias,
+        static_cast<__nv_bfloat16*>(y), y_pitch, stats);
+  B200_CHECK_LAUNCH("conv_direct_fprop");
+  return 0;
+}
+
+int conv_direct_dgrad(const ConvGeom& g, const void* dy, int64_t dy_pitch, const void* wd, const float* bias, void* dx,
+                      int64_t dx_pitch, cudaStream_t st) {
+  const int cig = (g.cin + 7) / 8;
+  const int64_t total = static_cast<int64_t>(g.n) * g.d * g.h * g.w * cig;
+  const bool vec = (g.cout % 8 == 0) && (dy_pitch % 8 == 0);
+  if (vec)
+    conv_direct_dgrad_kernel<true><<<grid_for(total, 256, kNumSMs * 8), 256, 0, st>>>(
+        g, static_cast<const __nv_bfloat16*>(dy), dy_pitch, static_cast<const __nv_bfloat16*>(wd), bias,
+        static_cast<__nv_bfloat16*>(dx), dx_pitch);
+  else
+    conv_direct_dgrad_kernel<false><<<grid_for(total, 256, kNumSMs * 8), 256, 0, st>>>(
+        g, static_cast<const __nv_bfloat16*>(dy), dy_pitch, static_cast<const __nv_bfloat16*>(wd), bias,
+        static_cast<__nv_bfloat16*>(dx), dx_pitch);
+  B200_CHECK_LAUNCH("conv_direct_dgrad");
+  return 0;
+}
+
+int conv_direct_wgrad(const ConvGeom& g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, float* dwp,
+                      cudaStream_t st) {
+  const int k3 = g.k * g.k * g.k;
+  const int tiles = ((g.cin + 31) / 32) * ((g.cout + 31) / 32);
+  const int64_t total = static_cast<int64_t>(g.n) * g.od * g.oh * g.ow;
+  // aim for ~8 blocks per SM overall, at least 256 voxels per block
+  int64_t want_z = (static_cast<int64_t>(kNumSMs) * 8 + static_cast<int64_t>(tiles) * k3 - 1) / (static_cast<int64_t>(tiles) * k3);
+  if (want_z < 1) want_z = 1;
+  int64_t vpb = (total + want_z - 1) / want_z;
+  if (vpb < 256) vpb = 256;
+  vpb = (vpb + 31) / 32 * 32;
+  const int64_t gz = (total + vpb - 1) / vpb;
+  if (tiles > 2147483647 || gz > 65535 || k3 > 65535) {
+    set_error("conv_direct_wgrad: grid too large");
+    return B200SEG_ERR_INVALID;
+  }
+  dim3 grid(tiles, k3, static_cast<unsigned>(gz));
+  conv_direct_wgrad_kernel<<<grid, 256, 0, st>>>(g, static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                                 static_cast<const __nv_bfloat16*>(dy), dy_pitch, dwp, vpb);
+  B200_CHECK_LAUNCH("conv_direct_wgrad");
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
+                             int dgrad, void* stream) {
+  B200_CHECK_ARG(w && packed && cout > 0 && cin > 0 && k > 0 && cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin,
+                 "pack_conv_weight: bad arguments");
+  const int k3 = k * k * k;
+  const int64_t total = static_cast<int64_t>(k3) * cout * cin_cnt;
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(packed), cout, cin, k3, cin_off, cin_cnt, dgrad);
+  B200_CHECK_LAUNCH("pack_conv_weight");
+  return 0;
+}
+
+int b200seg_unpack_conv_wgrad(const float* dw_packed, float* grad_w, int cout, int cin, int k, int cin_off,
+                              int cin_cnt, int accumulate, void* stream) {
+  B200_CHECK_ARG(dw_packed && grad_w && cout > 0 && cin > 0 && k > 0 && cin_off >= 0 && cin_cnt > 0 &&
+                     cin_off + cin_cnt <= cin,
+                 "unpack_conv_wgrad: bad arguments");
+  const int k3 = k * k * k;
+  const int64_t total = static_cast<int64_t>(k3) * cout * cin_cnt;
+  unpack_conv_wgrad_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dw_packed, grad_w, cout, cin, k3, cin_off, cin_cnt, accumulate);
+  B200_CHECK_LAUNCH("unpack_conv_wgrad");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// Internal interfaces between the convolution dispatcher (conv.cu) and its two back ends.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200seg.h"
+
+namespace b200 {
+
+typedef b200seg_conv_geom ConvGeom;
+
+// direct CUDA-core path (conv_direct.cu)
+int conv_direct_fprop(const ConvGeom& g, const void* x, int64_t x_pitch, const void* wp, const float* bias, void* y,
+                      int64_t y_pitch, float* stats, cudaStream_t st);
+int conv_direct_dgrad(const ConvGeom& g, const void* dy, int64_t dy_pitch, const void* wd, const float* bias, void* dx,
+                      int64_t dx_pitch, cudaStream_t st);
+int conv_direct_wgrad(const ConvGeom& g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, float* dwp,
+                      cudaStream_t st);
+
+// tcgen05 implicit-GEMM path (conv_umma.cu).  "Conv form": out[o][n] = sum_{tap,k} in[o - pad + tap*dil][k] * W[tap][n][k]
+// with stride 1; fprop uses it directly, dgrad uses it with the flipped pack and pad' = dil*(k-1) - pad.
+struct UmmaConvArgs {
+  int n, d, h, w;        // input extents
+  int od, oh, ow;        // output extents
+  int cin, cout;         // K and N of the implicit GEMM
+  int k, pad, dil;
+  const void* in;
+  int64_t in_pitch;
+  const void* wpack;     // [k^3][cout][cin] bf16
+  const float* bias;     // may be null
+  void* out;
+  int64_t out_pitch;
+  float* stats;          // may be null: {sum[cout], sumsq[cout]}
+};
+bool conv_umma_supported(const UmmaConvArgs& a);
+int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st);
+
+struct UmmaWgradArgs {
+  int n, d, h, w, od, oh, ow, cin, cout, k, pad, dil;
+  const void* x;
+  int64_t x_pitch;
+  const void* dy;
+  int64_t dy_pitch;
+  float* dwp;            // [k^3][cin][cout] fp32, accumulated into
+};
+bool wgrad_umma_supported(const UmmaWgradArgs& a);
+int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st);
+
+}  // namespace b200

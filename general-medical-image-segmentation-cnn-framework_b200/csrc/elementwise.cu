@@ -1,0 +1,703 @@
+// Bandwidth-bound kernels: layout conversion, normalisation (+activation) forward/backward, MaxPool3d(2,2),
+// nearest x2 upsample, add, fused Adam.  All operate on NDHWC bf16 rows with 128-bit accesses where C % 8 == 0.
+// Roofline for every kernel here is HBM: algorithmic bytes are stated per kernel in DESIGN.md.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ layout
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int c,
+                                      int64_t spatial) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t s0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int cc = c0 + i;
+    const int64_t s = s0 + threadIdx.x;
+    tile[i][threadIdx.x] = (cc < c && s < spatial) ? src[(static_cast<int64_t>(n) * c + cc) * spatial + s] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t s = s0 + i;
+    const int cc = c0 + threadIdx.x;
+    if (cc < c && s < spatial) dst[(static_cast<int64_t>(n) * spatial + s) * c + cc] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int c,
+                                      int64_t spatial) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t s0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t s = s0 + i;
+    const int cc = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (cc < c && s < spatial) ? __bfloat162float(src[(static_cast<int64_t>(n) * spatial + s) * c + cc]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int cc = c0 + i;
+    const int64_t s = s0 + threadIdx.x;
+    if (cc < c && s < spatial) dst[(static_cast<int64_t>(n) * c + cc) * spatial + s] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ norm
+// Row-major [groups][rows][C] with pitch; V = channels per thread access (8 = 128-bit, 1 = scalar tail shapes).
+template <int V>
+__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float (&f)[V]) {
+  if constexpr (V == 8) {
+    float t[8];
+    unpack8(ld8(p), t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = t[i];
+  } else {
+    f[0] = __bfloat162float(p[0]);
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&f)[V]) {
+  if constexpr (V == 8) {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = f[i];
+    st8(p, pack8(t));
+  } else {
+    p[0] = __float2bfloat16(f[0]);
+  }
+}
+
+// Block = (TX chunk lanes) x (TY row lanes), TX*TY = 256.  NS sums of V channels each are reduced over rows.
+template <int V, int NS, typename F>
+__device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __restrict__ out_group, int C, F&& body) {
+  extern __shared__ float red[];  // [TY][TX][NS*V]
+  const int TX = blockDim.x, TY = blockDim.y;
+  for (int ch = threadIdx.x; ch < cv; ch += TX) {
+    float acc[NS][V];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[s][i] = 0.f;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * TY + threadIdx.y; r < rows;
+         r += static_cast<int64_t>(gridDim.x) * TY)
+      body(r, ch, acc);
+    float* mine = red + (static_cast<size_t>(threadIdx.y) * TX + threadIdx.x) * (NS * V);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int i = 0; i < V; ++i) mine[s * V + i] = acc[s][i];
+    __syncthreads();
+    for (int st = TY >> 1; st > 0; st >>= 1) {
+      if (threadIdx.y < st) {
+        const float* other = red + (static_cast<size_t>(threadIdx.y + st) * TX + threadIdx.x) * (NS * V);
+#pragma unroll
+        for (int j = 0; j < NS * V; ++j) mine[j] += other[j];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.y == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < V; ++i) atomicAdd(out_group + static_cast<size_t>(s) * C + ch * V + i, mine[s * V + i]);
+    }
+    __syncthreads();
+  }
+}
+
+template <int V>
+__global__ void channel_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t pitch, int64_t rows, int C,
+                                     float* __restrict__ stats) {
+  const int g = blockIdx.y;
+  const __nv_bfloat16* xg = x + static_cast<int64_t>(g) * rows * pitch;
+  column_reduce<V, 2>(rows, C / V, stats + static_cast<size_t>(g) * 2 * C, C,
+                      [&](int64_t r, int ch, float (&acc)[2][V]) {
+                        float f[V];
+                        load_vec<V>(xg + r * pitch + ch * V, f);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) {
+                          acc[0][i] += f[i];
+                          acc[1][i] += f[i] * f[i];
+                        }
+                      });
+}
+
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, double count, int groups, int C,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                     float eps, int clamp_eps, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * C) return;
+  const int g = i / C, c = i % C;
+  const double s = stats[(static_cast<size_t>(g) * 2 + 0) * C + c];
+  const double q = stats[(static_cast<size_t>(g) * 2 + 1) * C + c];
+  const double mean = s / count;
+  double var = (q - s * mean) / count;  // batchnorm.py:116-120: sumvar = ssum - sum*mean
+  if (var < 0) var = 0;
+  const double inv_std = clamp_eps ? 1.0 / sqrt(var < eps ? static_cast<double>(eps) : var) : 1.0 / sqrt(var + eps);
+  if (running_mean != nullptr && groups == 1) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
+    running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+  const double ga = gamma ? gamma[c] : 1.0;
+  const double be = beta ? beta[c] : 0.0;
+  float* o = out + static_cast<size_t>(g) * 4 * C;
+  o[0 * C + c] = static_cast<float>(mean);
+  o[1 * C + c] = static_cast<float>(inv_std);
+  o[2 * C + c] = static_cast<float>(ga * inv_std);
+  o[3 * C + c] = static_cast<float>(be - mean * ga * inv_std);
+}
+
+template <int V>
+__global__ void norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
+                                    const float* __restrict__ coef, int64_t rows_per_group, int groups, int C, int act,
+                                    float act_param, const float* __restrict__ prelu_w,
+                                    const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
+                                    __nv_bfloat16* __restrict__ z, int64_t z_pitch) {
+  const int cv = C / V;
+  const int64_t total = rows_per_group * groups * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    const int64_t row = i / cv;
+    const int g = static_cast<int>(row / rows_per_group);
+    float f[V];
+    load_vec<V>(y + row * y_pitch + ch * V, f);
+    float r[V];
+    if (res) load_vec<V>(res + row * res_pitch + ch * V, r);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = ch * V + j;
+      float pre = f[j];
+      if (coef) pre = pre * coef[(static_cast<size_t>(g) * 4 + 2) * C + c] + coef[(static_cast<size_t>(g) * 4 + 3) * C + c];
+      if (res) pre += r[j];
+      const float slope = (act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
+      f[j] = act_fwd(pre, act, slope);
+    }
+    store_vec<V>(z + row * z_pitch + ch * V, f);
+  }
+}
+
+template <int V>
+__global__ void norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
+                                           const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
+                                           const float* __restrict__ coef, int64_t rows, int C, int act,
+                                           float act_param, const float* __restrict__ prelu_w,
+                                           const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
+                                           float* __restrict__ sums, float* __restrict__ dprelu) {
+  const int g = blockIdx.y;
+  const int64_t base = static_cast<int64_t>(g) * rows;
+  const float* cg = coef ? coef + static_cast<size_t>(g) * 4 * C : nullptr;
+  auto body = [&](int64_t r, int ch, auto& acc) {
+    float fy[V], fd[V], fr[V];
+    load_vec<V>(y + (base + r) * y_pitch + ch * V, fy);
+    load_vec<V>(dz + (base + r) * dz_pitch + ch * V, fd);
+    if (res) load_vec<V>(res + (base + r) * res_pitch + ch * V, fr);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = ch * V + j;
+      float pre = fy[j], xhat = fy[j];
+      if (cg) {
+        pre = fy[j] * cg[2 * C + c] + cg[3 * C + c];
+        xhat = (fy[j] - cg[0 * C + c]) * cg[1 * C + c];
+      }
+      if (res) pre += fr[j];
+      const float slope = (act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
+      const float dpre = fd[j] * act_bwd(pre, act, slope);
+      acc[0][j] += dpre;
+      acc[1][j] += dpre * xhat;
+      if constexpr (sizeof(acc) / sizeof(acc[0]) == 3) acc[2][j] += (pre > 0.f) ? 0.f : fd[j] * pre;
+    }
+  };
+  if (dprelu) {
+    // third running sum = PReLU slope gradient; lands in a scratch row after the two sums of this group
+    column_reduce<V, 3>(rows, C / V, sums + static_cast<size_t>(g) * 3 * C, C,
+                        [&](int64_t r, int ch, float (&acc)[3][V]) { body(r, ch, acc); });
+  } else {
+    column_reduce<V, 2>(rows, C / V, sums + static_cast<size_t>(g) * 2 * C, C,
+                        [&](int64_t r, int ch, float (&acc)[2][V]) { body(r, ch, acc); });
+  }
+}
+
+template <int V>
+__global__ void norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
+                                          const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
+                                          const float* __restrict__ coef, const float* __restrict__ sums,
+                                          int sums_stride, float inv_count, int64_t rows_per_group, int groups, int C,
+                                          int act, float act_param, const float* __restrict__ prelu_w,
+                                          const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
+                                          __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
+                                          __nv_bfloat16* __restrict__ dres, int64_t dres_pitch) {
+  const int cv = C / V;
+  const int64_t total = rows_per_group * groups * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    const int64_t row = i / cv;
+    const int g = static_cast<int>(row / rows_per_group);
+    const float* cg = coef ? coef + static_cast<size_t>(g) * 4 * C : nullptr;
+    const float* sg = sums ? sums + static_cast<size_t>(g) * sums_stride * C : nullptr;
+    float fy[V], fd[V], fr[V], o[V], dr[V];
+    load_vec<V>(y + row * y_pitch + ch * V, fy);
+    load_vec<V>(dz + row * dz_pitch + ch * V, fd);
+    if (res) load_vec<V>(res + row * res_pitch + ch * V, fr);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = ch * V + j;
+      float pre = fy[j], xhat = fy[j], scale = 1.f;
+      if (cg) {
+        scale = cg[2 * C + c];
+        pre = fy[j] * scale + cg[3 * C + c];
+        xhat = (fy[j] - cg[0 * C + c]) * cg[1 * C + c];
+      }
+      if (res) pre += fr[j];
+      const float slope = (act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
+      const float dpre = fd[j] * act_bwd(pre, act, slope);
+      dr[j] = dpre;
+      float v = dpre;
+      if (sg) v = dpre - sg[0 * C + c] * inv_count - xhat * sg[1 * C + c] * inv_count;
+      o[j] = v * scale;
+    }
+    store_vec<V>(dy + row * dy_pitch + ch * V, o);
+    if (dres) store_vec<V>(dres + row * dres_pitch + ch * V, dr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+template <int V>
+__global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                                    __nv_bfloat16* __restrict__ y, int64_t y_pitch, uint8_t* __restrict__ idx, int n,
+                                    int d, int h, int w, int C) {
+  const int od = d / 2, oh = h / 2, ow = w / 2, cv = C / V;
+  const int64_t total = static_cast<int64_t>(n) * od * oh * ow * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    int64_t v = i / cv;
+    const int xo = static_cast<int>(v % ow);
+    v /= ow;
+    const int yo = static_cast<int>(v % oh);
+    v /= oh;
+    const int zo = static_cast<int>(v % od);
+    const int nn = static_cast<int>(v / od);
+    float best[V];
+    uint8_t bi[V];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int a = k >> 2, b = (k >> 1) & 1, e = k & 1;
+      const int64_t row = ((static_cast<int64_t>(nn) * d + 2 * zo + a) * h + 2 * yo + b) * w + 2 * xo + e;
+      float f[V];
+      load_vec<V>(x + row * x_pitch + ch * V, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        // torch: strictly-greater replaces; a NaN candidate replaces a non-NaN best and then sticks
+        const bool take = (k == 0) || (f[j] > best[j]) || (f[j] != f[j] && best[j] == best[j]);
+        if (take) {
+          best[j] = f[j];
+          bi[j] = static_cast<uint8_t>(k);
+        }
+      }
+    }
+    const int64_t orow = i / cv;
+    store_vec<V>(y + orow * y_pitch + ch * V, best);
+#pragma unroll
+    for (int j = 0; j < V; ++j) idx[orow * C + ch * V + j] = bi[j];
+  }
+}
+
+template <int V>
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
+                                    const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx, int64_t dx_pitch,
+                                    int n, int d, int h, int w, int C) {
+  const int od = d / 2, oh = h / 2, ow = w / 2, cv = C / V;
+  const int64_t total = static_cast<int64_t>(n) * od * oh * ow * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    const int64_t orow = i / cv;
+    int64_t v = orow;
+    const int xo = static_cast<int>(v % ow);
+    v /= ow;
+    const int yo = static_cast<int>(v % oh);
+    v /= oh;
+    const int zo = static_cast<int>(v % od);
+    const int nn = static_cast<int>(v / od);
+    float g[V];
+    load_vec<V>(dy + orow * dy_pitch + ch * V, g);
+    uint8_t bi[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) bi[j] = idx[orow * C + ch * V + j];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int a = k >> 2, b = (k >> 1) & 1, e = k & 1;
+      const int64_t row = ((static_cast<int64_t>(nn) * d + 2 * zo + a) * h + 2 * yo + b) * w + 2 * xo + e;
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = (bi[j] == k) ? g[j] : 0.f;
+      store_vec<V>(dx + row * dx_pitch + ch * V, o);
+    }
+  }
+}
+
+__global__ void maxpool2_idx_to_torch_kernel(const uint8_t* __restrict__ idx, int64_t* __restrict__ out, int n, int d,
+                                             int h, int w, int C) {
+  const int od = d / 2, oh = h / 2, ow = w / 2;
+  const int64_t total = static_cast<int64_t>(n) * C * od * oh * ow;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t v = i;  // NCDHW order of the output
+    const int xo = static_cast<int>(v % ow);
+    v /= ow;
+    const int yo = static_cast<int>(v % oh);
+    v /= oh;
+    const int zo = static_cast<int>(v % od);
+    v /= od;
+    const int c = static_cast<int>(v % C);
+    const int nn = static_cast<int>(v / C);
+    const int64_t orow = ((static_cast<int64_t>(nn) * od + zo) * oh + yo) * ow + xo;
+    const int k = idx[orow * C + c];
+    const int a = k >> 2, b = (k >> 1) & 1, e = k & 1;
+    out[i] = (static_cast<int64_t>(2 * zo + a) * h + 2 * yo + b) * w + 2 * xo + e;
+  }
+}
+
+template <int V>
+__global__ void upsample2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                                     __nv_bfloat16* __restrict__ y, int64_t y_pitch, int n, int d, int h, int w, int C) {
+  const int cv = C / V;
+  const int64_t total = static_cast<int64_t>(n) * d * h * w * 8 * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    int64_t v = i / cv;  // output voxel index in [n][2d][2h][2w]
+    const int64_t orow = v;
+    const int xo = static_cast<int>(v % (2 * w));
+    v /= 2 * w;
+    const int yo = static_cast<int>(v % (2 * h));
+    v /= 2 * h;
+    const int zo = static_cast<int>(v % (2 * d));
+    const int nn = static_cast<int>(v / (2 * d));
+    const int64_t irow = ((static_cast<int64_t>(nn) * d + zo / 2) * h + yo / 2) * w + xo / 2;
+    float f[V];
+    load_vec<V>(x + irow * x_pitch + ch * V, f);
+    store_vec<V>(y + orow * y_pitch + ch * V, f);
+  }
+}
+
+template <int V>
+__global__ void upsample2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
+                                     __nv_bfloat16* __restrict__ dx, int64_t dx_pitch, int n, int d, int h, int w,
+                                     int C) {
+  const int cv = C / V;
+  const int64_t total = static_cast<int64_t>(n) * d * h * w * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    const int64_t irow = i / cv;
+    int64_t v = irow;
+    const int xi = static_cast<int>(v % w);
+    v /= w;
+    const int yi = static_cast<int>(v % h);
+    v /= h;
+    const int zi = static_cast<int>(v % d);
+    const int nn = static_cast<int>(v / d);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int a = k >> 2, b = (k >> 1) & 1, e = k & 1;
+      const int64_t orow = ((static_cast<int64_t>(nn) * 2 * d + 2 * zi + a) * 2 * h + 2 * yi + b) * 2 * w + 2 * xi + e;
+      float f[V];
+      load_vec<V>(dy + orow * dy_pitch + ch * V, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += f[j];
+    }
+    store_vec<V>(dx + irow * dx_pitch + ch * V, acc);
+  }
+}
+
+template <int V>
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, int64_t a_pitch, const __nv_bfloat16* __restrict__ b,
+                           int64_t b_pitch, __nv_bfloat16* __restrict__ out, int64_t out_pitch, int64_t rows, int C) {
+  const int cv = C / V;
+  const int64_t total = rows * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    const int64_t row = i / cv;
+    float fa[V], fb[V];
+    load_vec<V>(a + row * a_pitch + ch * V, fa);
+    load_vec<V>(b + row * b_pitch + ch * V, fb);
+#pragma unroll
+    for (int j = 0; j < V; ++j) fa[j] += fb[j];
+    store_vec<V>(out + row * out_pitch + ch * V, fa);
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t numel, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt, float gscale) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float grad = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) grad += wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * grad;
+    const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200seg_version(void) { return "b200seg 0.1 (sm_100a)"; }
+const char* b200seg_last_error(void) { return b200::get_error(); }
+
+int b200seg_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int n, int c, int64_t spatial, void* stream) {
+  B200_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "ncdhw_to_ndhwc: bad arguments");
+  dim3 grid(static_cast<unsigned>((spatial + 31) / 32), (c + 31) / 32, n), block(32, 8);
+  ncdhw_to_ndhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), c, spatial);
+  B200_CHECK_LAUNCH("ncdhw_to_ndhwc");
+  return 0;
+}
+int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, int64_t spatial, void* stream) {
+  B200_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "ndhwc_to_ncdhw: bad arguments");
+  dim3 grid(static_cast<unsigned>((spatial + 31) / 32), (c + 31) / 32, n), block(32, 8);
+  ndhwc_to_ncdhw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, c, spatial);
+  B200_CHECK_LAUNCH("ndhwc_to_ncdhw");
+  return 0;
+}
+
+static inline bool vec_ok(int c, int64_t p0, int64_t p1 = 0, int64_t p2 = 0, int64_t p3 = 0) {
+  return c % 8 == 0 && p0 % 8 == 0 && p1 % 8 == 0 && p2 % 8 == 0 && p3 % 8 == 0;
+}
+static inline dim3 reduce_block(int cv) {
+  int tx = 1;
+  while (tx < cv && tx < 64) tx <<= 1;
+  return dim3(tx, 256 / tx);
+}
+
+int b200seg_channel_stats(const void* x, int64_t pitch, int64_t rows_per_group, int groups, int c, float* stats,
+                          void* stream) {
+  B200_CHECK_ARG(x && stats && rows_per_group > 0 && groups > 0 && c > 0 && pitch >= c, "channel_stats: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  const auto* xp = static_cast<const __nv_bfloat16*>(x);
+  if (vec_ok(c, pitch)) {
+    dim3 block = reduce_block(c / 8);
+    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    channel_stats_kernel<8><<<grid, block, 256 * 16 * sizeof(float), st>>>(xp, pitch, rows_per_group, c, stats);
+  } else {
+    dim3 block = reduce_block(c);
+    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    channel_stats_kernel<1><<<grid, block, 256 * 2 * sizeof(float), st>>>(xp, pitch, rows_per_group, c, stats);
+  }
+  B200_CHECK_LAUNCH("channel_stats");
+  return 0;
+}
+
+int b200seg_norm_finalize(const float* stats, double count, int groups, int c, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float momentum, float eps, int clamp_eps,
+                          float* out, void* stream) {
+  B200_CHECK_ARG(stats && out && count > 0 && groups > 0 && c > 0, "norm_finalize: bad arguments");
+  const int total = groups * c;
+  norm_finalize_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, count, groups, c, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps, out);
+  B200_CHECK_LAUNCH("norm_finalize");
+  return 0;
+}
+
+int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int64_t rows_per_group, int groups, int c,
+                         int act, float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                         void* z, int64_t z_pitch, void* stream) {
+  B200_CHECK_ARG(y && z && rows_per_group > 0 && groups > 0 && c > 0, "norm_act_fwd: bad arguments");
+  B200_CHECK_ARG(act != B200SEG_ACT_PRELU || prelu_w, "norm_act_fwd: PReLU needs a slope vector");
+  auto st = static_cast<cudaStream_t>(stream);
+  const auto* yp = static_cast<const __nv_bfloat16*>(y);
+  const auto* rp = static_cast<const __nv_bfloat16*>(residual);
+  auto* zp = static_cast<__nv_bfloat16*>(z);
+  if (vec_ok(c, y_pitch, z_pitch, residual ? res_pitch : 0)) {
+    const int64_t total = rows_per_group * groups * (c / 8);
+    norm_act_fwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
+                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch);
+  } else {
+    const int64_t total = rows_per_group * groups * c;
+    norm_act_fwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
+                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch);
+  }
+  B200_CHECK_LAUNCH("norm_act_fwd");
+  return 0;
+}
+
+int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch, const float* coef,
+                                int64_t rows_per_group, int groups, int c, int act, float act_param,
+                                const float* prelu_w, const void* residual, int64_t res_pitch, float* sums,
+                                float* dprelu, void* stream) {
+  B200_CHECK_ARG(dz && y && sums && rows_per_group > 0 && groups > 0 && c > 0, "norm_act_bwd_reduce: bad arguments");
+  B200_CHECK_ARG(!dprelu || groups == 1, "norm_act_bwd_reduce: PReLU gradient needs groups == 1");
+  auto st = static_cast<cudaStream_t>(stream);
+  const auto* dzp = static_cast<const __nv_bfloat16*>(dz);
+  const auto* yp = static_cast<const __nv_bfloat16*>(y);
+  const auto* rp = static_cast<const __nv_bfloat16*>(residual);
+  // with dprelu the caller passes sums sized [3][c]; the third row is the slope gradient (== dprelu target)
+  if (vec_ok(c, dz_pitch, y_pitch, residual ? res_pitch : 0)) {
+    dim3 block = reduce_block(c / 8);
+    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    norm_act_bwd_reduce_kernel<8><<<grid, block, 256 * 24 * sizeof(float), st>>>(
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu);
+  } else {
+    dim3 block = reduce_block(c);
+    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    norm_act_bwd_reduce_kernel<1><<<grid, block, 256 * 3 * sizeof(float), st>>>(
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu);
+  }
+  B200_CHECK_LAUNCH("norm_act_bwd_reduce");
+  return 0;
+}
+
+int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch, const float* coef,
+                               const float* sums, double count, int64_t rows_per_group, int groups, int c, int act,
+                               float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                               void* dy, int64_t dy_pitch, void* dres, int64_t dres_pitch, void* stream) {
+  B200_CHECK_ARG(dz && y && dy && rows_per_group > 0 && groups > 0 && c > 0, "norm_act_bwd_apply: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  const auto* dzp = static_cast<const __nv_bfloat16*>(dz);
+  const auto* yp = static_cast<const __nv_bfloat16*>(y);
+  const auto* rp = static_cast<const __nv_bfloat16*>(residual);
+  auto* dyp = static_cast<__nv_bfloat16*>(dy);
+  auto* drp = static_cast<__nv_bfloat16*>(dres);
+  const float inv_count = sums ? static_cast<float>(1.0 / count) : 0.f;
+  const int sums_stride = (act == B200SEG_ACT_PRELU) ? 3 : 2;
+  if (vec_ok(c, dz_pitch, y_pitch, dy_pitch, (residual ? res_pitch : 0) | (dres ? dres_pitch : 0))) {
+    const int64_t total = rows_per_group * groups * (c / 8);
+    norm_act_bwd_apply_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(
+        dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
+        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch);
+  } else {
+    const int64_t total = rows_per_group * groups * c;
+    norm_act_bwd_apply_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(
+        dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
+        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch);
+  }
+  B200_CHECK_LAUNCH("norm_act_bwd_apply");
+  return 0;
+}
+
+int b200seg_maxpool2_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, uint8_t* idx, int n, int d, int h,
+                         int w, int c, void* stream) {
+  B200_CHECK_ARG(x && y && idx && n > 0 && d >= 2 && h >= 2 && w >= 2 && c > 0, "maxpool2_fwd: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t ov = static_cast<int64_t>(n) * (d / 2) * (h / 2) * (w / 2);
+  if (vec_ok(c, x_pitch, y_pitch))
+    maxpool2_fwd_kernel<8><<<grid_for(ov * (c / 8), 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, idx, n, d, h, w, c);
+  else
+    maxpool2_fwd_kernel<1><<<grid_for(ov * c, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, idx, n, d, h, w, c);
+  B200_CHECK_LAUNCH("maxpool2_fwd");
+  return 0;
+}
+int b200seg_maxpool2_bwd(const void* dy, int64_t dy_pitch, const uint8_t* idx, void* dx, int64_t dx_pitch, int n,
+                         int d, int h, int w, int c, void* stream) {
+  B200_CHECK_ARG(dy && dx && idx && n > 0 && d >= 2 && h >= 2 && w >= 2 && c > 0, "maxpool2_bwd: bad arguments");
+  B200_CHECK_ARG(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool2_bwd: odd extents leave uncovered voxels; zero dx first");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t ov = static_cast<int64_t>(n) * (d / 2) * (h / 2) * (w / 2);
+  if (vec_ok(c, dy_pitch, dx_pitch))
+    maxpool2_bwd_kernel<8><<<grid_for(ov * (c / 8), 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pitch, idx, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c);
+  else
+    maxpool2_bwd_kernel<1><<<grid_for(ov * c, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pitch, idx, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c);
+  B200_CHECK_LAUNCH("maxpool2_bwd");
+  return 0;
+}
+int b200seg_maxpool2_idx_to_torch(const uint8_t* idx, int64_t* out, int n, int d, int h, int w, int c, void* stream) {
+  B200_CHECK_ARG(idx && out && n > 0 && c > 0, "maxpool2_idx_to_torch: bad arguments");
+  const int64_t total = static_cast<int64_t>(n) * c * (d / 2) * (h / 2) * (w / 2);
+  maxpool2_idx_to_torch_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, out, n, d, h,
+                                                                                                   w, c);
+  B200_CHECK_LAUNCH("maxpool2_idx_to_torch");
+  return 0;
+}
+
+int b200seg_upsample2_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int n, int d, int h, int w, int c,
+                          void* stream) {
+  B200_CHECK_ARG(x && y && n > 0 && c > 0, "upsample2_fwd: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t ov = static_cast<int64_t>(n) * d * h * w * 8;
+  if (vec_ok(c, x_pitch, y_pitch))
+    upsample2_fwd_kernel<8><<<grid_for(ov * (c / 8), 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, n, d, h, w, c);
+  else
+    upsample2_fwd_kernel<1><<<grid_for(ov * c, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, n, d, h, w, c);
+  B200_CHECK_LAUNCH("upsample2_fwd");
+  return 0;
+}
+int b200seg_upsample2_bwd(const void* dy, int64_t dy_pitch, void* dx, int64_t dx_pitch, int n, int d, int h, int w,
+                          int c, void* stream) {
+  B200_CHECK_ARG(dy && dx && n > 0 && c > 0, "upsample2_bwd: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t iv = static_cast<int64_t>(n) * d * h * w;
+  if (vec_ok(c, dy_pitch, dx_pitch))
+    upsample2_bwd_kernel<8><<<grid_for(iv * (c / 8), 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pitch, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c);
+  else
+    upsample2_bwd_kernel<1><<<grid_for(iv * c, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_pitch, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c);
+  B200_CHECK_LAUNCH("upsample2_bwd");
+  return 0;
+}
+int b200seg_add(const void* a, int64_t a_pitch, const void* b, int64_t b_pitch, void* out, int64_t out_pitch,
+                int64_t rows, int c, void* stream) {
+  B200_CHECK_ARG(a && b && out && rows > 0 && c > 0, "add: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  if (vec_ok(c, a_pitch, b_pitch, out_pitch))
+    add_kernel<8><<<grid_for(rows * (c / 8), 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(a), a_pitch, static_cast<const __nv_bfloat16*>(b), b_pitch,
+        static_cast<__nv_bfloat16*>(out), out_pitch, rows, c);
+  else
+    add_kernel<1><<<grid_for(rows * c, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(a), a_pitch, static_cast<const __nv_bfloat16*>(b), b_pitch,
+        static_cast<__nv_bfloat16*>(out), out_pitch, rows, c);
+  B200_CHECK_LAUNCH("add");
+  return 0;
+}
+
+int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                      void* stream) {
+  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, "adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adam_kernel<<<grid_for(numel, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  B200_CHECK_LAUNCH("adam_step");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+// Head (1x1x1 conv to class logits), fused softmax + Dice + CE (+ sigmoid-Dice, BCE) reduction and gradient,
+// arg-max label maps, segmentation counts (Dice/IoU metric) and the sliding-window aggregator.
+// All HBM-bound: one pass over their inputs, 128-bit loads where the layout allows.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kMaxClasses = 8;
+
+// ------------------------------------------------------------------------------------------------ head conv
+// x: [n*spatial][cin] bf16 (pitch), logits: [n][classes][spatial] fp32.
+__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, const float* __restrict__ w,
+                                const float* __restrict__ b, float* __restrict__ logits, int n, int64_t spatial,
+                                int cin, int classes) {
+  extern __shared__ float sw[];  // [classes][cin] + [classes]
+  for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < classes; i += blockDim.x) sw[classes * cin + i] = b ? b[i] : 0.f;
+  __syncthreads();
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float acc[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) acc[k] = (k < classes) ? sw[classes * cin + k] : 0.f;
+    const __nv_bfloat16* xr = x + v * x_pitch;
+    if ((cin & 7) == 0 && (x_pitch & 7) == 0) {
+      for (int c0 = 0; c0 < cin; c0 += 8) {
+        float f[8];
+        unpack8(ld8(xr + c0), f);
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k)
+          if (k < classes) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k] += f[j] * sw[k * cin + c0 + j];
+          }
+      }
+    } else {
+      for (int c = 0; c < cin; ++c) {
+        const float f = __bfloat162float(xr[c]);
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k)
+          if (k < classes) acc[k] += f * sw[k * cin + c];
+      }
+    }
+    const int64_t nn = v / spatial, s = v % spatial;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) logits[(nn * classes + k) * spatial + s] = acc[k];
+  }
+}
+
+// dx[v][c] = sum_k dl[k][v] w[k][c];  grad_w[k][c] += sum_v dl[k][v] x[v][c];  grad_b[k] += sum_v dl[k][v]
+__global__ void head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x,
+                                int64_t x_pitch, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
+                                int64_t dx_pitch, float* __restrict__ grad_w, float* __restrict__ grad_b, int n,
+                                int64_t spatial, int cin, int classes) {
+  extern __shared__ float sm[];  // w [classes*cin] | gw [classes*cin] | gb [classes]
+  float* sw = sm;
+  float* gw = sm + classes * cin;
+  float* gb = gw + classes * cin;
+  for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) {
+    sw[i] = w[i];
+    gw[i] = 0.f;
+  }
+  for (int i = threadIdx.x; i < classes; i += blockDim.x) gb[i] = 0.f;
+  __syncthreads();
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  const int lane = threadIdx.x & 31;
+  for (int64_t v0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) - lane; v0 < total;
+       v0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t v = v0 + lane;
+    const bool valid = v < total;
+    float dl[kMaxClasses];
+    const int64_t nn = valid ? v / spatial : 0, s = valid ? v % spatial : 0;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      dl[k] = (valid && k < classes) ? dlogits[(nn * classes + k) * spatial + s] : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        const float t = warp_sum(dl[k]);
+        if (lane == 0) atomicAdd(&gb[k], t);
+      }
+    for (int c = 0; c < cin; ++c) {
+      const float xv = valid ? __bfloat162float(x[v * x_pitch + c]) : 0.f;
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < classes) {
+          d += dl[k] * sw[k * cin + c];
+          const float t = warp_sum(dl[k] * xv);
+          if (lane == 0) atomicAdd(&gw[k * cin + c], t);
+        }
+      if (valid) dx[v * dx_pitch + c] = __float2bfloat16(d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) atomicAdd(&grad_w[i], gw[i]);
+  for (int i = threadIdx.x; i < classes; i += blockDim.x) atomicAdd(&grad_b[i], gb[i]);
+}
+
+__global__ void argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ labels, int n, int64_t spatial,
+                              int classes) {
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t nn = v / spatial, s = v % spatial;
+    float best = logits[(nn * classes) * spatial + s];
+    int bi = 0;
+    for (int k = 1; k < classes; ++k) {
+      const float f = logits[(nn * classes + k) * spatial + s];
+      if (f > best || (f != f && best == best)) {  // ties keep the lowest index; NaN wins like torch.argmax
+        best = f;
+        bi = k;
+      }
+    }
+    labels[v] = static_cast<uint8_t>(bi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void loss_reduce_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int n,
+                                   int64_t spatial, int classes, double* __restrict__ partial) {
+  const int nsum = 1 + 3 * classes + 4;
+  float acc[1 + 3 * kMaxClasses + 4];
+#pragma unroll
+  for (int i = 0; i < 1 + 3 * kMaxClasses + 4; ++i) acc[i] = 0.f;
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t nn = v / spatial, s = v % spatial;
+    const int t = labels[v];
+    float l[kMaxClasses];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        l[k] = logits[(nn * classes + k) * spatial + s];
+        m = fmaxf(m, l[k]);
+      }
+    float z = 0.f, e[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        e[k] = expf(l[k] - m);
+        z += e[k];
+      }
+    const float inv_z = 1.f / z, logz = logf(z);
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        const float p = e[k] * inv_z;
+        const float tk = (k == t) ? 1.f : 0.f;
+        if (k == t) acc[0] += -(l[k] - m - logz);
+        acc[1 + 3 * k + 0] += p * tk;
+        acc[1 + 3 * k + 1] += p * p;
+        acc[1 + 3 * k + 2] += tk;
+        const float sg = sigmoidf_(l[k]);
+        acc[1 + 3 * classes + 0] += sg * tk;
+        acc[1 + 3 * classes + 1] += sg;
+        acc[1 + 3 * classes + 2] += tk;
+        acc[1 + 3 * classes + 3] += fmaxf(l[k], 0.f) - l[k] * tk + log1pf(expf(-fabsf(l[k])));
+      }
+  }
+  __shared__ double red[1 + 3 * kMaxClasses + 4];
+  for (int i = threadIdx.x; i < nsum; i += blockDim.x) red[i] = 0.0;
+  __syncthreads();
+  for (int i = 0; i < nsum; ++i) {
+    const double t = warp_sum_d(static_cast<double>(acc[i]));
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nsum; i += blockDim.x) atomicAdd(&partial[i], red[i]);
+}
+
+__global__ void loss_grad_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int n,
+                                 int64_t spatial, int classes, const double* __restrict__ partial, float w_ce,
+                                 float w_dice, float w_sdice, float w_bce, const float* __restrict__ gscale_p,
+                                 float* __restrict__ dlogits) {
+  const float gscale = gscale_p ? *gscale_p : 1.f;
+  __shared__ float ck_t[kMaxClasses], ck_p[kMaxClasses];  // dDice/dp_k = ck_t*t_k + ck_p*p_k
+  __shared__ float sd_t, sd_c;
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  if (threadIdx.x < classes) {
+    const int k = threadIdx.x;
+    const double smooth = 1e-5;
+    const double I = partial[1 + 3 * k], Z = partial[2 + 3 * k], Y = partial[3 + 3 * k];
+    const double D = Z + Y + smooth;
+    // L_k = 1 - (2I+s)/D ; dL_k/dp = -2 t / D + (2I+s) * 2p / D^2 ; averaged over classes
+    ck_t[k] = static_cast<float>(-2.0 / D / classes);
+    ck_p[k] = static_cast<float>(2.0 * (2.0 * I + smooth) / (D * D) / classes);
+  }
+  if (threadIdx.x == 0) {
+    const double eps = 1e-5;
+    const double I = partial[1 + 3 * classes], U = partial[2 + 3 * classes] + partial[3 + 3 * classes];
+    // L = 1 - 2(I+e)/(U+e): dL/dsig = -2 [ t (U+e) - (I+e) ] / (U+e)^2
+    sd_t = static_cast<float>(-2.0 / (U + eps));
+    sd_c = static_cast<float>(2.0 * (I + eps) / ((U + eps) * (U + eps)));
+  }
+  __syncthreads();
+  const float inv_vox = 1.f / static_cast<float>(total);
+  const float inv_elems = inv_vox / classes;
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t nn = v / spatial, s = v % spatial;
+    const int t = labels[v];
+    float l[kMaxClasses], p[kMaxClasses], a[kMaxClasses];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        l[k] = logits[(nn * classes + k) * spatial + s];
+        m = fmaxf(m, l[k]);
+      }
+    float z = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        p[k] = expf(l[k] - m);
+        z += p[k];
+      }
+    const float inv_z = 1.f / z;
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        p[k] *= inv_z;
+        const float tk = (k == t) ? 1.f : 0.f;
+        a[k] = ck_t[k] * tk + ck_p[k] * p[k];
+        dot += a[k] * p[k];
+      }
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) {
+        const float tk = (k == t) ? 1.f : 0.f;
+        float g = w_ce * (p[k] - tk) * inv_vox + w_dice * p[k] * (a[k] - dot);
+        if (w_sdice != 0.f || w_bce != 0.f) {
+          const float sg = sigmoidf_(l[k]);
+          g += w_sdice * (sd_t * tk + sd_c) * sg * (1.f - sg) + w_bce * (sg - tk) * inv_elems;
+        }
+        dlogits[(nn * classes + k) * spatial + s] = g * gscale;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ metric
+__global__ void seg_counts_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred, int64_t numel,
+                                  unsigned long long* __restrict__ counts) {
+  unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  const int64_t nvec = numel / 16;
+  const uint4* g4 = reinterpret_cast<const uint4*>(gt);
+  const uint4* p4 = reinterpret_cast<const uint4*>(pred);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0;
+  auto one = [&](unsigned g, unsigned p) {
+    c0 += g;
+    c1 += p;
+    c2 += (g & p) != 0;
+    c3 += (g | p) != 0;
+  };
+  int64_t done = 0;
+  if (aligned) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const uint4 a = g4[i], b = p4[i];
+      const unsigned aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) one((aw[q] >> (8 * j)) & 0xFF, (bw[q] >> (8 * j)) & 0xFF);
+    }
+    done = nvec * 16;
+  }
+  for (int64_t i = done + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    one(gt[i], pred[i]);
+  unsigned long long vals[4] = {c0, c1, c2, c3};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    unsigned long long t = vals[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&counts[q], t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sliding window
+__global__ void window_crop_kernel(const uint8_t* __restrict__ patches, const int64_t* __restrict__ loc, int pw,
+                                   int ph, int pd, int ow, int oh, int od, uint8_t* __restrict__ out, int vw, int vh,
+                                   int vd) {
+  const int b = blockIdx.y;
+  const int64_t* L = loc + static_cast<int64_t>(b) * 6;
+  const int i0 = static_cast<int>(L[0]), j0 = static_cast<int>(L[1]), k0 = static_cast<int>(L[2]);
+  const int i1 = static_cast<int>(L[3]), j1 = static_cast<int>(L[4]), k1 = static_cast<int>(L[5]);
+  // trim overlap/2 from every face that is not on the volume border
+  const int li = i0 > 0 ? ow / 2 : 0, lj = j0 > 0 ? oh / 2 : 0, lk = k0 > 0 ? od / 2 : 0;
+  const int hi = i1 < vw ? ow / 2 : 0, hj = j1 < vh ? oh / 2 : 0, hk = k1 < vd ? od / 2 : 0;
+  const int64_t pvox = static_cast<int64_t>(pw) * ph * pd;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < pvox;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(t % pd);
+    const int j = static_cast<int>((t / pd) % ph);
+    const int i = static_cast<int>(t / (static_cast<int64_t>(pd) * ph));
+    if (i < li || i >= pw - hi || j < lj || j >= ph - hj || k < lk || k >= pd - hk) continue;
+    out[(static_cast<int64_t>(i0 + i) * vh + (j0 + j)) * vd + (k0 + k)] = patches[b * pvox + t];
+  }
+}
+
+__global__ void window_avg_kernel(const float* __restrict__ patches, const int64_t* __restrict__ loc, int c, int pw,
+                                  int ph, int pd, float* __restrict__ acc, float* __restrict__ count, int vw, int vh,
+                                  int vd) {
+  const int b = blockIdx.y;
+  const int64_t* L = loc + static_cast<int64_t>(b) * 6;
+  const int i0 = static_cast<int>(L[0]), j0 = static_cast<int>(L[1]), k0 = static_cast<int>(L[2]);
+  const int64_t pvox = static_cast<int64_t>(pw) * ph * pd;
+  const int64_t vvox = static_cast<int64_t>(vw) * vh * vd;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < pvox;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(t % pd);
+    const int j = static_cast<int>((t / pd) % ph);
+    const int i = static_cast<int>(t / (static_cast<int64_t>(pd) * ph));
+    const int64_t o = (static_cast<int64_t>(i0 + i) * vh + (j0 + j)) * vd + (k0 + k);
+    for (int ch = 0; ch < c; ++ch) atomicAdd(&acc[ch * vvox + o], patches[(static_cast<int64_t>(b) * c + ch) * pvox + t]);
+    atomicAdd(&count[o], 1.f);
+  }
+}
+
+__global__ void window_finalize_kernel(float* __restrict__ acc, const float* __restrict__ count, int c, int64_t voxels,
+                                       uint8_t* __restrict__ labels) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < voxels;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float inv = 1.f / fmaxf(count[v], 1.f);
+    float best = 0.f;
+    int bi = 0;
+    for (int ch = 0; ch < c; ++ch) {
+      const float f = acc[ch * voxels + v] * inv;
+      acc[ch * voxels + v] = f;
+      if (ch == 0 || f > best) {
+        best = f;
+        bi = ch;
+      }
+    }
+    if (labels) labels[v] = static_cast<uint8_t>(bi);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200seg_head_conv1x1_fwd(const void* x, int64_t x_pitch, const float* w, const float* b, float* logits, int n,
+                             int64_t spatial, int cin, int classes, void* stream) {
+  B200_CHECK_ARG(x && w && logits && n > 0 && spatial > 0 && cin > 0, "head_conv1x1_fwd: bad arguments");
+  B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "head_conv1x1_fwd: classes must be in [1,%d]", kMaxClasses);
+  const size_t smem = (static_cast<size_t>(classes) * cin + classes) * sizeof(float);
+  head_fwd_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, w, b, logits, n, spatial, cin, classes);
+  B200_CHECK_LAUNCH("head_conv1x1_fwd");
+  return 0;
+}
+
+int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitch, const float* w, void* dx,
+                             int64_t dx_pitch, float* grad_w, float* grad_b, int n, int64_t spatial, int cin,
+                             int classes, void* stream) {
+  B200_CHECK_ARG(dlogits && x && w && dx && grad_w && grad_b && n > 0 && spatial > 0 && cin > 0,
+                 "head_conv1x1_bwd: bad arguments");
+  B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "head_conv1x1_bwd: classes must be in [1,%d]", kMaxClasses);
+  const size_t smem = (2 * static_cast<size_t>(classes) * cin + classes) * sizeof(float);
+  head_bwd_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256, kNumSMs * 4), 256, smem,
+                    static_cast<cudaStream_t>(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(x), x_pitch, w,
+                                                         static_cast<__nv_bfloat16*>(dx), dx_pitch, grad_w, grad_b, n,
+                                                         spatial, cin, classes);
+  B200_CHECK_LAUNCH("head_conv1x1_bwd");
+  return 0;
+}
+
+int b200seg_argmax_labels(const float* logits, uint8_t* labels, int n, int64_t spatial, int classes, void* stream) {
+  B200_CHECK_ARG(logits && labels && n > 0 && spatial > 0 && classes >= 1 && classes <= 255, "argmax_labels: bad arguments");
+  argmax_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, labels, n, spatial, classes);
+  B200_CHECK_LAUNCH("argmax_labels");
+  return 0;
+}
+
+int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
+                        double* partial, void* stream) {
+  B200_CHECK_ARG(logits && labels && partial && n > 0 && spatial > 0, "loss_reduce: bad arguments");
+  B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "loss_reduce: classes must be in [1,%d]", kMaxClasses);
+  loss_reduce_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256, kNumSMs * 8), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(logits, labels, n, spatial, classes, partial);
+  B200_CHECK_LAUNCH("loss_reduce");
+  return 0;
+}
+
+int b200seg_loss_grad(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
+                      const double* partial, float w_ce, float w_dice, float w_sdice, float w_bce,
+                      const float* gscale, float* dlogits, void* stream) {
+  B200_CHECK_ARG(logits && labels && partial && dlogits && n > 0 && spatial > 0, "loss_grad: bad arguments");
+  B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "loss_grad: classes must be in [1,%d]", kMaxClasses);
+  loss_grad_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, labels, n, spatial, classes, partial, w_ce, w_dice, w_sdice, w_bce, gscale, dlogits);
+  B200_CHECK_LAUNCH("loss_grad");
+  return 0;
+}
+
+int b200seg_seg_counts(const uint8_t* gt, const uint8_t* pred, int64_t numel, unsigned long long* counts,
+                       void* stream) {
+  B200_CHECK_ARG(gt && pred && counts && numel >= 0, "seg_counts: bad arguments");
+  if (numel == 0) return 0;
+  seg_counts_kernel<<<grid_for((numel + 15) / 16, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gt, pred, numel, counts);
+  B200_CHECK_LAUNCH("seg_counts");
+  return 0;
+}
+
+int b200seg_window_accumulate_crop(const uint8_t* patches, const int64_t* locations, int batch, int pw, int ph, int pd,
+                                   int ow, int oh, int od, uint8_t* out, int vw, int vh, int vd, void* stream) {
+  B200_CHECK_ARG(patches && locations && out && batch > 0 && pw > 0 && ph > 0 && pd > 0, "window_crop: bad arguments");
+  B200_CHECK_ARG(ow % 2 == 0 && oh % 2 == 0 && od % 2 == 0, "window_crop: overlap must be even");
+  dim3 grid(grid_for(static_cast<int64_t>(pw) * ph * pd, 256, kNumSMs * 4), batch);
+  window_crop_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(patches, locations, pw, ph, pd, ow, oh, od,
+                                                                          out, vw, vh, vd);
+  B200_CHECK_LAUNCH("window_crop");
+  return 0;
+}
+
+int b200seg_window_accumulate_average(const float* patches, const int64_t* locations, int batch, int c, int pw, int ph,
+                                      int pd, float* acc, float* count, int vw, int vh, int vd, void* stream) {
+  B200_CHECK_ARG(patches && locations && acc && count && batch > 0 && c > 0, "window_average: bad arguments");
+  dim3 grid(grid_for(static_cast<int64_t>(pw) * ph * pd, 256, kNumSMs * 4), batch);
+  window_avg_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(patches, locations, c, pw, ph, pd, acc, count,
+                                                                         vw, vh, vd);
+  B200_CHECK_LAUNCH("window_average");
+  return 0;
+}
+
+int b200seg_window_finalize(float* acc, const float* count, int c, int64_t voxels, uint8_t* labels, void* stream) {
+  B200_CHECK_ARG(acc && count && c > 0 && c <= 255 && voxels > 0, "window_finalize: bad arguments");
+  window_finalize_kernel<<<grid_for(voxels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, count, c, voxels,
+                                                                                              labels);
+  B200_CHECK_LAUNCH("window_finalize");
+  return 0;
+}
+
+}  // extern "C"

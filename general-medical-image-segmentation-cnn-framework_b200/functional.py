@@ -1,0 +1,601 @@
+"""Autograd-facing wrappers around the C ABI (include/b200seg.h).
+
+Activations travel between these functions as channels-last bf16 tensors of shape [N, D, H, W, C]; the innermost
+dimension is contiguous and consecutive voxels are `pitch` elements apart, so a tensor may be a channel slice of a
+wider buffer (that is how the U-Net skip concatenation is made copy-free).  Parameters, statistics and parameter
+gradients are fp32.  PyTorch supplies memory, streams and the autograd tape; all arithmetic is in the kernels.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from ._lib import ConvGeom, call
+
+ACT = {"none": 0, None: 0, "relu": 1, "leaky_relu": 2, "elu": 3, "prelu": 4}
+
+# kernels launched since the last reset (bench.py reports it as gpu_launches)
+_LAUNCHES = [0]
+
+
+def launches():
+    return _LAUNCHES[0]
+
+
+def reset_launches():
+    _LAUNCHES[0] = 0
+
+
+def _call(name, *args):
+    _LAUNCHES[0] += 1
+    call(name, *args)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _pitched(t):
+    """True when t is a [N,D,H,W,C] bf16 view with unit channel stride and a uniform voxel pitch."""
+    if t.dim() != 5 or t.stride(4) != 1:
+        return False
+    n, d, h, w, c = t.shape
+    p = t.stride(3)
+    return p >= c and t.stride(2) == w * p and t.stride(1) == h * w * p and t.stride(0) == d * h * w * p
+
+
+def _as_rows(t):
+    """Return (tensor usable by the kernels, pitch)."""
+    assert t.is_cuda and t.dtype == torch.bfloat16, "expected a CUDA bf16 NDHWC tensor"
+    if not _pitched(t):
+        t = t.contiguous()
+    return t, t.stride(3)
+
+
+def _adjacent(a, b):
+    """a and b are back-to-back channel slices of one wider NDHWC buffer."""
+    return (_pitched(a) and _pitched(b) and a.shape[:4] == b.shape[:4] and a.stride() == b.stride()
+            and b.data_ptr() == a.data_ptr() + a.shape[4] * a.element_size() and a.stride(3) >= a.shape[4] + b.shape[4])
+
+
+def merge_channels(a, b):
+    """cat((a, b), channel) -- free when the two are adjacent slices of one buffer (see alloc_concat)."""
+    if _adjacent(a, b):
+        n, d, h, w, c = a.shape
+        return a.as_strided((n, d, h, w, c + b.shape[4]), a.stride())
+    return torch.cat((a, b), dim=4)
+
+
+def alloc_concat(n, d, h, w, c_first, c_second, device):
+    """One [n,d,h,w,c_first+c_second] buffer and its two channel-slice views (torch.cat replacement, unet3d.py:59)."""
+    buf = torch.empty((n, d, h, w, c_first + c_second), dtype=torch.bfloat16, device=device)
+    return buf, buf[..., :c_first], buf[..., c_first:]
+
+
+def conv_out(size, k, stride, pad, dil):
+    return (size + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def _geom(x_shape, cin, cout, k, stride, pad, dil):
+    n, d, h, w = x_shape[:4]
+    return ConvGeom(n, d, h, w, cin, conv_out(d, k, stride, pad, dil), conv_out(h, k, stride, pad, dil),
+                    conv_out(w, k, stride, pad, dil), cout, k, stride, pad, dil)
+
+
+def pack_conv_weight(weight, cin_off=0, cin_cnt=None, dgrad=False):
+    cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
+    cin_cnt = cin if cin_cnt is None else cin_cnt
+    packed = torch.empty(k ** 3 * cout * cin_cnt, dtype=torch.bfloat16, device=weight.device)
+    _call("b200seg_pack_conv_weight", _ptr(weight), _ptr(packed), cout, cin, k, cin_off, cin_cnt, int(dgrad), _stream())
+    return packed
+
+
+# ------------------------------------------------------------------------------------------------ raw op helpers
+def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats):
+    x, xp = _as_rows(x)
+    cout, cin = weight.shape[0], weight.shape[1]
+    assert x.shape[4] == cin, "input has %d channels, weight expects %d" % (x.shape[4], cin)
+    g = _geom(x.shape, cin, cout, k, stride, pad, dil)
+    y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
+    stats = torch.zeros((1, 2, cout), dtype=torch.float32, device=x.device) if want_stats else None
+    wp = pack_conv_weight(weight.detach())
+    b = bias.detach().float() if bias is not None else None
+    _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), cout, _ptr(stats),
+          None, 0, _stream())
+    return y, stats, g
+
+
+def conv3d_dgrad_raw(g, dy, weight):
+    dy, dyp = _as_rows(dy)
+    wd = pack_conv_weight(weight.detach(), dgrad=True)
+    dx = torch.empty((g.n, g.d, g.h, g.w, g.cin), dtype=torch.bfloat16, device=dy.device)
+    _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, None, 0, _stream())
+    return dx
+
+
+def conv3d_wgrad_raw(g, x, dy, weight_shape):
+    x, xp = _as_rows(x)
+    dy, dyp = _as_rows(dy)
+    k3 = g.k ** 3
+    dwp = torch.zeros(k3 * g.cin * g.cout, dtype=torch.float32, device=x.device)
+    _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), None, 0, _stream())
+    gw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
+    _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(gw), g.cout, g.cin, g.k, 0, g.cin, 0, _stream())
+    return gw
+
+
+def channel_stats(x, groups=1):
+    """[groups][2][C] fp32 sums / sums of squares over the voxels of each group (group = sample for instance norm)."""
+    x, xp = _as_rows(x)
+    n, d, h, w, c = x.shape
+    rows = n * d * h * w // groups
+    stats = torch.zeros((groups, 2, c), dtype=torch.float32, device=x.device)
+    _call("b200seg_channel_stats", _ptr(x), xp, rows, groups, c, _ptr(stats), _stream())
+    return stats
+
+
+def _norm_coef(stats, count, groups, c, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps, device):
+    coef = torch.empty((groups, 4, c), dtype=torch.float32, device=device)
+    _call("b200seg_norm_finalize", _ptr(stats), float(count), groups, c, _ptr(gamma), _ptr(beta),
+          _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), int(clamp_eps), _ptr(coef), _stream())
+    return coef
+
+
+def _eval_coef(gamma, beta, running_mean, running_var, eps, c, device):
+    """Inference-mode normalisation constants from the running statistics (C-element vectors)."""
+    inv_std = torch.rsqrt(running_var.float() + eps)
+    scale = inv_std * gamma.float() if gamma is not None else inv_std
+    shift = (beta.float() if beta is not None else torch.zeros(c, device=device)) - running_mean.float() * scale
+    return torch.stack((running_mean.float(), inv_std, scale, shift)).unsqueeze(0).contiguous()
+
+
+class NormSpec:
+    """What follows a convolution: normalisation kind, activation, and where the statistics come from."""
+
+    def __init__(self, kind=None, act="none", act_param=0.0, eps=1e-5, momentum=0.1, training=True, sync=False,
+                 clamp_eps=False, process_group=None):
+        assert kind in (None, "batch", "instance")
+        self.kind, self.act, self.act_param = kind, ACT[act], float(act_param)
+        self.eps, self.momentum, self.training = eps, momentum, training
+        self.sync, self.clamp_eps, self.process_group = sync, clamp_eps, process_group
+
+
+def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_w, residual, out):
+    """y (raw conv output or block input) -> z = act(norm(y) [+ residual]).  Returns z, coef, count, groups."""
+    y, yp = _as_rows(y)
+    n, d, h, w, c = y.shape
+    groups, count, coef = 1, float(n * d * h * w), None
+    if spec.kind == "instance":
+        groups, count = n, float(d * h * w)
+        coef = _norm_coef(channel_stats(y, groups), count, groups, c, None, None, None, None, 0.0, spec.eps, False,
+                          y.device)
+    elif spec.kind == "batch":
+        if spec.training:
+            if stats is None:
+                stats = channel_stats(y, 1)
+            if spec.sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(spec.process_group) > 1:
+                dist.all_reduce(stats, group=spec.process_group)  # {sum, sumsq}: sync_batchnorm/batchnorm.py:102
+                count *= dist.get_world_size(spec.process_group)
+            coef = _norm_coef(stats, count, 1, c, gamma, beta, running_mean, running_var, spec.momentum, spec.eps,
+                              spec.clamp_eps, y.device)
+        else:
+            coef = _eval_coef(gamma, beta, running_mean, running_var, spec.eps, c, y.device)
+    if out is None:
+        out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device)
+    assert _pitched(out) and out.shape == y.shape
+    res, resp = (None, 0)
+    if residual is not None:
+        res, resp = _as_rows(residual)
+    rows = n * d * h * w // groups
+    _call("b200seg_norm_act_fwd", _ptr(y), yp, _ptr(coef), rows, groups, c, spec.act, spec.act_param, _ptr(prelu_w),
+          _ptr(res), resp, _ptr(out), out.stride(3), _stream())
+    return out, coef, count, groups
+
+
+def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dres):
+    """Returns dy (bf16, contiguous), dres, sums ([groups][2 or 3][C] fp32: sum dpre, sum dpre*xhat[, dPReLU])."""
+    dz, dzp = _as_rows(dz)
+    y, yp = _as_rows(y)
+    n, d, h, w, c = y.shape
+    rows = n * d * h * w // groups
+    res, resp = (None, 0)
+    if residual is not None:
+        res, resp = _as_rows(residual)
+    nrow = 3 if spec.act == ACT["prelu"] else 2
+    sums = torch.zeros((groups, nrow, c), dtype=torch.float32, device=y.device)
+    dprelu = sums[0, 2] if nrow == 3 else None
+    _call("b200seg_norm_act_bwd_reduce", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), rows, groups, c, spec.act,
+          spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(sums), _ptr(dprelu), _stream())
+    use_batch_stats = spec.kind == "instance" or (spec.kind == "batch" and spec.training)
+    red = sums
+    if use_batch_stats and spec.kind == "batch" and spec.sync and dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size(spec.process_group) > 1:
+        red = sums.clone()
+        dist.all_reduce(red, group=spec.process_group)
+    dy = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device)
+    dres = torch.empty_like(dy) if want_dres else None
+    _call("b200seg_norm_act_bwd_apply", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), _ptr(red if use_batch_stats else None),
+          float(count), rows, groups, c, spec.act, spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(dy), c,
+          _ptr(dres), c, _stream())
+    return dy, dres, sums
+
+
+# ------------------------------------------------------------------------------------------------ autograd functions
+class _ToNDHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        n, c = x.shape[0], x.shape[1]
+        spatial = x[0, 0].numel()
+        x = x.contiguous().float()
+        out = torch.empty((n,) + tuple(x.shape[2:]) + (c,), dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_ncdhw_f32_to_ndhwc_bf16", _ptr(x), _ptr(out), n, c, spatial, _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        n, c = g.shape[0], g.shape[4]
+        spatial = g[0, ..., 0].numel()
+        out = torch.empty((n, c) + tuple(g.shape[1:4]), dtype=torch.float32, device=g.device)
+        _call("b200seg_ndhwc_bf16_to_ncdhw_f32", _ptr(g), _ptr(out), n, c, spatial, _stream())
+        return out
+
+
+def to_ndhwc(x):
+    """fp32 NCDHW (what train.py:195 feeds the model) -> bf16 NDHWC."""
+    return _ToNDHWC.apply(x)
+
+
+class _FromNDHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        n, c = x.shape[0], x.shape[4]
+        spatial = x[0, ..., 0].numel()
+        out = torch.empty((n, c) + tuple(x.shape[1:4]), dtype=torch.float32, device=x.device)
+        _call("b200seg_ndhwc_bf16_to_ncdhw_f32", _ptr(x), _ptr(out), n, c, spatial, _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return _ToNDHWC.forward(None, g)
+
+
+def from_ndhwc(x):
+    return _FromNDHWC.apply(x)
+
+
+class _ConvNormAct(torch.autograd.Function):
+    """conv (+bias) -> [batch / instance norm] -> activation [+ residual before the activation]."""
+
+    @staticmethod
+    def forward(ctx, x, x2, weight, bias, gamma, beta, prelu_w, residual, running_mean, running_var, cfg):
+        k, stride, pad, dil, spec, out = cfg
+        xin = x if x2 is None else merge_channels(x, x2)
+        fused_stats = spec.kind == "batch" and spec.training
+        y, stats, g = conv3d_fprop_raw(xin, weight, bias, k, stride, pad, dil, fused_stats)
+        if spec.kind is None and spec.act == 0 and residual is None:
+            z, coef, count, groups = y, None, 0.0, 1
+            if out is not None:
+                out.copy_(y)
+                z = out
+        else:
+            z, coef, count, groups = _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_w,
+                                                   residual, out)
+        ctx.save_for_backward(xin, y, coef, weight, gamma, prelu_w, residual)
+        ctx.cfg = (g, spec, count, groups, None if x2 is None else x.shape[4], bias is not None)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        xin, y, coef, weight, gamma, prelu_w, residual = ctx.saved_tensors
+        g, spec, count, groups, split, has_bias = ctx.cfg
+        need = ctx.needs_input_grad
+        dgamma = dbeta = dprelu = dres = None
+        plain = spec.kind is None and spec.act == 0 and residual is None
+        if plain:
+            dy = dz
+        else:
+            dy, dres, sums = _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual,
+                                            residual is not None and need[7])
+            if gamma is not None:
+                dgamma, dbeta = sums[:, 1].sum(0), sums[:, 0].sum(0)
+            if prelu_w is not None:
+                dprelu = sums[0, 2].clone()
+        dx = dx2 = dw = db = None
+        if need[0] or (split is not None and need[1]):
+            dxin = conv3d_dgrad_raw(g, dy, weight)
+            if split is None:
+                dx = dxin
+            else:
+                dx, dx2 = dxin[..., :split], dxin[..., split:]
+        if need[2]:
+            dw = conv3d_wgrad_raw(g, xin, dy, weight.shape)
+        if has_bias and need[3]:
+            if spec.kind is not None and (spec.training or spec.kind == "instance"):
+                # a bias in front of batch/instance statistics has an analytically zero gradient
+                db = torch.zeros(g.cout, dtype=torch.float32, device=dz.device)
+            else:
+                db = channel_stats(dy, 1)[0, 0]
+        return dx, dx2, dw, db, dgamma, dbeta, dprelu, dres, None, None, None
+
+
+def conv_norm_act(x, weight, bias=None, *, x2=None, k=3, stride=1, pad=1, dil=1, spec=None, gamma=None, beta=None,
+                  prelu_weight=None, residual=None, running_mean=None, running_var=None, out=None):
+    spec = spec or NormSpec()
+    return _ConvNormAct.apply(x, x2, weight, bias, gamma, beta, prelu_weight, residual, running_mean, running_var,
+                              (k, stride, pad, dil, spec, out))
+
+
+class _NormAct(torch.autograd.Function):
+    """Stand-alone normalisation + activation (pre-activation blocks: convolution.py:48-52, densevoxelnet3d.py:21-24)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, prelu_w, residual, running_mean, running_var, cfg):
+        spec, out = cfg
+        z, coef, count, groups = _norm_forward(y, None, spec, gamma, beta, running_mean, running_var, prelu_w, residual,
+                                               out)
+        ctx.save_for_backward(y, coef, gamma, prelu_w, residual)
+        ctx.cfg = (spec, count, groups)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, coef, gamma, prelu_w, residual = ctx.saved_tensors
+        spec, count, groups = ctx.cfg
+        dy, dres, sums = _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual,
+                                        residual is not None and ctx.needs_input_grad[4])
+        dgamma = dbeta = dprelu = None
+        if gamma is not None:
+            dgamma, dbeta = sums[:, 1].sum(0), sums[:, 0].sum(0)
+        if prelu_w is not None:
+            dprelu = sums[0, 2].clone()
+        return dy, dgamma, dbeta, dprelu, dres, None, None, None
+
+
+def norm_act(y, spec, gamma=None, beta=None, prelu_weight=None, residual=None, running_mean=None, running_var=None,
+             out=None):
+    return _NormAct.apply(y, gamma, beta, prelu_weight, residual, running_mean, running_var, (spec, out))
+
+
+class _MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x, xp = _as_rows(x)
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, d // 2, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+        idx = torch.empty((n, d // 2, h // 2, w // 2, c), dtype=torch.uint8, device=x.device)
+        _call("b200seg_maxpool2_fwd", _ptr(x), xp, _ptr(y), c, _ptr(idx), n, d, h, w, c, _stream())
+        ctx.save_for_backward(idx)
+        ctx.shape = (n, d, h, w, c)
+        ctx.mark_non_differentiable(idx)
+        return y, idx
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        (idx,) = ctx.saved_tensors
+        n, d, h, w, c = ctx.shape
+        dy, dyp = _as_rows(dy)
+        assert d % 2 == 0 and h % 2 == 0 and w % 2 == 0, "MaxPool3d(2,2) backward needs even extents"
+        dx = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=dy.device)
+        _call("b200seg_maxpool2_bwd", _ptr(dy), dyp, _ptr(idx), _ptr(dx), c, n, d, h, w, c, _stream())
+        return dx
+
+
+def max_pool2(x, return_indices=False):
+    """nn.MaxPool3d(2, 2).  Indices are uint8 local arg-max codes (see maxpool_indices_to_torch)."""
+    y, idx = _MaxPool2.apply(x)
+    return (y, idx) if return_indices else y
+
+
+def maxpool_indices_to_torch(idx, in_shape):
+    """uint8 local codes -> torch's int64 flat D*H*W indices, NCDHW layout (for the bit-exact comparison)."""
+    n, d, h, w, c = in_shape
+    out = torch.empty((n, c, d // 2, h // 2, w // 2), dtype=torch.int64, device=idx.device)
+    _call("b200seg_maxpool2_idx_to_torch", _ptr(idx), _ptr(out), n, d, h, w, c, _stream())
+    return out
+
+
+class _ConvT2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, out):
+        x, xp = _as_rows(x)
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[1]
+        assert weight.shape[0] == cin and tuple(weight.shape[2:]) == (2, 2, 2)
+        if out is None:
+            out = torch.empty((n, 2 * d, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=x.device)
+        assert _pitched(out) and tuple(out.shape) == (n, 2 * d, 2 * h, 2 * w, cout)
+        wp = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_pack_convt_weight", _ptr(weight.detach()), _ptr(wp), cin, cout, 0, _stream())
+        b = bias.detach().float() if bias is not None else None
+        _call("b200seg_convt_k2s2_fwd", _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(out), out.stride(3), n, d, h, w, cin, cout,
+              _stream())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[1]
+        dy, dyp = _as_rows(dy)
+        x, xp = _as_rows(x)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wd = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=x.device)
+            _call("b200seg_pack_convt_weight", _ptr(weight.detach()), _ptr(wd), cin, cout, 1, _stream())
+            dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=x.device)
+            _call("b200seg_convt_k2s2_dgrad", _ptr(dy), dyp, _ptr(wd), _ptr(dx), cin, n, d, h, w, cin, cout, _stream())
+        if ctx.needs_input_grad[1]:
+            dwp = torch.zeros(8 * cin * cout, dtype=torch.float32, device=x.device)
+            _call("b200seg_convt_k2s2_wgrad", _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), n, d, h, w, cin, cout, _stream())
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            # packed [8][cout_T][cin_T] is the strided conv's [k^3][cin_S][cout_S]: unpack with cout_S=cin_T, cin_S=cout_T
+            _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(dw), cin, cout, 2, 0, cout, 0, _stream())
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = channel_stats(dy, 1)[0, 0]
+        return dx, dw, db, None
+
+
+def conv_transpose_k2s2(x, weight, bias=None, out=None):
+    """nn.ConvTranspose3d(kernel_size=2, stride=2) (unet3d.py:29-43)."""
+    return _ConvT2.apply(x, weight, bias, out)
+
+
+class _Head(torch.autograd.Function):
+    """1x1x1 convolution to class logits, returned as fp32 NCDHW like the reference model's output (unet3d.py:70)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, xp = _as_rows(x)
+        n, d, h, w, cin = x.shape
+        classes = weight.shape[0]
+        w2 = weight.detach().reshape(classes, cin).float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        logits = torch.empty((n, classes, d, h, w), dtype=torch.float32, device=x.device)
+        _call("b200seg_head_conv1x1_fwd", _ptr(x), xp, _ptr(w2), _ptr(b), _ptr(logits), n, d * h * w, cin, classes,
+              _stream())
+        ctx.save_for_backward(x, w2)
+        ctx.wshape = weight.shape
+        ctx.has_bias = bias is not None
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        x, w2 = ctx.saved_tensors
+        x, xp = _as_rows(x)
+        n, d, h, w, cin = x.shape
+        classes = w2.shape[0]
+        dl = dl.contiguous().float()
+        dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=x.device)
+        gw = torch.zeros((classes, cin), dtype=torch.float32, device=x.device)
+        gb = torch.zeros(classes, dtype=torch.float32, device=x.device)
+        _call("b200seg_head_conv1x1_bwd", _ptr(dl), _ptr(x), xp, _ptr(w2), _ptr(dx), cin, _ptr(gw), _ptr(gb), n,
+              d * h * w, cin, classes, _stream())
+        return dx, gw.reshape(ctx.wshape), (gb if ctx.has_bias else None)
+
+
+def head_conv1x1(x, weight, bias=None):
+    return _Head.apply(x, weight, bias)
+
+
+class _Upsample2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x, xp = _as_rows(x)
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, 2 * d, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_upsample2_fwd", _ptr(x), xp, _ptr(y), c, n, d, h, w, c, _stream())
+        ctx.shape = (n, d, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, d, h, w, c = ctx.shape
+        dy, dyp = _as_rows(dy)
+        dx = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=dy.device)
+        _call("b200seg_upsample2_bwd", _ptr(dy), dyp, _ptr(dx), c, n, d, h, w, c, _stream())
+        return dx
+
+
+def upsample_nearest2(x):
+    return _Upsample2.apply(x)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, ap = _as_rows(a)
+        b, bp = _as_rows(b)
+        n, d, h, w, c = a.shape
+        out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=a.device)
+        _call("b200seg_add", _ptr(a), ap, _ptr(b), bp, _ptr(out), c, n * d * h * w, c, _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ losses / metrics
+def _labels_u8(target, n, spatial_shape):
+    t = target.reshape((n,) + tuple(spatial_shape))
+    return t.to(torch.uint8).contiguous()
+
+
+class _SegLoss(torch.autograd.Function):
+    """w_ce*cross_entropy_3D + w_dice*DiceLossss(softmax=True) + w_sdice*DiceLoss(sigmoid) + w_bce*BCEWithLogits,
+    from one reduction pass over the logits (loss_function.py:8-16, 102-130, 148-185; train.py:115)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weights):
+        logits = logits.contiguous().float()
+        n, classes = logits.shape[0], logits.shape[1]
+        spatial = logits[0, 0].numel()
+        partial = torch.zeros(1 + 3 * classes + 4, dtype=torch.float64, device=logits.device)
+        _call("b200seg_loss_reduce", _ptr(logits), _ptr(labels), n, spatial, classes, _ptr(partial), _stream())
+        ctx.save_for_backward(logits, labels, partial)
+        ctx.weights = weights
+        w_ce, w_dice, w_sdice, w_bce = weights
+        vox = float(n * spatial)
+        smooth = 1e-5
+        loss = partial.new_zeros(())
+        if w_ce:
+            loss = loss + w_ce * partial[0] / vox
+        if w_dice:
+            pk = partial[1:1 + 3 * classes].view(classes, 3)
+            loss = loss + w_dice * (1 - (2 * pk[:, 0] + smooth) / (pk[:, 1] + pk[:, 2] + smooth)).mean()
+        tail = partial[1 + 3 * classes:]
+        if w_sdice:
+            loss = loss + w_sdice * (1 - 2 * (tail[0] + smooth) / (tail[1] + tail[2] + smooth))
+        if w_bce:
+            loss = loss + w_bce * tail[3] / (vox * classes)
+        return loss.float()
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, partial = ctx.saved_tensors
+        n, classes = logits.shape[0], logits.shape[1]
+        spatial = logits[0, 0].numel()
+        w_ce, w_dice, w_sdice, w_bce = ctx.weights
+        dl = torch.empty_like(logits)
+        gs = g.reshape(1).to(device=logits.device, dtype=torch.float32)
+        _call("b200seg_loss_grad", _ptr(logits), _ptr(labels), n, spatial, classes, _ptr(partial), float(w_ce),
+              float(w_dice), float(w_sdice), float(w_bce), _ptr(gs), _ptr(dl), _stream())
+        return dl, None, None
+
+
+def seg_loss(logits, target, w_ce=1.0, w_dice=1.0, w_sdice=0.0, w_bce=0.0):
+    """logits: fp32 [N, K, D, H, W]; target: integer class labels [N, D, H, W] or [N, 1, D, H, W]."""
+    n = logits.shape[0]
+    labels = _labels_u8(target, n, logits.shape[2:])
+    return _SegLoss.apply(logits, labels, (w_ce, w_dice, w_sdice, w_bce))
+
+
+def argmax_labels(logits):
+    """pred.argmax(dim=1, keepdim=True) as uint8 (train.py:204, predict.py:139); ties -> lowest class."""
+    logits = logits.contiguous().float()
+    n, classes = logits.shape[0], logits.shape[1]
+    out = torch.empty((n, 1) + tuple(logits.shape[2:]), dtype=torch.uint8, device=logits.device)
+    _call("b200seg_argmax_labels", _ptr(logits), _ptr(out), n, logits[0, 0].numel(), classes, _stream())
+    return out
+
+
+def seg_counts(gt, pred):
+    """uint64[4] = {sum gt, sum pred, |gt & pred| != 0, |gt | pred| != 0} (metric.py:36-46), on the device."""
+    gt = gt.to(torch.uint8).contiguous()
+    pred = pred.to(torch.uint8).contiguous()
+    assert gt.numel() == pred.numel()
+    counts = torch.zeros(4, dtype=torch.int64, device=gt.device)
+    _call("b200seg_seg_counts", _ptr(gt), _ptr(pred), gt.numel(), _ptr(counts), _stream())
+    return counts

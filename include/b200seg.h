@@ -1,0 +1,181 @@
+/*
+ * b200seg -- C ABI of the B200-native volumetric segmentation hot path.
+ *
+ * The reference (QingYunA/General-Medical-Image-Segmentation-CNN-Framework) is 100 % Python over torch.nn: it has no
+ * FFI.  Its seam is the nn.Module protocol (train.py:324-373 builds the model, train.py:203-214 runs
+ * forward / loss / backward).  Each entry point below replaces the library kernel(s) PyTorch launches for one
+ * reference call site; the Python package binds them with ctypes.
+ *
+ * Conventions
+ *   - activations: channels-last NDHWC, bf16, innermost dim contiguous; `*_pitch` = elements between voxels.
+ *   - parameters / statistics / gradients of parameters: fp32.
+ *   - every function enqueues on `stream` (a cudaStream_t), never synchronises, never allocates persistent memory;
+ *     all buffers (incl. workspaces) are owned by the caller.
+ *   - return 0 on success, negative b200seg_status otherwise; b200seg_last_error() gives a thread-local message.
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200SEG_OK = 0,
+  B200SEG_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  B200SEG_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  B200SEG_ERR_WORKSPACE = -3    /* workspace too small */
+} b200seg_status;
+
+typedef enum { B200SEG_ACT_NONE = 0, B200SEG_ACT_RELU = 1, B200SEG_ACT_LEAKY = 2, B200SEG_ACT_ELU = 3,
+               B200SEG_ACT_PRELU = 4 } b200seg_act;
+
+/* Cubic-kernel 3-D convolution geometry (nn.Conv3d: unet3d.py:80-98, vnet3d.py:25,47,65,111,
+ * residual_unet3d.py:29-44, convolution.py:57-63).  Input [n,d,h,w,cin], output [n,od,oh,ow,cout]. */
+typedef struct {
+  int32_t n, d, h, w, cin;
+  int32_t od, oh, ow, cout;
+  int32_t k, stride, pad, dil;
+} b200seg_conv_geom;
+
+const char* b200seg_version(void);
+const char* b200seg_last_error(void);
+/* 1 if the tcgen05 implicit-GEMM path handles this geometry, 0 if the direct CUDA-core path is used. */
+int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g);
+
+/* ---- layout / packing ------------------------------------------------------------------------------------- */
+/* fp32 NCDHW -> bf16 NDHWC (model input, train.py:195) and back (logits handed to the caller as NCDHW fp32). */
+int b200seg_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int n, int c, int64_t spatial, void* stream);
+int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, int64_t spatial, void* stream);
+/* Conv3d weight [cout][cin][k^3] fp32 -> fprop pack [k^3][cout][cin] bf16 (flip=0) or dgrad pack
+ * [k^3 flipped][cin][cout] bf16 (flip=1).  cin_off/cin_cnt select an input-channel slice (concat-free decoders). */
+int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
+                             int dgrad, void* stream);
+/* wgrad result [k^3][cin_cnt][cout] fp32 -> accumulate into torch-layout grad [cout][cin][k^3] fp32 slice. */
+int b200seg_unpack_conv_wgrad(const float* dw_packed, float* grad_w, int cout, int cin, int k, int cin_off,
+                              int cin_cnt, int accumulate, void* stream);
+
+/* ---- Conv3d (nn.Conv3d fwd / autograd bwd) ------------------------------------------------------------------ */
+/* y = conv(x, w) + bias; optionally also per-channel sum / sum-of-squares of the fp32 result (BatchNorm statistics
+ * fused into the epilogue, unet3d.py:88,100).  w_packed from b200seg_pack_conv_weight(dgrad=0).
+ * stats (may be NULL): float[2*cout] = {sum, sumsq}, accumulated into (caller zeroes). */
+size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g);
+int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
+                         const float* bias, void* y, int64_t y_pitch, float* stats, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* dx = conv_transpose(dy, w).  w_packed from b200seg_pack_conv_weight(dgrad=1).  g describes the FORWARD conv. */
+int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_pitch, const void* w_packed_dgrad,
+                         void* dx, int64_t dx_pitch, void* workspace, size_t workspace_bytes, void* stream);
+/* dw_packed[k^3][cin][cout] (fp32, accumulated into; caller zeroes) = sum_voxels x (*) dy. */
+int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* dy,
+                         int64_t dy_pitch, float* dw_packed, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- ConvTranspose3d k=2 s=2 (unet3d.py:29-43) ---------------------------------------------------------------- */
+/* weight [cin][cout][2][2][2] fp32 -> pack [8][cout][cin] bf16 (fwd) / [8][cin][cout] bf16 (dgrad). */
+int b200seg_pack_convt_weight(const float* w, void* packed, int cin, int cout, int dgrad, void* stream);
+int b200seg_convt_k2s2_fwd(const void* x, int64_t x_pitch, const void* w_packed, const float* bias, void* y,
+                           int64_t y_pitch, int n, int d, int h, int w, int cin, int cout, void* stream);
+int b200seg_convt_k2s2_dgrad(const void* dy, int64_t dy_pitch, const void* w_packed_dgrad, void* dx,
+                             int64_t dx_pitch, int n, int d, int h, int w, int cin, int cout, void* stream);
+/* dw_packed [8][cout][cin] fp32 is accumulated into (caller zeroes); b200seg_unpack_conv_wgrad(cout=cin, cin=cout,
+ * k=2) turns it into the [cin][cout][2][2][2] layout.  The bias gradient is b200seg_channel_stats(dy) row 0. */
+int b200seg_convt_k2s2_wgrad(const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, float* dw_packed,
+                             int n, int d, int h, int w, int cin, int cout, void* stream);
+
+/* ---- normalisation + activation (nn.BatchNorm3d / InstanceNorm3d / SynchronizedBatchNorm3d + ReLU family) ---- */
+/* stats[g][2][c] += {sum, sumsq} over the rows of group g; rows = voxels, groups = 1 (batch norm) or n (instance). */
+int b200seg_channel_stats(const void* x, int64_t pitch, int64_t rows_per_group, int groups, int c, float* stats,
+                          void* stream);
+/* From (all-reduced) sums: mean, inv_std, fused scale/shift; updates running stats when non-NULL (momentum, unbiased
+ * variance).  clamp_eps=1 reproduces sync_batchnorm/batchnorm.py:125 (var.clamp(eps)^-1/2), 0 = nn.BatchNorm.
+ * out: float[groups][4][c] = {mean, inv_std, scale, shift}.  gamma/beta may be NULL (affine=False). */
+int b200seg_norm_finalize(const float* stats, double count, int groups, int c, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                          int clamp_eps, float* out, void* stream);
+/* z = act(y*scale + shift [+ residual]).  coef = the [groups][4][c] block from norm_finalize (NULL: identity).
+ * act_param: leaky slope (scalar, host) ; prelu_w: per-channel slope (device) for B200SEG_ACT_PRELU. */
+int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int64_t rows_per_group, int groups,
+                         int c, int act, float act_param, const float* prelu_w, const void* residual,
+                         int64_t res_pitch, void* z, int64_t z_pitch, void* stream);
+/* Backward, pass 1: sums[g][2][c] += {sum(dpre), sum(dpre * xhat)}, dpre = dz * act'(pre).  Also accumulates the
+ * PReLU slope gradient when dprelu != NULL. */
+int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch,
+                                const float* coef, int64_t rows_per_group, int groups, int c, int act,
+                                float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                                float* sums, float* dprelu, void* stream);
+/* Backward, pass 2: dy = scale * (dpre - sum_dpre/count - xhat * sum_dpre_xhat/count) (training statistics), or
+ * dy = scale * dpre when sums == NULL (eval / no norm).  dres (may be NULL) = dpre (gradient of the residual). */
+int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch, const float* coef,
+                               const float* sums, double count, int64_t rows_per_group, int groups, int c, int act,
+                               float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                               void* dy, int64_t dy_pitch, void* dres, int64_t dres_pitch, void* stream);
+
+/* ---- MaxPool3d(2,2) (unet3d.py:19-25) -------------------------------------------------------------------------- */
+/* idx: uint8 per output element, local argmax 0..7 = (a*2+b)*2+e in (d,h,w) scan order; ties -> first, NaN wins. */
+int b200seg_maxpool2_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, uint8_t* idx, int n, int d,
+                         int h, int w, int c, void* stream);
+int b200seg_maxpool2_bwd(const void* dy, int64_t dy_pitch, const uint8_t* idx, void* dx, int64_t dx_pitch, int n,
+                         int d, int h, int w, int c, void* stream);
+/* local indices -> torch's int64 flat D*H*W indices in NCDHW order (for the bit-exact check). */
+int b200seg_maxpool2_idx_to_torch(const uint8_t* idx, int64_t* out, int n, int d, int h, int w, int c, void* stream);
+
+/* ---- nearest x2 upsample (residual_unet3d.py:19,103), elementwise add ----------------------------------------- */
+int b200seg_upsample2_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int n, int d, int h, int w,
+                          int c, void* stream);
+int b200seg_upsample2_bwd(const void* dy, int64_t dy_pitch, void* dx, int64_t dx_pitch, int n, int d, int h, int w,
+                          int c, void* stream);
+int b200seg_add(const void* a, int64_t a_pitch, const void* b, int64_t b_pitch, void* out, int64_t out_pitch,
+                int64_t rows, int c, void* stream);
+
+/* ---- head + loss (unet3d.py:46-48,70; loss_function.py:8-16,102-130,148-185; train.py:115,204) ---------------- */
+/* logits[n][classes][spatial] fp32 (NCDHW, what the module returns) = 1x1x1 conv of NDHWC bf16 features. */
+int b200seg_head_conv1x1_fwd(const void* x, int64_t x_pitch, const float* w, const float* b, float* logits, int n,
+                             int64_t spatial, int cin, int classes, void* stream);
+/* dx (bf16 NDHWC) = dlogits * w ; grad_w[classes][cin], grad_b[classes] accumulated into. */
+int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitch, const float* w, void* dx,
+                             int64_t dx_pitch, float* grad_w, float* grad_b, int n, int64_t spatial, int cin,
+                             int classes, void* stream);
+/* argmax over classes, ties -> lowest index; labels uint8 [n][spatial]. */
+int b200seg_argmax_labels(const float* logits, uint8_t* labels, int n, int64_t spatial, int classes, void* stream);
+/* One pass over logits (fp32 NCDHW) and labels (uint8): partial[0] += sum CE nll; partial[1+3k..] += per class
+ * {sum p*t, sum p*p, sum t}; partial[1+3*classes..] += sigmoid-dice / BCE sums {sum s*t, sum s, sum t, sum bce}.
+ * partial: double[1 + 3*classes + 4] (caller zeroes). */
+int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
+                        double* partial, void* stream);
+/* dlogits = w_ce * dCE + w_dice * dDiceLossss(softmax) + w_sdice * dDiceLoss(sigmoid) + w_bce * dBCE, scaled by the
+ * upstream gradient *gscale (a device scalar; NULL = 1), using the sums produced by loss_reduce. */
+int b200seg_loss_grad(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
+                      const double* partial, float w_ce, float w_dice, float w_sdice, float w_bce,
+                      const float* gscale, float* dlogits, void* stream);
+
+/* ---- metric (metric.py:20-75) ---------------------------------------------------------------------------------- */
+/* counts: uint64[4] += {sum gt, sum pred, |gt & pred| nonzero, |gt | pred| nonzero} over uint8 label volumes. */
+int b200seg_seg_counts(const uint8_t* gt, const uint8_t* pred, int64_t numel, unsigned long long* counts,
+                       void* stream);
+
+/* ---- sliding-window aggregation (predict.py:100-147; torchio GridAggregator) ----------------------------------- */
+/* crop mode: overwrite the cropped interior of each patch into out (uint8 labels [W][H][D] of the volume).
+ * patches: uint8 [batch][pw][ph][pd]; locations: int64 [batch][6] (i0,j0,k0,i1,j1,k1) on the device. */
+int b200seg_window_accumulate_crop(const uint8_t* patches, const int64_t* locations, int batch, int pw, int ph,
+                                   int pd, int ow, int oh, int od, uint8_t* out, int vw, int vh, int vd,
+                                   void* stream);
+/* average mode: sum fp32 patches [batch][c][pw][ph][pd] into acc [c][W][H][D] and count [W][H][D]. */
+int b200seg_window_accumulate_average(const float* patches, const int64_t* locations, int batch, int c, int pw,
+                                      int ph, int pd, float* acc, float* count, int vw, int vh, int vd,
+                                      void* stream);
+/* acc /= max(count,1), then argmax over c -> labels uint8 [W][H][D] (labels may be NULL). */
+int b200seg_window_finalize(float* acc, const float* count, int c, int64_t voxels, uint8_t* labels, void* stream);
+
+/* ---- optimiser (train.py:109,214) ------------------------------------------------------------------------------- */
+/* Fused Adam over a flat fp32 parameter arena (torch.optim.Adam semantics, no amsgrad, weight_decay as L2). */
+int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

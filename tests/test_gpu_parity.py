@@ -1,0 +1,365 @@
+"""GPU parity: every kernel reached through the C ABI is compared with the CPU oracle (and, where they exist, with
+the golden vectors produced by the reference itself).  Tolerances: activations are stored as bf16 (relative step
+2^-8), accumulation is fp32; integer outputs (pool indices, labels, counts, stitched label maps) are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import losses as olosses  # noqa: E402
+from oracle import metric as ometric  # noqa: E402
+from oracle import ops as oops  # noqa: E402
+from oracle import unet3d as ounet  # noqa: E402
+from oracle import window as owindow  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def F():
+    import b200seg.functional as F
+    return F
+
+
+DEV = "cuda"
+
+
+def bf(x):
+    """round an fp32 tensor to bf16 and back (what the kernels see)."""
+    return x.to(torch.bfloat16).float()
+
+
+def ndhwc(x):
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
+
+
+def ncdhw(x):
+    return x.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def rel_err(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def close(a, b, tol, what=""):
+    e = rel_err(a, b)
+    m = float((a - b).abs().max() / (b.abs().max() + 1e-12))
+    assert e < tol and m < 4 * tol, "%s rel-fro %.4g rel-max %.4g (tol %.3g)" % (what, e, m, tol)
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, pad, dil, (d,h,w), n
+    (1, 32, 3, 1, 1, 1, (8, 8, 8), 2),        # U-Net stem (direct path)
+    (32, 32, 3, 1, 1, 1, (8, 16, 8), 2),      # full-resolution U-Net layer
+    (64, 32, 3, 1, 1, 1, (8, 16, 16), 1),     # decoder conv1 (concat input)
+    (32, 64, 3, 1, 1, 1, (4, 16, 8), 2),
+    (64, 128, 3, 1, 1, 1, (8, 8, 8), 1),
+    (128, 64, 3, 1, 1, 1, (4, 8, 8), 2),
+    (16, 16, 3, 1, 2, 2, (10, 12, 16), 1),    # HighResNet dilation 2 ('same')
+    (16, 32, 3, 1, 0, 1, (10, 20, 12), 1),    # HighResNet: valid conv on pre-padded input
+    (16, 16, 5, 1, 2, 1, (8, 16, 8), 1),      # V-Net 5x5x5
+    (16, 32, 2, 2, 0, 1, (8, 8, 8), 2),       # V-Net down conv
+    (32, 64, 3, 2, 1, 1, (8, 8, 8), 1),       # residual U-Net strided conv
+    (28, 12, 3, 1, 1, 1, (6, 6, 6), 1),       # DenseVoxelNet odd widths
+    (32, 2, 1, 1, 0, 1, (4, 4, 8), 2),        # 1x1x1
+    (256, 256, 3, 1, 1, 1, (2, 4, 8), 1),     # deep level, tiny spatial extent
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "ci%d_co%d_k%d_s%d_p%d_d%d_%s_n%d" % (
+    c[0], c[1], c[2], c[3], c[4], c[5], "x".join(map(str, c[6])), c[7]))
+def test_conv3d_fprop_dgrad_wgrad(F, case):
+    cin, cout, k, stride, pad, dil, size, n = case
+    g = torch.Generator().manual_seed(hash(case) % 2 ** 31)
+    x = bf(torch.randn(n, cin, *size, generator=g))
+    w = torch.randn(cout, cin, k, k, k, generator=g) * (2.0 / (cin * k ** 3)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    wq = bf(w)
+    xr = x.clone().requires_grad_(True)
+    wr = wq.clone().requires_grad_(True)
+    y_ref = oops.conv3d(xr, wr, b, stride, pad, dil)
+    dy = bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+
+    xd = ndhwc(x).requires_grad_(True)
+    wd = w.to(DEV).requires_grad_(True)
+    bd = b.to(DEV).requires_grad_(True)
+    y = F.conv_norm_act(xd, wd, bd, k=k, stride=stride, pad=pad, dil=dil)
+    close(ncdhw(y), y_ref.detach(), 8e-3, "fprop")
+    y.backward(ndhwc(dy))
+    close(ncdhw(xd.grad), xr.grad, 8e-3, "dgrad")
+    close(wd.grad.cpu(), wr.grad, 8e-3, "wgrad")
+    close(bd.grad.cpu(), dy.sum((0, 2, 3, 4)), 8e-3, "bias grad")
+
+
+def test_conv_stats_epilogue_matches_separate_reduction(F):
+    g = torch.Generator().manual_seed(3)
+    x = bf(torch.randn(2, 32, 8, 16, 8, generator=g))
+    w = torch.randn(32, 32, 3, 3, 3, generator=g) * 0.05
+    y, stats, _ = F.conv3d_fprop_raw(ndhwc(x), w.to(DEV), None, 3, 1, 1, 1, True)
+    ref = oops.conv3d(x, bf(w), None, 1, 1, 1)
+    s = torch.stack((ref.sum((0, 2, 3, 4)), (ref ** 2).sum((0, 2, 3, 4))))
+    close(stats[0].cpu(), s, 5e-3, "fused stats")
+    close(F.channel_stats(y)[0].cpu(), s, 1e-2, "stand-alone stats")
+
+
+@pytest.mark.parametrize("kind,act,c", [("batch", "relu", 32), ("batch", "elu", 16), ("instance", "leaky_relu", 32),
+                                        ("batch", "prelu", 16), ("batch", "none", 2), (None, "relu", 12),
+                                        ("batch", "relu", 12)])
+def test_norm_act_forward_backward(F, kind, act, c):
+    g = torch.Generator().manual_seed(7)
+    x = bf(torch.randn(2, c, 6, 8, 8, generator=g) * 1.5 + 0.3)
+    gamma = (torch.rand(c, generator=g) + 0.5) if kind == "batch" else None
+    beta = torch.randn(c, generator=g) * 0.2 if kind == "batch" else None
+    slope = torch.full((c,), 0.25) if act == "prelu" else None
+    res = bf(torch.randn(x.shape, generator=g)) if act == "elu" else None
+
+    xr = x.clone().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True) if gamma is not None else None
+    br = beta.clone().requires_grad_(True) if beta is not None else None
+    sr = slope.clone().requires_grad_(True) if slope is not None else None
+    rr = res.clone().requires_grad_(True) if res is not None else None
+    if kind == "batch":
+        h, mean, var = oops.batch_norm_train(xr, gr, br)
+    elif kind == "instance":
+        h = oops.instance_norm(xr)
+    else:
+        h = xr
+    if rr is not None:
+        h = h + rr
+    z_ref = oops.ACTIVATIONS[act](h, sr)
+    dz = bf(torch.randn(z_ref.shape, generator=g))
+    z_ref.backward(dz)
+
+    xd = ndhwc(x).requires_grad_(True)
+    gd = gamma.to(DEV).requires_grad_(True) if gamma is not None else None
+    bd = beta.to(DEV).requires_grad_(True) if beta is not None else None
+    sd = slope.to(DEV).requires_grad_(True) if slope is not None else None
+    rd = ndhwc(res).requires_grad_(True) if res is not None else None
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    spec = F.NormSpec(kind, act, act_param=0.01)
+    z = F.norm_act(xd, spec, gd, bd, sd, rd, rm if kind == "batch" else None, rv if kind == "batch" else None)
+    close(ncdhw(z), z_ref.detach(), 1e-2, "forward")
+    z.backward(ndhwc(dz))
+    close(ncdhw(xd.grad), xr.grad, 2e-2, "dx")
+    if gamma is not None:
+        close(gd.grad.cpu(), gr.grad, 2e-2, "dgamma")
+        close(bd.grad.cpu(), br.grad, 2e-2, "dbeta")
+        cnt = x.numel() // c
+        erm, erv = oops.batch_norm_running_update(torch.zeros(c), torch.ones(c), mean.detach(), var.detach(), cnt)
+        close(rm.cpu(), erm, 1e-2, "running_mean")
+        close(rv.cpu(), erv, 1e-2, "running_var")
+    if slope is not None:
+        close(sd.grad.cpu(), sr.grad, 2e-2, "dprelu")
+    if res is not None:
+        close(ncdhw(rd.grad), rr.grad, 1e-2, "dresidual")
+
+
+def test_batchnorm_eval_mode(F):
+    g = torch.Generator().manual_seed(11)
+    c = 16
+    x = bf(torch.randn(1, c, 4, 8, 8, generator=g))
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    rm, rv = torch.randn(c, generator=g) * 0.1, torch.rand(c, generator=g) + 0.5
+    ref = torch.relu(oops.batch_norm_eval(x, gamma, beta, rm, rv))
+    spec = F.NormSpec("batch", "relu", training=False)
+    z = F.norm_act(ndhwc(x), spec, gamma.to(DEV), beta.to(DEV), None, None, rm.to(DEV), rv.to(DEV))
+    close(ncdhw(z), ref, 1e-2, "eval bn")
+
+
+def test_maxpool_indices_bit_exact_with_ties_and_nan(F, golden):
+    gz = golden("pool_argmax")
+    x = torch.from_numpy(gz["x"])
+    xd = ndhwc(x).requires_grad_(True)
+    y, idx = F.max_pool2(xd, return_indices=True)
+    tidx = F.maxpool_indices_to_torch(idx, xd.shape).cpu().numpy()
+    assert np.array_equal(tidx, gz["idx"])                       # reference (torch) indices, bit-exact
+    o_y, o_idx = oops.max_pool3d_k2s2(bf(x).numpy())
+    assert np.array_equal(tidx, o_idx)
+    yy = ncdhw(y).numpy()
+    assert np.array_equal(np.isnan(yy), np.isnan(o_y)) and np.array_equal(np.nan_to_num(yy), np.nan_to_num(o_y))
+    # backward: gradient lands exactly on the arg-max voxel
+    dy = bf(torch.randn(y.shape))
+    y.backward(dy.to(torch.bfloat16).to(DEV))
+    xr = torch.nan_to_num(bf(x)).requires_grad_(True)
+    yr, ir = torch.nn.functional.max_pool3d(xr, 2, 2, return_indices=True)
+    gref = torch.zeros(x.shape).flatten(2)
+    gref.scatter_(2, torch.from_numpy(gz["idx"]).flatten(2), ncdhw(dy).flatten(2))
+    assert torch.equal(ncdhw(xd.grad), gref.view(x.shape))
+
+
+def test_conv_transpose_k2s2(F):
+    g = torch.Generator().manual_seed(5)
+    for cin, cout, size in [(64, 32, (4, 4, 8)), (16, 8, (3, 5, 4)), (32, 32, (2, 2, 2))]:
+        x = bf(torch.randn(2, cin, *size, generator=g))
+        w = torch.randn(cin, cout, 2, 2, 2, generator=g) * 0.1
+        b = torch.randn(cout, generator=g) * 0.1
+        xr, wr = x.clone().requires_grad_(True), bf(w).requires_grad_(True)
+        y_ref = oops.conv_transpose3d_k2s2(xr, wr, b)
+        dy = bf(torch.randn(y_ref.shape, generator=g))
+        y_ref.backward(dy)
+        xd, wd, bd = ndhwc(x).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        y = F.conv_transpose_k2s2(xd, wd, bd)
+        close(ncdhw(y), y_ref.detach(), 8e-3, "convT fwd")
+        y.backward(ndhwc(dy))
+        close(ncdhw(xd.grad), xr.grad, 8e-3, "convT dgrad")
+        close(wd.grad.cpu(), wr.grad, 8e-3, "convT wgrad")
+        close(bd.grad.cpu(), dy.sum((0, 2, 3, 4)), 8e-3, "convT bias grad")
+
+
+def test_concat_free_decoder_input_equals_torch_cat(F):
+    g = torch.Generator().manual_seed(9)
+    a = bf(torch.randn(1, 16, 4, 8, 8, generator=g))
+    b = bf(torch.randn(1, 16, 4, 8, 8, generator=g))
+    w = torch.randn(32, 32, 3, 3, 3, generator=g) * 0.05
+    buf, va, vb = F.alloc_concat(1, 4, 8, 8, 16, 16, DEV)
+    va.copy_(ndhwc(a))
+    vb.copy_(ndhwc(b))
+    va.requires_grad_(True)
+    vb.requires_grad_(True)
+    y = F.conv_norm_act(va, w.to(DEV), None, x2=vb, k=3, pad=1)
+    cat = torch.cat((a, b), 1).requires_grad_(True)
+    ref = oops.conv3d(cat, bf(w), None, 1, 1, 1)
+    close(ncdhw(y), ref.detach(), 8e-3, "concat-free fprop")
+    dy = bf(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    y.backward(ndhwc(dy))
+    close(ncdhw(va.grad), cat.grad[:, :16], 8e-3, "d(first half)")
+    close(ncdhw(vb.grad), cat.grad[:, 16:], 8e-3, "d(second half)")
+
+
+def test_losses_match_reference_golden(F, golden):
+    gz = golden("losses")
+    pred = torch.from_numpy(gz["pred"])
+    lab = torch.from_numpy(gz["lab"])
+    cases = {"cross_entropy_3D": (1, 0, 0, 0), "DiceLossss_softmax": (0, 1, 0, 0), "DiceLoss": (0, 0, 1, 0),
+             "BCEWithLogits": (0, 0, 0, 1)}
+    for name, wts in cases.items():
+        p = pred.to(DEV).requires_grad_(True)
+        loss = F.seg_loss(p, lab.to(DEV), *[float(v) for v in wts])
+        loss.backward()
+        assert abs(loss.item() - float(gz[name])) < 2e-6, name
+        assert torch.allclose(p.grad.cpu(), torch.from_numpy(gz[name + ".grad"]), rtol=2e-4, atol=1e-8), name
+    # combined criterion with an upstream scale
+    p = pred.to(DEV).requires_grad_(True)
+    (3.0 * F.seg_loss(p, lab.to(DEV), 1.0, 1.0)).backward()
+    ref = 3.0 * (torch.from_numpy(gz["cross_entropy_3D.grad"]) + torch.from_numpy(gz["DiceLossss_softmax.grad"]))
+    assert torch.allclose(p.grad.cpu(), ref, rtol=2e-4, atol=1e-8)
+
+
+def test_reference_named_loss_classes(golden):
+    from b200seg.utils.loss_function import (Binary_Loss, DiceCELoss, DiceLoss, DiceLossss, cross_entropy_3D)
+    gz = golden("losses")
+    pred = torch.from_numpy(gz["pred"]).to(DEV)
+    lab = torch.from_numpy(gz["lab"]).to(DEV)
+    onehot = torch.stack([(lab == 0), (lab == 1)], 1).float()
+    assert abs(cross_entropy_3D(pred, lab).item() - float(gz["cross_entropy_3D"])) < 2e-6
+    assert abs(DiceLossss(2)(pred, lab, softmax=True).item() - float(gz["DiceLossss_softmax"])) < 2e-6
+    assert abs(DiceLoss()(pred, onehot).item() - float(gz["DiceLoss"])) < 2e-6
+    assert abs(Binary_Loss()(pred, onehot).item() - float(gz["BCEWithLogits"])) < 2e-6
+    both = float(gz["cross_entropy_3D"]) + float(gz["DiceLossss_softmax"])
+    assert abs(DiceCELoss(2)(pred, lab).item() - both) < 4e-6
+    with pytest.raises(NotImplementedError):
+        DiceLossss(2)(pred, lab, softmax=False)
+
+
+def test_argmax_and_metric_bit_exact(F, golden):
+    gz = golden("pool_argmax")
+    lab = F.argmax_labels(torch.from_numpy(gz["logits"]).to(DEV))
+    assert np.array_equal(lab.cpu().numpy().astype(np.int64), gz["argmax"])
+    gm = golden("metric")
+    from b200seg.utils.metric import metric
+    for i in (0, 1):
+        gt, pred = torch.from_numpy(gm["gt%d" % i]), torch.from_numpy(gm["pred%d" % i])
+        j, d = metric(gt.to(DEV), pred.to(DEV))
+        assert j == float(gm["jaccard%d" % i]) and d == float(gm["dice%d" % i])
+        c = F.seg_counts(gt.to(DEV), pred.to(DEV)).tolist()
+        oc = ometric.counts(gt.numpy(), pred.numpy())
+        assert c == [oc["gt_sum"], oc["pred_sum"], oc["intersection"], oc["union"]]
+    # a large ragged size exercises the vector body + scalar tail
+    g = torch.Generator().manual_seed(1)
+    a = (torch.rand(1000003, generator=g) > 0.5).to(torch.uint8)
+    b = (torch.rand(1000003, generator=g) > 0.3).to(torch.uint8)
+    c = F.seg_counts(a.to(DEV), b.to(DEV)).tolist()
+    assert c == [int(a.sum()), int(b.sum()), int((a & b).sum()), int((a | b).sum())]
+
+
+def test_unet_against_reference_golden(golden):
+    from b200seg.models.three_d.unet3d import UNet3D
+    from b200seg.utils.loss_function import DiceCELoss
+    gz = golden("unet_f4_s32_b2")
+    sd = {k[4:]: torch.from_numpy(gz[k]) for k in gz.files if k.startswith("sd0.")}
+    net = UNet3D(1, 2, 4).to(DEV)
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    net.train()
+    x, lab = torch.from_numpy(gz["x"]).to(DEV), torch.from_numpy(gz["lab"]).to(DEV)
+    out = net(x)
+    ref = torch.from_numpy(gz["out_train"])
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    close(out.cpu(), ref, 3e-2, "train-mode logits")
+    loss = DiceCELoss(2)(out, lab)
+    assert abs(loss.item() - float(gz["loss"])) < 5e-3            # Dice within 1e-4 is checked on equal inputs below
+    loss.backward()
+    for name, p in net.named_parameters():
+        r = torch.from_numpy(gz["grad." + name])
+        if r.abs().max() < 1e-6:                                   # conv biases in front of BN: analytically zero
+            assert p.grad.abs().max().item() < 1e-4, name
+            continue
+        assert rel_err(p.grad.cpu(), r) < 0.12, "%s %.3f" % (name, rel_err(p.grad.cpu(), r))
+    for k in gz.files:
+        if k.startswith("sd1."):
+            close(net.state_dict()[k[4:]].cpu(), torch.from_numpy(gz[k]), 2e-2, k)
+    net.eval()
+    with torch.no_grad():
+        oe = net(x)
+    close(oe.cpu(), torch.from_numpy(gz["out_eval"]), 4e-2, "eval logits")
+    import b200seg.functional as F
+    agree = (F.argmax_labels(oe).cpu().numpy() == gz["argmax_eval"]).mean()
+    assert agree > 0.99, agree
+
+
+def test_unet_f32_against_live_oracle():
+    """Tensor-core-eligible widths (32..512 channels), compared with the oracle evaluated on the box's CPU."""
+    from b200seg.models.three_d.unet3d import UNet3D
+    from b200seg.utils.loss_function import DiceCELoss
+    torch.manual_seed(0)
+    sd = ounet.init_state_dict(1, 2, 32, seed=0)
+    net = UNet3D(1, 2, 32).to(DEV)
+    net.load_state_dict(sd)
+    net.train()
+    x = torch.randn(1, 1, 32, 32, 32)
+    lab = (torch.rand(1, 32, 32, 32) > 0.8).long()
+    out = net(x.to(DEV))
+    loss = DiceCELoss(2)(out, lab.to(DEV))
+    loss.backward()
+    rsd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    rout = ounet.forward(rsd, x, training=True)
+    rloss = olosses.dice_ce(rout, lab)
+    rloss.backward()
+    close(out.cpu(), rout.detach(), 4e-2, "logits")
+    assert abs(loss.item() - rloss.item()) < 1e-2
+    for name, p in net.named_parameters():
+        r = rsd[name].grad
+        if r.abs().max() < 1e-6:
+            continue
+        assert rel_err(p.grad.cpu(), r) < 0.15, "%s %.3f" % (name, rel_err(p.grad.cpu(), r))
+
+
+def test_sliding_window_aggregator_bit_exact():
+    from b200seg.inference import GridAggregator, GridSampler
+    rng = np.random.default_rng(0)
+    vol = rng.integers(0, 3, size=(1, 40, 36, 50)).astype(np.int64)
+    for mode in ("crop", "average"):
+        sampler = GridSampler(vol.shape[1:], (16, 16, 16), (4, 4, 6))
+        assert np.array_equal(sampler.locations.numpy(), owindow.grid_locations(vol.shape[1:], (16,) * 3, (4, 4, 6)))
+        agg = GridAggregator(sampler, overlap_mode=mode, device=DEV)
+        oagg = owindow.Aggregator(vol.shape[1:], (4, 4, 6), mode)
+        locs = sampler.locations
+        for s in range(0, len(locs), 7):
+            lb = locs[s:s + 7]
+            patches = np.stack([vol[:, a:d, b:e, c:f] for a, b, c, d, e, f in lb.numpy()])
+            agg.add_batch(torch.from_numpy(patches).to(DEV), lb)
+            oagg.add_batch(patches, lb.numpy())
+        out = agg.get_output_tensor().cpu().numpy()
+        assert np.array_equal(out.astype(np.int64), oagg.get_output_tensor().astype(np.int64))
+        assert np.array_equal(out.astype(np.int64), vol)
