@@ -9,16 +9,46 @@ import torch.nn.functional as F
 
 from . import ops
 
+
+
+class _RoundBoth(torch.autograd.Function):
+    """bf16 storage of an activation: value rounded in forward, its gradient rounded in backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+class _RoundFwd(torch.autograd.Function):
+    """bf16 copy of an fp32 master weight: rounded value, fp32 gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _ident(x):
+    return x
+
+
 LEVELS = (("encoder1", "enc1"), ("encoder2", "enc2"), ("encoder3", "enc3"), ("encoder4", "enc4"))
 DECODERS = (("decoder4", "dec4", "upconv4"), ("decoder3", "dec3", "upconv3"), ("decoder2", "dec2", "upconv2"),
             ("decoder1", "dec1", "upconv1"))
 
 
-def _block(sd, x, prefix, name, training, new_stats, acts):
+def _block(sd, x, prefix, name, training, new_stats, acts, ra=_ident, rw=_ident):
     for i in (1, 2):
         k = "%s.%sconv%d" % (prefix, name, i)
         nk = "%s.%snorm%d" % (prefix, name, i)
-        x = ops.conv3d(x, sd[k + ".weight"], sd[k + ".bias"], padding=1)
+        x = ra(ops.conv3d(x, rw(sd[k + ".weight"]), sd[k + ".bias"], padding=1))
         if acts is not None:
             acts[k] = x
         if training:
@@ -31,28 +61,34 @@ def _block(sd, x, prefix, name, training, new_stats, acts):
         else:
             x = ops.batch_norm_eval(x, sd[nk + ".weight"], sd[nk + ".bias"], sd[nk + ".running_mean"],
                                     sd[nk + ".running_var"])
-        x = torch.relu(x)
+        x = ra(torch.relu(x))
         if acts is not None:
             acts[nk] = x
     return x
 
 
-def forward(sd, x, training=True, new_stats=None, acts=None):
-    """sd: mapping with the 136 reference keys (tensors; parameters may require grad). x: [N,C,D,H,W] fp32."""
+def forward(sd, x, training=True, new_stats=None, acts=None, storage="fp32"):
+    """sd: mapping with the 136 reference keys (tensors; parameters may require grad). x: [N,C,D,H,W] fp32.
+
+    storage="fp32" is the reference arithmetic.  storage="bf16" keeps fp32 arithmetic but rounds every stored
+    activation (and its gradient) and every conv weight to bf16 at the points where the CUDA path stores bf16; the
+    distance between the two is the error floor any bf16-storage implementation of this network has, and tests use
+    it to calibrate their end-to-end tolerances."""
+    ra, rw = (_RoundBoth.apply, _RoundFwd.apply) if storage == "bf16" else (_ident, _ident)
     skips = []
-    h = x
+    h = ra(x)
     for li, (prefix, name) in enumerate(LEVELS):
         if li:
             h = F.max_pool3d(h, 2, 2)
-        h = _block(sd, h, prefix, name, training, new_stats, acts)
+        h = _block(sd, h, prefix, name, training, new_stats, acts, ra, rw)
         skips.append(h)
-    h = _block(sd, F.max_pool3d(h, 2, 2), "bottleneck", "bottleneck", training, new_stats, acts)
+    h = _block(sd, F.max_pool3d(h, 2, 2), "bottleneck", "bottleneck", training, new_stats, acts, ra, rw)
     for (prefix, name, up), skip in zip(DECODERS, reversed(skips)):
-        h = ops.conv_transpose3d_k2s2(h, sd[up + ".weight"], sd[up + ".bias"])
+        h = ra(ops.conv_transpose3d_k2s2(h, rw(sd[up + ".weight"]), sd[up + ".bias"]))
         if acts is not None:
             acts[up] = h
         h = torch.cat((h, skip), dim=1)
-        h = _block(sd, h, prefix, name, training, new_stats, acts)
+        h = _block(sd, h, prefix, name, training, new_stats, acts, ra, rw)
     return ops.conv3d(h, sd["conv.weight"], sd["conv.bias"])
 
 
