@@ -1,0 +1,499 @@
+// tcgen05 implicit-GEMM 3-D convolution (stride 1, cubic kernel k in {1,3,5}, dilation, zero padding).
+//
+//   out[voxel][n] = bias[n] + sum_{tap,c} in[voxel - pad + tap*dil][c] * W[tap][n][c]          (fp32 accumulate)
+//
+// GEMM view: M = output voxels, N = C_out, K = k^3 * C_in.  One CTA owns P accumulators of 128 voxels x NT channels in
+// TMEM.  The input is NOT re-fetched per tap: a halo'd box of the channels-last input is brought into shared memory
+// once per K-chunk by TMA (out-of-bounds coordinates give the zero padding) and every tap reads a *shifted view* of
+// it -- the UMMA shared-memory descriptor starts (tap offset) rows later, with the 8-row group stride set to the box
+// row pitch.  The 128B/64B/32B swizzle is a function of the absolute shared-memory address on both the TMA write and
+// the UMMA read (verified on hardware by probes/probe.cu), which is what makes unaligned tap views legal.
+//
+//   plane mode (H_out >= 16): tile = 8 (w) x 16 (h) voxels of one d-plane per accumulator, P consecutive d-planes per
+//       CTA; input planes live in a ring of slots, each plane is loaded once and used by up to k accumulators.
+//   flat  mode (small H/W):   the whole halo'd (d,h,w) box of a sample is one slot; accumulator p covers box rows
+//       [128p, 128p+128) in flattened order (rows that fall in the halo are computed and discarded).
+//
+// Warp roles (256 threads): 0 = TMA producer for input boxes, 1 = TMA producer for weight tiles, 2 = MMA issuer,
+// 3 = TMEM allocator, 4..7 = epilogue (TMEM -> registers -> +bias, per-channel sum / sum-of-squares -> bf16 -> HBM).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "conv_impl.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct UmmaConvParams {
+  int n, od, oh, ow, cout;
+  long long out_pitch;
+  int k, pad, dil;
+  int KC, nchunks, NT, n_ntiles, P, flat;
+  int WB, HB, U, UP, S, NB, DT;
+  int tiles_w, tiles_h, tiles_d;
+  unsigned slotA, slotB, rowbytes, swz, bytesA_unit, bytesB, tmem_cols;
+  __nv_bfloat16* out;
+  const float* bias;
+  float* stats;
+};
+
+__device__ __forceinline__ void butterfly_colsum(float (&v)[32], int lane) {
+  // after the call, v[0] on lane l holds sum over the 32 lanes of the original v[l]
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = (up ? v[i + s] : v[i]) + recv;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+    conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const UmmaConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + static_cast<size_t>(p.S) * p.slotA;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(p.NB) * p.slotB);
+  uint64_t* emptyA = fullA + p.S;
+  uint64_t* fullB = emptyA + p.S;
+  uint64_t* emptyB = fullB + p.NB;
+  uint64_t* accFull = emptyB + p.NB;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accFull + 1);
+  float* s_stats = reinterpret_cast<float*>(tmem_ptr + 2);  // [2][NT]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- which tile ------------------------------------------------------------------------------------------
+  int bid = blockIdx.x;
+  const int nt = bid % p.n_ntiles;
+  bid /= p.n_ntiles;
+  const int tw = bid % p.tiles_w;
+  bid /= p.tiles_w;
+  const int th = bid % p.tiles_h;
+  bid /= p.tiles_h;
+  const int td = bid % p.tiles_d;
+  const int nn = bid / p.tiles_d;
+  const int w0 = p.flat ? 0 : tw * 8, h0 = p.flat ? 0 : th * 16, d0 = td * p.DT;
+  const int k = p.k, k3 = k * k * k;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.S; ++i) {
+      mbar_init(&fullA[i], 1);
+      mbar_init(&emptyA[i], 1);
+    }
+    for (int i = 0; i < p.NB; ++i) {
+      mbar_init(&fullB[i], 1);
+      mbar_init(&emptyB[i], 1);
+    }
+    mbar_init(accFull, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 2 * p.NT; i += blockDim.x) s_stats[i] = 0.f;
+  if (warp == 3) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
+  if (warp == 1 && lane == 0) tma_prefetch_desc(&tmB);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== input-box producer ===========================
+    if (lane == 0) {
+      int L = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        for (int u = 0; u < p.U; ++u, ++L) {
+          const int s = L % p.S;
+          const uint32_t ph = (L / p.S) & 1;
+          mbar_wait(&emptyA[s], ph ^ 1);
+          mbar_arrive_expect_tx(&fullA[s], p.bytesA_unit);
+          tma_load_5d(sA + static_cast<size_t>(s) * p.slotA, &tmA, &fullA[s], c * p.KC, w0 - p.pad, h0 - p.pad,
+                      d0 - p.pad + u * p.UP, nn);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== weight-tile producer ===========================
+    if (lane == 0) {
+      int L = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        for (int t = 0; t < k3; ++t, ++L) {
+          const int s = L % p.NB;
+          const uint32_t ph = (L / p.NB) & 1;
+          mbar_wait(&emptyB[s], ph ^ 1);
+          mbar_arrive_expect_tx(&fullB[s], p.bytesB);
+          tma_load_3d(sB + static_cast<size_t>(s) * p.slotB, &tmB, &fullB[s], c * p.KC, nt * p.NT, t);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
+      const uint32_t a_sbo = (p.flat ? 8u : static_cast<uint32_t>(p.WB)) * p.rowbytes;
+      const uint32_t b_sbo = 8u * p.rowbytes;
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      const int ksteps = p.KC / 16;
+      int LB = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        int waited = 0;  // units of this chunk whose full barrier has been observed
+        for (int a = 0; a < k; ++a) {
+          const int need = p.flat ? 1 : min(p.U, p.P + a * p.dil);
+          for (; waited < need; ++waited) {
+            const int L = c * p.U + waited;
+            mbar_wait(&fullA[L % p.S], (L / p.S) & 1);
+          }
+          tc_fence_after();
+          for (int b = 0; b < k; ++b) {
+            for (int e = 0; e < k; ++e, ++LB) {
+              const int bs = LB % p.NB;
+              mbar_wait(&fullB[bs], (LB / p.NB) & 1);
+              tc_fence_after();
+              const uint32_t b_addr = sB_addr + bs * p.slotB;
+              for (int acc = 0; acc < p.P; ++acc) {
+                uint32_t a_addr;
+                if (p.flat) {
+                  const int L = c * p.U;
+                  a_addr = sA_addr + (L % p.S) * p.slotA +
+                           static_cast<uint32_t>(acc * 128 + (a * p.dil * p.HB + b * p.dil) * p.WB + e * p.dil) * p.rowbytes;
+                } else {
+                  const int L = c * p.U + acc + a * p.dil;
+                  a_addr = sA_addr + (L % p.S) * p.slotA +
+                           static_cast<uint32_t>((b * p.dil) * p.WB + e * p.dil) * p.rowbytes;
+                }
+                const uint32_t first = (c == 0 && a == 0 && b == 0 && e == 0) ? 1u : 0u;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                  const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, a_sbo, p.swz);
+                  const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, b_sbo, p.swz);
+                  umma_f16(tbase + acc * p.NT, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+                }
+              }
+              umma_commit(&emptyB[bs]);  // weight tile consumed once these MMAs retire
+            }
+          }
+          // release input units whose last use was this kd iteration
+          if (p.flat) {
+            if (a == k - 1) umma_commit(&emptyA[(c * p.U) % p.S]);
+          } else {
+            for (int j = 0; j < p.U; ++j) {
+              const int a_last = min(k - 1, j / p.dil);
+              if (a_last == a) umma_commit(&emptyA[(c * p.U + j) % p.S]);
+            }
+          }
+        }
+      }
+      umma_commit(accFull);
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int nchunk32 = (p.NT + 31) / 32;
+    float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};
+    mbar_wait(accFull, 0);
+    tc_fence_after();
+    for (int acc = 0; acc < p.P; ++acc) {
+      int od_, oh_, ow_;
+      bool valid;
+      if (p.flat) {
+        const int R = acc * 128 + m;
+        const int plane = p.HB * p.WB;
+        const int dz = R / plane, rem = R - dz * plane;
+        const int hy = rem / p.WB, wx = rem - hy * p.WB;
+        od_ = d0 + dz;
+        oh_ = hy;
+        ow_ = wx;
+        valid = dz < p.DT && od_ < p.od && hy < p.oh && wx < p.ow;
+      } else {
+        od_ = d0 + acc;
+        oh_ = h0 + (m >> 3);
+        ow_ = w0 + (m & 7);
+        valid = od_ < p.od && oh_ < p.oh && ow_ < p.ow;
+      }
+      const long long vox = ((static_cast<long long>(nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+      __nv_bfloat16* orow = p.out + vox * p.out_pitch + nt * p.NT;
+      for (int cc = 0; cc < nchunk32; ++cc) {
+        const int ncol = min(32, p.NT - cc * 32);
+        uint32_t raw[32];
+        const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + acc * p.NT + cc * 32;
+        if (ncol == 32) {
+          tmem_ld_32x32(taddr, raw);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_32x16(taddr, r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) raw[j] = r16[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) raw[j] = 0u;
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(raw[j]);
+          if (p.bias != nullptr && j < ncol) v[j] += p.bias[nt * p.NT + cc * 32 + j];
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncol) {
+              float t8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t8[i] = v[j + i];
+              st8(orow + cc * 32 + j, pack8(t8));
+            }
+          }
+        }
+        if (p.stats != nullptr) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = (valid && j < ncol) ? v[j] : 0.f;
+            s1[j] = t;
+            s2[j] = t * t;
+          }
+          butterfly_colsum(s1, lane);
+          butterfly_colsum(s2, lane);
+          csum[cc] += s1[0];
+          csq[cc] += s2[0];
+        }
+      }
+    }
+    if (p.stats != nullptr) {
+      for (int cc = 0; cc < nchunk32; ++cc) {
+        const int col = cc * 32 + lane;
+        if (col < p.NT) {
+          atomicAdd(&s_stats[col], csum[cc]);
+          atomicAdd(&s_stats[p.NT + col], csq[cc]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (p.stats != nullptr) {
+    for (int i = tid; i < p.NT; i += blockDim.x) {
+      atomicAdd(&p.stats[nt * p.NT + i], s_stats[i]);
+      atomicAdd(&p.stats[p.cout + nt * p.NT + i], s_stats[p.NT + i]);
+    }
+  }
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tbase, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static bool encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, int kc) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return false;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
+
+static constexpr size_t kSmemBudget = 200 * 1024;
+
+// Chooses the tiling; returns false when the geometry is not handled by this path.
+static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
+  if (getenv("B200SEG_DISABLE_UMMA")) return false;
+  if (a.cin % 16 || a.cout % 16) return false;
+  if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
+  if (a.in_pitch % 8 || a.out_pitch % 8) return false;
+  const int halo = (a.k - 1) * a.dil;
+  if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
+  p = UmmaConvParams{};
+  p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.out_pitch = a.out_pitch;
+  p.k = a.k; p.pad = a.pad; p.dil = a.dil;
+  p.KC = a.cin % 64 == 0 ? 64 : (a.cin % 32 == 0 ? 32 : 16);
+  p.nchunks = a.cin / p.KC;
+  p.rowbytes = p.KC * 2;
+  p.swz = p.KC == 64 ? SWZ_128B : (p.KC == 32 ? SWZ_64B : SWZ_32B);
+  // N tile: the whole C_out when it fits one accumulator comfortably, else 128 / 64 / 32 / 16
+  if (a.cout <= 128) p.NT = a.cout;
+  else if (a.cout % 128 == 0) p.NT = 128;
+  else if (a.cout % 64 == 0) p.NT = 64;
+  else if (a.cout % 32 == 0) p.NT = 32;
+  else p.NT = 16;
+  p.n_ntiles = a.cout / p.NT;
+  p.NB = 4;
+  p.slotB = (p.NT * p.rowbytes + 1023) & ~1023u;
+  p.bytesB = p.NT * p.rowbytes;
+  const size_t fixed = static_cast<size_t>(p.NB) * p.slotB + 2048 + 2 * p.NT * sizeof(float);
+  const int k3 = a.k * a.k * a.k;
+  (void)k3;
+
+  if (a.oh >= 16 && a.ow >= 8) {
+    // ---- plane mode
+    p.flat = 0;
+    p.WB = 8 + halo;
+    p.HB = 16 + halo;
+    if (p.WB > 256 || p.HB > 256) return false;
+    p.UP = 1;
+    p.slotA = (static_cast<unsigned>(p.WB * p.HB) * p.rowbytes + 1023) & ~1023u;
+    p.bytesA_unit = static_cast<unsigned>(p.WB * p.HB) * p.rowbytes;
+    int best = 0;
+    const int pmax = std::min(std::min(512 / p.NT, a.od), 8);
+    for (int P = pmax; P >= 1; --P) {
+      const int U = P + halo;
+      const int S = U + 2;
+      if (fixed + static_cast<size_t>(S) * p.slotA <= kSmemBudget) {
+        best = P;
+        break;
+      }
+    }
+    if (!best) return false;
+    p.P = best;
+    p.DT = best;
+    p.U = best + halo;
+    p.S = p.U + 2;
+    p.tiles_w = (a.ow + 7) / 8;
+    p.tiles_h = (a.oh + 15) / 16;
+    p.tiles_d = (a.od + p.DT - 1) / p.DT;
+  } else {
+    // ---- flat mode: one halo'd box of the whole (h, w) extent and DT d-planes per CTA
+    p.flat = 1;
+    p.WB = a.ow + halo;
+    p.HB = a.oh + halo;
+    if (p.WB > 256 || p.HB > 256) return false;
+    const int plane_rows = p.WB * p.HB;
+    const int maxoff = halo * (plane_rows + p.WB + 1);
+    int best_dt = 0, best_p = 0;
+    for (int DT = std::min(a.od, 256 - halo); DT >= 1; --DT) {
+      const int P = (DT * plane_rows + 127) / 128;
+      if (P * p.NT > 512) continue;
+      const size_t slot = ((static_cast<size_t>(P) * 128 + maxoff) * p.rowbytes + 1023) & ~size_t(1023);
+      const size_t loaded = static_cast<size_t>(DT + halo) * plane_rows * p.rowbytes;
+      if (loaded > slot) continue;
+      const int S = p.nchunks > 1 ? 2 : 1;
+      if (fixed + S * slot <= kSmemBudget) {
+        best_dt = DT;
+        best_p = P;
+        break;
+      }
+    }
+    if (!best_dt) return false;
+    p.DT = best_dt;
+    p.P = best_p;
+    p.U = 1;
+    p.UP = best_dt + halo;
+    p.S = p.nchunks > 1 ? 2 : 1;
+    p.slotA = static_cast<unsigned>(((static_cast<size_t>(p.P) * 128 + maxoff) * p.rowbytes + 1023) & ~size_t(1023));
+    p.bytesA_unit = static_cast<unsigned>(p.UP) * plane_rows * p.rowbytes;
+    p.tiles_w = p.tiles_h = 1;
+    p.tiles_d = (a.od + p.DT - 1) / p.DT;
+  }
+  unsigned cols = 32;
+  while (cols < static_cast<unsigned>(p.P * p.NT)) cols <<= 1;
+  if (cols > 512) return false;
+  p.tmem_cols = cols;
+  smem_bytes = static_cast<size_t>(p.S) * p.slotA + fixed + 1024;
+  const long long ctas = static_cast<long long>(a.n) * p.tiles_d * p.tiles_h * p.tiles_w * p.n_ntiles;
+  if (ctas > 2147483647LL) return false;
+  return smem_bytes <= 227 * 1024;
+}
+
+bool conv_umma_supported(const UmmaConvArgs& a) {
+  UmmaConvParams p;
+  size_t smem;
+  return plan(a, p, smem);
+}
+
+int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
+  UmmaConvParams p;
+  size_t smem;
+  if (!plan(a, p, smem)) {
+    set_error("conv_umma_run: unsupported geometry");
+    return B200SEG_ERR_INVALID;
+  }
+  p.out = static_cast<__nv_bfloat16*>(a.out);
+  p.bias = a.bias;
+  p.stats = a.stats;
+  if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.wpack)) & 15) {
+    set_error("conv_umma_run: buffers must be 16-byte aligned");
+    return B200SEG_ERR_INVALID;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[5] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.w), static_cast<uint64_t>(a.h),
+                              static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.n)};
+    const uint64_t pb = static_cast<uint64_t>(a.in_pitch) * 2;
+    const uint64_t str[4] = {pb, pb * a.w, pb * a.w * a.h, pb * a.w * a.h * a.d};
+    const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB),
+                             static_cast<uint32_t>(p.UP), 1u};
+    if (!encode_bf16_map(&tmA, a.in, 5, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
+  }
+  {
+    const int k3 = a.k * a.k * a.k;
+    const uint64_t dims[3] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.cout), static_cast<uint64_t>(k3)};
+    const uint64_t str[2] = {static_cast<uint64_t>(a.cin) * 2, static_cast<uint64_t>(a.cin) * a.cout * 2};
+    const uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.NT), 1u};
+    if (!encode_bf16_map(&tmB, a.wpack, 3, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("conv_umma_run: cannot raise the dynamic shared memory limit");
+      return B200SEG_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int ctas = a.n * p.tiles_d * p.tiles_h * p.tiles_w * p.n_ntiles;
+  conv_umma_kernel<<<ctas, 256, smem, st>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH("conv_umma");
+  return 0;
+}
+
+bool wgrad_umma_supported(const UmmaWgradArgs&) { return false; }
+int wgrad_umma_run(const UmmaWgradArgs&, cudaStream_t) {
+  set_error("wgrad_umma_run: not available");
+  return B200SEG_ERR_INVALID;
+}
+
+}  // namespace b200

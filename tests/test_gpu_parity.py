@@ -62,6 +62,11 @@ CONV_CASES = [
     (28, 12, 3, 1, 1, 1, (6, 6, 6), 1),       # DenseVoxelNet odd widths
     (32, 2, 1, 1, 0, 1, (4, 4, 8), 2),        # 1x1x1
     (256, 256, 3, 1, 1, 1, (2, 4, 8), 1),     # deep level, tiny spatial extent
+    (32, 32, 3, 1, 1, 1, (20, 32, 24), 1),    # several d-tiles: input-plane ring wraps around
+    (64, 64, 3, 1, 1, 1, (6, 32, 16), 2),     # multiple h/w tiles, batch 2
+    (128, 128, 3, 1, 1, 1, (4, 16, 16), 1),   # two K chunks in plane mode
+    (512, 256, 3, 1, 1, 1, (4, 4, 4), 1),     # 8 K chunks, 2 N tiles, flat mode
+    (32, 32, 3, 1, 1, 1, (5, 17, 11), 1),     # ragged extents: masked rows in the last tiles
 ]
 
 
