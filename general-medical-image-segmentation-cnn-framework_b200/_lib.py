@@ -53,6 +53,7 @@ SIGNATURES = {
 }
 STRING_FUNCS = ("b200seg_version", "b200seg_last_error")
 SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g"}
+INT64_FUNCS = {"b200seg_umma_launch_count": ""}
 
 
 class B200SegError(RuntimeError):
@@ -85,6 +86,9 @@ def load():
     for name, codes in SIZE_FUNCS.items():
         getattr(lib, name).restype = ctypes.c_size_t
         getattr(lib, name).argtypes = types(codes)
+    for name, codes in INT64_FUNCS.items():
+        getattr(lib, name).restype = ctypes.c_int64
+        getattr(lib, name).argtypes = types(codes)
     _lib = lib
     return lib
 
@@ -98,4 +102,4 @@ def call(name, *args):
 
 
 def exported_symbols():
-    return list(SIGNATURES) + list(STRING_FUNCS) + list(SIZE_FUNCS)
+    return list(SIGNATURES) + list(STRING_FUNCS) + list(SIZE_FUNCS) + list(INT64_FUNCS)

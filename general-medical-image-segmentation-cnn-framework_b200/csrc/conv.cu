@@ -37,6 +37,8 @@ static UmmaConvArgs dgrad_args(const b200seg_conv_geom* g, const void* dy, int64
 
 extern "C" {
 
+int64_t b200seg_umma_launch_count(void) { return g_umma_launches; }
+
 int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g) {
   if (!g || g->stride != 1) return 0;
   UmmaConvArgs a = fprop_args(g, nullptr, g->cin, nullptr, nullptr, nullptr, g->cout, nullptr);

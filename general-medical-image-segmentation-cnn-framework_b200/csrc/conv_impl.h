@@ -32,6 +32,7 @@ struct UmmaConvArgs {
   int64_t out_pitch;
   float* stats;          // may be null: {sum[cout], sumsq[cout]}
 };
+extern long long g_umma_launches;
 bool conv_umma_supported(const UmmaConvArgs& a);
 int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st);
 

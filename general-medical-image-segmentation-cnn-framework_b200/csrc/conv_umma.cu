@@ -338,6 +338,8 @@ static bool encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const u
   return true;
 }
 
+long long g_umma_launches = 0;
+
 static constexpr size_t kSmemBudget = 200 * 1024;
 
 // Chooses the tiling; returns false when the geometry is not handled by this path.
@@ -487,6 +489,7 @@ int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
   const int ctas = a.n * p.tiles_d * p.tiles_h * p.tiles_w * p.n_ntiles;
   conv_umma_kernel<<<ctas, 256, smem, st>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv_umma");
+  ++g_umma_launches;
   return 0;
 }
 

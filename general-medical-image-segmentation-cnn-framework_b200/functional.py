@@ -26,9 +26,50 @@ def reset_launches():
     _LAUNCHES[0] = 0
 
 
-def _call(name, *args):
+# optional per-kernel timing (bench.py roofline): list of (name, work, start_event, end_event)
+_PROFILE = [None]
+
+
+def profile_begin():
+    _PROFILE[0] = []
+
+
+def profile_end():
+    rec, _PROFILE[0] = _PROFILE[0], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, work, e0, e1 in rec:
+        t = out.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+        t["launches"] += 1
+        t["ms"] += e0.elapsed_time(e1)
+        t["work"] += work
+    return out
+
+
+def _call(name, *args, work=0.0, tag=None):
     _LAUNCHES[0] += 1
+    if _PROFILE[0] is None:
+        call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     call(name, *args)
+    e1.record()
+    _PROFILE[0].append((tag or name, work, e0, e1))
+
+
+def umma_launch_count():
+    from ._lib import load
+    return load().b200seg_umma_launch_count()
+
+
+def conv_uses_tensor_cores(g):
+    from ._lib import load
+    return bool(load().b200seg_conv3d_uses_tensor_cores(ctypes.byref(g)))
+
+
+def _conv_flops(g):
+    return 2.0 * g.n * g.od * g.oh * g.ow * g.cout * g.cin * g.k ** 3
 
 
 def _stream():
@@ -105,7 +146,7 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats):
     wp = pack_conv_weight(weight.detach())
     b = bias.detach().float() if bias is not None else None
     _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), cout, _ptr(stats),
-          None, 0, _stream())
+          None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_tc" if conv_uses_tensor_cores(g) else "conv_fprop_direct")
     return y, stats, g
 
 
@@ -113,7 +154,8 @@ def conv3d_dgrad_raw(g, dy, weight):
     dy, dyp = _as_rows(dy)
     wd = pack_conv_weight(weight.detach(), dgrad=True)
     dx = torch.empty((g.n, g.d, g.h, g.w, g.cin), dtype=torch.bfloat16, device=dy.device)
-    _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, None, 0, _stream())
+    _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, None, 0, _stream(),
+          work=_conv_flops(g), tag="conv_dgrad")
     return dx
 
 
@@ -122,7 +164,8 @@ def conv3d_wgrad_raw(g, x, dy, weight_shape):
     dy, dyp = _as_rows(dy)
     k3 = g.k ** 3
     dwp = torch.zeros(k3 * g.cin * g.cout, dtype=torch.float32, device=x.device)
-    _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), None, 0, _stream())
+    _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), None, 0, _stream(),
+          work=_conv_flops(g), tag="conv_wgrad")
     gw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
     _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(gw), g.cout, g.cin, g.k, 0, g.cin, 0, _stream())
     return gw

@@ -1,0 +1,63 @@
+"""Fused Adam over one flat fp32 parameter arena (torch.optim.Adam semantics; train.py:109,214).
+
+All parameters (and their gradients) are re-homed as views into two contiguous buffers so that the optimiser step is
+one kernel launch, zero_grad is one memset and the data-parallel gradient all-reduce is one NCCL call over the arena.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from .functional import _call, _ptr, _stream
+
+
+class FusedAdam:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        dev = self.params[0].device
+        # 64-element (256 B) alignment per tensor keeps every view 16-byte aligned for vector access
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        self.numel = total
+        self.param_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, self.offsets):
+            view = self.param_arena[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad_arena[off:off + p.numel()].view_as(p)
+
+    def zero_grad(self, set_to_none=False):
+        self.grad_arena.zero_()
+        for p, off in zip(self.params, self.offsets):   # autograd accumulates in place into these views
+            if p.grad is None or p.grad.data_ptr() != self.grad_arena.data_ptr() + 4 * off:
+                p.grad = self.grad_arena[off:off + p.numel()].view_as(p)
+
+    def all_reduce_grads(self, group=None):
+        """Data-parallel gradient averaging (what DDP does inside accelerator.backward, train.py:211)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad_arena, group=group)
+            return 1.0 / dist.get_world_size(group)
+        return 1.0
+
+    def step(self, grad_scale=1.0):
+        self.step_count += 1
+        _call("b200seg_adam_step", _ptr(self.param_arena), _ptr(self.grad_arena), _ptr(self.exp_avg),
+              _ptr(self.exp_avg_sq), self.numel, float(self.lr), float(self.betas[0]), float(self.betas[1]),
+              float(self.eps), float(self.weight_decay), self.step_count, float(grad_scale), _stream())
+
+    def state_dict(self):
+        return {"step": self.step_count, "lr": self.lr, "betas": self.betas, "eps": self.eps,
+                "weight_decay": self.weight_decay, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+    def load_state_dict(self, sd):
+        self.step_count, self.lr = sd["step"], sd["lr"]
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -43,6 +43,8 @@ typedef struct {
 
 const char* b200seg_version(void);
 const char* b200seg_last_error(void);
+/* Number of tcgen05 kernels launched by this process so far (diagnostic: proves which path ran). */
+int64_t b200seg_umma_launch_count(void);
 /* 1 if the tcgen05 implicit-GEMM path handles this geometry, 0 if the direct CUDA-core path is used. */
 int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g);
 

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _header_decls():
     hdr = open(os.path.join(ROOT, "include", "b200seg.h")).read()
-    return re.findall(r"\n(?:int|size_t|const char\*)\s+(b200seg_\w+)\s*\(([^;]*?)\)\s*;", hdr, re.S)
+    return re.findall(r"\n(?:int|int64_t|size_t|const char\*)\s+(b200seg_\w+)\s*\(([^;]*?)\)\s*;", hdr, re.S)
 
 
 def _code(arg):
@@ -36,7 +36,7 @@ def test_build_and_exports_match_header():
     for name, args in decls:
         assert hasattr(lib, name), "missing export " + name
         codes = "".join(_code(a) for a in args.replace("\n", " ").split(","))
-        bound = _lib.SIGNATURES.get(name, _lib.SIZE_FUNCS.get(name, "" if name in _lib.STRING_FUNCS else None))
+        bound = _lib.SIGNATURES.get(name, _lib.SIZE_FUNCS.get(name, _lib.INT64_FUNCS.get(name, "" if name in _lib.STRING_FUNCS else None)))
         assert bound == codes, (name, bound, codes)
     assert set(_lib.exported_symbols()) == {n for n, _ in decls}
     assert b"sm_100a" in lib.b200seg_version()
