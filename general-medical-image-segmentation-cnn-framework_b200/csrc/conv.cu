@@ -110,6 +110,16 @@ int b200seg_convt_k2s2_fwd(const void* x, int64_t x_pitch, const void* w_packed,
                            int64_t y_pitch, int n, int d, int h, int w, int cin, int cout, void* stream) {
   B200_CHECK_ARG(x && w_packed && y && n > 0 && d > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && x_pitch >= cin &&
                      y_pitch >= cout, "convt_k2s2_fwd: bad arguments");
+  {
+    // tensor-core path: pointwise GEMM [voxels x cin] . [cin x 8*cout] with a pixel-shuffle scatter epilogue.
+    // The dgrad pack of the equivalent strided conv is [7 - abe][cout][cin] == a [8*cout][cin] K-major matrix.
+    UmmaConvArgs a{};
+    a.n = n; a.d = d; a.h = h; a.w = w; a.od = d; a.oh = h; a.ow = w;
+    a.cin = cin; a.cout = 8 * cout; a.k = 1; a.pad = 0; a.dil = 1;
+    a.in = x; a.in_pitch = x_pitch; a.wpack = w_packed; a.bias = bias; a.out = y; a.out_pitch = y_pitch;
+    a.stats = nullptr; a.scatter_cout = cout; a.gather2 = 0;
+    if (conv_umma_supported(a)) return conv_umma_run(a, static_cast<cudaStream_t>(stream));
+  }
   const b200seg_conv_geom g = convt_as_conv(n, d, h, w, cin, cout);
   return conv_direct_dgrad(g, x, x_pitch, w_packed, bias, y, y_pitch, static_cast<cudaStream_t>(stream));
 }
@@ -118,6 +128,16 @@ int b200seg_convt_k2s2_dgrad(const void* dy, int64_t dy_pitch, const void* w_pac
                              int n, int d, int h, int w, int cin, int cout, void* stream) {
   B200_CHECK_ARG(dy && w_packed_dgrad && dx && n > 0 && d > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 &&
                      dy_pitch >= cout && dx_pitch >= cin, "convt_k2s2_dgrad: bad arguments");
+  {
+    // tensor-core path: K runs over (abe, cout); K-chunk group abe reads the sub-lattice dy[2v + abe] through its
+    // own strided tensor map.  The fprop pack of the equivalent strided conv is [abe][cin][cout].
+    UmmaConvArgs a{};
+    a.n = n; a.d = d; a.h = h; a.w = w; a.od = d; a.oh = h; a.ow = w;
+    a.cin = 8 * cout; a.cout = cin; a.k = 1; a.pad = 0; a.dil = 1;
+    a.in = dy; a.in_pitch = dy_pitch; a.wpack = w_packed_dgrad; a.bias = nullptr; a.out = dx; a.out_pitch = dx_pitch;
+    a.stats = nullptr; a.scatter_cout = 0; a.gather2 = 1;
+    if (conv_umma_supported(a)) return conv_umma_run(a, static_cast<cudaStream_t>(stream));
+  }
   const b200seg_conv_geom g = convt_as_conv(n, d, h, w, cin, cout);
   return conv_direct_fprop(g, dy, dy_pitch, w_packed_dgrad, nullptr, dx, dx_pitch, nullptr,
                            static_cast<cudaStream_t>(stream));

@@ -31,6 +31,12 @@ struct UmmaConvArgs {
   void* out;
   int64_t out_pitch;
   float* stats;          // may be null: {sum[cout], sumsq[cout]}
+  // ConvTranspose3d(k2,s2) forward as a pointwise GEMM with N = 8*cout_t and a 2x2x2 pixel-shuffle scatter epilogue:
+  // column n -> flipped tap t' = n / cout_t (offset abe = 7 - t'), channel n % cout_t; out is [n,2od,2oh,2ow,cout_t].
+  int scatter_cout;      // 0 = ordinary epilogue
+  // ConvTranspose3d(k2,s2) backward-data as a pointwise GEMM with K = 8*cin_each: K-chunk group g reads the strided
+  // sub-lattice (2v + abe_g) of `in` through its own tensor map.  0 = single input map.
+  int gather2;           // 1 = `in` is [n,2d,2h,2w,cin/8] and K runs over (abe, channel)
 };
 extern long long g_umma_launches;
 bool conv_umma_supported(const UmmaConvArgs& a);

@@ -34,10 +34,15 @@ struct UmmaConvParams {
   int KC, nchunks, NT, n_ntiles, P, flat;
   int WB, HB, U, UP, S, NB, DT;
   int tiles_w, tiles_h, tiles_d;
+  int scatter_cout, cpm;  // pixel-shuffle epilogue channel count (0 = off); K-chunks per input tensor map
   unsigned slotA, slotB, rowbytes, swz, bytesA_unit, bytesB, tmem_cols;
   __nv_bfloat16* out;
   const float* bias;
   float* stats;
+};
+
+struct TensorMaps8 {
+  CUtensorMap m[8];
 };
 
 __device__ __forceinline__ void butterfly_colsum(float (&v)[32], int lane) {
@@ -55,7 +60,7 @@ __device__ __forceinline__ void butterfly_colsum(float (&v)[32], int lane) {
 }
 
 __global__ void __launch_bounds__(256, 1)
-    conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+    conv_umma_kernel(const __grid_constant__ TensorMaps8 tmAs, const __grid_constant__ CUtensorMap tmB,
                      const UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(256, 1)
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmAs.m[0]);
   if (warp == 1 && lane == 0) tma_prefetch_desc(&tmB);
   tc_fence_before();
   __syncthreads();
@@ -118,8 +123,8 @@ __global__ void __launch_bounds__(256, 1)
           const uint32_t ph = (L / p.S) & 1;
           mbar_wait(&emptyA[s], ph ^ 1);
           mbar_arrive_expect_tx(&fullA[s], p.bytesA_unit);
-          tma_load_5d(sA + static_cast<size_t>(s) * p.slotA, &tmA, &fullA[s], c * p.KC, w0 - p.pad, h0 - p.pad,
-                      d0 - p.pad + u * p.UP, nn);
+          tma_load_5d(sA + static_cast<size_t>(s) * p.slotA, &tmAs.m[c / p.cpm], &fullA[s], (c % p.cpm) * p.KC,
+                      w0 - p.pad, h0 - p.pad, d0 - p.pad + u * p.UP, nn);
         }
       }
     }
@@ -133,7 +138,9 @@ __global__ void __launch_bounds__(256, 1)
           const uint32_t ph = (L / p.NB) & 1;
           mbar_wait(&emptyB[s], ph ^ 1);
           mbar_arrive_expect_tx(&fullB[s], p.bytesB);
-          tma_load_3d(sB + static_cast<size_t>(s) * p.slotB, &tmB, &fullB[s], c * p.KC, nt * p.NT, t);
+          // multi-map (gather) mode: the map index doubles as the weight "tap"
+          tma_load_3d(sB + static_cast<size_t>(s) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT,
+                      p.cpm < p.nchunks ? c / p.cpm : t);
         }
       }
     }
@@ -225,6 +232,14 @@ __global__ void __launch_bounds__(256, 1)
       __nv_bfloat16* orow = p.out + vox * p.out_pitch + nt * p.NT;
       for (int cc = 0; cc < nchunk32; ++cc) {
         const int ncol = min(32, p.NT - cc * 32);
+        if (p.scatter_cout) {
+          // 2x2x2 pixel shuffle: this 32-column chunk belongs to one (a,b,e) offset of the up-sampled grid
+          const int col0 = nt * p.NT + cc * 32;
+          const int abe = 7 - col0 / p.scatter_cout, co0 = col0 % p.scatter_cout;
+          const long long ovox = ((static_cast<long long>(nn) * 2 * p.od + 2 * od_ + (abe >> 2)) * 2 * p.oh + 2 * oh_ +
+                                  ((abe >> 1) & 1)) * 2 * p.ow + 2 * ow_ + (abe & 1);
+          orow = p.out + ovox * p.out_pitch + co0 - cc * 32;
+        }
         uint32_t raw[32];
         const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + acc * p.NT + cc * 32;
         if (ncol == 32) {
@@ -242,7 +257,8 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           v[j] = __uint_as_float(raw[j]);
-          if (p.bias != nullptr && j < ncol) v[j] += p.bias[nt * p.NT + cc * 32 + j];
+          if (p.bias != nullptr && j < ncol)
+            v[j] += p.bias[p.scatter_cout ? (nt * p.NT + cc * 32 + j) % p.scatter_cout : nt * p.NT + cc * 32 + j];
         }
         if (valid) {
 #pragma unroll
@@ -353,12 +369,17 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
   p = UmmaConvParams{};
   p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.out_pitch = a.out_pitch;
   p.k = a.k; p.pad = a.pad; p.dil = a.dil;
-  p.KC = a.cin % 64 == 0 ? 64 : (a.cin % 32 == 0 ? 32 : 16);
+  p.scatter_cout = a.scatter_cout;
+  if (a.scatter_cout && (a.scatter_cout % 32 || a.cout != 8 * a.scatter_cout || a.k != 1 || a.stats)) return false;
+  const int cin_map = a.gather2 ? a.cin / 8 : a.cin;   // channels behind one input tensor map
+  if (a.gather2 && (a.cin % 8 || a.k != 1 || cin_map % 16)) return false;
+  p.KC = cin_map % 64 == 0 ? 64 : (cin_map % 32 == 0 ? 32 : 16);
   p.nchunks = a.cin / p.KC;
+  p.cpm = cin_map / p.KC;
   p.rowbytes = p.KC * 2;
   p.swz = p.KC == 64 ? SWZ_128B : (p.KC == 32 ? SWZ_64B : SWZ_32B);
   // N tile: the whole C_out when it fits one accumulator comfortably, else 128 / 64 / 32 / 16
-  if (a.cout <= 128) p.NT = a.cout;
+  if (a.cout <= 128 && !a.scatter_cout) p.NT = a.cout;
   else if (a.cout % 128 == 0) p.NT = 128;
   else if (a.cout % 64 == 0) p.NT = 64;
   else if (a.cout % 32 == 0) p.NT = 32;
@@ -461,20 +482,38 @@ int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
     set_error("conv_umma_run: buffers must be 16-byte aligned");
     return B200SEG_ERR_INVALID;
   }
-  CUtensorMap tmA, tmB;
-  {
+  TensorMaps8 tmAs;
+  CUtensorMap tmB;
+  if (!a.gather2) {
     const uint64_t dims[5] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.w), static_cast<uint64_t>(a.h),
                               static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.n)};
     const uint64_t pb = static_cast<uint64_t>(a.in_pitch) * 2;
     const uint64_t str[4] = {pb, pb * a.w, pb * a.w * a.h, pb * a.w * a.h * a.d};
     const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB),
                              static_cast<uint32_t>(p.UP), 1u};
-    if (!encode_bf16_map(&tmA, a.in, 5, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
+    if (!encode_bf16_map(&tmAs.m[0], a.in, 5, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
+    for (int i = 1; i < 8; ++i) tmAs.m[i] = tmAs.m[0];
+  } else {
+    // `in` is the fine grid [n, 2d, 2h, 2w, cin/8]; map g = the sub-lattice with offset (a,b,e) = bits of g
+    const int cm = a.cin / 8;
+    const uint64_t pb = static_cast<uint64_t>(a.in_pitch) * 2;
+    const uint64_t W2 = 2ull * a.w, H2 = 2ull * a.h, D2 = 2ull * a.d;
+    for (int g = 0; g < 8; ++g) {
+      const uint64_t off = (((g >> 2) * H2 + ((g >> 1) & 1)) * W2 + (g & 1)) * pb;
+      const uint64_t dims[5] = {static_cast<uint64_t>(cm), static_cast<uint64_t>(a.w), static_cast<uint64_t>(a.h),
+                                static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.n)};
+      const uint64_t str[4] = {2 * pb, 2 * pb * W2, 2 * pb * W2 * H2, pb * W2 * H2 * D2};
+      const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB),
+                               static_cast<uint32_t>(p.UP), 1u};
+      if (!encode_bf16_map(&tmAs.m[g], static_cast<const uint8_t*>(a.in) + off, 5, dims, str, box, p.KC))
+        return B200SEG_ERR_CUDA;
+    }
   }
   {
-    const int k3 = a.k * a.k * a.k;
-    const uint64_t dims[3] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.cout), static_cast<uint64_t>(k3)};
-    const uint64_t str[2] = {static_cast<uint64_t>(a.cin) * 2, static_cast<uint64_t>(a.cin) * a.cout * 2};
+    const int k3 = a.gather2 ? 8 : a.k * a.k * a.k;
+    const uint64_t cin_w = a.gather2 ? a.cin / 8 : a.cin;   // weight pack is [taps][cout][cin_w]
+    const uint64_t dims[3] = {cin_w, static_cast<uint64_t>(a.cout), static_cast<uint64_t>(k3)};
+    const uint64_t str[2] = {cin_w * 2, cin_w * a.cout * 2};
     const uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.NT), 1u};
     if (!encode_bf16_map(&tmB, a.wpack, 3, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
   }
@@ -487,16 +526,10 @@ int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   const int ctas = a.n * p.tiles_d * p.tiles_h * p.tiles_w * p.n_ntiles;
-  conv_umma_kernel<<<ctas, 256, smem, st>>>(tmA, tmB, p);
+  conv_umma_kernel<<<ctas, 256, smem, st>>>(tmAs, tmB, p);
   B200_CHECK_LAUNCH("conv_umma");
   ++g_umma_launches;
   return 0;
-}
-
-bool wgrad_umma_supported(const UmmaWgradArgs&) { return false; }
-int wgrad_umma_run(const UmmaWgradArgs&, cudaStream_t) {
-  set_error("wgrad_umma_run: not available");
-  return B200SEG_ERR_INVALID;
 }
 
 }  // namespace b200

@@ -88,9 +88,15 @@ def test_conv3d_fprop_dgrad_wgrad(F, case):
     xd = ndhwc(x).requires_grad_(True)
     wd = w.to(DEV).requires_grad_(True)
     bd = b.to(DEV).requires_grad_(True)
+    n0 = F.umma_launch_count()
     y = F.conv_norm_act(xd, wd, bd, k=k, stride=stride, pad=pad, dil=dil)
     close(ncdhw(y), y_ref.detach(), 8e-3, "fprop")
     y.backward(ndhwc(dy))
+    # which path ran: tcgen05 for stride-1 k in {1,3,5} with 16-aligned channels (wgrad: C_in % 32 == 0)
+    if stride == 1 and k in (1, 3, 5) and cin % 16 == 0 and cout % 16 == 0:
+        assert F.umma_launch_count() - n0 == (3 if cin % 32 == 0 else 2), "tensor-core path was not taken"
+    else:
+        assert F.umma_launch_count() == n0
     close(ncdhw(xd.grad), xr.grad, 8e-3, "dgrad")
     close(wd.grad.cpu(), wr.grad, 8e-3, "wgrad")
     close(bd.grad.cpu(), dy.sum((0, 2, 3, 4)), 8e-3, "bias grad")
@@ -194,7 +200,8 @@ def test_maxpool_indices_bit_exact_with_ties_and_nan(F, golden):
 
 def test_conv_transpose_k2s2(F):
     g = torch.Generator().manual_seed(5)
-    for cin, cout, size in [(64, 32, (4, 4, 8)), (16, 8, (3, 5, 4)), (32, 32, (2, 2, 2))]:
+    for cin, cout, size in [(64, 32, (4, 4, 8)), (16, 8, (3, 5, 4)), (32, 32, (2, 2, 2)), (64, 32, (4, 16, 16)),
+                            (128, 64, (3, 16, 8)), (512, 256, (2, 2, 2)), (64, 32, (3, 18, 10))]:
         x = bf(torch.randn(2, cin, *size, generator=g))
         w = torch.randn(cin, cout, 2, 2, 2, generator=g) * 0.1
         b = torch.randn(cout, generator=g) * 0.1
