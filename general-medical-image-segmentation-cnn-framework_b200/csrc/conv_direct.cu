@@ -279,9 +279,149 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ stem (C_in = 1)
+// First layer of every model on the path: 1 input channel, k^3 taps, COUT <= 32 channels ('same' padding, stride 1).
+// 26 FLOP/B: HBM-bound on the bf16 output.  fprop: thread = voxel, all COUT accumulators in registers, weights
+// broadcast from shared memory.  wgrad: lane = output channel, 27 accumulators per lane, the 27 input taps of a voxel
+// are fetched by 27 lanes and broadcast with shuffles.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+    stem_fprop_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                      const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ y, int64_t y_pitch, float* __restrict__ stats) {
+  __shared__ __align__(16) float sw[125 * COUT];
+  __shared__ float sred[2 * COUT];
+  const int k = g.k, k3 = k * k * k;
+  for (int i = threadIdx.x; i < k3 * COUT; i += blockDim.x) sw[i] = __bfloat162float(wp[i]);  // [t][co][ci=1]
+  for (int i = threadIdx.x; i < 2 * COUT; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float s1[COUT], s2[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) s1[j] = s2[j] = 0.f;
+  const int64_t total = static_cast<int64_t>(g.n) * g.d * g.h * g.w;
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t r = v;
+    const int xo = static_cast<int>(r % g.w);
+    r /= g.w;
+    const int yo = static_cast<int>(r % g.h);
+    r /= g.h;
+    const int zo = static_cast<int>(r % g.d);
+    const int nn = static_cast<int>(r / g.d);
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = bias ? bias[j] : 0.f;
+    for (int a = 0; a < k; ++a) {
+      const int zi = zo - g.pad + a;
+      if (zi < 0 || zi >= g.d) continue;
+      for (int b = 0; b < k; ++b) {
+        const int yi = yo - g.pad + b;
+        if (yi < 0 || yi >= g.h) continue;
+        const __nv_bfloat16* row = x + ((static_cast<int64_t>(nn) * g.d + zi) * g.h + yi) * g.w * x_pitch;
+        for (int e = 0; e < k; ++e) {
+          const int xi = xo - g.pad + e;
+          if (xi < 0 || xi >= g.w) continue;
+          const float xv = __bfloat162float(row[xi * x_pitch]);
+          const float4* w4 = reinterpret_cast<const float4*>(sw + ((a * k + b) * k + e) * COUT);
+#pragma unroll
+          for (int j = 0; j < COUT / 4; ++j) {
+            const float4 t = w4[j];
+            acc[4 * j + 0] += xv * t.x;
+            acc[4 * j + 1] += xv * t.y;
+            acc[4 * j + 2] += xv * t.z;
+            acc[4 * j + 3] += xv * t.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; j += 8) {
+      float t8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        t8[i] = acc[j + i];
+        s1[j + i] += acc[j + i];
+        s2[j + i] += acc[j + i] * acc[j + i];
+      }
+      st8(y + v * y_pitch + j, pack8(t8));
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+      const float a1 = warp_sum(s1[j]), a2 = warp_sum(s2[j]);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sred[j], a1);
+        atomicAdd(&sred[COUT + j], a2);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * COUT; i += blockDim.x) atomicAdd(&stats[i], sred[i]);
+  }
+}
+
+// dwp[t][0][co] += sum_v x[v + off_t] * dy[v][co];  k = 3, COUT = 32 (lane = co).
+__global__ void __launch_bounds__(256)
+    stem_wgrad_k3_c32_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                             const __nv_bfloat16* __restrict__ dy, int64_t dy_pitch, float* __restrict__ dwp) {
+  __shared__ float sacc[27 * 32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t warp_id = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * warps_per_block;
+  // lane t < 27 fetches tap t = (a, b, e)
+  const int ta = lane / 9 - 1, tb = (lane / 3) % 3 - 1, te = lane % 3 - 1;
+  float acc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  const int64_t rows = static_cast<int64_t>(g.n) * g.d * g.h;   // one (n, z, y) line of w voxels per iteration
+  for (int64_t r = warp_id; r < rows; r += nwarps) {
+    const int yo = static_cast<int>(r % g.h);
+    const int zo = static_cast<int>((r / g.h) % g.d);
+    const int nn = static_cast<int>(r / (static_cast<int64_t>(g.h) * g.d));
+    const int zi = zo + ta, yi = yo + tb;
+    const bool row_ok = lane < 27 && zi >= 0 && zi < g.d && yi >= 0 && yi < g.h;
+    const __nv_bfloat16* xrow = x + ((static_cast<int64_t>(nn) * g.d + zi) * g.h + yi) * g.w * x_pitch;
+    const __nv_bfloat16* drow = dy + r * g.w * dy_pitch + lane;
+    for (int xo = 0; xo < g.w; ++xo) {
+      const int xi = xo + te;
+      const float xv = (row_ok && xi >= 0 && xi < g.w) ? __bfloat162float(xrow[xi * x_pitch]) : 0.f;
+      const float dv = __bfloat162float(drow[xo * dy_pitch]);
+#pragma unroll
+      for (int t = 0; t < 27; ++t) acc[t] += __shfl_sync(0xffffffffu, xv, t) * dv;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 27; ++t) atomicAdd(&sacc[t * 32 + lane], acc[t]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) atomicAdd(&dwp[i], sacc[i]);
+}
+
+static bool is_stem(const ConvGeom& g) {
+  return g.cin == 1 && g.stride == 1 && g.dil == 1 && g.k <= 5 && (g.k & 1) && g.pad == (g.k - 1) / 2 &&
+         (g.cout == 32 || g.cout == 16);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int conv_direct_fprop(const ConvGeom& g, const void* x, int64_t x_pitch, const void* wp, const float* bias, void* y,
                       int64_t y_pitch, float* stats, cudaStream_t st) {
+  if (is_stem(g) && y_pitch % 8 == 0) {
+    const int64_t total = static_cast<int64_t>(g.n) * g.d * g.h * g.w;
+    const int blocks = grid_for(total, 256, kNumSMs * 4);
+    if (g.cout == 32)
+      stem_fprop_kernel<32><<<blocks, 256, 0, st>>>(g, static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                                     static_cast<const __nv_bfloat16*>(wp), bias,
+                                                     static_cast<__nv_bfloat16*>(y), y_pitch, stats);
+    else
+      stem_fprop_kernel<16><<<blocks, 256, 0, st>>>(g, static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                                     static_cast<const __nv_bfloat16*>(wp), bias,
+                                                     static_cast<__nv_bfloat16*>(y), y_pitch, stats);
+    B200_CHECK_LAUNCH("stem_fprop");
+    return 0;
+  }
   const int cog = (g.cout + 7) / 8;
   const int64_t total = static_cast<int64_t>(g.n) * g.od * g.oh * g.ow * cog;
   // blockDim * gridDim must be a multiple of cog so each thread keeps one channel group (see kernel)
@@ -328,6 +468,12 @@ int conv_direct_dgrad(const ConvGeom& g, const void* dy, int64_t dy_pitch, const
 
 int conv_direct_wgrad(const ConvGeom& g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, float* dwp,
                       cudaStream_t st) {
+  if (is_stem(g) && g.k == 3 && g.cout == 32) {
+    stem_wgrad_k3_c32_kernel<<<kNumSMs * 4, 256, 0, st>>>(g, static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                                           static_cast<const __nv_bfloat16*>(dy), dy_pitch, dwp);
+    B200_CHECK_LAUNCH("stem_wgrad");
+    return 0;
+  }
   const int k3 = g.k * g.k * g.k;
   const int tiles = ((g.cin + 31) / 32) * ((g.cout + 31) / 32);
   const int64_t total = static_cast<int64_t>(g.n) * g.od * g.oh * g.ow;

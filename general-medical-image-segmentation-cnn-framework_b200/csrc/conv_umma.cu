@@ -146,58 +146,91 @@ __global__ void __launch_bounds__(256, 1)
     }
   } else if (warp == 2) {
     // =========================== MMA issuer ===========================
+    // One thread issues every tcgen05.mma of the CTA, so this loop is written to cost a handful of integer
+    // instructions per MMA: descriptors are (constant high word | running low word), ring slots advance by
+    // add-and-wrap instead of modulo, and nothing is multiplied inside the accumulator loop.
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
       const uint32_t a_sbo = (p.flat ? 8u : static_cast<uint32_t>(p.WB)) * p.rowbytes;
       const uint32_t b_sbo = 8u * p.rowbytes;
+      const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 16, a_sbo, p.swz) >> 32);
+      const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 16, b_sbo, p.swz) >> 32);
+      const uint32_t lo_fixed = 1u << 16;  // leading byte offset field (16 B), ignored for swizzled K-major
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      const uint32_t ringA_end = sA_addr + p.S * p.slotA;
       const int ksteps = p.KC / 16;
-      int LB = 0;
+      const uint32_t acc_stride_flat = 128u * p.rowbytes;
+      int bs = 0;                 // weight ring slot
+      uint32_t bphase = 0;
+      int unit0_slot = 0;         // ring slot of unit 0 of the current chunk
+      uint32_t unit0_phase = 0;   // its parity
       for (int c = 0; c < p.nchunks; ++c) {
-        int waited = 0;  // units of this chunk whose full barrier has been observed
+        int waited = 0;           // units of this chunk whose full barrier has been observed
+        int wslot = unit0_slot;
+        uint32_t wphase = unit0_phase;
         for (int a = 0; a < k; ++a) {
           const int need = p.flat ? 1 : min(p.U, p.P + a * p.dil);
           for (; waited < need; ++waited) {
-            const int L = c * p.U + waited;
-            mbar_wait(&fullA[L % p.S], (L / p.S) & 1);
+            mbar_wait(&fullA[wslot], wphase);
+            if (++wslot == p.S) {
+              wslot = 0;
+              wphase ^= 1;
+            }
           }
           tc_fence_after();
+          // address of the slot holding plane (a*dil) of this chunk (plane mode) / of the box (flat mode)
+          int aslot = unit0_slot + (p.flat ? 0 : a * p.dil);
+          if (aslot >= p.S) aslot -= p.S;
+          const uint32_t a_first = sA_addr + aslot * p.slotA;
           for (int b = 0; b < k; ++b) {
-            for (int e = 0; e < k; ++e, ++LB) {
-              const int bs = LB % p.NB;
-              mbar_wait(&fullB[bs], (LB / p.NB) & 1);
+            for (int e = 0; e < k; ++e) {
+              mbar_wait(&fullB[bs], bphase);
               tc_fence_after();
-              const uint32_t b_addr = sB_addr + bs * p.slotB;
+              const uint32_t b_lo = (((sB_addr + bs * p.slotB) >> 4) & 0x3FFF) | lo_fixed;
+              const uint32_t tapoff = p.flat
+                  ? static_cast<uint32_t>((a * p.dil * p.HB + b * p.dil) * p.WB + e * p.dil) * p.rowbytes
+                  : static_cast<uint32_t>((b * p.dil) * p.WB + e * p.dil) * p.rowbytes;
+              uint32_t a_addr = a_first + tapoff;
+              uint32_t d_tmem = tbase;
+              const uint32_t accum0 = (c | a | b | e) != 0 ? 1u : 0u;
               for (int acc = 0; acc < p.P; ++acc) {
-                uint32_t a_addr;
-                if (p.flat) {
-                  const int L = c * p.U;
-                  a_addr = sA_addr + (L % p.S) * p.slotA +
-                           static_cast<uint32_t>(acc * 128 + (a * p.dil * p.HB + b * p.dil) * p.WB + e * p.dil) * p.rowbytes;
-                } else {
-                  const int L = c * p.U + acc + a * p.dil;
-                  a_addr = sA_addr + (L % p.S) * p.slotA +
-                           static_cast<uint32_t>((b * p.dil) * p.WB + e * p.dil) * p.rowbytes;
-                }
-                const uint32_t first = (c == 0 && a == 0 && b == 0 && e == 0) ? 1u : 0u;
+                const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | lo_fixed;
                 for (int kk = 0; kk < ksteps; ++kk) {
-                  const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, a_sbo, p.swz);
-                  const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, b_sbo, p.swz);
-                  umma_f16(tbase + acc * p.NT, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * kk);
+                  const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk);
+                  umma_f16(d_tmem, ad, bd, idesc, accum0 | (kk != 0 ? 1u : 0u));
+                }
+                d_tmem += p.NT;
+                if (p.flat) {
+                  a_addr += acc_stride_flat;
+                } else {
+                  a_addr += p.slotA;
+                  if (a_addr >= ringA_end + tapoff) a_addr -= p.S * p.slotA;
                 }
               }
               umma_commit(&emptyB[bs]);  // weight tile consumed once these MMAs retire
+              if (++bs == p.NB) {
+                bs = 0;
+                bphase ^= 1;
+              }
             }
           }
           // release input units whose last use was this kd iteration
           if (p.flat) {
-            if (a == k - 1) umma_commit(&emptyA[(c * p.U) % p.S]);
+            if (a == k - 1) umma_commit(&emptyA[unit0_slot]);
           } else {
+            int rs = unit0_slot;
             for (int j = 0; j < p.U; ++j) {
               const int a_last = min(k - 1, j / p.dil);
-              if (a_last == a) umma_commit(&emptyA[(c * p.U + j) % p.S]);
+              if (a_last == a) umma_commit(&emptyA[rs]);
+              if (++rs == p.S) rs = 0;
             }
           }
+        }
+        unit0_slot += p.U;
+        while (unit0_slot >= p.S) {
+          unit0_slot -= p.S;
+          unit0_phase ^= 1;
         }
       }
       umma_commit(accFull);

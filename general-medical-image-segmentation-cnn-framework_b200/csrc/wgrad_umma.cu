@@ -134,26 +134,43 @@ __global__ void __launch_bounds__(192, 1)
       const uint32_t a_sbo = static_cast<uint32_t>(p.a_sbo_rows) * p.rowbytesA;
       const uint32_t a_adv = static_cast<uint32_t>(p.a_kadv_rows) * p.rowbytesA;
       const uint32_t b_sbo = 8u * p.rowbytesB, b_adv = 16u * p.rowbytesB;
-      int L = 0;
-      for (long long it = it0; it < it1; ++it, ++L) {
-        const int s = L % p.stages;
-        mbar_wait(&full[s], (L / p.stages) & 1);
+      const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 16, b_sbo, p.swzB) >> 32);
+      const uint32_t a_adv16 = a_adv >> 4, b_adv16 = b_adv >> 4;
+      const uint32_t kd_rows = (p.flat && p.asplit > 1) ? static_cast<uint32_t>(asel * p.dil * p.HB * p.WB) : 0u;
+      // per-group constants: descriptor high word (LBO differs per group) and byte offset inside a stage
+      uint32_t g_hi[kMaxGroups], g_off[kMaxGroups], g_lbo[kMaxGroups];
+      for (int g = 0; g < p.ngroups; ++g) {
+        const WgradGroup& G = p.groups[g];
+        g_off[g] = G.plane * p.slotX + (static_cast<uint32_t>(G.base_rows) + kd_rows) * p.rowbytesA;
+        const uint64_t d = make_smem_desc(0, static_cast<uint32_t>(G.lbo_rows) * p.rowbytesA, a_sbo, p.swzA);
+        g_hi[g] = static_cast<uint32_t>(d >> 32);
+        g_lbo[g] = static_cast<uint32_t>(d) & 0x3FFF0000u;
+      }
+      int s = 0;
+      uint32_t phase = 0, accum = 0;
+      for (long long it = it0; it < it1; ++it) {
+        mbar_wait(&full[s], phase);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
-        const uint32_t y_addr = st + p.nplanes * p.slotX;
+        const uint32_t y_lo0 = (((st + p.nplanes * p.slotX) >> 4) & 0x3FFF) | (1u << 16);
         for (int g = 0; g < p.ngroups; ++g) {
-          const WgradGroup& G = p.groups[g];
-          // flat mode with the taps split over CTAs: the kd shift is a row offset inside the single box
-          const uint32_t kd_rows = (p.flat && p.asplit > 1) ? static_cast<uint32_t>(asel * p.dil * p.HB * p.WB) : 0u;
-          const uint32_t x_addr = st + G.plane * p.slotX + (static_cast<uint32_t>(G.base_rows) + kd_rows) * p.rowbytesA;
-          const uint32_t a_lbo = static_cast<uint32_t>(G.lbo_rows) * p.rowbytesA;
+          uint32_t a_lo = (((st + g_off[g]) >> 4) & 0x3FFF) | g_lbo[g];
+          uint32_t y_lo = y_lo0;
+          const uint32_t d_tmem = tbase + g * p.NT;
           for (int ks = 0; ks < p.ksteps; ++ks) {
-            const uint64_t ad = make_smem_desc(x_addr + ks * a_adv, a_lbo, a_sbo, p.swzA);
-            const uint64_t bd = make_smem_desc(y_addr + ks * b_adv, 16, b_sbo, p.swzB);
-            umma_f16(tbase + g * p.NT, ad, bd, idesc, (L == 0 && ks == 0) ? 0u : 1u);
+            const uint64_t ad = (static_cast<uint64_t>(g_hi[g]) << 32) | a_lo;
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | y_lo;
+            umma_f16(d_tmem, ad, bd, idesc, accum | (ks != 0 ? 1u : 0u));
+            a_lo += a_adv16;
+            y_lo += b_adv16;
           }
         }
+        accum = 1;
         umma_commit(&empty[s]);
+        if (++s == p.stages) {
+          s = 0;
+          phase ^= 1;
+        }
       }
       umma_commit(accFull);
     }

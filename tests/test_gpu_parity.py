@@ -48,7 +48,9 @@ def close(a, b, tol, what=""):
 
 CONV_CASES = [
     # cin, cout, k, stride, pad, dil, (d,h,w), n
-    (1, 32, 3, 1, 1, 1, (8, 8, 8), 2),        # U-Net stem (direct path)
+    (1, 32, 3, 1, 1, 1, (8, 8, 8), 2),        # U-Net stem (dedicated C_in=1 kernels)
+    (1, 32, 3, 1, 1, 1, (9, 20, 33), 1),      # stem, ragged extents
+    (1, 16, 5, 1, 2, 1, (8, 8, 12), 1),       # V-Net stem 5x5x5
     (32, 32, 3, 1, 1, 1, (8, 16, 8), 2),      # full-resolution U-Net layer
     (64, 32, 3, 1, 1, 1, (8, 16, 16), 1),     # decoder conv1 (concat input)
     (32, 64, 3, 1, 1, 1, (4, 16, 8), 2),
