@@ -39,6 +39,7 @@ struct UmmaConvParams {
   __nv_bfloat16* out;
   const float* bias;
   float* stats;
+  long long* dbg;  // optional timeline of CTA 0 (clock64 stamps), enabled by B200SEG_DEBUG_TIMELINE
 };
 
 struct TensorMaps8 {
@@ -59,7 +60,7 @@ __device__ __forceinline__ void butterfly_colsum(float (&v)[32], int lane) {
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
     conv_umma_kernel(const __grid_constant__ TensorMaps8 tmAs, const __grid_constant__ CUtensorMap tmB,
                      const UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* accFull = emptyB + p.NB;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accFull + 1);
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 2);  // [2][NT]
+  float* s_bias = s_stats + 2 * p.NT;                        // [NT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256, 1)
     fence_mbar_init();
   }
   for (int i = tid; i < 2 * p.NT; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = tid; i < p.NT; i += blockDim.x)
+    s_bias[i] = p.bias ? p.bias[p.scatter_cout ? (nt * p.NT + i) % p.scatter_cout : nt * p.NT + i] : 0.f;
   if (warp == 3) {
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
@@ -112,6 +116,8 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+  if (dbg && tid == 0) p.dbg[0] = clock64();
 
   if (warp == 0) {
     // =========================== input-box producer ===========================
@@ -149,7 +155,8 @@ __global__ void __launch_bounds__(256, 1)
     // One thread issues every tcgen05.mma of the CTA, so this loop is written to cost a handful of integer
     // instructions per MMA: descriptors are (constant high word | running low word), ring slots advance by
     // add-and-wrap instead of modulo, and nothing is multiplied inside the accumulator loop.
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();  // the one lane whose tcgen05 instructions take effect
       const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
       const uint32_t a_sbo = (p.flat ? 8u : static_cast<uint32_t>(p.WB)) * p.rowbytes;
       const uint32_t b_sbo = 8u * p.rowbytes;
@@ -157,7 +164,6 @@ __global__ void __launch_bounds__(256, 1)
       const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 16, b_sbo, p.swz) >> 32);
       const uint32_t lo_fixed = 1u << 16;  // leading byte offset field (16 B), ignored for swizzled K-major
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-      const uint32_t ringA_end = sA_addr + p.S * p.slotA;
       const int ksteps = p.KC / 16;
       const uint32_t acc_stride_flat = 128u * p.rowbytes;
       int bs = 0;                 // weight ring slot
@@ -178,10 +184,20 @@ __global__ void __launch_bounds__(256, 1)
             }
           }
           tc_fence_after();
+          if (dbg && c == 0 && lane == 0) p.dbg[1 + a] = clock64();
           // address of the slot holding plane (a*dil) of this chunk (plane mode) / of the box (flat mode)
           int aslot = unit0_slot + (p.flat ? 0 : a * p.dil);
           if (aslot >= p.S) aslot -= p.S;
           const uint32_t a_first = sA_addr + aslot * p.slotA;
+          uint32_t a_lo_acc[8];
+          {
+            int sl = aslot;
+#pragma unroll
+            for (int acc = 0; acc < 8; ++acc) {
+              a_lo_acc[acc] = (((sA_addr + sl * p.slotA) >> 4) & 0x3FFF) | lo_fixed;
+              if (++sl == p.S) sl = 0;
+            }
+          }
           for (int b = 0; b < k; ++b) {
             for (int e = 0; e < k; ++e) {
               mbar_wait(&fullB[bs], bphase);
@@ -190,25 +206,38 @@ __global__ void __launch_bounds__(256, 1)
               const uint32_t tapoff = p.flat
                   ? static_cast<uint32_t>((a * p.dil * p.HB + b * p.dil) * p.WB + e * p.dil) * p.rowbytes
                   : static_cast<uint32_t>((b * p.dil) * p.WB + e * p.dil) * p.rowbytes;
-              uint32_t a_addr = a_first + tapoff;
-              uint32_t d_tmem = tbase;
               const uint32_t accum0 = (c | a | b | e) != 0 ? 1u : 0u;
-              for (int acc = 0; acc < p.P; ++acc) {
-                const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | lo_fixed;
-                for (int kk = 0; kk < ksteps; ++kk) {
-                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * kk);
-                  const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk);
-                  umma_f16(d_tmem, ad, bd, idesc, accum0 | (kk != 0 ? 1u : 0u));
+              if (!p.flat) {
+                // plane mode: P <= 8 accumulators, descriptors precomputed per kd iteration (a_lo_acc), fully unrolled
+                const uint32_t tap16 = tapoff >> 4;
+#pragma unroll
+                for (int acc = 0; acc < 8; ++acc) {
+                  if (acc < p.P) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                      if (kk < ksteps) {
+                        const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo_acc[acc] + tap16 + 2u * kk);
+                        const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk);
+                        umma_f16_pred(tbase + acc * p.NT, ad, bd, idesc, accum0 | (kk != 0 ? 1u : 0u), leader);
+                      }
+                    }
+                  }
                 }
-                d_tmem += p.NT;
-                if (p.flat) {
+              } else {
+                uint32_t a_addr = a_first + tapoff;
+                uint32_t d_tmem = tbase;
+                for (int acc = 0; acc < p.P; ++acc) {
+                  const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | lo_fixed;
+                  for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * kk);
+                    const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk);
+                    umma_f16_pred(d_tmem, ad, bd, idesc, accum0 | (kk != 0 ? 1u : 0u), leader);
+                  }
+                  d_tmem += p.NT;
                   a_addr += acc_stride_flat;
-                } else {
-                  a_addr += p.slotA;
-                  if (a_addr >= ringA_end + tapoff) a_addr -= p.S * p.slotA;
                 }
               }
-              umma_commit(&emptyB[bs]);  // weight tile consumed once these MMAs retire
+              umma_commit_pred(&emptyB[bs], leader);  // weight tile consumed once these MMAs retire
               if (++bs == p.NB) {
                 bs = 0;
                 bphase ^= 1;
@@ -217,12 +246,12 @@ __global__ void __launch_bounds__(256, 1)
           }
           // release input units whose last use was this kd iteration
           if (p.flat) {
-            if (a == k - 1) umma_commit(&emptyA[unit0_slot]);
+            if (a == k - 1) umma_commit_pred(&emptyA[unit0_slot], leader);
           } else {
             int rs = unit0_slot;
             for (int j = 0; j < p.U; ++j) {
               const int a_last = min(k - 1, j / p.dil);
-              if (a_last == a) umma_commit(&emptyA[rs]);
+              if (a_last == a) umma_commit_pred(&emptyA[rs], leader);
               if (++rs == p.S) rs = 0;
             }
           }
@@ -233,104 +262,102 @@ __global__ void __launch_bounds__(256, 1)
           unit0_phase ^= 1;
         }
       }
-      umma_commit(accFull);
+      umma_commit_pred(accFull, leader);
+      if (dbg && lane == 0) p.dbg[8] = clock64();
     }
   } else if (warp >= 4) {
     // =========================== epilogue ===========================
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int nchunk32 = (p.NT + 31) / 32;
-    float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};
     mbar_wait(accFull, 0);
     tc_fence_after();
-    for (int acc = 0; acc < p.P; ++acc) {
-      int od_, oh_, ow_;
-      bool valid;
-      if (p.flat) {
-        const int R = acc * 128 + m;
-        const int plane = p.HB * p.WB;
-        const int dz = R / plane, rem = R - dz * plane;
-        const int hy = rem / p.WB, wx = rem - hy * p.WB;
-        od_ = d0 + dz;
-        oh_ = hy;
-        ow_ = wx;
-        valid = dz < p.DT && od_ < p.od && hy < p.oh && wx < p.ow;
-      } else {
-        od_ = d0 + acc;
-        oh_ = h0 + (m >> 3);
-        ow_ = w0 + (m & 7);
-        valid = od_ < p.od && oh_ < p.oh && ow_ < p.ow;
-      }
-      const long long vox = ((static_cast<long long>(nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
-      __nv_bfloat16* orow = p.out + vox * p.out_pitch + nt * p.NT;
-      for (int cc = 0; cc < nchunk32; ++cc) {
-        const int ncol = min(32, p.NT - cc * 32);
+    if (dbg && tid == 128) p.dbg[9] = clock64();
+    const int plane_rows = p.HB * p.WB;
+    for (int c16 = 0; c16 < p.NT; c16 += 16) {
+      float bias_r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bias_r[j] = s_bias[c16 + j];
+      float s1[16], s2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s1[j] = s2[j] = 0.f;
+      for (int acc = 0; acc < p.P; ++acc) {
+        int od_, oh_, ow_;
+        bool valid;
+        if (p.flat) {
+          const int R = acc * 128 + m;
+          const int dz = R / plane_rows, rem = R - dz * plane_rows;
+          const int hy = rem / p.WB, wx = rem - hy * p.WB;
+          od_ = d0 + dz;
+          oh_ = hy;
+          ow_ = wx;
+          valid = dz < p.DT && od_ < p.od && hy < p.oh && wx < p.ow;
+        } else {
+          od_ = d0 + acc;
+          oh_ = h0 + (m >> 3);
+          ow_ = w0 + (m & 7);
+          valid = od_ < p.od && oh_ < p.oh && ow_ < p.ow;
+        }
+        __nv_bfloat16* optr;
         if (p.scatter_cout) {
-          // 2x2x2 pixel shuffle: this 32-column chunk belongs to one (a,b,e) offset of the up-sampled grid
-          const int col0 = nt * p.NT + cc * 32;
+          // 2x2x2 pixel shuffle: this 16-column chunk belongs to one (a,b,e) offset of the up-sampled grid
+          const int col0 = nt * p.NT + c16;
           const int abe = 7 - col0 / p.scatter_cout, co0 = col0 % p.scatter_cout;
           const long long ovox = ((static_cast<long long>(nn) * 2 * p.od + 2 * od_ + (abe >> 2)) * 2 * p.oh + 2 * oh_ +
                                   ((abe >> 1) & 1)) * 2 * p.ow + 2 * ow_ + (abe & 1);
-          orow = p.out + ovox * p.out_pitch + co0 - cc * 32;
-        }
-        uint32_t raw[32];
-        const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + acc * p.NT + cc * 32;
-        if (ncol == 32) {
-          tmem_ld_32x32(taddr, raw);
+          optr = p.out + ovox * p.out_pitch + co0;
         } else {
-          uint32_t r16[16];
-          tmem_ld_32x16(taddr, r16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) raw[j] = r16[j];
-#pragma unroll
-          for (int j = 16; j < 32; ++j) raw[j] = 0u;
+          const long long vox = ((static_cast<long long>(nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
+          optr = p.out + vox * p.out_pitch + nt * p.NT + c16;
         }
+        uint32_t raw[16];
+        tmem_ld_32x16(tbase + (static_cast<uint32_t>(q * 32) << 16) + acc * p.NT + c16, raw);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(raw[j]);
-          if (p.bias != nullptr && j < ncol)
-            v[j] += p.bias[p.scatter_cout ? (nt * p.NT + cc * 32 + j) % p.scatter_cout : nt * p.NT + cc * 32 + j];
-        }
         if (valid) {
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncol) {
-              float t8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) t8[i] = v[j + i];
-              st8(orow + cc * 32 + j, pack8(t8));
-            }
+          for (int j = 0; j < 16; ++j) {
+            v[j] = __uint_as_float(raw[j]) + bias_r[j];
+            s1[j] += v[j];
+            s2[j] += v[j] * v[j];
           }
-        }
-        if (p.stats != nullptr) {
-          float s1[32], s2[32];
+          float t8[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = (valid && j < ncol) ? v[j] : 0.f;
-            s1[j] = t;
-            s2[j] = t * t;
-          }
-          butterfly_colsum(s1, lane);
-          butterfly_colsum(s2, lane);
-          csum[cc] += s1[0];
-          csq[cc] += s2[0];
+          for (int i = 0; i < 8; ++i) t8[i] = v[i];
+          st8(optr, pack8(t8));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = v[8 + i];
+          st8(optr + 8, pack8(t8));
         }
       }
-    }
-    if (p.stats != nullptr) {
-      for (int cc = 0; cc < nchunk32; ++cc) {
-        const int col = cc * 32 + lane;
-        if (col < p.NT) {
-          atomicAdd(&s_stats[col], csum[cc]);
-          atomicAdd(&s_stats[p.NT + col], csq[cc]);
+      if (p.stats != nullptr) {
+        // fold the two half-warps, then a 16-lane butterfly: lane l ends with column (l & 15)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+        }
+#pragma unroll
+        for (int st = 8; st >= 1; st >>= 1) {
+          const bool up = (lane & st) != 0;
+#pragma unroll
+          for (int i = 0; i < st; ++i) {
+            const float a1 = up ? s1[i] : s1[i + st], a2 = up ? s2[i] : s2[i + st];
+            const float r1 = __shfl_xor_sync(0xffffffffu, a1, st), r2 = __shfl_xor_sync(0xffffffffu, a2, st);
+            s1[i] = (up ? s1[i + st] : s1[i]) + r1;
+            s2[i] = (up ? s2[i + st] : s2[i]) + r2;
+          }
+        }
+        if (lane < 16) {
+          atomicAdd(&s_stats[c16 + lane], s1[0]);
+          atomicAdd(&s_stats[p.NT + c16 + lane], s2[0]);
         }
       }
     }
     tc_fence_before();
+    if (dbg && tid == 128) p.dbg[10] = clock64();
   }
   __syncthreads();
+  if (dbg && tid == 0) p.dbg[11] = clock64();
   if (p.stats != nullptr) {
     for (int i = tid; i < p.NT; i += blockDim.x) {
       atomicAdd(&p.stats[nt * p.NT + i], s_stats[i]);
@@ -418,10 +445,10 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
   else if (a.cout % 32 == 0) p.NT = 32;
   else p.NT = 16;
   p.n_ntiles = a.cout / p.NT;
-  p.NB = 4;
   p.slotB = (p.NT * p.rowbytes + 1023) & ~1023u;
+  p.NB = static_cast<int>(std::min<size_t>(8, std::max<size_t>(3, 32768 / p.slotB)));  // hide the TMA round trip
   p.bytesB = p.NT * p.rowbytes;
-  const size_t fixed = static_cast<size_t>(p.NB) * p.slotB + 2048 + 2 * p.NT * sizeof(float);
+  const size_t fixed = static_cast<size_t>(p.NB) * p.slotB + 2048 + 3 * p.NT * sizeof(float);
   const int k3 = a.k * a.k * a.k;
   (void)k3;
 
@@ -434,21 +461,26 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
     p.UP = 1;
     p.slotA = (static_cast<unsigned>(p.WB * p.HB) * p.rowbytes + 1023) & ~1023u;
     p.bytesA_unit = static_cast<unsigned>(p.WB * p.HB) * p.rowbytes;
-    int best = 0;
+    // Prefer a footprint that lets two CTAs share an SM (<= 112 KB smem, <= 256 TMEM columns): one CTA's epilogue
+    // then overlaps the other's MMA phase.  Otherwise take the largest P that fits one CTA per SM.
     const int pmax = std::min(std::min(512 / p.NT, a.od), 8);
-    for (int P = pmax; P >= 1; --P) {
-      const int U = P + halo;
-      const int S = U + 2;
-      if (fixed + static_cast<size_t>(S) * p.slotA <= kSmemBudget) {
-        best = P;
-        break;
+    const int extra = p.nchunks > 1 ? 2 : 0;   // ring slots beyond one chunk's planes (prefetch of the next chunk)
+    int best = 0, best_S = 0;
+    for (int P = pmax; P >= std::min(4, pmax) && !best; --P) {
+      const int S = P + halo + extra;
+      if (P * p.NT <= 256 && fixed + static_cast<size_t>(S) * p.slotA + 1024 <= 112 * 1024) best = P, best_S = S;
+    }
+    for (int P = pmax; P >= 1 && !best; --P) {
+      for (int ex = extra; ex >= (p.nchunks > 1 ? 1 : 0) && !best; --ex) {
+        const int S = P + halo + ex;
+        if (fixed + static_cast<size_t>(S) * p.slotA <= kSmemBudget) best = P, best_S = S;
       }
     }
     if (!best) return false;
     p.P = best;
     p.DT = best;
     p.U = best + halo;
-    p.S = p.U + 2;
+    p.S = best_S;
     p.tiles_w = (a.ow + 7) / 8;
     p.tiles_h = (a.oh + 15) / 16;
     p.tiles_d = (a.od + p.DT - 1) / p.DT;
@@ -559,9 +591,23 @@ int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   const int ctas = a.n * p.tiles_d * p.tiles_h * p.tiles_w * p.n_ntiles;
+  p.dbg = nullptr;
+  if (getenv("B200SEG_DEBUG_TIMELINE")) {
+    cudaMalloc(&p.dbg, 16 * sizeof(long long));
+    cudaMemset(p.dbg, 0, 16 * sizeof(long long));
+  }
   conv_umma_kernel<<<ctas, 256, smem, st>>>(tmAs, tmB, p);
   B200_CHECK_LAUNCH("conv_umma");
   ++g_umma_launches;
+  if (p.dbg) {
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    fprintf(stderr, "[timeline] ctas %d P %d NT %d KC %d chunks %d S %d U %d flat %d smem %zu | a0 %lld a1 %lld a2 %lld issued %lld "
+            "epi_start %lld epi_end %lld cta_end %lld\n", ctas, p.P, p.NT, p.KC, p.nchunks, p.S, p.U, p.flat, smem,
+            h[1] - h[0], h[2] - h[0], h[3] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0], h[11] - h[0]);
+  }
   return 0;
 }
 

@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(192, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && it0 < it1) {
+    if (it0 < it1) {  // warp-uniform issue loop; only the elected lane's tcgen05 instructions take effect
+      const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, p.NT, 1, 1);
       const uint32_t a_sbo = static_cast<uint32_t>(p.a_sbo_rows) * p.rowbytesA;
       const uint32_t a_adv = static_cast<uint32_t>(p.a_kadv_rows) * p.rowbytesA;
@@ -160,19 +161,19 @@ __global__ void __launch_bounds__(192, 1)
           for (int ks = 0; ks < p.ksteps; ++ks) {
             const uint64_t ad = (static_cast<uint64_t>(g_hi[g]) << 32) | a_lo;
             const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | y_lo;
-            umma_f16(d_tmem, ad, bd, idesc, accum | (ks != 0 ? 1u : 0u));
+            umma_f16_pred(d_tmem, ad, bd, idesc, accum | (ks != 0 ? 1u : 0u), leader);
             a_lo += a_adv16;
             y_lo += b_adv16;
           }
         }
         accum = 1;
-        umma_commit(&empty[s]);
+        umma_commit_pred(&empty[s], leader);
         if (++s == p.stages) {
           s = 0;
           phase ^= 1;
         }
       }
-      umma_commit(accFull);
+      umma_commit_pred(accFull, leader);
     }
   } else if (it0 < it1) {
     // =========================== epilogue: TMEM -> red.global.add.f32 ===========================
