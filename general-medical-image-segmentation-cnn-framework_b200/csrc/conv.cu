@@ -85,7 +85,7 @@ int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pi
   auto st = static_cast<cudaStream_t>(stream);
   if (g->stride == 1) {
     UmmaWgradArgs a{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, g->cin, g->cout, g->k, g->pad, g->dil,
-                    x, x_pitch, dy, dy_pitch, dw_packed};
+                    x, x_pitch, dy, dy_pitch, dw_packed, 0};
     if (wgrad_umma_supported(a)) return wgrad_umma_run(a, st);
   }
   return conv_direct_wgrad(*g, x, x_pitch, dy, dy_pitch, dw_packed, st);
@@ -149,6 +149,10 @@ int b200seg_convt_k2s2_wgrad(const void* x, int64_t x_pitch, const void* dy, int
                      dy_pitch >= cout, "convt_k2s2_wgrad: bad arguments");
   // S wgrad: dW_S[tap][cin_S = cout_T][cout_S = cin_T] = sum x_S(*)dy_S with x_S = dy_T, dy_S = x_T.
   const b200seg_conv_geom g = convt_as_conv(n, d, h, w, cin, cout);
+  {
+    UmmaWgradArgs a{g.n, g.d, g.h, g.w, g.od, g.oh, g.ow, g.cin, g.cout, 2, 0, 1, dy, dy_pitch, x, x_pitch, dw_packed, 1};
+    if (wgrad_umma_supported(a)) return wgrad_umma_run(a, static_cast<cudaStream_t>(stream));
+  }
   return conv_direct_wgrad(g, dy, dy_pitch, x, x_pitch, dw_packed, static_cast<cudaStream_t>(stream));
 }
 

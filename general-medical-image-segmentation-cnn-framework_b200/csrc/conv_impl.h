@@ -49,6 +49,9 @@ struct UmmaWgradArgs {
   const void* dy;
   int64_t dy_pitch;
   float* dwp;            // [k^3][cin][cout] fp32, accumulated into
+  // ConvTranspose3d(k2,s2) weight gradient: x is the FINE grid [n,2od,2oh,2ow,cin] (the up-sampled gradient), dy the
+  // coarse grid [n,od,oh,ow,cout]; tap abe pairs coarse voxel v with fine voxel 2v+abe.  k must be 2, pad 0.
+  int gather2;
 };
 bool wgrad_umma_supported(const UmmaWgradArgs& a);
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st);

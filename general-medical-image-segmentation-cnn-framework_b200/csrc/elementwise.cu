@@ -80,9 +80,32 @@ __device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&f)[V])
   }
 }
 
+// Raw (unconverted) vector: lets a thread keep several loads in flight at 4 registers each.
+template <int V> struct RawVec { bf16x8 v; };
+template <> struct RawVec<1> { __nv_bfloat16 v; };
+template <int V>
+__device__ __forceinline__ RawVec<V> ld_raw(const __nv_bfloat16* p) {
+  RawVec<V> r;
+  if constexpr (V == 8) r.v = ld8(p); else r.v = p[0];
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void cvt_raw(const RawVec<V>& r, float (&f)[V]) {
+  if constexpr (V == 8) {
+    float t[8];
+    unpack8(r.v, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = t[i];
+  } else {
+    f[0] = __bfloat162float(r.v);
+  }
+}
+
 // Block = (TX chunk lanes) x (TY row lanes), TX*TY = 256.  NS sums of V channels each are reduced over rows.
-template <int V, int NS, typename F>
-__device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __restrict__ out_group, int C, F&& body) {
+template <int V, int NS, int NT, typename FL, typename FA>
+__device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __restrict__ out_group, int C, FL&& load,
+                                              FA&& accum) {
+  // load(r, ch, raw[NT]) fetches the NT tensors of row r unconverted; accum(ch, raw[NT], acc) folds one row in.
   extern __shared__ float red[];  // [TY][TX][NS*V]
   const int TX = blockDim.x, TY = blockDim.y;
   for (int ch = threadIdx.x; ch < cv; ch += TX) {
@@ -91,9 +114,21 @@ __device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __res
     for (int s = 0; s < NS; ++s)
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[s][i] = 0.f;
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * TY + threadIdx.y; r < rows;
-         r += static_cast<int64_t>(gridDim.x) * TY)
-      body(r, ch, acc);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * TY;
+    int64_t r = static_cast<int64_t>(blockIdx.x) * TY + threadIdx.y;
+    constexpr int U = NT == 1 ? 4 : 2;   // rows in flight; 4 registers per pending vector
+    for (; r + (U - 1) * stride < rows; r += U * stride) {
+      RawVec<V> raw[U][NT];
+#pragma unroll
+      for (int u = 0; u < U; ++u) load(r + u * stride, ch, raw[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) accum(ch, raw[u], acc);
+    }
+    for (; r < rows; r += stride) {
+      RawVec<V> raw[NT];
+      load(r, ch, raw);
+      accum(ch, raw, acc);
+    }
     float* mine = red + (static_cast<size_t>(threadIdx.y) * TX + threadIdx.x) * (NS * V);
 #pragma unroll
     for (int s = 0; s < NS; ++s)
@@ -119,20 +154,22 @@ __device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __res
 }
 
 template <int V>
-__global__ void channel_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t pitch, int64_t rows, int C,
+__global__ void __launch_bounds__(256, 4) channel_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t pitch, int64_t rows, int C,
                                      float* __restrict__ stats) {
   const int g = blockIdx.y;
   const __nv_bfloat16* xg = x + static_cast<int64_t>(g) * rows * pitch;
-  column_reduce<V, 2>(rows, C / V, stats + static_cast<size_t>(g) * 2 * C, C,
-                      [&](int64_t r, int ch, float (&acc)[2][V]) {
-                        float f[V];
-                        load_vec<V>(xg + r * pitch + ch * V, f);
+  column_reduce<V, 2, 1>(
+      rows, C / V, stats + static_cast<size_t>(g) * 2 * C, C,
+      [&](int64_t r, int ch, RawVec<V>(&raw)[1]) { raw[0] = ld_raw<V>(xg + r * pitch + ch * V); },
+      [&](int, const RawVec<V>(&raw)[1], float(&acc)[2][V]) {
+        float f[V];
+        cvt_raw<V>(raw[0], f);
 #pragma unroll
-                        for (int i = 0; i < V; ++i) {
-                          acc[0][i] += f[i];
-                          acc[1][i] += f[i] * f[i];
-                        }
-                      });
+        for (int i = 0; i < V; ++i) {
+          acc[0][i] += f[i];
+          acc[1][i] += f[i] * f[i];
+        }
+      });
 }
 
 __global__ void norm_finalize_kernel(const float* __restrict__ stats, double count, int groups, int C,
@@ -163,37 +200,74 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, double cou
 }
 
 template <int V>
-__global__ void norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
+__global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
                                     const float* __restrict__ coef, int64_t rows_per_group, int groups, int C, int act,
                                     float act_param, const float* __restrict__ prelu_w,
                                     const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
                                     __nv_bfloat16* __restrict__ z, int64_t z_pitch) {
+  // Host guarantees (gridDim.x * blockDim.x) % (C / V) == 0: a thread keeps one channel chunk for its whole life,
+  // so scale / shift / slope live in registers; rows are walked 4 at a time to keep 4 loads in flight.
   const int cv = C / V;
-  const int64_t total = rows_per_group * groups * cv;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(i % cv);
-    const int64_t row = i / cv;
-    const int g = static_cast<int>(row / rows_per_group);
-    float f[V];
-    load_vec<V>(y + row * y_pitch + ch * V, f);
-    float r[V];
-    if (res) load_vec<V>(res + row * res_pitch + ch * V, r);
+  const int64_t gtid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int ch = static_cast<int>(gtid % cv);
+  const int64_t row0 = gtid / cv, rstep = nthr / cv;
+  const int64_t rows = rows_per_group * groups;
+  float sc[V], sh[V], sl[V];
+  int cur_g = -1;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    sc[j] = 1.f;
+    sh[j] = 0.f;
+    sl[j] = (act == B200SEG_ACT_PRELU) ? prelu_w[ch * V + j] : act_param;
+  }
+  auto load_coef = [&](int g) {
+    if (coef == nullptr || g == cur_g) return;
+    cur_g = g;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const int c = ch * V + j;
-      float pre = f[j];
-      if (coef) pre = pre * coef[(static_cast<size_t>(g) * 4 + 2) * C + c] + coef[(static_cast<size_t>(g) * 4 + 3) * C + c];
-      if (res) pre += r[j];
-      const float slope = (act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
-      f[j] = act_fwd(pre, act, slope);
+      sc[j] = coef[(static_cast<size_t>(g) * 4 + 2) * C + ch * V + j];
+      sh[j] = coef[(static_cast<size_t>(g) * 4 + 3) * C + ch * V + j];
     }
-    store_vec<V>(z + row * z_pitch + ch * V, f);
+  };
+  auto one = [&](int64_t row, const float (&f)[V], const float (&r)[V]) {
+    float o[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float pre = f[j] * sc[j] + sh[j];
+      if (res) pre += r[j];
+      o[j] = act_fwd(pre, act, sl[j]);
+    }
+    store_vec<V>(z + row * z_pitch + ch * V, o);
+  };
+  int64_t row = row0;
+  for (; row + 3 * rstep < rows; row += 4 * rstep) {
+    RawVec<V> ry[4], rr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
+      if (res) rr[u] = ld_raw<V>(res + (row + u * rstep) * res_pitch + ch * V);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[V], r[V];
+      cvt_raw<V>(ry[u], f);
+      if (res) cvt_raw<V>(rr[u], r);
+      load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+      one(row + u * rstep, f, r);
+    }
+  }
+  for (; row < rows; row += rstep) {
+    float f[V], r[V];
+    load_vec<V>(y + row * y_pitch + ch * V, f);
+    if (res) load_vec<V>(res + row * res_pitch + ch * V, r);
+    load_coef(static_cast<int>(row / rows_per_group));
+    one(row, f, r);
   }
 }
 
 template <int V>
-__global__ void norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
                                            const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
                                            const float* __restrict__ coef, int64_t rows, int C, int act,
                                            float act_param, const float* __restrict__ prelu_w,
@@ -202,21 +276,46 @@ __global__ void norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz,
   const int g = blockIdx.y;
   const int64_t base = static_cast<int64_t>(g) * rows;
   const float* cg = coef ? coef + static_cast<size_t>(g) * 4 * C : nullptr;
-  auto body = [&](int64_t r, int ch, auto& acc) {
+  // each thread normally owns exactly one channel chunk (cv <= blockDim.x): keep its coefficients in registers
+  const int ch0 = threadIdx.x;
+  const bool hoisted = (C / V) <= static_cast<int>(blockDim.x);
+  float h_mean[V], h_istd[V], h_sc[V], h_sh[V], h_sl[V];   // h_mean holds mean*inv_std: xhat = y*inv_std - h_mean
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = ch0 * V + j;
+    const bool ok = hoisted && c < C;
+    h_istd[j] = (ok && cg) ? cg[C + c] : 1.f;
+    h_mean[j] = (ok && cg) ? cg[c] * h_istd[j] : 0.f;
+    h_sc[j] = (ok && cg) ? cg[2 * C + c] : 1.f;
+    h_sh[j] = (ok && cg) ? cg[3 * C + c] : 0.f;
+    h_sl[j] = (ok && act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
+  }
+  auto load = [&](int64_t r, int ch, RawVec<V>(&raw)[3]) {
+    raw[0] = ld_raw<V>(y + (base + r) * y_pitch + ch * V);
+    raw[1] = ld_raw<V>(dz + (base + r) * dz_pitch + ch * V);
+    if (res) raw[2] = ld_raw<V>(res + (base + r) * res_pitch + ch * V);
+  };
+  auto accum = [&](int ch, const RawVec<V>(&raw)[3], auto& acc) {
     float fy[V], fd[V], fr[V];
-    load_vec<V>(y + (base + r) * y_pitch + ch * V, fy);
-    load_vec<V>(dz + (base + r) * dz_pitch + ch * V, fd);
-    if (res) load_vec<V>(res + (base + r) * res_pitch + ch * V, fr);
+    cvt_raw<V>(raw[0], fy);
+    cvt_raw<V>(raw[1], fd);
+    if (res) cvt_raw<V>(raw[2], fr);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const int c = ch * V + j;
-      float pre = fy[j], xhat = fy[j];
-      if (cg) {
-        pre = fy[j] * cg[2 * C + c] + cg[3 * C + c];
-        xhat = (fy[j] - cg[0 * C + c]) * cg[1 * C + c];
+      float mean = h_mean[j], istd = h_istd[j], sc = h_sc[j], sh = h_sh[j], slope = h_sl[j];
+      if (!hoisted) {
+        const int c = ch * V + j;
+        if (cg) {
+          istd = cg[C + c];
+          mean = cg[c] * istd;
+          sc = cg[2 * C + c];
+          sh = cg[3 * C + c];
+        }
+        slope = (act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
       }
+      float pre = fy[j] * sc + sh;
+      const float xhat = fy[j] * istd - mean;
       if (res) pre += fr[j];
-      const float slope = (act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
       const float dpre = fd[j] * act_bwd(pre, act, slope);
       acc[0][j] += dpre;
       acc[1][j] += dpre * xhat;
@@ -225,16 +324,16 @@ __global__ void norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz,
   };
   if (dprelu) {
     // third running sum = PReLU slope gradient; lands in a scratch row after the two sums of this group
-    column_reduce<V, 3>(rows, C / V, sums + static_cast<size_t>(g) * 3 * C, C,
-                        [&](int64_t r, int ch, float (&acc)[3][V]) { body(r, ch, acc); });
+    column_reduce<V, 3, 3>(rows, C / V, sums + static_cast<size_t>(g) * 3 * C, C, load,
+                           [&](int ch, const RawVec<V>(&raw)[3], float(&acc)[3][V]) { accum(ch, raw, acc); });
   } else {
-    column_reduce<V, 2>(rows, C / V, sums + static_cast<size_t>(g) * 2 * C, C,
-                        [&](int64_t r, int ch, float (&acc)[2][V]) { body(r, ch, acc); });
+    column_reduce<V, 2, 3>(rows, C / V, sums + static_cast<size_t>(g) * 2 * C, C, load,
+                           [&](int ch, const RawVec<V>(&raw)[3], float(&acc)[2][V]) { accum(ch, raw, acc); });
   }
 }
 
 template <int V>
-__global__ void norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
                                           const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
                                           const float* __restrict__ coef, const float* __restrict__ sums,
                                           int sums_stride, float inv_count, int64_t rows_per_group, int groups, int C,
@@ -242,38 +341,87 @@ __global__ void norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, 
                                           const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
                                           __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
                                           __nv_bfloat16* __restrict__ dres, int64_t dres_pitch) {
+  // dy = scale * (dpre - m1 - xhat * m2), xhat = (y - mean) * inv_std, m1 = sum(dpre)/n, m2 = sum(dpre*xhat)/n.
+  // Same thread -> channel-chunk binding as the forward kernel (host guarantees divisibility).
   const int cv = C / V;
-  const int64_t total = rows_per_group * groups * cv;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(i % cv);
-    const int64_t row = i / cv;
-    const int g = static_cast<int>(row / rows_per_group);
-    const float* cg = coef ? coef + static_cast<size_t>(g) * 4 * C : nullptr;
-    const float* sg = sums ? sums + static_cast<size_t>(g) * sums_stride * C : nullptr;
-    float fy[V], fd[V], fr[V], o[V], dr[V];
-    load_vec<V>(y + row * y_pitch + ch * V, fy);
-    load_vec<V>(dz + row * dz_pitch + ch * V, fd);
-    if (res) load_vec<V>(res + row * res_pitch + ch * V, fr);
+  const int64_t gtid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int ch = static_cast<int>(gtid % cv);
+  const int64_t row0 = gtid / cv, rstep = nthr / cv;
+  const int64_t rows = rows_per_group * groups;
+  // dy = sc*dpre - (A + y*B) with B = inv_std*m2*sc, A = m1*sc - mean*B  (4 fused coefficients per channel)
+  float sc[V], sh[V], ca[V], cb[V], sl[V];
+  int cur_g = -1;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    sc[j] = 1.f;
+    sh[j] = 0.f;
+    ca[j] = cb[j] = 0.f;
+    sl[j] = (act == B200SEG_ACT_PRELU) ? prelu_w[ch * V + j] : act_param;
+  }
+  auto load_coef = [&](int g) {
+    if (g == cur_g) return;
+    cur_g = g;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int c = ch * V + j;
-      float pre = fy[j], xhat = fy[j], scale = 1.f;
-      if (cg) {
-        scale = cg[2 * C + c];
-        pre = fy[j] * scale + cg[3 * C + c];
-        xhat = (fy[j] - cg[0 * C + c]) * cg[1 * C + c];
+      float mean = 0.f, istd = 1.f, m1 = 0.f, m2 = 0.f;
+      if (coef) {
+        const float* cg = coef + static_cast<size_t>(g) * 4 * C;
+        mean = cg[c];
+        istd = cg[C + c];
+        sc[j] = cg[2 * C + c];
+        sh[j] = cg[3 * C + c];
       }
+      if (sums) {
+        const float* sg = sums + static_cast<size_t>(g) * sums_stride * C;
+        m1 = sg[c] * inv_count;
+        m2 = sg[C + c] * inv_count;
+      }
+      // without normalisation (coef == nullptr) xhat is never subtracted: sums are null in that case
+      cb[j] = coef ? istd * m2 * sc[j] : 0.f;
+      ca[j] = m1 * sc[j] - mean * cb[j];
+    }
+  };
+  auto one = [&](int64_t row, const float (&fy)[V], const float (&fd)[V], const float (&fr)[V]) {
+    float o[V], dr[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float pre = fy[j] * sc[j] + sh[j];
       if (res) pre += fr[j];
-      const float slope = (act == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
-      const float dpre = fd[j] * act_bwd(pre, act, slope);
+      const float dpre = fd[j] * act_bwd(pre, act, sl[j]);
       dr[j] = dpre;
-      float v = dpre;
-      if (sg) v = dpre - sg[0 * C + c] * inv_count - xhat * sg[1 * C + c] * inv_count;
-      o[j] = v * scale;
+      o[j] = dpre * sc[j] - (ca[j] + fy[j] * cb[j]);
     }
     store_vec<V>(dy + row * dy_pitch + ch * V, o);
     if (dres) store_vec<V>(dres + row * dres_pitch + ch * V, dr);
+  };
+  int64_t row = row0;
+  for (; row + rstep < rows; row += 2 * rstep) {
+    RawVec<V> ry[2], rd[2], rr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
+      rd[u] = ld_raw<V>(dz + (row + u * rstep) * dz_pitch + ch * V);
+      if (res) rr[u] = ld_raw<V>(res + (row + u * rstep) * res_pitch + ch * V);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float fy[V], fd[V], fr[V];
+      cvt_raw<V>(ry[u], fy);
+      cvt_raw<V>(rd[u], fd);
+      if (res) cvt_raw<V>(rr[u], fr);
+      load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+      one(row + u * rstep, fy, fd, fr);
+    }
+  }
+  for (; row < rows; row += rstep) {
+    float fy[V], fd[V], fr[V];
+    load_vec<V>(y + row * y_pitch + ch * V, fy);
+    load_vec<V>(dz + row * dz_pitch + ch * V, fd);
+    if (res) load_vec<V>(res + row * res_pitch + ch * V, fr);
+    load_coef(static_cast<int>(row / rows_per_group));
+    one(row, fy, fd, fr);
   }
 }
 
@@ -495,6 +643,16 @@ int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, i
 static inline bool vec_ok(int c, int64_t p0, int64_t p1 = 0, int64_t p2 = 0, int64_t p3 = 0) {
   return c % 8 == 0 && p0 % 8 == 0 && p1 % 8 == 0 && p2 % 8 == 0 && p3 % 8 == 0;
 }
+// Grid for the norm/act elementwise kernels: gridDim.x * 256 must be a multiple of the channel-chunk count cv.
+static inline int ew_grid(int64_t total_items, int cv) {
+  int blocks = grid_for(total_items, 256, kNumSMs * 8);
+  int64_t m = cv;           // smallest block multiple: lcm(cv, 256) / 256
+  int64_t a = cv, b = 256;
+  while (b) { const int64_t t = a % b; a = b; b = t; }
+  m = cv / a;
+  blocks = static_cast<int>((blocks + m - 1) / m * m);
+  return blocks;
+}
 static inline dim3 reduce_block(int cv) {
   int tx = 1;
   while (tx < cv && tx < 64) tx <<= 1;
@@ -541,11 +699,11 @@ int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int6
   auto* zp = static_cast<__nv_bfloat16*>(z);
   if (vec_ok(c, y_pitch, z_pitch, residual ? res_pitch : 0)) {
     const int64_t total = rows_per_group * groups * (c / 8);
-    norm_act_fwd_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
+    norm_act_fwd_kernel<8><<<ew_grid(total, c / 8), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
                                                                  act_param, prelu_w, rp, res_pitch, zp, z_pitch);
   } else {
     const int64_t total = rows_per_group * groups * c;
-    norm_act_fwd_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
+    norm_act_fwd_kernel<1><<<ew_grid(total, c), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
                                                                  act_param, prelu_w, rp, res_pitch, zp, z_pitch);
   }
   B200_CHECK_LAUNCH("norm_act_fwd");
@@ -593,12 +751,12 @@ int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, 
   const int sums_stride = (act == B200SEG_ACT_PRELU) ? 3 : 2;
   if (vec_ok(c, dz_pitch, y_pitch, dy_pitch, (residual ? res_pitch : 0) | (dres ? dres_pitch : 0))) {
     const int64_t total = rows_per_group * groups * (c / 8);
-    norm_act_bwd_apply_kernel<8><<<grid_for(total, 256), 256, 0, st>>>(
+    norm_act_bwd_apply_kernel<8><<<ew_grid(total, c / 8), 256, 0, st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
         prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch);
   } else {
     const int64_t total = rows_per_group * groups * c;
-    norm_act_bwd_apply_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(
+    norm_act_bwd_apply_kernel<1><<<ew_grid(total, c), 256, 0, st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
         prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch);
   }

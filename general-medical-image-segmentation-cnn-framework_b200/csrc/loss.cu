@@ -50,53 +50,70 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_p
 }
 
 // dx[v][c] = sum_k dl[k][v] w[k][c];  grad_w[k][c] += sum_v dl[k][v] x[v][c];  grad_b[k] += sum_v dl[k][v]
-__global__ void head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x,
-                                int64_t x_pitch, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
-                                int64_t dx_pitch, float* __restrict__ grad_w, float* __restrict__ grad_b, int n,
-                                int64_t spatial, int cin, int classes) {
-  extern __shared__ float sm[];  // w [classes*cin] | gw [classes*cin] | gb [classes]
-  float* sw = sm;
-  float* gw = sm + classes * cin;
-  float* gb = gw + classes * cin;
-  for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) {
-    sw[i] = w[i];
-    gw[i] = 0.f;
-  }
-  for (int i = threadIdx.x; i < classes; i += blockDim.x) gb[i] = 0.f;
-  __syncthreads();
-  const int64_t total = static_cast<int64_t>(n) * spatial;
+// lane = channel (c, c+32, ... up to 4 per lane): x rows and dx rows are read / written coalesced, the class
+// gradients of a voxel are warp-uniform broadcast loads, and every lane keeps its own grad_w accumulators in
+// registers -- no shuffles in the loop.
+__global__ void __launch_bounds__(256)
+    head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                    const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t dx_pitch,
+                    float* __restrict__ grad_w, float* __restrict__ grad_b, int n, int64_t spatial, int cin,
+                    int classes) {
+  constexpr int CPL = 4;  // channels per lane (cin <= 128)
   const int lane = threadIdx.x & 31;
-  for (int64_t v0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) - lane; v0 < total;
-       v0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t v = v0 + lane;
-    const bool valid = v < total;
+  const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float wr[kMaxClasses][CPL], gw[kMaxClasses][CPL], gb[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    gb[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c = lane + 32 * j;
+      wr[k][j] = (k < classes && c < cin) ? w[k * cin + c] : 0.f;
+      gw[k][j] = 0.f;
+    }
+  }
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  for (int64_t v = warp_id; v < total; v += nwarps) {
+    const int64_t nn = v / spatial, s = v % spatial;
     float dl[kMaxClasses];
-    const int64_t nn = valid ? v / spatial : 0, s = valid ? v % spatial : 0;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      dl[k] = (valid && k < classes) ? dlogits[(nn * classes + k) * spatial + s] : 0.f;
+    for (int k = 0; k < kMaxClasses; ++k) dl[k] = (k < classes) ? dlogits[(nn * classes + k) * spatial + s] : 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      if (k < classes) {
-        const float t = warp_sum(dl[k]);
-        if (lane == 0) atomicAdd(&gb[k], t);
-      }
-    for (int c = 0; c < cin; ++c) {
-      const float xv = valid ? __bfloat162float(x[v * x_pitch + c]) : 0.f;
-      float d = 0.f;
+    for (int k = 0; k < kMaxClasses; ++k) gb[k] += dl[k];
 #pragma unroll
-      for (int k = 0; k < kMaxClasses; ++k)
-        if (k < classes) {
-          d += dl[k] * sw[k * cin + c];
-          const float t = warp_sum(dl[k] * xv);
-          if (lane == 0) atomicAdd(&gw[k * cin + c], t);
+    for (int j = 0; j < CPL; ++j) {
+      const int c = lane + 32 * j;
+      if (c < cin) {
+        const float xv = __bfloat162float(x[v * x_pitch + c]);
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+          d += dl[k] * wr[k][j];
+          gw[k][j] += dl[k] * xv;
         }
-      if (valid) dx[v * dx_pitch + c] = __float2bfloat16(d);
+        dx[v * dx_pitch + c] = __float2bfloat16(d);
+      }
+    }
+  }
+  __shared__ float sgw[kMaxClasses * 128], sgb[kMaxClasses];
+  for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) sgw[i] = 0.f;
+  if (threadIdx.x < kMaxClasses) sgb[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    if (k < classes) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < cin) atomicAdd(&sgw[k * cin + c], gw[k][j]);
+      }
+      if (lane == 0) atomicAdd(&sgb[k], gb[k]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) atomicAdd(&grad_w[i], gw[i]);
-  for (int i = threadIdx.x; i < classes; i += blockDim.x) atomicAdd(&grad_b[i], gb[i]);
+  for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) atomicAdd(&grad_w[i], sgw[i]);
+  if (threadIdx.x < classes) atomicAdd(&grad_b[threadIdx.x], sgb[threadIdx.x]);
 }
 
 __global__ void argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ labels, int n, int64_t spatial,
@@ -368,9 +385,8 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
   B200_CHECK_ARG(dlogits && x && w && dx && grad_w && grad_b && n > 0 && spatial > 0 && cin > 0,
                  "head_conv1x1_bwd: bad arguments");
   B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "head_conv1x1_bwd: classes must be in [1,%d]", kMaxClasses);
-  const size_t smem = (2 * static_cast<size_t>(classes) * cin + classes) * sizeof(float);
-  head_bwd_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256, kNumSMs * 4), 256, smem,
-                    static_cast<cudaStream_t>(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(x), x_pitch, w,
+  B200_CHECK_ARG(cin <= 128, "head_conv1x1_bwd: at most 128 input channels");
+  head_bwd_kernel<<<kNumSMs * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(x), x_pitch, w,
                                                          static_cast<__nv_bfloat16*>(dx), dx_pitch, grad_w, grad_b, n,
                                                          spatial, cin, classes);
   B200_CHECK_LAUNCH("head_conv1x1_bwd");

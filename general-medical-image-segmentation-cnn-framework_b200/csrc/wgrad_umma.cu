@@ -33,6 +33,10 @@ struct WgradGroup {
   int tap[8];     // tap index of each M-block, -1 = unused block
 };
 
+struct TensorMaps8W {
+  CUtensorMap m[8];
+};
+
 struct WgradParams {
   int n, od, oh, ow, cin, cout, k, pad, dil;
   int KC, MB, NT, flat;
@@ -47,13 +51,13 @@ struct WgradParams {
   long long items;             // work items (voxel tiles) in the whole tensor
   int splits;                  // CTAs sharing one (asplit, chunk, ntile) combination
   int nchunks, n_ntiles, asplit;
-  int stages;
+  int stages, gather2;
   unsigned slotX, slotY, stage_bytes, rowbytesA, rowbytesB, swzA, swzB, bytesX, bytesY, tmem_cols;
   float* dwp;
 };
 
 __global__ void __launch_bounds__(192, 1)
-    wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+    wgrad_umma_kernel(const __grid_constant__ TensorMaps8W tmXs, const __grid_constant__ CUtensorMap tmY,
                       const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(192, 1)
 
   if (warp == 0) {
     if (lane == 0 && it0 < it1) {
-      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmXs.m[0]);
       tma_prefetch_desc(&tmY);
       int L = 0;
       for (long long it = it0; it < it1; ++it, ++L) {
@@ -122,8 +126,11 @@ __global__ void __launch_bounds__(192, 1)
         mbar_arrive_expect_tx(&full[s], p.bytesX * p.nplanes + p.bytesY);
         for (int j = 0; j < p.nplanes; ++j) {
           const int a = p.asplit > 1 ? asel : p.plane_a[j];
-          tma_load_5d(st + static_cast<size_t>(j) * p.slotX, &tmX, &full[s], chunk * p.KC, w0 - p.pad, h0 - p.pad,
-                      d0 - p.pad + (p.flat ? 0 : a * p.dil), nn);
+          if (p.gather2)   // sub-lattice j of the fine grid, no halo
+            tma_load_5d(st + static_cast<size_t>(j) * p.slotX, &tmXs.m[j], &full[s], chunk * p.KC, w0, h0, d0, nn);
+          else
+            tma_load_5d(st + static_cast<size_t>(j) * p.slotX, &tmXs.m[0], &full[s], chunk * p.KC, w0 - p.pad,
+                        h0 - p.pad, d0 - p.pad + (p.flat ? 0 : a * p.dil), nn);
         }
         tma_load_5d(st + static_cast<size_t>(p.nplanes) * p.slotX, &tmY, &full[s], nt * p.NT, w0, h0, d0, nn);
       }
@@ -259,17 +266,48 @@ static bool encode5(CUtensorMap* tm, const void* base, int c, int w, int h, int 
   return true;
 }
 
+// Every second voxel of a fine grid [n, fd, fh, fw, c] seen as a coarse tensor [n, d, h, w, c].
+static bool encode5_strided(CUtensorMap* tm, const void* base, int c, int w, int h, int d, int n, long long pitch,
+                            int fw, int fh, int fd, const uint32_t* box, int chans_per_row) {
+  PFN_encodeTiled enc = get_encode_w();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return false;
+  }
+  const cuuint64_t gd[5] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                            static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
+  const cuuint64_t pb = static_cast<cuuint64_t>(pitch) * 2;
+  const cuuint64_t gs[4] = {2 * pb, 2 * pb * fw, 2 * pb * fw * fh, pb * fw * fh * fd};
+  const cuuint32_t bx[5] = {box[0], box[1], box[2], box[3], box[4]};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = chans_per_row == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : chans_per_row == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
+
 static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_bytes) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_UMMA_WGRAD")) return false;
   if (a.cin % 32 || a.cout % 16) return false;
-  if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
   if (a.x_pitch % 8 || a.dy_pitch % 8) return false;
-  const int halo = (a.k - 1) * a.dil;
-  if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
+  const int halo = a.gather2 ? 0 : (a.k - 1) * a.dil;
+  if (a.gather2) {
+    if (a.k != 2 || a.pad != 0 || a.dil != 1 || a.d != 2 * a.od || a.h != 2 * a.oh || a.w != 2 * a.ow) return false;
+  } else {
+    if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
+    if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
+  }
   p = WgradParams{};
   p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cin = a.cin; p.cout = a.cout;
   p.k = a.k; p.pad = a.pad; p.dil = a.dil;
-  p.KC = a.cin % 64 == 0 ? 64 : 32;
+  p.gather2 = a.gather2;
+  p.KC = (a.cin % 64 == 0 && !a.gather2) ? 64 : 32;   // gather mode keeps 8 boxes per stage: use the narrow chunk
   p.MB = 128 / p.KC;
   p.nchunks = a.cin / p.KC;
   p.NT = a.cout % 64 == 0 ? 64 : (a.cout % 32 == 0 ? 32 : 16);
@@ -306,7 +344,9 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
   struct G2 { int base, lbo, tap[8]; };
   G2 per_plane[16];
   int gpp = 0;
-  if (p.KC == 64) {
+  if (a.gather2) {
+    // filled in below: groups are runs of MB consecutive sub-lattice boxes (LBO = one box)
+  } else if (p.KC == 64) {
     for (int i = 0; i < k * k; i += 2) {
       G2 g{};
       for (int j = 0; j < 8; ++j) g.tap[j] = -1;
@@ -334,9 +374,9 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
         per_plane[gpp++] = g;
       }
   }
-  p.asplit = (k * gpp * p.NT <= 512 && k * gpp <= kMaxGroups) ? 1 : k;
+  p.asplit = a.gather2 ? 1 : ((k * gpp * p.NT <= 512 && k * gpp <= kMaxGroups) ? 1 : k);
   if (gpp * p.NT > 512 || gpp > kMaxGroups) return false;
-  const int planes_in_cta = p.asplit == 1 ? k : 1;
+  const int planes_in_cta = a.gather2 ? 0 : (p.asplit == 1 ? k : 1);
   p.ngroups = 0;
   for (int pa = 0; pa < planes_in_cta; ++pa)
     for (int gi = 0; gi < gpp; ++gi) {
@@ -354,14 +394,20 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
   p.tmem_cols = cols;
 
   const size_t budget = 200 * 1024;
+  if (a.gather2) {
+    if ((8 / p.MB) * p.NT > 512) return false;
+    unsigned cols2 = 32;
+    while (cols2 < static_cast<unsigned>((8 / p.MB) * p.NT)) cols2 <<= 1;
+    p.tmem_cols = cols2;
+  }
   if (!p.flat) {
-    p.nplanes = planes_in_cta;
+    p.nplanes = a.gather2 ? 8 : planes_in_cta;
     p.slotX = (static_cast<unsigned>(plane_rows) * p.rowbytesA + 1023) & ~1023u;
     p.bytesX = static_cast<unsigned>(plane_rows) * p.rowbytesA;
     p.slotY = (128u * p.rowbytesB + 1023) & ~1023u;
     p.bytesY = 128u * p.rowbytesB;
   } else {
-    p.nplanes = 1;
+    p.nplanes = a.gather2 ? 8 : 1;
     const int maxoff = halo * (plane_rows + p.WB + 1);
     int best = 0;
     for (int DT = std::min(a.od, 255 - halo); DT >= 1; --DT) {
@@ -369,7 +415,7 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
       const size_t sx = ((static_cast<size_t>(rows_k) + maxoff + 8) * p.rowbytesA + 1023) & ~size_t(1023);
       const size_t sy = (static_cast<size_t>(rows_k) * p.rowbytesB + 1023) & ~size_t(1023);
       if (static_cast<size_t>(DT + halo) * plane_rows * p.rowbytesA > sx) continue;
-      if (2 * (sx + sy) + 1024 <= budget) {
+      if (2 * (p.nplanes * sx + sy) + 1024 <= budget) {
         best = DT;
         p.slotX = static_cast<unsigned>(sx);
         p.slotY = static_cast<unsigned>(sy);
@@ -383,6 +429,16 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
     p.tiles_d = (a.od + best - 1) / best;
     p.bytesX = static_cast<unsigned>(p.UPX) * plane_rows * p.rowbytesA;
     p.bytesY = static_cast<unsigned>(p.DT) * plane_rows * p.rowbytesB;
+  }
+  if (a.gather2) {
+    // groups of MB consecutive sub-lattice boxes; M-block stride = one box slot
+    for (int g0 = 0; g0 < 8; g0 += p.MB) {
+      WgradGroup& G = p.groups[p.ngroups++];
+      G.plane = g0;
+      G.base_rows = 0;
+      G.lbo_rows = static_cast<int>(p.slotX / p.rowbytesA);
+      for (int j = 0; j < 8; ++j) G.tap[j] = j < p.MB ? g0 + j : -1;
+    }
   }
   p.stage_bytes = p.nplanes * p.slotX + p.slotY;
   p.stages = static_cast<int>(std::min<size_t>(4, budget / p.stage_bytes));
@@ -416,11 +472,23 @@ int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st) {
     set_error("wgrad_umma_run: buffers must be 16-byte aligned");
     return B200SEG_ERR_INVALID;
   }
-  CUtensorMap tmX, tmY;
-  {
+  TensorMaps8W tmXs;
+  CUtensorMap tmY;
+  if (!a.gather2) {
     const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB),
                              static_cast<uint32_t>(p.UPX), 1u};
-    if (!encode5(&tmX, a.x, a.cin, a.w, a.h, a.d, a.n, a.x_pitch, box, p.KC)) return B200SEG_ERR_CUDA;
+    if (!encode5(&tmXs.m[0], a.x, a.cin, a.w, a.h, a.d, a.n, a.x_pitch, box, p.KC)) return B200SEG_ERR_CUDA;
+    for (int i = 1; i < 8; ++i) tmXs.m[i] = tmXs.m[0];
+  } else {
+    // sub-lattice g = (a,b,e) of the fine grid: coarse extents, doubled strides, shifted base
+    const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB),
+                             static_cast<uint32_t>(p.flat ? p.DT : 1), 1u};
+    for (int g = 0; g < 8; ++g) {
+      const long long off = ((static_cast<long long>(g >> 2) * a.h + ((g >> 1) & 1)) * a.w + (g & 1)) * a.x_pitch;
+      if (!encode5_strided(&tmXs.m[g], static_cast<const __nv_bfloat16*>(a.x) + off, a.cin, a.ow, a.oh, a.od, a.n,
+                           a.x_pitch, a.w, a.h, a.d, box, p.KC))
+        return B200SEG_ERR_CUDA;
+    }
   }
   {
     uint32_t box[5] = {static_cast<uint32_t>(p.NT), 8u, 16u, 1u, 1u};
@@ -440,7 +508,7 @@ int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   const int ctas = p.asplit * p.nchunks * p.n_ntiles * p.splits;
-  wgrad_umma_kernel<<<ctas, 192, smem, st>>>(tmX, tmY, p);
+  wgrad_umma_kernel<<<ctas, 192, smem, st>>>(tmXs, tmY, p);
   B200_CHECK_LAUNCH("wgrad_umma");
   ++g_umma_launches;
   return 0;
