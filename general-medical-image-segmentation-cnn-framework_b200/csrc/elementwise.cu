@@ -199,12 +199,14 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, double cou
   o[3 * C + c] = static_cast<float>(be - mean * ga * inv_std);
 }
 
-template <int V>
+template <int V, int ACT>
 __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
-                                    const float* __restrict__ coef, int64_t rows_per_group, int groups, int C, int act,
+                                    const float* __restrict__ coef, int64_t rows_per_group, int groups, int C, int act_rt,
                                     float act_param, const float* __restrict__ prelu_w,
                                     const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
                                     __nv_bfloat16* __restrict__ z, int64_t z_pitch) {
+  constexpr int act = ACT;
+  (void)act_rt;
   // Host guarantees (gridDim.x * blockDim.x) % (C / V) == 0: a thread keeps one channel chunk for its whole life,
   // so scale / shift / slope live in registers; rows are walked 4 at a time to keep 4 loads in flight.
   const int cv = C / V;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat1
     }
     store_vec<V>(z + row * z_pitch + ch * V, o);
   };
+  load_coef(0);
   int64_t row = row0;
   for (; row + 3 * rstep < rows; row += 4 * rstep) {
     RawVec<V> ry[4], rr[4];
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat1
       float f[V], r[V];
       cvt_raw<V>(ry[u], f);
       if (res) cvt_raw<V>(rr[u], r);
-      load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+      if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
       one(row + u * rstep, f, r);
     }
   }
@@ -261,18 +264,20 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat1
     float f[V], r[V];
     load_vec<V>(y + row * y_pitch + ch * V, f);
     if (res) load_vec<V>(res + row * res_pitch + ch * V, r);
-    load_coef(static_cast<int>(row / rows_per_group));
+    if (groups > 1) load_coef(static_cast<int>(row / rows_per_group));
     one(row, f, r);
   }
 }
 
-template <int V>
+template <int V, int ACT>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
                                            const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
-                                           const float* __restrict__ coef, int64_t rows, int C, int act,
+                                           const float* __restrict__ coef, int64_t rows, int C, int act_rt,
                                            float act_param, const float* __restrict__ prelu_w,
                                            const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
                                            float* __restrict__ sums, float* __restrict__ dprelu) {
+  constexpr int act = ACT;
+  (void)act_rt;
   const int g = blockIdx.y;
   const int64_t base = static_cast<int64_t>(g) * rows;
   const float* cg = coef ? coef + static_cast<size_t>(g) * 4 * C : nullptr;
@@ -332,15 +337,17 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_kernel(const __nv_
   }
 }
 
-template <int V>
+template <int V, int ACT>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
                                           const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
                                           const float* __restrict__ coef, const float* __restrict__ sums,
                                           int sums_stride, float inv_count, int64_t rows_per_group, int groups, int C,
-                                          int act, float act_param, const float* __restrict__ prelu_w,
+                                          int act_rt, float act_param, const float* __restrict__ prelu_w,
                                           const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
                                           __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
                                           __nv_bfloat16* __restrict__ dres, int64_t dres_pitch) {
+  constexpr int act = ACT;
+  (void)act_rt;
   // dy = scale * (dpre - m1 - xhat * m2), xhat = (y - mean) * inv_std, m1 = sum(dpre)/n, m2 = sum(dpre*xhat)/n.
   // Same thread -> channel-chunk binding as the forward kernel (host guarantees divisibility).
   const int cv = C / V;
@@ -396,6 +403,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_b
     store_vec<V>(dy + row * dy_pitch + ch * V, o);
     if (dres) store_vec<V>(dres + row * dres_pitch + ch * V, dr);
   };
+  load_coef(0);
   int64_t row = row0;
   for (; row + rstep < rows; row += 2 * rstep) {
     RawVec<V> ry[2], rd[2], rr[2];
@@ -411,7 +419,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_b
       cvt_raw<V>(ry[u], fy);
       cvt_raw<V>(rd[u], fd);
       if (res) cvt_raw<V>(rr[u], fr);
-      load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+      if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
       one(row + u * rstep, fy, fd, fr);
     }
   }
@@ -420,7 +428,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_b
     load_vec<V>(y + row * y_pitch + ch * V, fy);
     load_vec<V>(dz + row * dz_pitch + ch * V, fd);
     if (res) load_vec<V>(res + row * res_pitch + ch * V, fr);
-    load_coef(static_cast<int>(row / rows_per_group));
+    if (groups > 1) load_coef(static_cast<int>(row / rows_per_group));
     one(row, fy, fd, fr);
   }
 }
@@ -640,6 +648,17 @@ int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, i
   return 0;
 }
 
+// ACT is a template parameter so every instantiation carries only its own activation code (the runtime switch made the
+// kernels ~50 KB of SASS and instruction-cache bound).
+#define B200_ACT_DISPATCH(ACTV, ...)                                              \
+  switch (ACTV) {                                                                 \
+    case B200SEG_ACT_NONE: { constexpr int A_ = B200SEG_ACT_NONE; __VA_ARGS__; } break;   \
+    case B200SEG_ACT_RELU: { constexpr int A_ = B200SEG_ACT_RELU; __VA_ARGS__; } break;   \
+    case B200SEG_ACT_LEAKY: { constexpr int A_ = B200SEG_ACT_LEAKY; __VA_ARGS__; } break; \
+    case B200SEG_ACT_ELU: { constexpr int A_ = B200SEG_ACT_ELU; __VA_ARGS__; } break;     \
+    default: { constexpr int A_ = B200SEG_ACT_PRELU; __VA_ARGS__; } break;                \
+  }
+
 static inline bool vec_ok(int c, int64_t p0, int64_t p1 = 0, int64_t p2 = 0, int64_t p3 = 0) {
   return c % 8 == 0 && p0 % 8 == 0 && p1 % 8 == 0 && p2 % 8 == 0 && p3 % 8 == 0;
 }
@@ -699,12 +718,12 @@ int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int6
   auto* zp = static_cast<__nv_bfloat16*>(z);
   if (vec_ok(c, y_pitch, z_pitch, residual ? res_pitch : 0)) {
     const int64_t total = rows_per_group * groups * (c / 8);
-    norm_act_fwd_kernel<8><<<ew_grid(total, c / 8), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
-                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch);
+    B200_ACT_DISPATCH(act, norm_act_fwd_kernel<8, A_><<<ew_grid(total, c / 8), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
+                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch));
   } else {
     const int64_t total = rows_per_group * groups * c;
-    norm_act_fwd_kernel<1><<<ew_grid(total, c), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
-                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch);
+    B200_ACT_DISPATCH(act, norm_act_fwd_kernel<1, A_><<<ew_grid(total, c), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
+                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch));
   }
   B200_CHECK_LAUNCH("norm_act_fwd");
   return 0;
@@ -724,13 +743,13 @@ int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y,
   if (vec_ok(c, dz_pitch, y_pitch, residual ? res_pitch : 0)) {
     dim3 block = reduce_block(c / 8);
     dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
-    norm_act_bwd_reduce_kernel<8><<<grid, block, 256 * 24 * sizeof(float), st>>>(
-        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu);
+    B200_ACT_DISPATCH(act, norm_act_bwd_reduce_kernel<8, A_><<<grid, block, 256 * 24 * sizeof(float), st>>>(
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu));
   } else {
     dim3 block = reduce_block(c);
     dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
-    norm_act_bwd_reduce_kernel<1><<<grid, block, 256 * 3 * sizeof(float), st>>>(
-        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu);
+    B200_ACT_DISPATCH(act, norm_act_bwd_reduce_kernel<1, A_><<<grid, block, 256 * 3 * sizeof(float), st>>>(
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu));
   }
   B200_CHECK_LAUNCH("norm_act_bwd_reduce");
   return 0;
@@ -751,14 +770,14 @@ int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, 
   const int sums_stride = (act == B200SEG_ACT_PRELU) ? 3 : 2;
   if (vec_ok(c, dz_pitch, y_pitch, dy_pitch, (residual ? res_pitch : 0) | (dres ? dres_pitch : 0))) {
     const int64_t total = rows_per_group * groups * (c / 8);
-    norm_act_bwd_apply_kernel<8><<<ew_grid(total, c / 8), 256, 0, st>>>(
+    B200_ACT_DISPATCH(act, norm_act_bwd_apply_kernel<8, A_><<<ew_grid(total, c / 8), 256, 0, st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
-        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch);
+        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch));
   } else {
     const int64_t total = rows_per_group * groups * c;
-    norm_act_bwd_apply_kernel<1><<<ew_grid(total, c), 256, 0, st>>>(
+    B200_ACT_DISPATCH(act, norm_act_bwd_apply_kernel<1, A_><<<ew_grid(total, c), 256, 0, st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
-        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch);
+        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch));
   }
   B200_CHECK_LAUNCH("norm_act_bwd_apply");
   return 0;

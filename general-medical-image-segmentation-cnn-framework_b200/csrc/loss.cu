@@ -53,18 +53,18 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_p
 // lane = channel (c, c+32, ... up to 4 per lane): x rows and dx rows are read / written coalesced, the class
 // gradients of a voxel are warp-uniform broadcast loads, and every lane keeps its own grad_w accumulators in
 // registers -- no shuffles in the loop.
+template <int KC_, int CPL>   // KC_ = class slots kept in registers (>= classes), CPL = channels per lane
 __global__ void __launch_bounds__(256)
     head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
                     const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t dx_pitch,
                     float* __restrict__ grad_w, float* __restrict__ grad_b, int n, int64_t spatial, int cin,
                     int classes) {
-  constexpr int CPL = 4;  // channels per lane (cin <= 128)
   const int lane = threadIdx.x & 31;
   const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  float wr[kMaxClasses][CPL], gw[kMaxClasses][CPL], gb[kMaxClasses];
+  float wr[KC_][CPL], gw[KC_][CPL], gb[KC_];
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < KC_; ++k) {
     gb[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
@@ -73,26 +73,29 @@ __global__ void __launch_bounds__(256)
       gw[k][j] = 0.f;
     }
   }
-  const int64_t total = static_cast<int64_t>(n) * spatial;
-  for (int64_t v = warp_id; v < total; v += nwarps) {
-    const int64_t nn = v / spatial, s = v % spatial;
-    float dl[kMaxClasses];
+  for (int nn = 0; nn < n; ++nn) {
+    const float* dl_n = dlogits + static_cast<int64_t>(nn) * classes * spatial;
+    const __nv_bfloat16* x_n = x + static_cast<int64_t>(nn) * spatial * x_pitch;
+    __nv_bfloat16* dx_n = dx + static_cast<int64_t>(nn) * spatial * dx_pitch;
+    for (int64_t s = warp_id; s < spatial; s += nwarps) {
+      float dl[KC_];
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) dl[k] = (k < classes) ? dlogits[(nn * classes + k) * spatial + s] : 0.f;
+      for (int k = 0; k < KC_; ++k) dl[k] = (k < classes) ? dl_n[k * spatial + s] : 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) gb[k] += dl[k];
+      for (int k = 0; k < KC_; ++k) gb[k] += dl[k];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      const int c = lane + 32 * j;
-      if (c < cin) {
-        const float xv = __bfloat162float(x[v * x_pitch + c]);
-        float d = 0.f;
+      for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < cin) {
+          const float xv = __bfloat162float(x_n[s * x_pitch + c]);
+          float d = 0.f;
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) {
-          d += dl[k] * wr[k][j];
-          gw[k][j] += dl[k] * xv;
+          for (int k = 0; k < KC_; ++k) {
+            d += dl[k] * wr[k][j];
+            gw[k][j] += dl[k] * xv;
+          }
+          dx_n[s * dx_pitch + c] = __float2bfloat16(d);
         }
-        dx[v * dx_pitch + c] = __float2bfloat16(d);
       }
     }
   }
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x < kMaxClasses) sgb[threadIdx.x] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < KC_; ++k) {
     if (k < classes) {
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
@@ -386,9 +389,18 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
                  "head_conv1x1_bwd: bad arguments");
   B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "head_conv1x1_bwd: classes must be in [1,%d]", kMaxClasses);
   B200_CHECK_ARG(cin <= 128, "head_conv1x1_bwd: at most 128 input channels");
-  head_bwd_kernel<<<kNumSMs * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(x), x_pitch, w,
-                                                         static_cast<__nv_bfloat16*>(dx), dx_pitch, grad_w, grad_b, n,
-                                                         spatial, cin, classes);
+  auto st = static_cast<cudaStream_t>(stream);
+  const auto* xp = static_cast<const __nv_bfloat16*>(x);
+  auto* dxp = static_cast<__nv_bfloat16*>(dx);
+  const int grid = kNumSMs * 8;
+#define B200_HEAD_BWD(KC_, CPL_) \
+  head_bwd_kernel<KC_, CPL_><<<grid, 256, 0, st>>>(dlogits, xp, x_pitch, w, dxp, dx_pitch, grad_w, grad_b, n, spatial, cin, classes)
+  const int cpl = (cin + 31) / 32;
+  if (classes <= 2 && cpl == 1) B200_HEAD_BWD(2, 1);
+  else if (classes <= 4 && cpl == 1) B200_HEAD_BWD(4, 1);
+  else if (classes <= 4 && cpl <= 2) B200_HEAD_BWD(4, 2);
+  else B200_HEAD_BWD(8, 4);
+#undef B200_HEAD_BWD
   B200_CHECK_LAUNCH("head_conv1x1_bwd");
   return 0;
 }
