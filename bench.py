@@ -156,22 +156,20 @@ def run_b200(args):
     from b200seg.optim import FusedAdam
     from b200seg.utils.loss_function import DiceCELoss
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from b200seg import parallel
+    rank, local, world = parallel.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234 + rank)
 
     net = UNet3D(1, 2, FEATURES).to(dev)
     if world > 1:
-        for p in net.parameters():
-            dist.broadcast(p.data, 0)
-        convert_model(net)
+        parallel.broadcast_parameters(net)
+        convert_model(net)       # nn.BatchNorm3d -> SynchronizedBatchNorm3d (statistics all-reduced over NCCL)
     net.train()
     opt = FusedAdam(net.parameters(), lr=1e-3)
+    if world > 1:
+        opt.attach_reducer()     # bucketed gradient all-reduce on a side stream, overlapped with backward
     crit = DiceCELoss(2)
     vox = PATCH ** 3
     x_host = torch.randn(BATCH, 1, PATCH, PATCH, PATCH).pin_memory()

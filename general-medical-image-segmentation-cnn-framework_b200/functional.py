@@ -11,6 +11,7 @@ import torch
 import torch.distributed as dist
 
 from ._lib import ConvGeom, call
+from .parallel import all_reduce_stats, is_parallel
 
 ACT = {"none": 0, None: 0, "relu": 1, "leaky_relu": 2, "elu": 3, "prelu": 4}
 
@@ -220,9 +221,8 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
         if spec.training:
             if stats is None:
                 stats = channel_stats(y, 1)
-            if spec.sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(spec.process_group) > 1:
-                dist.all_reduce(stats, group=spec.process_group)  # {sum, sumsq}: sync_batchnorm/batchnorm.py:102
-                count *= dist.get_world_size(spec.process_group)
+            if spec.sync:
+                count *= all_reduce_stats(stats, spec.process_group)  # {sum, sumsq}: sync_batchnorm/batchnorm.py:102
             coef = _norm_coef(stats, count, 1, c, gamma, beta, running_mean, running_var, spec.momentum, spec.eps,
                               spec.clamp_eps, y.device)
         else:
@@ -255,10 +255,9 @@ def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dre
           spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(sums), _ptr(dprelu), _stream())
     use_batch_stats = spec.kind == "instance" or (spec.kind == "batch" and spec.training)
     red = sums
-    if use_batch_stats and spec.kind == "batch" and spec.sync and dist.is_available() and dist.is_initialized() \
-            and dist.get_world_size(spec.process_group) > 1:
+    if use_batch_stats and spec.kind == "batch" and spec.sync and is_parallel(spec.process_group):
         red = sums.clone()
-        dist.all_reduce(red, group=spec.process_group)
+        all_reduce_stats(red, spec.process_group)
     dy = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device)
     dres = torch.empty_like(dy) if want_dres else None
     _call("b200seg_norm_act_bwd_apply", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), _ptr(red if use_batch_stats else None),

@@ -40,8 +40,17 @@ class FusedAdam:
             if p.grad is None or p.grad.data_ptr() != self.grad_arena.data_ptr() + 4 * off:
                 p.grad = self.grad_arena[off:off + p.numel()].view_as(p)
 
+    def attach_reducer(self, group=None, bucket_bytes=32 << 20):
+        """Overlap the data-parallel gradient all-reduce with backward (parallel.GradBucketReducer)."""
+        from .parallel import GradBucketReducer
+        self.reducer = GradBucketReducer(self.grad_arena, self.params, self.offsets, bucket_bytes, group)
+        return self.reducer
+
     def all_reduce_grads(self, group=None):
-        """Data-parallel gradient averaging (what DDP does inside accelerator.backward, train.py:211)."""
+        """Data-parallel gradient averaging (what DDP does inside accelerator.backward, train.py:211).  Returns the
+        factor the summed gradients still have to be scaled by (folded into the Adam kernel)."""
+        if getattr(self, "reducer", None) is not None:
+            return self.reducer.finish()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.grad_arena, group=group)
             return 1.0 / dist.get_world_size(group)

@@ -1,0 +1,177 @@
+"""Data-parallel plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the exchanges.
+
+The reference gets data parallelism from HuggingFace accelerate -> DistributedDataParallel (train.py:167-169, 211:
+the gradient all-reduce runs inside `accelerator.backward(loss)`), and cross-device batch-norm statistics from the
+vendored thread/queue SyncBN (models/sync_batchnorm/batchnorm.py:90-111, comm.py:56-137).  Here:
+
+  * `init_from_env()` joins the process group the way torchrun launches it (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).
+  * `GradBucketReducer` all-reduces the flat gradient arena of optim.FusedAdam in contiguous buckets.  A bucket is
+    launched on a side stream as soon as the last gradient inside it has been produced (parameters are registered in
+    forward order, backward produces them roughly in reverse, so buckets are cut from the END of the arena), which
+    overlaps the exchange with the rest of the backward pass; `finish()` joins the side stream before the optimiser.
+  * `all_reduce_stats()` is the SyncBatchNorm exchange: one all-reduce of [sum, sum-of-squares] (forward) or
+    [sum dy, sum dy*xhat] (backward) per layer; every rank finalises locally, so the reference's master -> replica
+    broadcast (batchnorm.py:105) disappears.
+  * `shard_patches()` deals sliding-window patches round-robin to ranks and `reduce_volume()` merges the per-rank
+    output volumes (predict.py:111 shards the loader the same way but never merges -- SURVEY.md section 2d).
+
+Everything here is device-agnostic host logic (it is exercised with the gloo backend on CPU tensors in
+tests/test_parallel_cpu.py); the arithmetic stays in the kernels.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def is_parallel(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def world_size(group=None):
+    return dist.get_world_size(group) if is_parallel(group) else 1
+
+
+def rank(group=None):
+    return dist.get_rank(group) if is_parallel(group) else 0
+
+
+def init_from_env(backend=None):
+    """Join the default process group from torchrun's environment.  Returns (rank, local_rank, world_size)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rk = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, rank=rk, world_size=world, **kwargs)
+    return rk, local, world
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Make every rank start from rank `src`'s weights and buffers (what DDP does at construction)."""
+    if not is_parallel(group):
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src, group=group)
+
+
+def all_reduce_stats(stats, group=None):
+    """Sum a small fp32 statistics tensor over ranks, in place, in stream order.  Returns the number of ranks."""
+    if not is_parallel(group):
+        return 1
+    dist.all_reduce(stats, group=group)
+    return dist.get_world_size(group)
+
+
+def all_reduce_counts(counts, group=None):
+    """Integer metric counts (metric.py:36-46) summed over ranks: the TODO at train.py:220-224."""
+    if is_parallel(group):
+        dist.all_reduce(counts, group=group)
+    return counts
+
+
+class GradBucketReducer:
+    """Bucketed, backward-overlapped all-reduce of a flat gradient arena.
+
+    arena:    1-D tensor holding every gradient (optim.FusedAdam.grad_arena).
+    params:   the parameters, in arena order; offsets[i] / numels[i] locate parameter i inside the arena.
+    Buckets are contiguous arena ranges of at least `bucket_bytes`, cut from the last parameter backwards.
+    """
+
+    def __init__(self, arena, params, offsets, bucket_bytes=32 << 20, group=None):
+        self.arena, self.group = arena, group
+        self.params = list(params)
+        self.offsets = list(offsets)
+        self.enabled = is_parallel(group)
+        self.buckets = []          # (start, end, [param indices])
+        self._bucket_of = {}
+        esz = arena.element_size()
+        end, members, size = arena.numel(), [], 0
+        for i in range(len(self.params) - 1, -1, -1):
+            members.append(i)
+            size += self.params[i].numel() * esz
+            if size >= bucket_bytes or i == 0:
+                self.buckets.append((self.offsets[i], end, members))
+                end, members, size = self.offsets[i], [], 0
+        for b, (_, _, members) in enumerate(self.buckets):
+            for i in members:
+                self._bucket_of[i] = b
+        self._pending = [len(m) for _, _, m in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self._stream = torch.cuda.Stream() if (self.enabled and arena.is_cuda) else None
+        self._hooks = []
+        if self.enabled:
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+
+    def _make_hook(self, i):
+        def hook(_param):
+            self.mark_ready(i)
+        return hook
+
+    def reset(self):
+        self._pending = [len(m) for _, _, m in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+
+    def mark_ready(self, i):
+        """Gradient of parameter i is final (called from autograd hooks, or directly by fused backward kernels)."""
+        if not self.enabled:
+            return
+        b = self._bucket_of[i]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and not self._launched[b]:
+            self._launch(b)
+
+    def _launch(self, b):
+        start, end, _ = self.buckets[b]
+        view = self.arena[start:end]
+        self._launched[b] = True
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                dist.all_reduce(view, group=self.group)
+        else:
+            self._works.append(dist.all_reduce(view, group=self.group, async_op=True))
+
+    def finish(self):
+        """Launch whatever has not fired (parameters without gradient this step), join, return the averaging factor."""
+        if not self.enabled:
+            return 1.0
+        for b in range(len(self.buckets)):
+            if not self._launched[b]:
+                self._launch(b)
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        for w in self._works:
+            w.wait()
+        self.reset()
+        return 1.0 / dist.get_world_size(self.group)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def shard_patches(num_patches, group=None):
+    """Indices of the sliding-window patches this rank runs (round-robin, predict.py:111)."""
+    return list(range(rank(group), num_patches, world_size(group)))
+
+
+def reduce_volume(volume, group=None, op="sum"):
+    """Merge per-rank aggregator volumes in place.
+
+    Average mode (op="sum"): logit sums and visit counts add.  Crop mode (op="max"): torchio lets a later patch
+    overwrite an earlier one where their cropped interiors overlap (the extra window at the far border), so each
+    voxel carries an int32 key ((global patch index + 1) << 8 | label); the maximum over ranks is the label written
+    by the last patch in sampler order, exactly what a single sequential aggregator produces."""
+    if is_parallel(group):
+        dist.all_reduce(volume, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=group)
+    return volume
