@@ -176,14 +176,11 @@ def run_b200(args):
     lab_host = (torch.rand(BATCH, PATCH, PATCH, PATCH) > 0.9).to(torch.uint8).pin_memory()
     x_dev, lab_dev = x_host.to(dev), lab_host.to(dev)
 
+    from b200seg.engine import TrainStep
+    train_step = TrainStep(net, crit, opt, use_graph=not args.no_graph)   # train.py:187-214 as one CUDA graph
+
     def step(x, lab):
-        opt.zero_grad()
-        out = net(x)
-        loss = crit(out, lab)
-        loss.backward()
-        scale = opt.all_reduce_grads()
-        opt.step(grad_scale=scale)
-        return loss
+        return train_step(x, lab)[0]
 
     def barrier():
         if world > 1:
@@ -203,7 +200,7 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + 2):   # TrainStep runs 3 eager steps, captures, then replays
         step(x_dev, lab_dev)
     barrier()
 
@@ -215,6 +212,9 @@ def run_b200(args):
     ms_total = timed(lambda: step(x_dev, lab_dev), args.steps)
     launches = F.launches()
     umma_launches = F.umma_launch_count() - umma0
+    if train_step.graph is not None:   # replays do not pass through the Python wrappers: count the graph's kernel nodes
+        launches = train_step.kernels_per_step * args.steps
+        umma_launches = train_step.umma_per_step * args.steps
 
     # end to end through the public API: pinned host batch -> device, result (loss) read back on the host every step
     def e2e_step():
@@ -225,10 +225,12 @@ def run_b200(args):
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-kernel timing pass (CUDA events around every conv launch on the launching stream) -> roofline
+    # per-kernel timing pass (CUDA events around every launch on the launching stream, eager) -> roofline
+    eager = TrainStep(net, crit, opt, use_graph=False)
+    eager(x_dev, lab_dev)
     F.profile_begin()
     for _ in range(2):
-        step(x_dev, lab_dev)
+        eager(x_dev, lab_dev)
     prof = F.profile_end()
 
     if rank == 0:
@@ -253,6 +255,7 @@ def run_b200(args):
             "config": {"workload": "UNet3D(1,2,32) train step, batch 2x1x128^3 per GPU, Dice+CE, %s, fused Adam "
                                    "(BASELINE.json configs[1])" % ("SyncBatchNorm" if world > 1 else "BatchNorm"),
                        "global_batch": patches, "parallelism": "dp%d" % world,
+                       "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "l2": "no flush needed: each step streams >10 GB of activations, far larger than the 126 MB L2"},
             "voxels_per_s": value * vox,
             "e2e": {"value": patches / (ms_e2e / args.steps * 1e-3), "unit": "patches/s",
@@ -285,6 +288,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
+                                                            "the captured CUDA graph of the step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200seg_window_accumulate_average": "pp" + "iiiii" + "pp" + "iii" + "p",
     "b200seg_window_finalize": "pp" + "il" + "pp",
     "b200seg_adam_step": "pppp" + "l" + "fffff" + "i" + "f" + "p",
+    "b200seg_adam_step_dev": "pppp" + "l" + "pp" + "p",
 }
 STRING_FUNCS = ("b200seg_version", "b200seg_last_error")
 SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g"}

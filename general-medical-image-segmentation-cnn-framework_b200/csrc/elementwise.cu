@@ -622,6 +622,38 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Graph-capturable variant: step count and hyper-parameters live in device memory, so a captured launch stays correct
+// when it is replayed (state[0] = step, incremented here by the last block to finish; hyper = {lr, b1, b2, eps, wd, gscale}).
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t numel, const float* __restrict__ hyper,
+                                int* __restrict__ state) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gscale = hyper[5];
+  const float step = static_cast<float>(state[0] + 1);
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float grad = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) grad += wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * grad;
+    const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(&state[1], 1);
+    if (done == static_cast<int>(gridDim.x) - 1) {   // every block has read state[0]: safe to advance it
+      state[1] = 0;
+      state[0] = state[0] + 1;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -874,6 +906,15 @@ int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   adam_kernel<<<grid_for(numel, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
   B200_CHECK_LAUNCH("adam_step");
+  return 0;
+}
+
+int b200seg_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                          const float* hyper, int32_t* state, void* stream) {
+  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && numel > 0 && hyper && state, "adam_step_dev: bad arguments");
+  adam_dev_kernel<<<grid_for(numel, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, numel, hyper, state);
+  B200_CHECK_LAUNCH("adam_step_dev");
   return 0;
 }
 

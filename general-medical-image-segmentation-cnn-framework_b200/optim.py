@@ -56,13 +56,30 @@ class FusedAdam:
             return 1.0 / dist.get_world_size(group)
         return 1.0
 
+    def _sync_hyper(self, grad_scale):
+        """Hyper-parameters and the step counter live on the device so a CUDA-graph-captured step replays correctly;
+        the host copy is only pushed when a value changed (e.g. StepLR, train.py:119-120)."""
+        want = (float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                float(grad_scale))
+        if getattr(self, "_hyper_host", None) != want:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedAdam: hyper-parameters changed inside a CUDA graph capture")
+            if getattr(self, "_hyper", None) is None:
+                self._hyper = torch.zeros(6, dtype=torch.float32, device=self.param_arena.device)
+                self._state = torch.zeros(2, dtype=torch.int32, device=self.param_arena.device)
+                self._state[0] = self.step_count
+            self._hyper.copy_(torch.tensor(want, dtype=torch.float32))
+            self._hyper_host = want
+
     def step(self, grad_scale=1.0):
+        self._sync_hyper(grad_scale)
         self.step_count += 1
-        _call("b200seg_adam_step", _ptr(self.param_arena), _ptr(self.grad_arena), _ptr(self.exp_avg),
-              _ptr(self.exp_avg_sq), self.numel, float(self.lr), float(self.betas[0]), float(self.betas[1]),
-              float(self.eps), float(self.weight_decay), self.step_count, float(grad_scale), _stream())
+        _call("b200seg_adam_step_dev", _ptr(self.param_arena), _ptr(self.grad_arena), _ptr(self.exp_avg),
+              _ptr(self.exp_avg_sq), self.numel, _ptr(self._hyper), _ptr(self._state), _stream())
 
     def state_dict(self):
+        if getattr(self, "_state", None) is not None:
+            self.step_count = int(self._state[0].item())   # graph replays advance the device counter only
         return {"step": self.step_count, "lr": self.lr, "betas": self.betas, "eps": self.eps,
                 "weight_decay": self.weight_decay, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
 
@@ -70,3 +87,6 @@ class FusedAdam:
         self.step_count, self.lr = sd["step"], sd["lr"]
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self._hyper_host = None
+        if getattr(self, "_state", None) is not None:
+            self._state[0] = self.step_count

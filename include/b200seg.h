@@ -177,6 +177,12 @@ int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* ex
                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                       void* stream);
 
+/* Same update with the step counter and hyper-parameters in device memory, so that a launch captured in a CUDA graph
+ * stays correct on replay: hyper = float[6] {lr, beta1, beta2, eps, weight_decay, grad_scale}; state = int32[2]
+ * {completed steps (incremented by the kernel), scratch (must be 0)}. */
+int b200seg_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                          const float* hyper, int32_t* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

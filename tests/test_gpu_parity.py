@@ -396,3 +396,39 @@ def test_sliding_window_aggregator_bit_exact():
         out = agg.get_output_tensor().cpu().numpy()
         assert np.array_equal(out.astype(np.int64), oagg.get_output_tensor().astype(np.int64))
         assert np.array_equal(out.astype(np.int64), vol)
+
+
+@pytest.mark.gpu
+def test_graph_captured_train_step_matches_eager():
+    """engine.TrainStep: the CUDA-graph replay of (zero_grad, forward, Dice+CE, backward, fused Adam) follows the same
+    trajectory as enqueueing every kernel eagerly (train.py:187-214).  Differences come only from the order of
+    floating-point atomics in the statistics / weight-gradient reductions."""
+    from b200seg.engine import TrainStep
+    from b200seg.models.three_d.unet3d import UNet3D
+    from b200seg.optim import FusedAdam
+    from b200seg.utils.loss_function import DiceCELoss
+    from oracle import unet3d as ounet
+    dev = torch.device("cuda")
+    sd = ounet.init_state_dict(1, 2, 16, seed=3)
+    torch.manual_seed(5)
+    xs = [torch.randn(2, 1, 32, 32, 32, device=dev) for _ in range(6)]
+    labs = [(torch.rand(2, 32, 32, 32, device=dev) > 0.8).to(torch.uint8) for _ in range(6)]
+    results = []
+    for use_graph in (False, True):
+        net = UNet3D(1, 2, 16).to(dev)
+        net.load_state_dict(sd)
+        net.train()
+        opt = FusedAdam(net.parameters(), lr=1e-3)
+        step = TrainStep(net, DiceCELoss(2), opt, use_graph=use_graph, warmup=2)
+        losses = [float(step(x, y)[0]) for x, y in zip(xs, labs)]
+        assert (step.graph is not None) == use_graph
+        if use_graph:
+            assert step.kernels_per_step > 100 and step.umma_per_step > 20
+        assert opt.state_dict()["step"] == 6
+        results.append((losses, {k: v.clone() for k, v in net.state_dict().items()}))
+    (l0, p0), (l1, p1) = results
+    assert max(abs(a - b) for a, b in zip(l0, l1)) < 6e-3, (l0, l1)
+    assert p0["encoder1.enc1norm1.num_batches_tracked"] == p1["encoder1.enc1norm1.num_batches_tracked"] == 6
+    for k in ("encoder1.enc1conv1.weight", "decoder1.dec1conv2.weight", "bottleneck.bottleneckconv1.weight",
+              "encoder2.enc2norm1.running_var", "conv.weight"):
+        close(p1[k].float().cpu(), p0[k].float().cpu(), 2e-2, k)
