@@ -387,7 +387,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static bool encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+bool encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                             const uint64_t* strides_bytes, const uint32_t* box, int kc) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -528,12 +528,14 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
 }
 
 bool conv_umma_supported(const UmmaConvArgs& a) {
+  if (conv_umma_plane_supported(a)) return true;
   UmmaConvParams p;
   size_t smem;
   return plan(a, p, smem);
 }
 
 int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
+  if (conv_umma_plane_supported(a)) return conv_umma_plane_run(a, st);   // persistent kernel (conv_umma_p.cu)
   UmmaConvParams p;
   size_t smem;
   if (!plan(a, p, smem)) {
