@@ -58,5 +58,8 @@ struct UmmaWgradArgs {
 };
 bool wgrad_umma_supported(const UmmaWgradArgs& a);
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st);
+// persistent plane-mode kernel with tap blocks on both operands (wgrad_umma_p.cu)
+bool wgrad_umma_plane_supported(const UmmaWgradArgs& a);
+int wgrad_umma_plane_run(const UmmaWgradArgs& a, cudaStream_t st);
 
 }  // namespace b200

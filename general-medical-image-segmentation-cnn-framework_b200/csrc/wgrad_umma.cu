@@ -455,12 +455,14 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
 }
 
 bool wgrad_umma_supported(const UmmaWgradArgs& a) {
+  if (wgrad_umma_plane_supported(a)) return true;
   WgradParams p;
   size_t smem;
   return plan_wgrad(a, p, smem);
 }
 
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st) {
+  if (wgrad_umma_plane_supported(a)) return wgrad_umma_plane_run(a, st);   // wgrad_umma_p.cu
   WgradParams p;
   size_t smem;
   if (!plan_wgrad(a, p, smem)) {

@@ -43,14 +43,19 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(Args p) {
     const uint32_t leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(128, p.N, p.mn_major, p.mn_major);
     const uint32_t swz = p.KC == 64 ? SWZ_128B : (p.KC == 32 ? SWZ_64B : SWZ_32B);
-    const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 16, p.a_sbo_rows * rowbytes, swz) >> 32);
-    const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 16, 8 * rowbytes, swz) >> 32);
+    // K-major: LBO ignored, SBO = 8-row group stride.  MN-major (weight-gradient form): rows are K (voxels), each row
+    // holds KC channels of one M/N block; LBO = byte distance between blocks (here: one row, i.e. shifted views),
+    // SBO = distance between 8-row K groups.
+    const uint32_t a_hi = p.mn_major ? static_cast<uint32_t>(make_smem_desc(0, rowbytes, p.a_sbo_rows * rowbytes, swz) >> 32)
+                                     : static_cast<uint32_t>(make_smem_desc(0, 16, p.a_sbo_rows * rowbytes, swz) >> 32);
+    const uint32_t b_hi = p.mn_major ? static_cast<uint32_t>(make_smem_desc(0, 24 * rowbytes, 8 * rowbytes, swz) >> 32)
+                                     : static_cast<uint32_t>(make_smem_desc(0, 16, 8 * rowbytes, swz) >> 32);
     const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + p.a_tiles * a_bytes);
     const int ksteps = p.KC / 16;
     const long long t0 = clock64();
     // descriptors are loop-invariant: the loop body is nothing but UTCHMMA issue slots (8 instructions per trip)
-    const uint32_t a_lo = ((sA >> 4) & 0x3FFF) | (1u << 16);
-    const uint32_t b_lo = ((sB >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t a_lo = ((sA >> 4) & 0x3FFF) | (p.mn_major ? ((rowbytes >> 4) << 16) : (1u << 16));
+    const uint32_t b_lo = ((sB >> 4) & 0x3FFF) | (p.mn_major ? (((24 * rowbytes) >> 4) << 16) : (1u << 16));
     const uint64_t ad0 = (static_cast<uint64_t>(a_hi) << 32) | a_lo, ad1 = ad0 + 2 + (p.a_tiles > 1 ? 8 * p.a_sbo_rows * rowbytes / 16 : 0);
     const uint64_t bd0 = (static_cast<uint64_t>(b_hi) << 32) | b_lo, bd1 = bd0 + 2;
     (void)ksteps;
@@ -85,13 +90,17 @@ int main() {
       cases.push_back({N, KC, 512 / N > 8 ? 8 : 512 / N, 1, 8, 1});
       cases.push_back({N, KC, 512 / N > 8 ? 8 : 512 / N, 4, 10, 1});
     }
-  cases.push_back({32, 32, 8, 4, 10, 2});
-  cases.push_back({64, 64, 4, 4, 10, 2});
+  // MN-major (wgrad form), marked by ctas_per_sm = -1: N = blocks x KC channels
+  for (int KC : {32, 64})
+    for (int N : {KC, 2 * KC, 3 * KC, 4 * KC}) {
+      if (N > 256) continue;
+      cases.push_back({N, KC, 512 / N > 4 ? 4 : 512 / N, 1, 10, -1});
+    }
   for (const Case& c : cases) {
-    Args a{c.N, c.KC, iters, c.nacc, c.a_tiles, c.sbo, 0, d_cycles};
+    Args a{c.N, c.KC, iters, c.nacc, c.a_tiles, c.sbo, c.ctas_per_sm < 0 ? 1 : 0, d_cycles};
     const unsigned rowbytes = c.KC * 2;
     const size_t smem = static_cast<size_t>(c.a_tiles) * (160 * c.sbo / 8 * rowbytes) + 256 * rowbytes + 2048;
-    const int ctas = 148 * c.ctas_per_sm;
+    const int ctas = 148;
     // with 2 CTAs per SM each CTA can only own 256 TMEM columns; the kernel allocates 512, so emulate by halving
     if (c.ctas_per_sm > 1) continue;
     cudaEvent_t e0, e1;
@@ -115,7 +124,7 @@ int main() {
     avg /= ctas;
     const double mmas = static_cast<double>(iters);
     const double flops = mmas * 2.0 * 128 * c.N * 16 * ctas;
-    printf("%-6d %-4d %-4d %-7d %-5d %-6d | %7.1f  %8.1f  (kernel %.3f ms)\n", c.N, c.KC, c.nacc, c.a_tiles, c.sbo, ctas,
+    printf("%s%-6d %-4d %-4d %-7d %-5d %-6d | %7.1f  %8.1f  (kernel %.3f ms)\n", c.ctas_per_sm < 0 ? "MN " : "", c.N, c.KC, c.nacc, c.a_tiles, c.sbo, ctas,
            avg / mmas, flops / (ms * 1e-3) / 1e12, ms);
   }
   return 0;
