@@ -112,31 +112,36 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
     if (lane == 0 && s0 < s1) {
       tma_prefetch_desc(&tmX);
       tma_prefetch_desc(&tmY);
-      long long q = 0;   // dy planes issued so far
+      int yslot = 0;        // ring slot of the next dy plane, and the parity its empty barrier has to show
+      uint32_t yph = 0;
       int sx = 0;
       uint32_t phx = 0;
       auto load_y = [&](int nn, int h0, int w0, int plane) {
-        const int slot = static_cast<int>(q % p.RY);
-        const uint32_t ph = static_cast<uint32_t>((q / p.RY) & 1);
-        mbar_wait(&emptyY[slot], ph ^ 1);
-        const bool mirror = slot < p.span - 1;
-        mbar_arrive_expect_tx(&fullY[slot], mirror ? 2 * p.bytesY : p.bytesY);
-        tma_load_5d(sY + static_cast<size_t>(slot) * p.slotY, &tmY, &fullY[slot], nt * p.NT, w0, h0, plane, nn);
+        mbar_wait(&emptyY[yslot], yph ^ 1);
+        const bool mirror = yslot < p.span - 1;
+        mbar_arrive_expect_tx(&fullY[yslot], mirror ? 2 * p.bytesY : p.bytesY);
+        tma_load_5d(sY + static_cast<size_t>(yslot) * p.slotY, &tmY, &fullY[yslot], nt * p.NT, w0, h0, plane, nn);
         if (mirror)
-          tma_load_5d(sY + static_cast<size_t>(slot + p.RY) * p.slotY, &tmY, &fullY[slot], nt * p.NT, w0, h0, plane, nn);
-        ++q;
+          tma_load_5d(sY + static_cast<size_t>(yslot + p.RY) * p.slotY, &tmY, &fullY[yslot], nt * p.NT, w0, h0, plane, nn);
+        if (++yslot == p.RY) {
+          yslot = 0;
+          yph ^= 1;
+        }
       };
+      // position of the first step: (column, dx) = (s0 / d, s0 % d), column over (nn, th, tw)
+      int dx = static_cast<int>(s0 % p.d);
+      long long col = s0 / p.d;
+      int tw = static_cast<int>(col % p.tiles_w);
+      col /= p.tiles_w;
+      int th = static_cast<int>(col % p.tiles_h);
+      int nn = static_cast<int>(col / p.tiles_h);
+      bool fresh = true;
       for (long long s = s0; s < s1; ++s) {
-        const int dx = static_cast<int>(s % p.d);
-        long long col = s / p.d;
-        const int tw = static_cast<int>(col % p.tiles_w);
-        col /= p.tiles_w;
-        const int th = static_cast<int>(col % p.tiles_h);
-        const int nn = static_cast<int>(col / p.tiles_h);
         const int h0 = th * 16, w0 = tw * 8;
-        if (s == s0 || dx == 0) {
+        if (fresh) {
           // (re)prime the ring: planes dx + pad - back .. dx + pad - 1 (out-of-range planes arrive as zeros)
           for (int j = back; j >= 1; --j) load_y(nn, h0, w0, dx + p.pad - j);
+          fresh = false;
         }
         load_y(nn, h0, w0, dx + p.pad);
         mbar_wait(&emptyX[sx], phx ^ 1);
@@ -145,6 +150,17 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
         if (++sx == p.SX) {
           sx = 0;
           phx ^= 1;
+        }
+        if (++dx == p.d) {
+          dx = 0;
+          fresh = true;
+          if (++tw == p.tiles_w) {
+            tw = 0;
+            if (++th == p.tiles_h) {
+              th = 0;
+              ++nn;
+            }
+          }
         }
       }
     }
@@ -170,24 +186,28 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
         g_off16[g] = static_cast<uint32_t>((b * p.dil) * p.WB + p.groups[g].e0 * p.dil) * rowA16;
       }
       const uint32_t NTOT = p.NBLK * p.NT;
-      long long q = 0;
+      // dy ring bookkeeping without divisions: `oslot` = slot of the OLDEST plane of the current step, `wslot`/`wph` =
+      // slot and parity of the next plane whose arrival has not been observed yet
+      int oslot = 0, wslot = 0;
+      uint32_t wph = 0;
       int sx = 0;
       uint32_t phx = 0, accum = 0;
+      int dx = static_cast<int>(s0 % p.d);
+      bool fresh = true;
       for (long long s = s0; s < s1; ++s) {
-        const int dx = static_cast<int>(s % p.d);
-        if (s == s0 || dx == 0) q += back;          // priming planes of this column
-        // newest plane of this step has index q; wait for it (older ones were waited for on earlier steps / just now)
-        {
-          const long long first_new = (s == s0 || dx == 0) ? q - back : q;
-          for (long long j = first_new; j <= q; ++j)
-            mbar_wait(&fullY[static_cast<int>(j % p.RY)], static_cast<uint32_t>((j / p.RY) & 1));
+        const int nwait = fresh ? back + 1 : 1;     // planes that arrive for this step
+        for (int j = 0; j < nwait; ++j) {
+          mbar_wait(&fullY[wslot], wph);
+          if (++wslot == p.RY) {
+            wslot = 0;
+            wph ^= 1;
+          }
         }
+        fresh = false;
         mbar_wait(&fullX[sx], phx);
         tc_fence_after();
-        // B operand starts at the OLDEST plane (index q - back); use its mirrored copy when the k planes would wrap
-        const int yslot = static_cast<int>((q - back) % p.RY);
         // (planes that wrapped to slots 0 .. span-2 are read through their mirrors at RY + slot)
-        const uint32_t b_lo0 = ((sY16 + yslot * slotY16) & 0x3FFF) | b_lbo;
+        const uint32_t b_lo0 = ((sY16 + oslot * slotY16) & 0x3FFF) | b_lbo;
         const uint32_t x_lo0 = (sX16 + sx * slotX16);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -205,17 +225,20 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
         }
         accum = 1;
         umma_commit_pred(&emptyX[sx], leader);
-        // the oldest plane is not needed by the next step of this column; at a column end every plane is released
-        const bool last_of_col = (dx == p.d - 1) || (s + 1 == s1);
-        if (last_of_col) {
-          for (long long j = q - back; j <= q; ++j) umma_commit_pred(&emptyY[static_cast<int>(j % p.RY)], leader);
-        } else {
-          umma_commit_pred(&emptyY[static_cast<int>((q - back) % p.RY)], leader);
-        }
-        ++q;
         if (++sx == p.SX) {
           sx = 0;
           phx ^= 1;
+        }
+        // the oldest plane is not needed by the next step of this column; at a column end every plane is released
+        const bool last_of_col = (dx == p.d - 1) || (s + 1 == s1);
+        const int nrel = last_of_col ? back + 1 : 1;
+        for (int j = 0; j < nrel; ++j) {
+          umma_commit_pred(&emptyY[oslot], leader);
+          if (++oslot == p.RY) oslot = 0;
+        }
+        if (++dx == p.d) {
+          dx = 0;
+          fresh = true;
         }
       }
       umma_commit_pred(accFull, leader);
@@ -324,8 +347,8 @@ static bool plan_wgrad_plane(const UmmaWgradArgs& a, WgradPParams& p, size_t& sm
     p.RY = p.span + 1;
     if (total() > budget) return false;
   } else {
-    while (p.RY < 2 * p.span + 2 && total() + p.slotY <= budget) ++p.RY;
-    while (p.SX < 4 && total() + p.slotX <= budget) ++p.SX;
+    while (p.RY < 2 * p.span + 4 && total() + p.slotY <= budget) ++p.RY;
+    while (p.SX < 6 && total() + p.slotX <= budget) ++p.SX;
   }
   p.tiles_w = (a.ow + 7) / 8;
   p.tiles_h = (a.oh + 15) / 16;
