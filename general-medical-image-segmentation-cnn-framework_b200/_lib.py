@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200seg.so")
 
 _P, _I, _L, _F, _D, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
-_CODES = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D, "z": _Z}
+_CODES = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D, "z": _Z, "Q": ctypes.c_uint64}
 
 
 class ConvGeom(ctypes.Structure):
@@ -40,6 +40,9 @@ SIGNATURES = {
     "b200seg_upsample2_fwd": "plpl" + "iiiii" + "p",
     "b200seg_upsample2_bwd": "plpl" + "iiiii" + "p",
     "b200seg_add": "plplpl" + "li" + "p",
+    "b200seg_dropout": "plpl" + "ll" + "if" + "pQ" + "i" + "p",
+    "b200seg_classmap_up2_add": "ppp" + "liii" + "p",
+    "b200seg_classmap_down2_sum": "pp" + "liii" + "p",
     "b200seg_head_conv1x1_fwd": "plppp" + "ilii" + "p",
     "b200seg_head_conv1x1_bwd": "ppl" + "p" + "pl" + "pp" + "ilii" + "p",
     "b200seg_argmax_labels": "pp" + "ili" + "p",

@@ -605,6 +605,77 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, int64_t a_pitch,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ dropout
+// Counter-based mask: keep = hash(seed, index) >= p * 2^32.  Forward and backward call the same kernel with the same
+// (seed, salt), so no mask is stored.  `seed` lives in device memory (a captured CUDA graph sees a fresh value on every
+// replay once the host bumps it); `salt` distinguishes the call sites of one step.
+__device__ __forceinline__ uint32_t mix_hash(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return static_cast<uint32_t>(x >> 16);
+}
+
+// channel_mode = 0: nn.Dropout (one draw per element); 1: nn.Dropout3d (one draw per (sample, channel)).
+__global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, __nv_bfloat16* __restrict__ y,
+                               int64_t y_pitch, int64_t rows, int64_t rows_per_sample, int C, float p,
+                               const unsigned long long* __restrict__ seed, unsigned long long salt, int channel_mode) {
+  const unsigned long long s = (seed ? *seed : 0ULL) * 0x9E3779B97F4A7C15ULL + salt * 0xD1B54A32D192ED03ULL;
+  const uint32_t thresh = p >= 1.f ? 0xFFFFFFFFu : static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+  const float scale = p >= 1.f ? 0.f : 1.f / (1.f - p);
+  const int64_t total = rows * C;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int64_t row = i / C;
+    const unsigned long long idx = channel_mode ? static_cast<unsigned long long>((row / rows_per_sample) * C + c)
+                                                : static_cast<unsigned long long>(i);
+    const bool keep = mix_hash(s + idx) >= thresh;
+    const float v = __bfloat162float(x[row * x_pitch + c]);
+    y[row * y_pitch + c] = __float2bfloat16(keep ? v * scale : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ class maps
+// fp32 NCDHW class-score maps (deep supervision, residual_unet3d.py:196-202): out = nearest_x2(coarse) [+ fine].
+__global__ void classmap_up2_add_kernel(const float* __restrict__ coarse, const float* __restrict__ fine,
+                                        float* __restrict__ out, int64_t planes, int d, int h, int w) {
+  const int64_t total = planes * 8 * d * h * w;
+  const int W2 = 2 * w, H2 = 2 * h, D2 = 2 * d;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W2);
+    const int y = static_cast<int>((i / W2) % H2);
+    const int z = static_cast<int>((i / (static_cast<int64_t>(W2) * H2)) % D2);
+    const int64_t pl = i / (static_cast<int64_t>(W2) * H2 * D2);
+    const float v = coarse[((pl * d + (z >> 1)) * h + (y >> 1)) * w + (x >> 1)];
+    out[i] = fine ? v + fine[i] : v;
+  }
+}
+// backward of the up-sampling: dcoarse = sum of the 8 fine gradients.
+__global__ void classmap_down2_sum_kernel(const float* __restrict__ dfine, float* __restrict__ dcoarse, int64_t planes,
+                                          int d, int h, int w) {
+  const int64_t total = planes * d * h * w;
+  const int W2 = 2 * w, H2 = 2 * h;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    const int y = static_cast<int>((i / w) % h);
+    const int z = static_cast<int>((i / (static_cast<int64_t>(w) * h)) % d);
+    const int64_t pl = i / (static_cast<int64_t>(w) * h * d);
+    const float* src = dfine + ((pl * 2 * d + 2 * z) * H2 + 2 * y) * W2 + 2 * x;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) acc += src[(static_cast<int64_t>(a) * H2 + b) * W2] + src[(static_cast<int64_t>(a) * H2 + b) * W2 + 1];
+    dcoarse[i] = acc;
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t numel, float lr, float b1, float b2, float eps, float wd,
                             float bc1, float bc2_sqrt, float gscale) {
@@ -894,6 +965,34 @@ int b200seg_add(const void* a, int64_t a_pitch, const void* b, int64_t b_pitch, 
         static_cast<const __nv_bfloat16*>(a), a_pitch, static_cast<const __nv_bfloat16*>(b), b_pitch,
         static_cast<__nv_bfloat16*>(out), out_pitch, rows, c);
   B200_CHECK_LAUNCH("add");
+  return 0;
+}
+
+
+int b200seg_dropout(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int64_t rows, int64_t rows_per_sample,
+                    int c, float p, const unsigned long long* seed, unsigned long long salt, int channel_mode,
+                    void* stream) {
+  B200_CHECK_ARG(x && y && rows > 0 && rows_per_sample > 0 && c > 0 && p >= 0.f && p <= 1.f, "dropout: bad arguments");
+  dropout_kernel<<<grid_for(rows * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, rows, rows_per_sample, c, p,
+      seed, salt, channel_mode);
+  B200_CHECK_LAUNCH("dropout");
+  return 0;
+}
+
+int b200seg_classmap_up2_add(const float* coarse, const float* fine, float* out, int64_t planes, int d, int h, int w,
+                             void* stream) {
+  B200_CHECK_ARG(coarse && out && planes > 0 && d > 0 && h > 0 && w > 0, "classmap_up2_add: bad arguments");
+  classmap_up2_add_kernel<<<grid_for(planes * 8 * d * h * w, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      coarse, fine, out, planes, d, h, w);
+  B200_CHECK_LAUNCH("classmap_up2_add");
+  return 0;
+}
+int b200seg_classmap_down2_sum(const float* dfine, float* dcoarse, int64_t planes, int d, int h, int w, void* stream) {
+  B200_CHECK_ARG(dfine && dcoarse && planes > 0 && d > 0 && h > 0 && w > 0, "classmap_down2_sum: bad arguments");
+  classmap_down2_sum_kernel<<<grid_for(planes * d * h * w, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dfine, dcoarse, planes, d, h, w);
+  B200_CHECK_LAUNCH("classmap_down2_sum");
   return 0;
 }
 

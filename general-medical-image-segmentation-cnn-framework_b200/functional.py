@@ -93,8 +93,8 @@ def _pitched(t):
 def _as_rows(t):
     """Return (tensor usable by the kernels, pitch)."""
     assert t.is_cuda and t.dtype == torch.bfloat16, "expected a CUDA bf16 NDHWC tensor"
-    if not _pitched(t):
-        t = t.contiguous()
+    if not _pitched(t) or (t.data_ptr() % 16 and t.shape[4] % 8 == 0 and t.stride(3) % 8 == 0):
+        t = t.contiguous()   # the 128-bit kernels need 16-byte aligned rows
     return t, t.stride(3)
 
 
@@ -137,16 +137,20 @@ def pack_conv_weight(weight, cin_off=0, cin_cnt=None, dgrad=False):
 
 
 # ------------------------------------------------------------------------------------------------ raw op helpers
-def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats):
+def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=None):
     x, xp = _as_rows(x)
     cout, cin = weight.shape[0], weight.shape[1]
     assert x.shape[4] == cin, "input has %d channels, weight expects %d" % (x.shape[4], cin)
     g = _geom(x.shape, cin, cout, k, stride, pad, dil)
-    y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
+    if y_out is not None and _pitched(y_out) and tuple(y_out.shape) == (g.n, g.od, g.oh, g.ow, cout) \
+            and y_out.data_ptr() % 16 == 0 and y_out.stride(3) % 8 == 0:
+        y = y_out
+    else:
+        y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
     stats = torch.zeros((1, 2, cout), dtype=torch.float32, device=x.device) if want_stats else None
     wp = pack_conv_weight(weight.detach())
     b = bias.detach().float() if bias is not None else None
-    _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), cout, _ptr(stats),
+    _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), y.stride(3), _ptr(stats),
           None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_tc" if conv_uses_tensor_cores(g) else "conv_fprop_direct")
     return y, stats, g
 
@@ -249,11 +253,13 @@ def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dre
     if residual is not None:
         res, resp = _as_rows(residual)
     nrow = 3 if spec.act == ACT["prelu"] else 2
-    sums = torch.zeros((groups, nrow, c), dtype=torch.float32, device=y.device)
-    dprelu = sums[0, 2] if nrow == 3 else None
-    _call("b200seg_norm_act_bwd_reduce", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), rows, groups, c, spec.act,
-          spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(sums), _ptr(dprelu), _stream())
     use_batch_stats = spec.kind == "instance" or (spec.kind == "batch" and spec.training)
+    sums = None
+    if use_batch_stats or nrow == 3 or (spec.kind == "batch" and coef is not None):
+        sums = torch.zeros((groups, nrow, c), dtype=torch.float32, device=y.device)
+        dprelu = sums[0, 2] if nrow == 3 else None
+        _call("b200seg_norm_act_bwd_reduce", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), rows, groups, c, spec.act,
+              spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(sums), _ptr(dprelu), _stream())
     red = sums
     if use_batch_stats and spec.kind == "batch" and spec.sync and is_parallel(spec.process_group):
         red = sums.clone()
@@ -319,10 +325,11 @@ class _ConvNormAct(torch.autograd.Function):
         k, stride, pad, dil, spec, out = cfg
         xin = x if x2 is None else merge_channels(x, x2)
         fused_stats = spec.kind == "batch" and spec.training
-        y, stats, g = conv3d_fprop_raw(xin, weight, bias, k, stride, pad, dil, fused_stats)
-        if spec.kind is None and spec.act == 0 and residual is None:
+        plain = spec.kind is None and spec.act == 0 and residual is None
+        y, stats, g = conv3d_fprop_raw(xin, weight, bias, k, stride, pad, dil, fused_stats, y_out=out if plain else None)
+        if plain:
             z, coef, count, groups = y, None, 0.0, 1
-            if out is not None:
+            if out is not None and y is not out:
                 out.copy_(y)
                 z = out
         else:
@@ -641,3 +648,163 @@ def seg_counts(gt, pred):
     counts = torch.zeros(4, dtype=torch.int64, device=gt.device)
     _call("b200seg_seg_counts", _ptr(gt), _ptr(pred), gt.numel(), _ptr(counts), _stream())
     return counts
+
+
+# ------------------------------------------------------------------------------------------------ more graph ops
+def activation(x, act, act_param=0.0, prelu_weight=None, residual=None, out=None):
+    """act(x [+ residual]) without normalisation (nn.ELU / nn.PReLU / nn.LeakyReLU / nn.ReLU call sites such as
+    vnet3d.py:58,79,103 and residual_unet3d.py:113,120)."""
+    return norm_act(x, NormSpec(None, act, act_param), prelu_weight=prelu_weight, residual=residual, out=out)
+
+
+_SEEDS = {}
+_SALT = [0]
+
+
+def dropout_seed(device):
+    """Device-resident seed of the dropout masks (int64).  engine.TrainStep bumps it once per step."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SEEDS:
+        _SEEDS[key] = torch.full((1,), 0x5DEECE66D, dtype=torch.int64, device=torch.device("cuda", key))
+    return _SEEDS[key]
+
+
+def advance_dropout_seed(device):
+    dropout_seed(device).add_(1)
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg):
+        p, channel_mode, salt, out = cfg
+        x, xp = _as_rows(x)
+        n, d, h, w, c = x.shape
+        if out is None:
+            out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device)
+        assert _pitched(out) and out.shape == x.shape
+        seed = dropout_seed(x.device)
+        _call("b200seg_dropout", _ptr(x), xp, _ptr(out), out.stride(3), n * d * h * w, d * h * w, c, float(p), _ptr(seed),
+              salt, int(channel_mode), _stream())
+        ctx.cfg = (p, channel_mode, salt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, channel_mode, salt = ctx.cfg
+        g, gp = _as_rows(g)
+        n, d, h, w, c = g.shape
+        dx = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=g.device)
+        seed = dropout_seed(g.device)
+        _call("b200seg_dropout", _ptr(g), gp, _ptr(dx), c, n * d * h * w, d * h * w, c, float(p), _ptr(seed), salt,
+              int(channel_mode), _stream())
+        return dx, None
+
+
+def dropout(x, p, training=True, channel=False, out=None):
+    """nn.Dropout (channel=False) / nn.Dropout3d (channel=True).  Identity when not training or p == 0 (how the parity
+    tests run: torch's Philox stream cannot be reproduced)."""
+    if not training or p == 0.0:
+        if out is not None:
+            out.copy_(x)
+            return out
+        return x
+    _SALT[0] += 1
+    return _Dropout.apply(x, (p, channel, _SALT[0], out))
+
+
+class _AddSlice(torch.autograd.Function):
+    """out[..., off:off+c_x] += x, in place (residual.py:74-83: the shortcut zero-padded to the wider channel count)."""
+
+    @staticmethod
+    def forward(ctx, out, x, off):
+        x, xp = _as_rows(x)
+        assert _pitched(out)
+        n, d, h, w, c = x.shape
+        view = out[..., off:off + c]
+        _call("b200seg_add", _ptr(view), out.stride(3), _ptr(x), xp, _ptr(view), out.stride(3), n * d * h * w, c,
+              _stream())
+        ctx.mark_dirty(out)
+        ctx.cfg = (off, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        off, c = ctx.cfg
+        return g, g[..., off:off + c], None
+
+
+def add_channel_padded(out, x):
+    """x zero-padded symmetrically to out's channel count, plus out (ResidualBlock 'pad' shortcut)."""
+    diff = out.shape[4] - x.shape[4]
+    if diff == 0:
+        return add(out, x)
+    return _AddSlice.apply(out, x, diff // 2)
+
+
+class _ClassmapUp2Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coarse, fine):
+        coarse = coarse.contiguous().float()
+        n, k, d, h, w = coarse.shape
+        out = torch.empty((n, k, 2 * d, 2 * h, 2 * w), dtype=torch.float32, device=coarse.device)
+        f = fine.contiguous().float() if fine is not None else None
+        _call("b200seg_classmap_up2_add", _ptr(coarse), _ptr(f), _ptr(out), n * k, d, h, w, _stream())
+        ctx.shape = (n, k, d, h, w)
+        ctx.has_fine = fine is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, k, d, h, w = ctx.shape
+        g = g.contiguous().float()
+        dc = torch.empty((n, k, d, h, w), dtype=torch.float32, device=g.device)
+        _call("b200seg_classmap_down2_sum", _ptr(g), _ptr(dc), n * k, d, h, w, _stream())
+        return dc, (g if ctx.has_fine else None)
+
+
+def classmap_up2_add(coarse, fine=None):
+    """nearest x2 up-sampling of an fp32 NCDHW class-score map, plus `fine` (residual_unet3d.py:196-202)."""
+    return _ClassmapUp2Add.apply(coarse, fine)
+
+
+def zeros_ndhwc(n, d, h, w, c, device):
+    return torch.zeros((n, d, h, w, c), dtype=torch.bfloat16, device=device)
+
+
+def repeat_channels(x, times):
+    """x.repeat(1, times, 1, 1, 1) for a channels-last tensor (vnet3d.py:57; the input has 1-2 channels)."""
+    return x.repeat(1, 1, 1, 1, times)
+
+
+def spatial(x):
+    """(n, d, h, w) of an activation tensor."""
+    return tuple(x.shape[:4])
+
+
+def channels(x):
+    return x.shape[4]
+
+
+def device_of(x):
+    return x.device
+
+
+def channel_slice(x, lo, hi):
+    return x[..., lo:hi]
+
+
+class _Concat(torch.autograd.Function):
+    """torch.cat((a, b), channel) as a graph node: free when the two are the halves of one alloc_concat buffer."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[4]
+        return merge_channels(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[..., :ctx.ca], g[..., ctx.ca:]
+
+
+def concat_channels(a, b):
+    return _Concat.apply(a, b)

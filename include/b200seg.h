@@ -132,6 +132,21 @@ int b200seg_upsample2_bwd(const void* dy, int64_t dy_pitch, void* dx, int64_t dx
 int b200seg_add(const void* a, int64_t a_pitch, const void* b, int64_t b_pitch, void* out, int64_t out_pitch,
                 int64_t rows, int c, void* stream);
 
+/* ---- dropout (vnet3d.py:72,90,94 nn.Dropout3d; residual_unet3d.py:18; densevoxelnet3d.py:25-32 nn.Dropout) ------- */
+/* y = keep ? x / (1 - p) : 0 with a counter-based mask hash(*seed, salt, index): calling it again on the upstream
+ * gradient with the same (seed, salt) is the backward pass, no mask is stored.  channel_mode 1 draws once per
+ * (sample, channel) (Dropout3d; rows_per_sample = voxels of one sample), 0 once per element.  seed: device pointer. */
+int b200seg_dropout(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int64_t rows, int64_t rows_per_sample,
+                    int c, float p, const unsigned long long* seed, unsigned long long salt, int channel_mode,
+                    void* stream);
+
+/* ---- fp32 NCDHW class-score maps: deep-supervision sum (residual_unet3d.py:196-202) ----------------------------- */
+/* out[planes][2d][2h][2w] = nearest_x2(coarse[planes][d][h][w]) + fine (fine may be NULL); planes = n * classes. */
+int b200seg_classmap_up2_add(const float* coarse, const float* fine, float* out, int64_t planes, int d, int h, int w,
+                             void* stream);
+/* backward of the up-sampling: dcoarse = sum over each 2x2x2 cell of dfine. */
+int b200seg_classmap_down2_sum(const float* dfine, float* dcoarse, int64_t planes, int d, int h, int w, void* stream);
+
 /* ---- head + loss (unet3d.py:46-48,70; loss_function.py:8-16,102-130,148-185; train.py:115,204) ---------------- */
 /* logits[n][classes][spatial] fp32 (NCDHW, what the module returns) = 1x1x1 conv of NDHWC bf16 features. */
 int b200seg_head_conv1x1_fwd(const void* x, int64_t x_pitch, const float* w, const float* b, float* logits, int n,

@@ -23,7 +23,7 @@ def _code(arg):
         return "g"
     if "*" in a:
         return "p"
-    return {"int": "i", "int64_t": "l", "float": "f", "double": "d", "size_t": "z", "int32_t": "i"}[a.rsplit(" ", 1)[0].strip()]
+    return {"int": "i", "int64_t": "l", "float": "f", "double": "d", "size_t": "z", "int32_t": "i", "unsigned long long": "Q"}[a.rsplit(" ", 1)[0].strip()]
 
 
 def test_build_and_exports_match_header():
