@@ -335,7 +335,8 @@ class _ConvNormAct(torch.autograd.Function):
         else:
             z, coef, count, groups = _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_w,
                                                    residual, out)
-        ctx.save_for_backward(xin, y, coef, weight, gamma, prelu_w, residual)
+        # a plain conv's output is not needed by its own backward (and may be modified in place by a residual sum)
+        ctx.save_for_backward(xin, None if plain else y, coef, weight, gamma, prelu_w, residual)
         ctx.cfg = (g, spec, count, groups, None if x2 is None else x.shape[4], bias is not None)
         return z
 

@@ -37,15 +37,15 @@ def disable_dropout_(module):
 MODEL_CASES = {
     # name: (module path, class, kwargs, input size, batch)
     "vnet_elu": ("models.three_d.vnet3d", "VNet", dict(elu=True, in_channels=1, classes=2), 32, 2),
-    "vnet_prelu": ("models.three_d.vnet3d", "VNet", dict(elu=False, in_channels=1, classes=2), 16, 2),
-    "resunet8": ("models.three_d.residual_unet3d", "UNet", dict(in_channels=1, n_classes=2, base_n_filter=8), 32, 2),
+    "vnet_prelu": ("models.three_d.vnet3d", "VNet", dict(elu=False, in_channels=1, classes=2), 32, 2),
+    "resunet8": ("models.three_d.residual_unet3d", "UNet", dict(in_channels=1, n_classes=2, base_n_filter=8), 64, 1),
     "highres3d": ("models.three_d.highresnet", "HighRes3DNet", dict(in_channels=1, out_channels=2), 24, 1),
     "densevoxel": ("models.three_d.densevoxelnet3d", "DenseVoxelNet", dict(in_channels=1, classes=2), 32, 2),
 }
 
 
 def case_inputs(name, size, batch):
-    g = torch.Generator().manual_seed(hash(name) % 1000 if False else sum(map(ord, name)))
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
     x = torch.randn(batch, 1, size, size, size, generator=g)
     lab = (torch.rand(batch, size, size, size, generator=g) > 0.7).long()
     return x, lab
