@@ -49,7 +49,8 @@ SIGNATURES = {
     "b200seg_loss_reduce": "pp" + "ili" + "pp",
     "b200seg_loss_grad": "pp" + "ili" + "p" + "ffff" + "p" + "pp",
     "b200seg_seg_counts": "ppl" + "pp",
-    "b200seg_window_accumulate_crop": "pp" + "iiiiiii" + "p" + "iii" + "p",
+    "b200seg_window_accumulate_crop": "ppp" + "l" + "iiiiiii" + "p" + "iii" + "p",
+    "b200seg_window_keys_to_labels": "pp" + "l" + "p",
     "b200seg_window_accumulate_average": "pp" + "iiiii" + "pp" + "iii" + "p",
     "b200seg_window_finalize": "pp" + "il" + "pp",
     "b200seg_adam_step": "pppp" + "l" + "fffff" + "i" + "f" + "p",

@@ -306,13 +306,18 @@ __global__ void seg_counts_kernel(const uint8_t* __restrict__ gt, const uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------------ sliding window
-__global__ void window_crop_kernel(const uint8_t* __restrict__ patches, const int64_t* __restrict__ loc, int pw,
-                                   int ph, int pd, int ow, int oh, int od, uint8_t* __restrict__ out, int vw, int vh,
-                                   int vd) {
+// Crop mode keeps torchio's semantics where cropped interiors overlap (the extra window at the far border): the patch
+// that comes LATER in sampler order wins.  Every voxel holds a key ((patch id + 1) << 8 | label) and patches are merged
+// with atomicMax, which is order-independent: correct within a batch, across batches and across ranks (all-reduce MAX).
+__global__ void window_crop_kernel(const uint8_t* __restrict__ patches, const int64_t* __restrict__ loc,
+                                   const int64_t* __restrict__ patch_ids, int64_t first_id, int pw, int ph, int pd,
+                                   int ow, int oh, int od, int* __restrict__ keys, int vw, int vh, int vd) {
   const int b = blockIdx.y;
   const int64_t* L = loc + static_cast<int64_t>(b) * 6;
   const int i0 = static_cast<int>(L[0]), j0 = static_cast<int>(L[1]), k0 = static_cast<int>(L[2]);
   const int i1 = static_cast<int>(L[3]), j1 = static_cast<int>(L[4]), k1 = static_cast<int>(L[5]);
+  const int64_t id = patch_ids ? patch_ids[b] : first_id + b;
+  const int keyhi = static_cast<int>((id + 1) << 8);
   // trim overlap/2 from every face that is not on the volume border
   const int li = i0 > 0 ? ow / 2 : 0, lj = j0 > 0 ? oh / 2 : 0, lk = k0 > 0 ? od / 2 : 0;
   const int hi = i1 < vw ? ow / 2 : 0, hj = j1 < vh ? oh / 2 : 0, hk = k1 < vd ? od / 2 : 0;
@@ -323,8 +328,14 @@ __global__ void window_crop_kernel(const uint8_t* __restrict__ patches, const in
     const int j = static_cast<int>((t / pd) % ph);
     const int i = static_cast<int>(t / (static_cast<int64_t>(pd) * ph));
     if (i < li || i >= pw - hi || j < lj || j >= ph - hj || k < lk || k >= pd - hk) continue;
-    out[(static_cast<int64_t>(i0 + i) * vh + (j0 + j)) * vd + (k0 + k)] = patches[b * pvox + t];
+    atomicMax(&keys[(static_cast<int64_t>(i0 + i) * vh + (j0 + j)) * vd + (k0 + k)], keyhi | patches[b * pvox + t]);
   }
+}
+
+__global__ void window_keys_to_labels_kernel(const int* __restrict__ keys, uint8_t* __restrict__ labels, int64_t voxels) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < voxels;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    labels[v] = static_cast<uint8_t>(keys[v] & 255);
 }
 
 __global__ void window_avg_kernel(const float* __restrict__ patches, const int64_t* __restrict__ loc, int c, int pw,
@@ -444,14 +455,23 @@ int b200seg_seg_counts(const uint8_t* gt, const uint8_t* pred, int64_t numel, un
   return 0;
 }
 
-int b200seg_window_accumulate_crop(const uint8_t* patches, const int64_t* locations, int batch, int pw, int ph, int pd,
-                                   int ow, int oh, int od, uint8_t* out, int vw, int vh, int vd, void* stream) {
-  B200_CHECK_ARG(patches && locations && out && batch > 0 && pw > 0 && ph > 0 && pd > 0, "window_crop: bad arguments");
+int b200seg_window_accumulate_crop(const uint8_t* patches, const int64_t* locations, const int64_t* patch_ids,
+                                   int64_t first_id, int batch, int pw, int ph, int pd, int ow, int oh, int od,
+                                   int32_t* keys, int vw, int vh, int vd, void* stream) {
+  B200_CHECK_ARG(patches && locations && keys && batch > 0 && pw > 0 && ph > 0 && pd > 0, "window_crop: bad arguments");
   B200_CHECK_ARG(ow % 2 == 0 && oh % 2 == 0 && od % 2 == 0, "window_crop: overlap must be even");
+  B200_CHECK_ARG(first_id >= 0 && first_id + batch < (1 << 23), "window_crop: patch ids must fit 23 bits");
   dim3 grid(grid_for(static_cast<int64_t>(pw) * ph * pd, 256, kNumSMs * 4), batch);
-  window_crop_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(patches, locations, pw, ph, pd, ow, oh, od,
-                                                                          out, vw, vh, vd);
+  window_crop_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(patches, locations, patch_ids, first_id, pw, ph,
+                                                                          pd, ow, oh, od, keys, vw, vh, vd);
   B200_CHECK_LAUNCH("window_crop");
+  return 0;
+}
+
+int b200seg_window_keys_to_labels(const int32_t* keys, uint8_t* labels, int64_t voxels, void* stream) {
+  B200_CHECK_ARG(keys && labels && voxels > 0, "window_keys_to_labels: bad arguments");
+  window_keys_to_labels_kernel<<<grid_for(voxels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, labels, voxels);
+  B200_CHECK_LAUNCH("window_keys_to_labels");
   return 0;
 }
 

@@ -27,6 +27,8 @@ class TrainStep:
 
     # the reference's loop body, eager
     def _body(self, x, y):
+        for seed in F._SEEDS.values():    # fresh dropout masks every step (device-side counter: graph-replay safe)
+            seed.add_(1)
         self.optimizer.zero_grad()
         out = self.model(x)
         loss = self.criterion(out, y)

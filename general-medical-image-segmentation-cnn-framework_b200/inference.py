@@ -57,9 +57,13 @@ class GridAggregator:
         if overlap_mode not in ("crop", "average"):
             raise ValueError("overlap_mode must be 'crop' or 'average'")
         self.sampler, self.mode, self.device = sampler, overlap_mode, torch.device(device)
-        self.out = self.count = None
+        self.out = self.count = self.keys = None
+        self._added = 0
 
-    def add_batch(self, batch, locations):
+    def add_batch(self, batch, locations, patch_ids=None):
+        """batch: [B, C, pw, ph, pd] (labels for 'crop', class scores for 'average'); locations: [B, 6] int64.
+        patch_ids: position of each patch in sampler order (defaults to the order of the add_batch calls); needed when
+        a rank only sees a share of the patches, so that overlapping interiors resolve as in a sequential run."""
         vw, vh, vd = self.sampler.spatial_shape
         ow, oh, od = self.sampler.patch_overlap
         locations = locations.to(self.device, torch.int64).contiguous()
@@ -68,10 +72,11 @@ class GridAggregator:
             if c != 1:
                 raise ValueError("crop mode stitches single-channel label maps")
             patches = batch.to(self.device).to(torch.uint8).contiguous()
-            if self.out is None:
-                self.out = torch.zeros((1, vw, vh, vd), dtype=torch.uint8, device=self.device)
-            _call("b200seg_window_accumulate_crop", _ptr(patches), _ptr(locations), b, pw, ph, pd, ow, oh, od,
-                  _ptr(self.out), vw, vh, vd, _stream())
+            if self.keys is None:
+                self.keys = torch.zeros((vw, vh, vd), dtype=torch.int32, device=self.device)
+            ids = patch_ids.to(self.device, torch.int64).contiguous() if patch_ids is not None else None
+            _call("b200seg_window_accumulate_crop", _ptr(patches), _ptr(locations), _ptr(ids), self._added, b, pw, ph, pd,
+                  ow, oh, od, _ptr(self.keys), vw, vh, vd, _stream())
         else:
             patches = batch.to(self.device).float().contiguous()
             if self.out is None:
@@ -79,13 +84,58 @@ class GridAggregator:
                 self.count = torch.zeros((vw, vh, vd), dtype=torch.float32, device=self.device)
             _call("b200seg_window_accumulate_average", _ptr(patches), _ptr(locations), b, c, pw, ph, pd, _ptr(self.out),
                   _ptr(self.count), vw, vh, vd, _stream())
+        self._added += b
+
+    def all_reduce(self, group=None):
+        """Merge the volumes of ranks that each aggregated a share of the patches (parallel.shard_patches)."""
+        from . import parallel
+        if self.mode == "crop":
+            if self.keys is not None:
+                parallel.reduce_volume(self.keys, group, op="max")
+        elif self.out is not None:
+            parallel.reduce_volume(self.out, group)
+            parallel.reduce_volume(self.count, group)
 
     def get_output_tensor(self, return_labels=False):
         """[C, W, H, D].  Average mode divides by the visit count (and can also return the arg-max label map)."""
         if self.mode == "crop":
-            return self.out
+            labels = torch.empty(self.keys.shape, dtype=torch.uint8, device=self.device)
+            _call("b200seg_window_keys_to_labels", _ptr(self.keys), _ptr(labels), self.keys.numel(), _stream())
+            return labels.unsqueeze(0)
         acc = self.out.clone()
         labels = torch.empty(self.count.shape, dtype=torch.uint8, device=self.device) if return_labels else None
         _call("b200seg_window_finalize", _ptr(acc), _ptr(self.count), acc.shape[0], self.count.numel(), _ptr(labels),
               _stream())
         return (acc, labels.unsqueeze(0)) if return_labels else acc
+
+
+@torch.no_grad()
+def sliding_window_predict(model, volume, patch_size, patch_overlap, batch_size=16, overlap_mode="crop", group=None):
+    """predict.py:98-147 for one volume: grid patches -> batched eval-mode forward -> argmax -> stitched label volume.
+
+    volume: [C, W, H, D] tensor (host or device).  Returns uint8 labels [1, W, H, D] on the device ('crop': stitched
+    argmax patches, the reference's behaviour; 'average': argmax of the overlap-averaged class scores).  Under
+    torch.distributed every rank runs a round-robin share of the patches and the volumes are merged with one all-reduce
+    (the reference shards the same way, predict.py:111, but never merges)."""
+    from . import parallel
+    dev = next(model.parameters()).device
+    sampler = GridSampler(volume, patch_size, patch_overlap)
+    agg = GridAggregator(sampler, overlap_mode, device=dev)
+    mine = parallel.shard_patches(len(sampler), group)
+    vol = volume.to(dev, non_blocking=True)
+    was_training = model.training
+    model.eval()
+    for s in range(0, len(mine), batch_size):
+        ids = torch.tensor(mine[s:s + batch_size], dtype=torch.int64)
+        locs = sampler.locations[ids]
+        x = torch.stack([vol[..., a:d, b:e, c:f] for a, b, c, d, e, f in locs.tolist()]).float()
+        logits = model(x)
+        if overlap_mode == "crop":
+            agg.add_batch(F.argmax_labels(logits), locs, patch_ids=ids)
+        else:
+            agg.add_batch(logits, locs)
+    agg.all_reduce(group)
+    model.train(was_training)
+    if overlap_mode == "crop":
+        return agg.get_output_tensor()
+    return agg.get_output_tensor(return_labels=True)[1]

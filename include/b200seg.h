@@ -174,11 +174,17 @@ int b200seg_seg_counts(const uint8_t* gt, const uint8_t* pred, int64_t numel, un
                        void* stream);
 
 /* ---- sliding-window aggregation (predict.py:100-147; torchio GridAggregator) ----------------------------------- */
-/* crop mode: overwrite the cropped interior of each patch into out (uint8 labels [W][H][D] of the volume).
+/* crop mode (torchio's default, the one predict.py uses): each patch contributes its interior, i.e. the patch minus
+ * overlap/2 on every face that is not on the volume border; where two interiors still overlap the patch that comes later
+ * in sampler order wins.  keys: int32 [W][H][D], zero-initialised by the caller; every voxel receives
+ * max(key, (patch id + 1) << 8 | label) -- order-independent, so batches, streams and ranks (all-reduce MAX) can add in
+ * any order.  patch ids: patch_ids[b] (device int64) when non-NULL, else first_id + b.
  * patches: uint8 [batch][pw][ph][pd]; locations: int64 [batch][6] (i0,j0,k0,i1,j1,k1) on the device. */
-int b200seg_window_accumulate_crop(const uint8_t* patches, const int64_t* locations, int batch, int pw, int ph,
-                                   int pd, int ow, int oh, int od, uint8_t* out, int vw, int vh, int vd,
-                                   void* stream);
+int b200seg_window_accumulate_crop(const uint8_t* patches, const int64_t* locations, const int64_t* patch_ids,
+                                   int64_t first_id, int batch, int pw, int ph, int pd, int ow, int oh, int od,
+                                   int32_t* keys, int vw, int vh, int vd, void* stream);
+/* labels[v] = keys[v] & 255 (voxels no patch covered stay 0). */
+int b200seg_window_keys_to_labels(const int32_t* keys, uint8_t* labels, int64_t voxels, void* stream);
 /* average mode: sum fp32 patches [batch][c][pw][ph][pd] into acc [c][W][H][D] and count [W][H][D]. */
 int b200seg_window_accumulate_average(const float* patches, const int64_t* locations, int batch, int c, int pw,
                                       int ph, int pd, float* acc, float* count, int vw, int vh, int vd,

@@ -396,6 +396,24 @@ def test_sliding_window_aggregator_bit_exact():
         out = agg.get_output_tensor().cpu().numpy()
         assert np.array_equal(out.astype(np.int64), oagg.get_output_tensor().astype(np.int64))
         assert np.array_equal(out.astype(np.int64), vol)
+    # patches that DISAGREE where their cropped interiors overlap: the later patch must win, whatever the batching and
+    # the order in which a rank's share is added (torchio semantics, restated by the oracle)
+    shape, patch, ov = (40, 36, 50), (16, 16, 16), (4, 4, 6)
+    sampler = GridSampler(shape, patch, ov)
+    locs = sampler.locations
+    patches = torch.from_numpy(rng.integers(0, 5, size=(len(locs), 1) + patch).astype(np.uint8))
+    oagg = owindow.Aggregator(shape, ov, "crop")
+    oagg.add_batch(patches.numpy(), locs.numpy())
+    want = oagg.get_output_tensor().astype(np.int64)
+    agg = GridAggregator(sampler, "crop", device=DEV)
+    agg.add_batch(patches.to(DEV), locs)                         # one batch: overlapping writers inside one launch
+    assert np.array_equal(agg.get_output_tensor().cpu().numpy().astype(np.int64), want)
+    agg = GridAggregator(sampler, "crop", device=DEV)
+    perm = torch.from_numpy(rng.permutation(len(locs)))
+    for s in range(0, len(locs), 5):                             # shuffled shares with explicit patch ids
+        ids = perm[s:s + 5]
+        agg.add_batch(patches[ids].to(DEV), locs[ids], patch_ids=ids)
+    assert np.array_equal(agg.get_output_tensor().cpu().numpy().astype(np.int64), want)
 
 
 @pytest.mark.gpu
