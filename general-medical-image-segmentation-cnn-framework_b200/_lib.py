@@ -53,11 +53,15 @@ SIGNATURES = {
     "b200seg_window_keys_to_labels": "pp" + "l" + "p",
     "b200seg_window_accumulate_average": "pp" + "iiiii" + "pp" + "iii" + "p",
     "b200seg_window_finalize": "pp" + "il" + "pp",
+    "b200seg_p2p_alloc": "pp",
+    "b200seg_p2p_open": "pp",
+    "b200seg_p2p_close": "pi",
+    "b200seg_p2p_allreduce": "pi" + "p" + "ii" + "p" + "i" + "d" + "pppp" + "ff" + "i" + "p" + "p",
     "b200seg_adam_step": "pppp" + "l" + "fffff" + "i" + "f" + "p",
     "b200seg_adam_step_dev": "pppp" + "l" + "pp" + "p",
 }
 STRING_FUNCS = ("b200seg_version", "b200seg_last_error")
-SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g"}
+SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g", "b200seg_p2p_mailbox_bytes": ""}
 INT64_FUNCS = {"b200seg_umma_launch_count": ""}
 
 

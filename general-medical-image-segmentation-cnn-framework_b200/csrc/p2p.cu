@@ -1,0 +1,172 @@
+// Small all-reduce over NVLink peer memory, fused with the batch-norm statistics finalisation.
+//
+// SynchronizedBatchNorm needs, per layer and per step, the sum over ranks of 2*C+1 floats (sum, sum of squares, element
+// count) in the forward pass and of 2*C floats in the backward pass: 72 latency-bound exchanges per U-Net step, on the
+// critical path (the reference does them with Python threads, queues and two coalesced device copies per layer:
+// models/sync_batchnorm/batchnorm.py:90-111, comm.py:56-137).  An NCCL call per exchange costs a launch plus a
+// protocol round trip, and NCCL collectives cannot be captured into the training step's CUDA graph on this stack.
+// Here every rank owns a mailbox in its own HBM that its peers map through CUDA IPC.  One single-CTA kernel
+//   1. stores its vector into slot [seq % SLOTS][rank] of EVERY peer's mailbox (plain st.global over NVLink),
+//   2. fences system-wide and publishes flag[slot][rank] = seq in every peer's mailbox,
+//   3. spins (bounded) until its own mailbox shows seq from every rank, sums the world vectors in rank order -- the
+//      same order everywhere, so all ranks obtain bit-identical results -- and
+//   4. optionally finalises the statistics in the same launch (mean, inv_std, fused scale / shift, running stats).
+// `seq` lives in device memory and is advanced by the kernel, so a captured launch replays correctly.  A rank can be at
+// most one exchange ahead of the slowest one (it cannot finish exchange k+1 before everybody has written it, which they
+// do only after finishing k), hence SLOTS >= 2 makes slot reuse safe; 4 are used.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kP2PSlots = 4;
+constexpr int kP2PMaxWorld = 8;
+constexpr int kP2PMaxFloats = 2112;   // 2 * 1024 channels + count, padded
+
+struct P2PMailbox {
+  float data[kP2PSlots][kP2PMaxWorld][kP2PMaxFloats];
+  unsigned int flags[kP2PSlots][kP2PMaxWorld];
+};
+
+struct P2PPeers {
+  P2PMailbox* box[kP2PMaxWorld];
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// vec: n floats, reduced in place.  finalize != 0: vec = {sum[C], sumsq[C], count} and coef / running stats are produced
+// exactly like norm_finalize_kernel does from the reduced sums.
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(float* __restrict__ vec, int n, P2PPeers peers, int rank,
+                                                            int world, unsigned int* __restrict__ seq_ptr, int finalize,
+                                                            float local_count, int C, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                            float* __restrict__ running_var, float momentum, float eps,
+                                                            int clamp_eps, float* __restrict__ coef) {
+  const unsigned int seq = *seq_ptr + 1;
+  const int slot = seq % kP2PSlots;
+  if (finalize) {   // the element count travels with the sums (sum_size in batchnorm.py:58-62)
+    if (threadIdx.x == 0) vec[2 * C] = local_count;
+    __syncthreads();
+  }
+  // 1. scatter my vector into every rank's mailbox (my own included)
+  for (int r = 0; r < world; ++r) {
+    float* dst = peers.box[r]->data[slot][rank];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vec[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish
+  if (threadIdx.x < world) st_release_sys(&peers.box[threadIdx.x]->flags[slot][rank], seq);
+  // 3. wait for everybody
+  P2PMailbox* mine = peers.box[rank];
+  if (threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->flags[slot][threadIdx.x]) < seq) {
+      if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a peer never arrived (mismatched call sequence)
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < world; ++r) s += __ldcv(&mine->data[slot][r][i]);
+    vec[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *seq_ptr = seq;
+  if (!finalize) return;
+  // 4. statistics -> normalisation constants (same arithmetic as norm_finalize_kernel, elementwise.cu)
+  const double count = vec[2 * C];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s = vec[c], q = vec[C + c];
+    const double mean = s / count;
+    double var = (q - s * mean) / count;  // batchnorm.py:116-120: sumvar = ssum - sum*mean
+    if (var < 0) var = 0;
+    const double inv_std = clamp_eps ? 1.0 / sqrt(var < eps ? static_cast<double>(eps) : var) : 1.0 / sqrt(var + eps);
+    if (running_mean != nullptr) {
+      const double unbiased = count > 1 ? var * count / (count - 1) : var;
+      running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+    const double ga = gamma ? gamma[c] : 1.0;
+    const double be = beta ? beta[c] : 0.0;
+    coef[0 * C + c] = static_cast<float>(mean);
+    coef[1 * C + c] = static_cast<float>(inv_std);
+    coef[2 * C + c] = static_cast<float>(ga * inv_std);
+    coef[3 * C + c] = static_cast<float>(be - mean * ga * inv_std);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200seg_p2p_mailbox_bytes(void) { return sizeof(P2PMailbox); }
+
+int b200seg_p2p_alloc(void** dev_ptr, void* ipc_handle_out) {
+  B200_CHECK_ARG(dev_ptr && ipc_handle_out, "p2p_alloc: bad arguments");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sizeof(P2PMailbox));
+  if (e == cudaSuccess) e = cudaMemset(p, 0, sizeof(P2PMailbox));
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    set_error("p2p_alloc: %s", cudaGetErrorString(e));
+    if (p) cudaFree(p);
+    return B200SEG_ERR_CUDA;
+  }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return 0;
+}
+
+int b200seg_p2p_open(const void* ipc_handle, void** dev_ptr) {
+  B200_CHECK_ARG(ipc_handle && dev_ptr, "p2p_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  const cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    set_error("p2p_open: %s", cudaGetErrorString(e));
+    return B200SEG_ERR_CUDA;
+  }
+  return 0;
+}
+
+int b200seg_p2p_close(void* dev_ptr, int opened) {
+  const cudaError_t e = opened ? cudaIpcCloseMemHandle(dev_ptr) : cudaFree(dev_ptr);
+  if (e != cudaSuccess) {
+    set_error("p2p_close: %s", cudaGetErrorString(e));
+    return B200SEG_ERR_CUDA;
+  }
+  return 0;
+}
+
+int b200seg_p2p_allreduce(float* vec, int n, const void* const* mailboxes, int rank, int world, uint32_t* seq,
+                          int finalize_channels, double local_count, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, float momentum, float eps, int clamp_eps, float* coef, void* stream) {
+  B200_CHECK_ARG(vec && mailboxes && seq && n > 0 && n <= kP2PMaxFloats, "p2p_allreduce: at most %d floats", kP2PMaxFloats);
+  B200_CHECK_ARG(world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, "p2p_allreduce: bad rank / world");
+  B200_CHECK_ARG(finalize_channels == 0 || (coef && n == 2 * finalize_channels + 1), "p2p_allreduce: finalize needs "
+                 "{sum[C], sumsq[C], count} and a coefficient buffer");
+  P2PPeers peers{};
+  for (int r = 0; r < world; ++r) {
+    B200_CHECK_ARG(mailboxes[r] != nullptr, "p2p_allreduce: null mailbox for rank %d", r);
+    peers.box[r] = static_cast<P2PMailbox*>(const_cast<void*>(mailboxes[r]));
+  }
+  p2p_allreduce_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(
+      vec, n, peers, rank, world, seq, finalize_channels > 0, static_cast<float>(local_count), finalize_channels, gamma, beta, running_mean, running_var,
+      momentum, eps, clamp_eps, coef);
+  B200_CHECK_LAUNCH("p2p_allreduce");
+  return 0;
+}
+
+}  // extern "C"

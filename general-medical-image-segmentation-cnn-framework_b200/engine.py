@@ -14,6 +14,7 @@ private memory pool, so the TMA descriptors baked into the captured conv launche
 import torch
 
 from . import functional as F
+from . import parallel
 
 
 class TrainStep:
@@ -25,25 +26,39 @@ class TrainStep:
         self._seen = 0
         self.kernels_per_step = self.umma_per_step = 0   # b200seg kernels inside the captured graph
 
-    # the reference's loop body, eager
-    def _body(self, x, y):
+    # the reference's loop body: forward + loss + backward (captured) ...
+    def _fwd_bwd(self, x, y):
         for seed in F._SEEDS.values():    # fresh dropout masks every step (device-side counter: graph-replay safe)
             seed.add_(1)
         self.optimizer.zero_grad()
         out = self.model(x)
         loss = self.criterion(out, y)
         loss.backward()
+        return loss.detach(), out.detach()
+
+    # ... + gradient all-reduce + Adam.  On one GPU everything is captured.  On several, the SyncBatchNorm exchanges run
+    # over NVLink peer memory inside the graph (csrc/p2p.cu) while the NCCL gradient all-reduce -- which cannot be
+    # captured on this stack -- and the Adam launch follow the replay eagerly.
+    def _update(self):
         scale = self.optimizer.all_reduce_grads()
         self.optimizer.step(grad_scale=scale)
-        return loss.detach(), out.detach()
+
+    def _body(self, x, y):
+        res = self._fwd_bwd(x, y)
+        self._update()
+        return res
 
     def _capture(self, x, y):
         self._x, self._y = x.clone(), y.clone()
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         k0, u0 = F.launches(), F.umma_launch_count()
+        self._split = parallel.is_parallel()
+        reducer = getattr(self.optimizer, "reducer", None)
+        if self._split and reducer is not None:
+            reducer.enabled = False           # no NCCL launches from autograd hooks while capturing / replaying
         with torch.cuda.graph(self.graph):
-            self._loss, self._out = self._body(self._x, self._y)
+            self._loss, self._out = (self._fwd_bwd if self._split else self._body)(self._x, self._y)
         self.kernels_per_step, self.umma_per_step = F.launches() - k0, F.umma_launch_count() - u0
         torch.cuda.synchronize()
 
@@ -53,6 +68,8 @@ class TrainStep:
         if not self.use_graph:
             return self._body(x, y)
         if self.graph is None:
+            if not parallel.graph_safe():
+                return self._body(x, y)           # SyncBatchNorm over NCCL: stay eager
             if self._seen < self.warmup:          # eager steps first: lazy initialisation must not be captured
                 self._seen += 1
                 return self._body(x, y)
@@ -62,4 +79,6 @@ class TrainStep:
         self._x.copy_(x, non_blocking=True)
         self._y.copy_(y, non_blocking=True)
         self.graph.replay()
+        if self._split:
+            self._update()
         return self._loss, self._out

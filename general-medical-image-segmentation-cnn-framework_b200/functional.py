@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 from ._lib import ConvGeom, call
-from .parallel import all_reduce_stats, is_parallel
+from .parallel import all_reduce_stats, is_parallel, peer_exchange
 
 ACT = {"none": 0, None: 0, "relu": 1, "leaky_relu": 2, "elu": 3, "prelu": 4}
 
@@ -147,7 +147,8 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
         y = y_out
     else:
         y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
-    stats = torch.zeros((1, 2, cout), dtype=torch.float32, device=x.device) if want_stats else None
+    # flat {sum[C], sumsq[C], (count)}: the spare float lets the cross-GPU exchange carry the element count
+    stats = torch.zeros(2 * cout + 1, dtype=torch.float32, device=x.device) if want_stats else None
     wp = pack_conv_weight(weight.detach())
     b = bias.detach().float() if bias is not None else None
     _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), y.stride(3), _ptr(stats),
@@ -176,12 +177,17 @@ def conv3d_wgrad_raw(g, x, dy, weight_shape):
     return gw
 
 
-def channel_stats(x, groups=1):
-    """[groups][2][C] fp32 sums / sums of squares over the voxels of each group (group = sample for instance norm)."""
+def channel_stats(x, groups=1, spare=0):
+    """[groups][2][C] fp32 sums / sums of squares over the voxels of each group (group = sample for instance norm).
+    spare=1 (groups == 1 only) returns the flat {sum[C], sumsq[C], spare} form the cross-GPU exchange uses."""
     x, xp = _as_rows(x)
     n, d, h, w, c = x.shape
     rows = n * d * h * w // groups
-    stats = torch.zeros((groups, 2, c), dtype=torch.float32, device=x.device)
+    if spare:
+        assert groups == 1
+        stats = torch.zeros(2 * c + spare, dtype=torch.float32, device=x.device)
+    else:
+        stats = torch.zeros((groups, 2, c), dtype=torch.float32, device=x.device)
     _call("b200seg_channel_stats", _ptr(x), xp, rows, groups, c, _ptr(stats), _stream())
     return stats
 
@@ -224,11 +230,18 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
     elif spec.kind == "batch":
         if spec.training:
             if stats is None:
-                stats = channel_stats(y, 1)
-            if spec.sync:
-                count *= all_reduce_stats(stats, spec.process_group)  # {sum, sumsq}: sync_batchnorm/batchnorm.py:102
-            coef = _norm_coef(stats, count, 1, c, gamma, beta, running_mean, running_var, spec.momentum, spec.eps,
-                              spec.clamp_eps, y.device)
+                stats = channel_stats(y, 1, spare=1)
+            px = peer_exchange(spec.process_group) if (spec.sync and is_parallel(spec.process_group)) else None
+            if px is not None and 2 * c + 1 <= 2112:
+                # one kernel: NVLink exchange of {sum, sumsq, count} + _compute_mean_std (batchnorm.py:102-125)
+                coef = px.reduce_and_finalize(stats, count, c, gamma, beta, running_mean, running_var, spec.momentum,
+                                              spec.eps, spec.clamp_eps)
+                count *= px.world      # equal per-rank batches (what DDP + DistributedSampler guarantee)
+            else:
+                if spec.sync:
+                    count *= all_reduce_stats(stats[:2 * c], spec.process_group)
+                coef = _norm_coef(stats, count, 1, c, gamma, beta, running_mean, running_var, spec.momentum,
+                                  spec.eps, spec.clamp_eps, y.device)
         else:
             coef = _eval_coef(gamma, beta, running_mean, running_var, spec.eps, c, y.device)
     if out is None:

@@ -49,7 +49,7 @@ class FusedAdam:
     def all_reduce_grads(self, group=None):
         """Data-parallel gradient averaging (what DDP does inside accelerator.backward, train.py:211).  Returns the
         factor the summed gradients still have to be scaled by (folded into the Adam kernel)."""
-        if getattr(self, "reducer", None) is not None:
+        if getattr(self, "reducer", None) is not None and self.reducer.enabled:
             return self.reducer.finish()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.grad_arena, group=group)

@@ -60,11 +60,89 @@ def broadcast_parameters(module, src=0, group=None):
         dist.broadcast(t.data, src, group=group)
 
 
+class PeerExchange:
+    """Small all-reduce over NVLink peer memory (csrc/p2p.cu): one mailbox per rank, mapped by its peers through CUDA
+    IPC; each exchange is a single one-CTA kernel per rank, capturable in the training step's CUDA graph, optionally
+    fused with the batch-norm finalisation.  Replaces the master/slave pipes of sync_batchnorm/comm.py."""
+
+    def __init__(self, group=None):
+        import ctypes
+        from ._lib import call
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        call("b200seg_p2p_alloc", ctypes.byref(own), handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(own.value)
+            else:
+                p = ctypes.c_void_p()
+                call("b200seg_p2p_open", ctypes.create_string_buffer(h, 64), ctypes.byref(p))
+                ptrs.append(p.value)
+        self._ptrs = ptrs
+        self.boxes = (ctypes.c_void_p * self.world)(*ptrs)
+        self.seq = torch.zeros(1, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        dist.barrier(group=group)     # every mailbox is mapped (and zeroed) before anybody's first exchange
+
+    def _call(self, vec, n, finalize_c=0, count=0.0, gamma=None, beta=None, running_mean=None, running_var=None,
+              momentum=0.1, eps=1e-5, clamp_eps=False, coef=None):
+        import ctypes
+        from .functional import _call, _ptr, _stream
+        _call("b200seg_p2p_allreduce", _ptr(vec), int(n), self.boxes, self.rank, self.world, _ptr(self.seq),
+              int(finalize_c), float(count), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+              float(momentum), float(eps), int(clamp_eps), _ptr(coef), _stream())
+
+    def all_reduce_(self, vec):
+        """In-place sum over ranks of a contiguous fp32 vector of at most 2112 elements."""
+        assert vec.is_contiguous() and vec.dtype == torch.float32
+        self._call(vec, vec.numel())
+        return vec
+
+    def reduce_and_finalize(self, stats, count, c, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps):
+        """stats: flat fp32 [2c + 1] whose first 2c entries are this rank's {sum, sumsq}.  Returns coef [1][4][c]."""
+        coef = torch.empty((1, 4, c), dtype=torch.float32, device=stats.device)
+        self._call(stats, 2 * c + 1, c, count, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps, coef)
+        return coef
+
+
+_PEER = {}
+
+
+def peer_exchange(group=None):
+    """The process group's PeerExchange (created on first use), or None when the NVLink path is unavailable / disabled
+    (B200SEG_SYNCBN=nccl) -- callers then fall back to an NCCL all-reduce, which cannot be graph-captured here."""
+    if not is_parallel(group) or not torch.cuda.is_available() or os.environ.get("B200SEG_SYNCBN", "p2p") == "nccl":
+        return None
+    key = id(group) if group is not None else 0
+    if key not in _PEER:
+        try:
+            _PEER[key] = PeerExchange(group)
+        except Exception as e:     # no peer access between the GPUs of this box
+            import warnings
+            warnings.warn("b200seg: NVLink peer exchange unavailable (%s); SyncBatchNorm falls back to NCCL" % e)
+            _PEER[key] = None
+    return _PEER[key]
+
+
+def graph_safe(group=None):
+    """True when every collective inside the training step can be captured into a CUDA graph."""
+    return not is_parallel(group) or peer_exchange(group) is not None
+
+
 def all_reduce_stats(stats, group=None):
     """Sum a small fp32 statistics tensor over ranks, in place, in stream order.  Returns the number of ranks."""
     if not is_parallel(group):
         return 1
-    dist.all_reduce(stats, group=group)
+    px = peer_exchange(group) if stats.is_cuda else None
+    if px is not None and stats.numel() <= 2112 and stats.is_contiguous():
+        px.all_reduce_(stats)
+    else:
+        dist.all_reduce(stats, group=group)
     return dist.get_world_size(group)
 
 

@@ -192,6 +192,26 @@ int b200seg_window_accumulate_average(const float* patches, const int64_t* locat
 /* acc /= max(count,1), then argmax over c -> labels uint8 [W][H][D] (labels may be NULL). */
 int b200seg_window_finalize(float* acc, const float* count, int c, int64_t voxels, uint8_t* labels, void* stream);
 
+/* ---- cross-GPU exchange over NVLink peer memory (models/sync_batchnorm/batchnorm.py:90-111, comm.py:56-137) ------ */
+/* Every rank allocates one mailbox (b200seg_p2p_alloc: cudaMalloc + CUDA-IPC handle, 64 bytes), ships the handle to its
+ * peers (any side channel; the Python layer uses torch.distributed.all_gather_object) and maps theirs
+ * (b200seg_p2p_open).  b200seg_p2p_close(ptr, opened): opened=1 unmaps a peer's mailbox, 0 frees one's own. */
+size_t b200seg_p2p_mailbox_bytes(void);
+int b200seg_p2p_alloc(void** dev_ptr, void* ipc_handle_out);
+int b200seg_p2p_open(const void* ipc_handle, void** dev_ptr);
+int b200seg_p2p_close(void* dev_ptr, int opened);
+/* In-place sum over `world` ranks of vec[n] (n <= 2112 fp32) in ONE single-CTA launch per rank: store into every
+ * peer's mailbox, system fence, flag, bounded spin for all peers, sum in rank order (bit-identical on every rank).
+ * mailboxes: HOST array of `world` device pointers (mailboxes[rank] = own).  seq: device uint32 call counter advanced
+ * by the kernel (all ranks must issue the same sequence of calls; graph-replay safe).
+ * finalize_channels = C > 0: vec = {sum[C], sumsq[C], count} (the kernel stores local_count into vec[2C] first, so the
+ * element count travels with the sums like sum_size in batchnorm.py:58-62); after the reduction the same launch writes
+ * coef[4][C] = {mean, inv_std, scale, shift} and updates the running statistics exactly like b200seg_norm_finalize
+ * (this is _compute_mean_std, batchnorm.py:113-125, executed identically on every rank instead of on a master). */
+int b200seg_p2p_allreduce(float* vec, int n, const void* const* mailboxes, int rank, int world, uint32_t* seq,
+                          int finalize_channels, double local_count, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, float momentum, float eps, int clamp_eps, float* coef, void* stream);
+
 /* ---- optimiser (train.py:109,214) ------------------------------------------------------------------------------- */
 /* Fused Adam over a flat fp32 parameter arena (torch.optim.Adam semantics, no amsgrad, weight_decay as L2). */
 int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
