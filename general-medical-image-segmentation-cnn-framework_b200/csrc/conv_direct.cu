@@ -38,9 +38,11 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, float* _
     const int t = static_cast<int>(i % k3);
     const int ci = static_cast<int>((i / k3) % cin_cnt);
     const int co = static_cast<int>(i / (static_cast<int64_t>(k3) * cin_cnt));
-    const float v = dwp[(static_cast<int64_t>(t) * cin_cnt + ci) * cout + co];
+    float* srcp = const_cast<float*>(dwp) + (static_cast<int64_t>(t) * cin_cnt + ci) * cout + co;
+    const float v = *srcp;
+    if (accumulate & 2) *srcp = 0.f;   // read-and-clear: the packed accumulator is ready for its next use
     float* dst = grad + (static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + t;
-    *dst = accumulate ? *dst + v : v;
+    *dst = (accumulate & 1) ? *dst + v : v;
   }
 }
 

@@ -36,6 +36,21 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat
   }
 }
 
+// C == 1: the two layouts coincide, only the element type changes (the model input, train.py:195)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t numel) {
+  const int64_t nvec = numel / 8;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    st8(dst + 8 * i, pack8(t));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < numel - nvec * 8) {
+    const int64_t i = nvec * 8 + threadIdx.x;
+    dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
 __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int c,
                                       int64_t spatial) {
   __shared__ float tile[32][33];
@@ -736,6 +751,13 @@ const char* b200seg_last_error(void) { return b200::get_error(); }
 
 int b200seg_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int n, int c, int64_t spatial, void* stream) {
   B200_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "ncdhw_to_ndhwc: bad arguments");
+  if (c == 1 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int64_t numel = static_cast<int64_t>(n) * spatial;
+    f32_to_bf16_kernel<<<grid_for(numel / 8 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<__nv_bfloat16*>(dst), numel);
+    B200_CHECK_LAUNCH("ncdhw_to_ndhwc");
+    return 0;
+  }
   dim3 grid(static_cast<unsigned>((spatial + 31) / 32), (c + 31) / 32, n), block(32, 8);
   ncdhw_to_ndhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), c, spatial);

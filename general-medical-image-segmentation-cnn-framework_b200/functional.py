@@ -165,13 +165,33 @@ def conv3d_dgrad_raw(g, dy, weight):
     return dx
 
 
-def conv3d_wgrad_raw(g, x, dy, weight_shape):
+def _grad_target(param):
+    """(packed fp32 accumulator, gradient tensor) of a parameter managed by optim.FusedAdam, else (None, None).
+    The accumulator is a slice of an arena that FusedAdam.zero_grad clears together with the gradients, the gradient is
+    the parameter's view into the flat gradient arena: weight gradients then need no zero-fill, no temporary and no
+    autograd accumulation kernel."""
+    if param is None or not getattr(param, "_b200_direct_grad", False) or param.grad is None:
+        return None, None
+    if param._b200_dwp_used[0]:      # second use of a shared weight in one step (residual_unet3d.py:126-128)
+        return None, None
+    param._b200_dwp_used[0] = True   # cleared by FusedAdam.zero_grad together with the accumulator itself
+    return param._b200_dwp, param.grad
+
+
+def conv3d_wgrad_raw(g, x, dy, weight_shape, weight=None):
+    """Returns the weight gradient, or None when it was accumulated straight into weight.grad (FusedAdam arena)."""
     x, xp = _as_rows(x)
     dy, dyp = _as_rows(dy)
     k3 = g.k ** 3
-    dwp = torch.zeros(k3 * g.cin * g.cout, dtype=torch.float32, device=x.device)
+    dwp, grad = _grad_target(weight)
+    direct = dwp is not None
+    if not direct:
+        dwp = torch.zeros(k3 * g.cin * g.cout, dtype=torch.float32, device=x.device)
     _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), None, 0, _stream(),
           work=_conv_flops(g), tag="conv_wgrad")
+    if direct:
+        _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(grad), g.cout, g.cin, g.k, 0, g.cin, 1, _stream())
+        return None
     gw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
     _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(gw), g.cout, g.cin, g.k, 0, g.cin, 0, _stream())
     return gw
@@ -366,9 +386,9 @@ class _ConvNormAct(torch.autograd.Function):
             dy, dres, sums = _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual,
                                             residual is not None and need[7])
             if gamma is not None:
-                dgamma, dbeta = sums[:, 1].sum(0), sums[:, 0].sum(0)
+                dgamma, dbeta = (sums[0, 1], sums[0, 0]) if groups == 1 else (sums[:, 1].sum(0), sums[:, 0].sum(0))
             if prelu_w is not None:
-                dprelu = sums[0, 2].clone()
+                dprelu = sums[0, 2]
         dx = dx2 = dw = db = None
         if need[0] or (split is not None and need[1]):
             dxin = conv3d_dgrad_raw(g, dy, weight)
@@ -377,7 +397,7 @@ class _ConvNormAct(torch.autograd.Function):
             else:
                 dx, dx2 = dxin[..., :split], dxin[..., split:]
         if need[2]:
-            dw = conv3d_wgrad_raw(g, xin, dy, weight.shape)
+            dw = conv3d_wgrad_raw(g, xin, dy, weight.shape, weight)
         if has_bias and need[3]:
             if spec.kind is not None and (spec.training or spec.kind == "instance"):
                 # a bias in front of batch/instance statistics has an analytically zero gradient
@@ -414,9 +434,9 @@ class _NormAct(torch.autograd.Function):
                                         residual is not None and ctx.needs_input_grad[4])
         dgamma = dbeta = dprelu = None
         if gamma is not None:
-            dgamma, dbeta = sums[:, 1].sum(0), sums[:, 0].sum(0)
+            dgamma, dbeta = (sums[0, 1], sums[0, 0]) if groups == 1 else (sums[:, 1].sum(0), sums[:, 0].sum(0))
         if prelu_w is not None:
-            dprelu = sums[0, 2].clone()
+            dprelu = sums[0, 2]
         return dy, dgamma, dbeta, dprelu, dres, None, None, None
 
 
@@ -496,11 +516,17 @@ class _ConvT2(torch.autograd.Function):
             dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=x.device)
             _call("b200seg_convt_k2s2_dgrad", _ptr(dy), dyp, _ptr(wd), _ptr(dx), cin, n, d, h, w, cin, cout, _stream())
         if ctx.needs_input_grad[1]:
-            dwp = torch.zeros(8 * cin * cout, dtype=torch.float32, device=x.device)
+            dwp, grad = _grad_target(weight)
+            direct = dwp is not None
+            if not direct:
+                dwp = torch.zeros(8 * cin * cout, dtype=torch.float32, device=x.device)
             _call("b200seg_convt_k2s2_wgrad", _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), n, d, h, w, cin, cout, _stream())
-            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
             # packed [8][cout_T][cin_T] is the strided conv's [k^3][cin_S][cout_S]: unpack with cout_S=cin_T, cin_S=cout_T
-            _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(dw), cin, cout, 2, 0, cout, 0, _stream())
+            if direct:
+                _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(grad), cin, cout, 2, 0, cout, 1, _stream())
+            else:
+                dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+                _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(dw), cin, cout, 2, 0, cout, 0, _stream())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = channel_stats(dy, 1)[0, 0]
         return dx, dw, db, None

@@ -25,17 +25,28 @@ class FusedAdam:
             total += (p.numel() + 63) // 64 * 64
         self.numel = total
         self.param_arena = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        # gradients and the conv kernels' packed weight-gradient accumulators share one allocation: one memset clears both
+        self._zeroed = torch.zeros(2 * total, dtype=torch.float32, device=dev)
+        self.grad_arena = self._zeroed[:total]
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.dw_arena = self._zeroed[total:]       # see functional._grad_target
+        self._dwp_flags = []
         for p, off in zip(self.params, self.offsets):
             view = self.param_arena[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
             p.grad = self.grad_arena[off:off + p.numel()].view_as(p)
+            if p.dim() == 5:      # Conv3d / ConvTranspose3d weights: backward accumulates straight into p.grad
+                p._b200_dwp = self.dw_arena[off:off + p.numel()]
+                p._b200_dwp_used = [False]
+                p._b200_direct_grad = True
+                self._dwp_flags.append(p._b200_dwp_used)
 
     def zero_grad(self, set_to_none=False):
-        self.grad_arena.zero_()
+        self._zeroed.zero_()
+        for flag in self._dwp_flags:
+            flag[0] = False
         for p, off in zip(self.params, self.offsets):   # autograd accumulates in place into these views
             if p.grad is None or p.grad.data_ptr() != self.grad_arena.data_ptr() + 4 * off:
                 p.grad = self.grad_arena[off:off + p.numel()].view_as(p)

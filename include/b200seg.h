@@ -56,7 +56,9 @@ int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, i
  * [k^3 flipped][cin][cout] bf16 (flip=1).  cin_off/cin_cnt select an input-channel slice (concat-free decoders). */
 int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
                              int dgrad, void* stream);
-/* wgrad result [k^3][cin_cnt][cout] fp32 -> accumulate into torch-layout grad [cout][cin][k^3] fp32 slice. */
+/* wgrad result [k^3][cin_cnt][cout] fp32 -> torch-layout grad [cout][cin][k^3] fp32 slice.  accumulate bit 0: add to
+ * grad_w instead of overwriting; bit 1: clear dw_packed while reading it (a persistent, always-zero accumulator needs no
+ * memset between steps; dw_packed is written in that case despite the const). */
 int b200seg_unpack_conv_wgrad(const float* dw_packed, float* grad_w, int cout, int cin, int k, int cin_off,
                               int cin_cnt, int accumulate, void* stream);
 
