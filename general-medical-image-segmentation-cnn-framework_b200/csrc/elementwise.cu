@@ -131,7 +131,7 @@ __device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __res
       for (int i = 0; i < V; ++i) acc[s][i] = 0.f;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * TY;
     int64_t r = static_cast<int64_t>(blockIdx.x) * TY + threadIdx.y;
-    constexpr int U = NT == 1 ? 4 : 2;   // rows in flight; 4 registers per pending vector
+    constexpr int U = NT == 1 ? 8 : 2;   // rows in flight; 4 registers per pending vector
     for (; r + (U - 1) * stride < rows; r += U * stride) {
       RawVec<V> raw[U][NT];
 #pragma unroll
@@ -259,20 +259,37 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat1
   };
   load_coef(0);
   int64_t row = row0;
-  for (; row + 3 * rstep < rows; row += 4 * rstep) {
-    RawVec<V> ry[4], rr[4];
+  // Without a residual: 6 rows (96 bytes per thread) in flight -- B200 needs ~90 KB outstanding per SM to saturate HBM.
+  // With one: 3 rows of both tensors (the two loops keep the register count of either path below the 85 of 3 CTAs/SM).
+  if (res == nullptr) {
+    for (; row + 5 * rstep < rows; row += 6 * rstep) {
+      RawVec<V> ry[6];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
-      if (res) rr[u] = ld_raw<V>(res + (row + u * rstep) * res_pitch + ch * V);
+      for (int u = 0; u < 6; ++u) ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        float f[V], r[V];
+        cvt_raw<V>(ry[u], f);
+        if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+        one(row + u * rstep, f, r);
+      }
     }
+  } else {
+    for (; row + 2 * rstep < rows; row += 3 * rstep) {
+      RawVec<V> ry[3], rr[3];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[V], r[V];
-      cvt_raw<V>(ry[u], f);
-      if (res) cvt_raw<V>(rr[u], r);
-      if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
-      one(row + u * rstep, f, r);
+      for (int u = 0; u < 3; ++u) {
+        ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
+        rr[u] = ld_raw<V>(res + (row + u * rstep) * res_pitch + ch * V);
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        float f[V], r[V];
+        cvt_raw<V>(ry[u], f);
+        cvt_raw<V>(rr[u], r);
+        if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+        one(row + u * rstep, f, r);
+      }
     }
   }
   for (; row < rows; row += rstep) {
@@ -420,22 +437,41 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_b
   };
   load_coef(0);
   int64_t row = row0;
-  for (; row + rstep < rows; row += 2 * rstep) {
-    RawVec<V> ry[2], rd[2], rr[2];
+  if (res == nullptr) {
+    for (; row + 3 * rstep < rows; row += 4 * rstep) {
+      RawVec<V> ry[4], rd[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
-      rd[u] = ld_raw<V>(dz + (row + u * rstep) * dz_pitch + ch * V);
-      if (res) rr[u] = ld_raw<V>(res + (row + u * rstep) * res_pitch + ch * V);
+      for (int u = 0; u < 4; ++u) {
+        ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
+        rd[u] = ld_raw<V>(dz + (row + u * rstep) * dz_pitch + ch * V);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float fy[V], fd[V], fr[V];
+        cvt_raw<V>(ry[u], fy);
+        cvt_raw<V>(rd[u], fd);
+        if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+        one(row + u * rstep, fy, fd, fr);
+      }
     }
+  } else {
+    for (; row + rstep < rows; row += 2 * rstep) {
+      RawVec<V> ry[2], rd[2], rr[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float fy[V], fd[V], fr[V];
-      cvt_raw<V>(ry[u], fy);
-      cvt_raw<V>(rd[u], fd);
-      if (res) cvt_raw<V>(rr[u], fr);
-      if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
-      one(row + u * rstep, fy, fd, fr);
+      for (int u = 0; u < 2; ++u) {
+        ry[u] = ld_raw<V>(y + (row + u * rstep) * y_pitch + ch * V);
+        rd[u] = ld_raw<V>(dz + (row + u * rstep) * dz_pitch + ch * V);
+        rr[u] = ld_raw<V>(res + (row + u * rstep) * res_pitch + ch * V);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float fy[V], fd[V], fr[V];
+        cvt_raw<V>(ry[u], fy);
+        cvt_raw<V>(rd[u], fd);
+        cvt_raw<V>(rr[u], fr);
+        if (groups > 1) load_coef(static_cast<int>((row + u * rstep) / rows_per_group));
+        one(row + u * rstep, fy, fd, fr);
+      }
     }
   }
   for (; row < rows; row += rstep) {
@@ -797,6 +833,14 @@ static inline int ew_grid(int64_t total_items, int cv) {
   blocks = static_cast<int>((blocks + m - 1) / m * m);
   return blocks;
 }
+// Blocks of a column reduction: every block ends with a shared-memory tree and 2-3 atomics per channel, so a block must
+// own enough rows (>= 32 per thread row) to amortise that -- small tensors get few blocks, not 592 idle ones.
+static inline int reduce_grid(int64_t rows, int ty, int cap) {
+  int64_t b = (rows + static_cast<int64_t>(ty) * 32 - 1) / (static_cast<int64_t>(ty) * 32);
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return static_cast<int>(b);
+}
 static inline dim3 reduce_block(int cv) {
   int tx = 1;
   while (tx < cv && tx < 64) tx <<= 1;
@@ -810,11 +854,11 @@ int b200seg_channel_stats(const void* x, int64_t pitch, int64_t rows_per_group, 
   const auto* xp = static_cast<const __nv_bfloat16*>(x);
   if (vec_ok(c, pitch)) {
     dim3 block = reduce_block(c / 8);
-    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
     channel_stats_kernel<8><<<grid, block, 256 * 16 * sizeof(float), st>>>(xp, pitch, rows_per_group, c, stats);
   } else {
     dim3 block = reduce_block(c);
-    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
     channel_stats_kernel<1><<<grid, block, 256 * 2 * sizeof(float), st>>>(xp, pitch, rows_per_group, c, stats);
   }
   B200_CHECK_LAUNCH("channel_stats");
@@ -867,12 +911,12 @@ int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y,
   // with dprelu the caller passes sums sized [3][c]; the third row is the slope gradient (== dprelu target)
   if (vec_ok(c, dz_pitch, y_pitch, residual ? res_pitch : 0)) {
     dim3 block = reduce_block(c / 8);
-    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
     B200_ACT_DISPATCH(act, norm_act_bwd_reduce_kernel<8, A_><<<grid, block, 256 * 24 * sizeof(float), st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu));
   } else {
     dim3 block = reduce_block(c);
-    dim3 grid(grid_for(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
+    dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
     B200_ACT_DISPATCH(act, norm_act_bwd_reduce_kernel<1, A_><<<grid, block, 256 * 3 * sizeof(float), st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu));
   }
