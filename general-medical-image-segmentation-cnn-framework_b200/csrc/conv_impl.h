@@ -41,6 +41,9 @@ struct UmmaConvArgs {
 extern long long g_umma_launches;
 bool conv_umma_supported(const UmmaConvArgs& a);
 int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st);
+// narrow-output kernel with the kd taps stacked in N and rolling accumulators along d (conv_umma_roll.cu)
+bool conv_umma_roll_supported(const UmmaConvArgs& a);
+int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st);
 // persistent plane-mode kernel (conv_umma_p.cu); conv_umma_run dispatches to it when the geometry allows
 bool conv_umma_plane_supported(const UmmaConvArgs& a);
 int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st);

@@ -528,13 +528,14 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
 }
 
 bool conv_umma_supported(const UmmaConvArgs& a) {
-  if (conv_umma_plane_supported(a)) return true;
+  if (conv_umma_roll_supported(a) || conv_umma_plane_supported(a)) return true;
   UmmaConvParams p;
   size_t smem;
   return plan(a, p, smem);
 }
 
 int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
+  if (conv_umma_roll_supported(a)) return conv_umma_roll_run(a, st);     // narrow outputs: kd taps in N (conv_umma_roll.cu)
   if (conv_umma_plane_supported(a)) return conv_umma_plane_run(a, st);   // persistent kernel (conv_umma_p.cu)
   UmmaConvParams p;
   size_t smem;
