@@ -34,10 +34,16 @@ struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
 
+// 128-bit accesses spelled as uint4: a struct-of-bfloat162 copy is scalarised by nvcc into four 32-bit LDG/STG.
 __device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
-  return *reinterpret_cast<const bf16x8*>(p);
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  bf16x8 v;
+  *reinterpret_cast<uint4*>(&v) = u;
+  return v;
 }
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
 
 __device__ __forceinline__ void unpack8(const bf16x8& v, float (&f)[8]) {
 #pragma unroll
