@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200seg_ncdhw_f32_to_ndhwc_bf16": "ppiilp",
     "b200seg_ndhwc_bf16_to_ncdhw_f32": "ppiilp",
     "b200seg_pack_conv_weight": "ppiiiiiip",
+    "b200seg_pack_weights_batched": "pppip",
     "b200seg_unpack_conv_wgrad": "ppiiiiiip",
     "b200seg_conv3d_fprop": "gplppplppzp",
     "b200seg_conv3d_dgrad": "gplpplpzp",
@@ -35,7 +36,7 @@ SIGNATURES = {
     "b200seg_norm_act_bwd_reduce": "plpl" + "p" + "lii" + "if" + "p" + "pl" + "pp" + "p",
     "b200seg_norm_act_bwd_apply": "plpl" + "pp" + "d" + "lii" + "if" + "p" + "pl" + "pl" + "pl" + "p",
     "b200seg_maxpool2_fwd": "plplp" + "iiiii" + "p",
-    "b200seg_maxpool2_bwd": "plp" + "pl" + "iiiii" + "p",
+    "b200seg_maxpool2_bwd": "plp" + "pl" + "pl" + "iiiii" + "p",
     "b200seg_maxpool2_idx_to_torch": "pp" + "iiiii" + "p",
     "b200seg_upsample2_fwd": "plpl" + "iiiii" + "p",
     "b200seg_upsample2_bwd": "plpl" + "iiiii" + "p",

@@ -28,6 +28,36 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
   }
 }
 
+// Both packs of MANY weight tensors in one launch (blockIdx.y = descriptor): the optimiser calls it once per step over its
+// parameter arena instead of two small launches per convolution.  desc = {src offset (floats), dst offset (bf16 elements),
+// cout, cin, k3, dgrad}.
+struct PackDesc {
+  long long src, dst;
+  int cout, cin, k3, dgrad;
+};
+__global__ void pack_weights_batched_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ packs,
+                                            const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  const float* w = arena + d.src;
+  __nv_bfloat16* p = packs + d.dst;
+  const int64_t total = static_cast<int64_t>(d.k3) * d.cout * d.cin;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int t, co, ci;
+    if (!d.dgrad) {
+      ci = static_cast<int>(i % d.cin);
+      co = static_cast<int>((i / d.cin) % d.cout);
+      t = static_cast<int>(i / (static_cast<int64_t>(d.cin) * d.cout));
+      p[i] = __float2bfloat16(w[(static_cast<int64_t>(co) * d.cin + ci) * d.k3 + t]);
+    } else {
+      co = static_cast<int>(i % d.cout);
+      ci = static_cast<int>((i / d.cout) % d.cin);
+      t = static_cast<int>(i / (static_cast<int64_t>(d.cin) * d.cout));
+      p[i] = __float2bfloat16(w[(static_cast<int64_t>(co) * d.cin + ci) * d.k3 + (d.k3 - 1 - t)]);
+    }
+  }
+}
+
 // dw_packed [t][ci_local][co] fp32 -> grad [co][cin][k3] (+=)
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int cout, int cin,
                                          int k3, int cin_off, int cin_cnt, int accumulate) {
@@ -502,6 +532,16 @@ int conv_direct_wgrad(const ConvGeom& g, const void* x, int64_t x_pitch, const v
 using namespace b200;
 
 extern "C" {
+
+int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, void* stream) {
+  B200_CHECK_ARG(arena && packs && descs && ndesc > 0 && ndesc <= 65535, "pack_weights_batched: bad arguments");
+  static_assert(sizeof(b200::PackDesc) == 32, "descriptor layout is part of the ABI");
+  dim3 grid(96, ndesc);
+  b200::pack_weights_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      arena, static_cast<__nv_bfloat16*>(packs), static_cast<const b200::PackDesc*>(descs));
+  B200_CHECK_LAUNCH("pack_weights_batched");
+  return 0;
+}
 
 int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
                              int dgrad, void* stream) {

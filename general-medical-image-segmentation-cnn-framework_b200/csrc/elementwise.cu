@@ -529,6 +529,7 @@ __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t
 template <int V>
 __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
                                     const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx, int64_t dx_pitch,
+                                    const __nv_bfloat16* __restrict__ addend, int64_t add_pitch,
                                     int n, int d, int h, int w, int C) {
   const int od = d / 2, oh = h / 2, ow = w / 2, cv = C / V;
   const int64_t total = static_cast<int64_t>(n) * od * oh * ow * cv;
@@ -555,6 +556,12 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_
       float o[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) o[j] = (bi[j] == k) ? g[j] : 0.f;
+      if (addend != nullptr) {   // gradient arriving through the skip connection of the same tensor
+        float s[V];
+        load_vec<V>(addend + row * add_pitch + ch * V, s);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] += s[j];
+      }
       store_vec<V>(dx + row * dx_pitch + ch * V, o);
     }
   }
@@ -966,18 +973,21 @@ int b200seg_maxpool2_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitc
   B200_CHECK_LAUNCH("maxpool2_fwd");
   return 0;
 }
-int b200seg_maxpool2_bwd(const void* dy, int64_t dy_pitch, const uint8_t* idx, void* dx, int64_t dx_pitch, int n,
-                         int d, int h, int w, int c, void* stream) {
+int b200seg_maxpool2_bwd(const void* dy, int64_t dy_pitch, const uint8_t* idx, void* dx, int64_t dx_pitch,
+                         const void* addend, int64_t addend_pitch, int n, int d, int h, int w, int c, void* stream) {
   B200_CHECK_ARG(dy && dx && idx && n > 0 && d >= 2 && h >= 2 && w >= 2 && c > 0, "maxpool2_bwd: bad arguments");
   B200_CHECK_ARG(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool2_bwd: odd extents leave uncovered voxels; zero dx first");
   auto st = static_cast<cudaStream_t>(stream);
   const int64_t ov = static_cast<int64_t>(n) * (d / 2) * (h / 2) * (w / 2);
-  if (vec_ok(c, dy_pitch, dx_pitch))
+  const auto* ap = static_cast<const __nv_bfloat16*>(addend);
+  if (vec_ok(c, dy_pitch, dx_pitch, addend ? addend_pitch : 0) && (reinterpret_cast<uintptr_t>(addend) & 15) == 0)
     maxpool2_bwd_kernel<8><<<grid_for(ov * (c / 8), 256), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(dy), dy_pitch, idx, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c);
+        static_cast<const __nv_bfloat16*>(dy), dy_pitch, idx, static_cast<__nv_bfloat16*>(dx), dx_pitch, ap, addend_pitch,
+        n, d, h, w, c);
   else
     maxpool2_bwd_kernel<1><<<grid_for(ov * c, 256), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(dy), dy_pitch, idx, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c);
+        static_cast<const __nv_bfloat16*>(dy), dy_pitch, idx, static_cast<__nv_bfloat16*>(dx), dx_pitch, ap, addend_pitch,
+        n, d, h, w, c);
   B200_CHECK_LAUNCH("maxpool2_bwd");
   return 0;
 }

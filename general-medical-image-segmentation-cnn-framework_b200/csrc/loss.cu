@@ -119,6 +119,77 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x < classes) atomicAdd(&grad_b[threadIdx.x], sgb[threadIdx.x]);
 }
 
+// Fast path of the head backward pass (<= 2 classes, C_in in {16, 32, 64}, vectorisable rows): LPV = C_in / 8 lanes
+// share a voxel, each owning 8 channels (one 128-bit load of x, one 128-bit store of dx), so a warp streams
+// 32 / LPV whole feature rows per step; the 2 x 8 weight-gradient partial sums per lane are folded across the lanes that
+// own the same channels at the very end.
+template <int LPV>
+__global__ void __launch_bounds__(256)
+    head_bwd_vec_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                        const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t dx_pitch,
+                        float* __restrict__ grad_w, float* __restrict__ grad_b, int n, int64_t spatial, int classes) {
+  constexpr int CIN = LPV * 8;
+  __shared__ float sgw[2 * CIN + 2];
+  for (int i = threadIdx.x; i < 2 * CIN + 2; i += blockDim.x) sgw[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPV;                       // which 8-channel group of the voxel
+  const int c0 = sub * 8;
+  float w0[8], w1[8], gw0[8], gw1[8], gb0 = 0.f, gb1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    w0[j] = w[c0 + j];
+    w1[j] = classes > 1 ? w[CIN + c0 + j] : 0.f;
+    gw0[j] = gw1[j] = 0.f;
+  }
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  const int64_t gthread = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nvox_step = static_cast<int64_t>(gridDim.x) * blockDim.x / LPV;
+  for (int64_t v = gthread / LPV; v < total; v += nvox_step) {
+    const int64_t nn = v / spatial, sp = v - nn * spatial;
+    const float d0 = dlogits[(nn * classes) * spatial + sp];
+    const float d1 = classes > 1 ? dlogits[(nn * classes + 1) * spatial + sp] : 0.f;
+    float f[8], o[8];
+    unpack8(ld8(x + v * x_pitch + c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = d0 * w0[j] + d1 * w1[j];
+      gw0[j] += d0 * f[j];
+      gw1[j] += d1 * f[j];
+    }
+    st8(dx + v * dx_pitch + c0, pack8(o));
+    if (sub == 0) {
+      gb0 += d0;
+      gb1 += d1;
+    }
+  }
+  // fold the lanes that own the same channel group (lane, lane + LPV, lane + 2 LPV, ...)
+#pragma unroll
+  for (int off = LPV; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gw0[j] += __shfl_xor_sync(0xffffffffu, gw0[j], off);
+      gw1[j] += __shfl_xor_sync(0xffffffffu, gw1[j], off);
+    }
+  }
+  gb0 = warp_sum(gb0);
+  gb1 = warp_sum(gb1);
+  if (lane < LPV) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sgw[c0 + j], gw0[j]);
+      atomicAdd(&sgw[CIN + c0 + j], gw1[j]);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&sgw[2 * CIN], gb0);
+    atomicAdd(&sgw[2 * CIN + 1], gb1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < classes * CIN; i += blockDim.x) atomicAdd(&grad_w[i], sgw[i]);
+  if (threadIdx.x < classes) atomicAdd(&grad_b[threadIdx.x], sgw[2 * CIN + threadIdx.x]);
+}
+
 __global__ void argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ labels, int n, int64_t spatial,
                               int classes) {
   const int64_t total = static_cast<int64_t>(n) * spatial;
@@ -403,6 +474,18 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
   auto st = static_cast<cudaStream_t>(stream);
   const auto* xp = static_cast<const __nv_bfloat16*>(x);
   auto* dxp = static_cast<__nv_bfloat16*>(dx);
+  if (classes <= 2 && (cin == 16 || cin == 32 || cin == 64) && x_pitch % 8 == 0 && dx_pitch % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+    const int g = kNumSMs * 8;
+    if (cin == 16)
+      head_bwd_vec_kernel<2><<<g, 256, 0, st>>>(dlogits, xp, x_pitch, w, dxp, dx_pitch, grad_w, grad_b, n, spatial, classes);
+    else if (cin == 32)
+      head_bwd_vec_kernel<4><<<g, 256, 0, st>>>(dlogits, xp, x_pitch, w, dxp, dx_pitch, grad_w, grad_b, n, spatial, classes);
+    else
+      head_bwd_vec_kernel<8><<<g, 256, 0, st>>>(dlogits, xp, x_pitch, w, dxp, dx_pitch, grad_w, grad_b, n, spatial, classes);
+    B200_CHECK_LAUNCH("head_conv1x1_bwd");
+    return 0;
+  }
   const int grid = kNumSMs * 8;
 #define B200_HEAD_BWD(KC_, CPL_) \
   head_bwd_kernel<KC_, CPL_><<<grid, 256, 0, st>>>(dlogits, xp, x_pitch, w, dxp, dx_pitch, grad_w, grad_b, n, spatial, cin, classes)

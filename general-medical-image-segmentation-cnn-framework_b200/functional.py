@@ -128,9 +128,22 @@ def _geom(x_shape, cin, cout, k, stride, pad, dil):
                     conv_out(w, k, stride, pad, dil), cout, k, stride, pad, dil)
 
 
+def _cached_pack(weight, variant):
+    """bf16 pack kept fresh by optim.FusedAdam (one batched launch per step), valid while the parameter has not been
+    modified through torch since (its autograd version is unchanged)."""
+    if getattr(weight, "_b200_pack_ver", None) == weight._version:
+        return weight._b200_pack1 if variant else weight._b200_pack0
+    return None
+
+
 def pack_conv_weight(weight, cin_off=0, cin_cnt=None, dgrad=False):
     cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
     cin_cnt = cin if cin_cnt is None else cin_cnt
+    if cin_off == 0 and cin_cnt == cin:
+        cached = _cached_pack(weight, 1 if dgrad else 0)
+        if cached is not None:
+            return cached
+    weight = weight.detach()
     packed = torch.empty(k ** 3 * cout * cin_cnt, dtype=torch.bfloat16, device=weight.device)
     _call("b200seg_pack_conv_weight", _ptr(weight), _ptr(packed), cout, cin, k, cin_off, cin_cnt, int(dgrad), _stream())
     return packed
@@ -149,7 +162,7 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
         y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
     # flat {sum[C], sumsq[C], (count)}: the spare float lets the cross-GPU exchange carry the element count
     stats = torch.zeros(2 * cout + 1, dtype=torch.float32, device=x.device) if want_stats else None
-    wp = pack_conv_weight(weight.detach())
+    wp = pack_conv_weight(weight)
     b = bias.detach().float() if bias is not None else None
     _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), y.stride(3), _ptr(stats),
           None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_tc" if conv_uses_tensor_cores(g) else "conv_fprop_direct")
@@ -158,7 +171,7 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
 
 def conv3d_dgrad_raw(g, dy, weight):
     dy, dyp = _as_rows(dy)
-    wd = pack_conv_weight(weight.detach(), dgrad=True)
+    wd = pack_conv_weight(weight, dgrad=True)
     dx = torch.empty((g.n, g.d, g.h, g.w, g.cin), dtype=torch.bfloat16, device=dy.device)
     _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, None, 0, _stream(),
           work=_conv_flops(g), tag="conv_dgrad")
@@ -446,8 +459,11 @@ def norm_act(y, spec, gamma=None, beta=None, prelu_weight=None, residual=None, r
 
 
 class _MaxPool2(torch.autograd.Function):
+    """MaxPool3d(2, 2); with `skip=True` it also returns the input as a second output, so that the gradient arriving
+    through a skip connection is added inside the pooling backward kernel instead of by a separate autograd add."""
+
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, skip):
         x, xp = _as_rows(x)
         n, d, h, w, c = x.shape
         y = torch.empty((n, d // 2, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
@@ -456,23 +472,37 @@ class _MaxPool2(torch.autograd.Function):
         ctx.save_for_backward(idx)
         ctx.shape = (n, d, h, w, c)
         ctx.mark_non_differentiable(idx)
+        if skip:
+            return y, idx, x.as_strided(x.shape, x.stride())
         return y, idx
 
     @staticmethod
-    def backward(ctx, dy, _):
+    def backward(ctx, dy, _, dskip=None):
         (idx,) = ctx.saved_tensors
         n, d, h, w, c = ctx.shape
-        dy, dyp = _as_rows(dy)
         assert d % 2 == 0 and h % 2 == 0 and w % 2 == 0, "MaxPool3d(2,2) backward needs even extents"
+        if dy is None:
+            return dskip, None
+        dy, dyp = _as_rows(dy)
+        add, addp = (None, 0)
+        if dskip is not None:
+            add, addp = _as_rows(dskip)
         dx = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=dy.device)
-        _call("b200seg_maxpool2_bwd", _ptr(dy), dyp, _ptr(idx), _ptr(dx), c, n, d, h, w, c, _stream())
-        return dx
+        _call("b200seg_maxpool2_bwd", _ptr(dy), dyp, _ptr(idx), _ptr(dx), c, _ptr(add), addp, n, d, h, w, c, _stream())
+        return dx, None
 
 
 def max_pool2(x, return_indices=False):
     """nn.MaxPool3d(2, 2).  Indices are uint8 local arg-max codes (see maxpool_indices_to_torch)."""
-    y, idx = _MaxPool2.apply(x)
+    y, idx = _MaxPool2.apply(x, False)
     return (y, idx) if return_indices else y
+
+
+def max_pool2_skip(x):
+    """(MaxPool3d(2,2)(x), x): use the second value for the skip connection (unet3d.py:52-68); both gradients of x
+    are then combined by one kernel."""
+    y, _, xs = _MaxPool2.apply(x, True)
+    return y, xs
 
 
 def maxpool_indices_to_torch(idx, in_shape):
@@ -493,8 +523,10 @@ class _ConvT2(torch.autograd.Function):
         if out is None:
             out = torch.empty((n, 2 * d, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=x.device)
         assert _pitched(out) and tuple(out.shape) == (n, 2 * d, 2 * h, 2 * w, cout)
-        wp = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=x.device)
-        _call("b200seg_pack_convt_weight", _ptr(weight.detach()), _ptr(wp), cin, cout, 0, _stream())
+        wp = _cached_pack(weight, 1)     # ConvT forward = dgrad of the equivalent strided conv
+        if wp is None:
+            wp = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=x.device)
+            _call("b200seg_pack_convt_weight", _ptr(weight.detach()), _ptr(wp), cin, cout, 0, _stream())
         b = bias.detach().float() if bias is not None else None
         _call("b200seg_convt_k2s2_fwd", _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(out), out.stride(3), n, d, h, w, cin, cout,
               _stream())
@@ -511,8 +543,10 @@ class _ConvT2(torch.autograd.Function):
         x, xp = _as_rows(x)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wd = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=x.device)
-            _call("b200seg_pack_convt_weight", _ptr(weight.detach()), _ptr(wd), cin, cout, 1, _stream())
+            wd = _cached_pack(weight, 0)
+            if wd is None:
+                wd = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=x.device)
+                _call("b200seg_pack_convt_weight", _ptr(weight.detach()), _ptr(wd), cin, cout, 1, _stream())
             dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=x.device)
             _call("b200seg_convt_k2s2_dgrad", _ptr(dy), dyp, _ptr(wd), _ptr(dx), cin, n, d, h, w, cin, cout, _stream())
         if ctx.needs_input_grad[1]:

@@ -83,11 +83,12 @@ class UNet3D(nn.Module):
         _, up3, skip3 = F.alloc_concat(n, d // 4, hh // 4, w // 4, 4 * f, 4 * f, dev)
         _, up4, skip4 = F.alloc_concat(n, d // 8, hh // 8, w // 8, 8 * f, 8 * f, dev)
 
-        enc1 = self._run_block(self.encoder1, h, out=skip1)
-        enc2 = self._run_block(self.encoder2, F.max_pool2(enc1), out=skip2)
-        enc3 = self._run_block(self.encoder3, F.max_pool2(enc2), out=skip3)
-        enc4 = self._run_block(self.encoder4, F.max_pool2(enc3), out=skip4)
-        bottleneck = self._run_block(self.bottleneck, F.max_pool2(enc4))
+        # each encoder output feeds the pool AND the skip connection: max_pool2_skip sums both gradients in one kernel
+        p1, enc1 = F.max_pool2_skip(self._run_block(self.encoder1, h, out=skip1))
+        p2, enc2 = F.max_pool2_skip(self._run_block(self.encoder2, p1, out=skip2))
+        p3, enc3 = F.max_pool2_skip(self._run_block(self.encoder3, p2, out=skip3))
+        p4, enc4 = F.max_pool2_skip(self._run_block(self.encoder4, p3, out=skip4))
+        bottleneck = self._run_block(self.bottleneck, p4)
 
         dec4 = F.conv_transpose_k2s2(bottleneck, self.upconv4.weight, self.upconv4.bias, out=up4)
         dec4 = self._run_block(self.decoder4, dec4, enc4)

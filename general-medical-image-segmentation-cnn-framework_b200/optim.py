@@ -42,6 +42,42 @@ class FusedAdam:
                 p._b200_dwp_used = [False]
                 p._b200_direct_grad = True
                 self._dwp_flags.append(p._b200_dwp_used)
+        self._build_pack_table()
+        self.refresh_packs()
+
+    # ---- bf16 weight packs for the conv kernels, refreshed by ONE launch after every update -------------------------
+    def _build_pack_table(self):
+        import struct
+        recs, total = [], 0
+        self._packed = []
+        for p, off in zip(self.params, self.offsets):
+            if p.dim() != 5 or p.shape[2] != p.shape[3] or p.shape[3] != p.shape[4]:
+                continue
+            a, b, k3 = p.shape[0], p.shape[1], p.shape[2] ** 3     # Conv3d [cout][cin][k^3]; ConvTranspose3d alike
+            n = p.numel()
+            recs.append(struct.pack("<qqiiii", off, total, a, b, k3, 0))
+            recs.append(struct.pack("<qqiiii", off, total + n, a, b, k3, 1))
+            self._packed.append((p, total, n))
+            total += 2 * n
+        if not recs:
+            self._pack_desc = None
+            return
+        dev = self.param_arena.device
+        self._pack_arena = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        self._pack_desc = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
+        self._npack = len(recs)
+        for p, o, n in self._packed:
+            p._b200_pack0 = self._pack_arena[o:o + n]            # fprop layout [k^3][cout][cin]
+            p._b200_pack1 = self._pack_arena[o + n:o + 2 * n]    # dgrad layout [k^3 flipped][cin][cout]
+
+    def refresh_packs(self):
+        """Re-pack every conv weight (call after changing parameters outside step(), e.g. load_state_dict)."""
+        if self._pack_desc is None:
+            return
+        _call("b200seg_pack_weights_batched", _ptr(self.param_arena), _ptr(self._pack_arena), _ptr(self._pack_desc),
+              self._npack, _stream())
+        for p, _, _ in self._packed:
+            p._b200_pack_ver = p._version
 
     def zero_grad(self, set_to_none=False):
         self._zeroed.zero_()
@@ -87,6 +123,7 @@ class FusedAdam:
         self.step_count += 1
         _call("b200seg_adam_step_dev", _ptr(self.param_arena), _ptr(self.grad_arena), _ptr(self.exp_avg),
               _ptr(self.exp_avg_sq), self.numel, _ptr(self._hyper), _ptr(self._state), _stream())
+        self.refresh_packs()
 
     def state_dict(self):
         if getattr(self, "_state", None) is not None:

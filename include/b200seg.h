@@ -56,6 +56,9 @@ int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, i
  * [k^3 flipped][cin][cout] bf16 (flip=1).  cin_off/cin_cnt select an input-channel slice (concat-free decoders). */
 int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
                              int dgrad, void* stream);
+/* Both packs of many weight tensors in one launch.  descs: DEVICE array of ndesc 32-byte records
+ * {int64 src (float offset into arena), int64 dst (bf16 element offset into packs), int32 cout, cin, k^3, dgrad}. */
+int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, void* stream);
 /* wgrad result [k^3][cin_cnt][cout] fp32 -> torch-layout grad [cout][cin][k^3] fp32 slice.  accumulate bit 0: add to
  * grad_w instead of overwriting; bit 1: clear dw_packed while reading it (a persistent, always-zero accumulator needs no
  * memset between steps; dw_packed is written in that case despite the const). */
@@ -121,8 +124,11 @@ int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, 
 /* idx: uint8 per output element, local argmax 0..7 = (a*2+b)*2+e in (d,h,w) scan order; ties -> first, NaN wins. */
 int b200seg_maxpool2_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, uint8_t* idx, int n, int d,
                          int h, int w, int c, void* stream);
-int b200seg_maxpool2_bwd(const void* dy, int64_t dy_pitch, const uint8_t* idx, void* dx, int64_t dx_pitch, int n,
-                         int d, int h, int w, int c, void* stream);
+/* dx = scatter(dy by idx) [+ addend]: `addend` (may be NULL) is a second gradient of the pooled tensor -- in a U-Net the
+ * encoder output feeds both the pool and the skip connection (unet3d.py:52-68) -- summed here instead of in a separate
+ * pass. */
+int b200seg_maxpool2_bwd(const void* dy, int64_t dy_pitch, const uint8_t* idx, void* dx, int64_t dx_pitch,
+                         const void* addend, int64_t addend_pitch, int n, int d, int h, int w, int c, void* stream);
 /* local indices -> torch's int64 flat D*H*W indices in NCDHW order (for the bit-exact check). */
 int b200seg_maxpool2_idx_to_torch(const uint8_t* idx, int64_t* out, int n, int d, int h, int w, int c, void* stream);
 
