@@ -36,6 +36,7 @@ struct PlaneParams {
   int k, pad, dil;
   int KC, nchunks, NT, n_ntiles;
   int WB, HB, U, S, NB;
+  int stages;   // TMEM accumulator stages: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one (K-heavy) tile
   int tiles_w, tiles_h, tiles_d;
   long long tiles;
   int scatter_cout, cpm;
@@ -233,8 +234,9 @@ __global__ void __launch_bounds__(kThreadsP, 1)
     uint32_t unit0_phase = 0;
     uint32_t it = 0;
     for (long long t = first; t < p.tiles; t += step, ++it) {
-      const uint32_t stage = it & 1;
-      mbar_wait(&accEmpty[stage], ((it >> 1) & 1) ^ 1);
+      const uint32_t stage = p.stages == 2 ? (it & 1) : 0u;
+      const uint32_t use = p.stages == 2 ? (it >> 1) : it;
+      mbar_wait(&accEmpty[stage], (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_base = tbase + stage * kStageCols;
       for (int c = 0; c < p.nchunks; ++c) {
@@ -312,9 +314,10 @@ __global__ void __launch_bounds__(kThreadsP, 1)
     const bool want_stats = p.stats != nullptr;
     uint32_t it = 0;
     for (long long t = first; t < p.tiles; t += step, ++it) {
-      const uint32_t stage = it & 1;
+      const uint32_t stage = p.stages == 2 ? (it & 1) : 0u;
+      const uint32_t use = p.stages == 2 ? (it >> 1) : it;
       const TileCoord tc = decode_tile(p, t, P);
-      mbar_wait(&accFull[stage], (it >> 1) & 1);
+      mbar_wait(&accFull[stage], use & 1);
       tc_fence_after();
       const int oh_ = tc.h0 + (m >> 3), ow_ = tc.w0 + (m & 7);
       const bool hw_ok = oh_ < p.oh && ow_ < p.ow;
@@ -412,8 +415,13 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   p.slotB = (p.NT * p.rowbytes + 1023) & ~1023u;
   p.bytesB = p.NT * p.rowbytes;
   const size_t fixed_small = 2048 + static_cast<size_t>(a.cout) * sizeof(float) * (a.stats ? 3 : 1) + 1024;
-  // accumulators per stage: as many d-planes as fit 256 TMEM columns (<= 8), not more than the depth needs
-  int pmax = std::min(8, kStageCols / p.NT);
+  // accumulators per stage: as many d-planes as fit 256 TMEM columns (<= 8), not more than the depth needs.
+  // (A single 512-column stage with twice the planes per tile halves the weight traffic of K-heavy layers but also halves
+  // their tile count; measured on the 32^3 / 16^3 U-Net layers it loses -- they are short of tiles, not of L2 bandwidth --
+  // so it stays off unless B200SEG_SINGLE_STAGE is set.)
+  const long long mmas_per_acc = static_cast<long long>(p.nchunks) * a.k * a.k * a.k * KS;
+  p.stages = (getenv("B200SEG_SINGLE_STAGE") && mmas_per_acc >= 256 && p.NT >= 64) ? 1 : 2;
+  int pmax = std::min(8, (p.stages == 1 ? 512 : kStageCols) / p.NT);
   while (pmax > 1 && pmax / 2 >= a.od) pmax /= 2;
   const size_t budget = 225 * 1024;
   P = 0;
