@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200seg_ndhwc_bf16_to_ncdhw_f32": "ppiilp",
     "b200seg_pack_conv_weight": "ppiiiiiip",
     "b200seg_pack_weights_batched": "pppip",
+    "b200seg_pad_channels": "plipilp",
     "b200seg_unpack_conv_wgrad": "ppiiiiiip",
     "b200seg_conv3d_fprop": "gplppplppzp",
     "b200seg_conv3d_dgrad": "gplpplpzp",

@@ -18,13 +18,32 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
       ci = static_cast<int>(i % cin_cnt);
       co = static_cast<int>((i / cin_cnt) % cout);
       t = static_cast<int>(i / (static_cast<int64_t>(cin_cnt) * cout));
-      p[i] = __float2bfloat16(w[(static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + t]);
+      p[i] = cin_off + ci < cin ? __float2bfloat16(w[(static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + t])
+                                : __float2bfloat16(0.f);   // channels past the tensor: zero padding of the K dimension
     } else {
       co = static_cast<int>(i % cout);
       ci = static_cast<int>((i / cout) % cin_cnt);
       t = static_cast<int>(i / (static_cast<int64_t>(cin_cnt) * cout));
-      p[i] = __float2bfloat16(w[(static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + (k3 - 1 - t)]);
+      p[i] = cin_off + ci < cin ? __float2bfloat16(w[(static_cast<int64_t>(co) * cin + cin_off + ci) * k3 + (k3 - 1 - t)])
+                                : __float2bfloat16(0.f);
     }
+  }
+}
+
+// y[row][0:c] = x[row][0:c], y[row][c:cpad] = 0 (cpad a multiple of 8): widens a 1-4 channel tensor so that it can feed
+// the tensor-core kernels, whose K dimension comes in chunks of 16 channels.
+__global__ void pad_channels_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, int c,
+                                    __nv_bfloat16* __restrict__ y, int cpad, int64_t rows) {
+  const int groups = cpad / 8;
+  const int64_t total = rows * groups;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / groups;
+    const int c0 = static_cast<int>(i % groups) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c0 + j < c) ? __bfloat162float(x[row * x_pitch + c0 + j]) : 0.f;
+    st8(y + row * cpad + c0, pack8(f));
   }
 }
 
@@ -533,6 +552,14 @@ using namespace b200;
 
 extern "C" {
 
+int b200seg_pad_channels(const void* x, int64_t x_pitch, int c, void* y, int cpad, int64_t rows, void* stream) {
+  B200_CHECK_ARG(x && y && c > 0 && cpad >= c && cpad % 8 == 0 && rows > 0 && x_pitch >= c, "pad_channels: bad arguments");
+  b200::pad_channels_kernel<<<grid_for(rows * (cpad / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, c, static_cast<__nv_bfloat16*>(y), cpad, rows);
+  B200_CHECK_LAUNCH("pad_channels");
+  return 0;
+}
+
 int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, void* stream) {
   B200_CHECK_ARG(arena && packs && descs && ndesc > 0 && ndesc <= 65535, "pack_weights_batched: bad arguments");
   static_assert(sizeof(b200::PackDesc) == 32, "descriptor layout is part of the ABI");
@@ -545,8 +572,8 @@ int b200seg_pack_weights_batched(const float* arena, void* packs, const void* de
 
 int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
                              int dgrad, void* stream) {
-  B200_CHECK_ARG(w && packed && cout > 0 && cin > 0 && k > 0 && cin_off >= 0 && cin_cnt > 0 && cin_off + cin_cnt <= cin,
-                 "pack_conv_weight: bad arguments");
+  B200_CHECK_ARG(w && packed && cout > 0 && cin > 0 && k > 0 && cin_off >= 0 && cin_cnt > 0 && cin_off < cin,
+                 "pack_conv_weight: bad arguments");   // cin_off + cin_cnt > cin: the excess channels are packed as zeros
   const int k3 = k * k * k;
   const int64_t total = static_cast<int64_t>(k3) * cout * cin_cnt;
   pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -162,8 +162,20 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
         y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
     # flat {sum[C], sumsq[C], (count)}: the spare float lets the cross-GPU exchange carry the element count
     stats = torch.zeros(2 * cout + 1, dtype=torch.float32, device=x.device) if want_stats else None
-    wp = pack_conv_weight(weight)
     b = bias.detach().float() if bias is not None else None
+    # Stem layers (C_in = 1..8, e.g. unet3d.py:80): zero-pad the K dimension to 16 channels so the convolution runs on the
+    # tensor cores (the geometry handed back for the backward pass stays the original one)
+    gp = _geom(x.shape, 16, cout, k, stride, pad, dil) if (cin < 16 and stride == 1) else None
+    if gp is not None and conv_uses_tensor_cores(gp) and g.n * g.od * g.oh * g.ow >= (1 << 16):
+        rows = g.n * g.d * g.h * g.w
+        x16 = torch.empty((g.n, g.d, g.h, g.w, 16), dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_pad_channels", _ptr(x), xp, cin, _ptr(x16), 16, rows, _stream())
+        wp = torch.empty(k ** 3 * cout * 16, dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_pack_conv_weight", _ptr(weight.detach()), _ptr(wp), cout, cin, k, 0, 16, 0, _stream())
+        _call("b200seg_conv3d_fprop", ctypes.byref(gp), _ptr(x16), 16, _ptr(wp), _ptr(b), _ptr(y), y.stride(3),
+              _ptr(stats), None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_stem_tc")
+        return y, stats, g
+    wp = pack_conv_weight(weight)
     _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), y.stride(3), _ptr(stats),
           None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_tc" if conv_uses_tensor_cores(g) else "conv_fprop_direct")
     return y, stats, g

@@ -56,6 +56,10 @@ int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, i
  * [k^3 flipped][cin][cout] bf16 (flip=1).  cin_off/cin_cnt select an input-channel slice (concat-free decoders). */
 int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
                              int dgrad, void* stream);
+/* (cin_off + cin_cnt may exceed cin: the excess input channels are packed as zeros -- K-dimension padding.) */
+/* y[rows][cpad] (contiguous) = x[rows][0:c] followed by zeros; cpad a multiple of 8.  Used to widen the 1-channel network
+ * input to 16 channels so that the stem convolution (unet3d.py:80, C_in = 1) runs on the tensor-core path. */
+int b200seg_pad_channels(const void* x, int64_t x_pitch, int c, void* y, int cpad, int64_t rows, void* stream);
 /* Both packs of many weight tensors in one launch.  descs: DEVICE array of ndesc 32-byte records
  * {int64 src (float offset into arena), int64 dst (bf16 element offset into packs), int32 cout, cin, k^3, dgrad}. */
 int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, void* stream);

@@ -50,6 +50,8 @@ CONV_CASES = [
     # cin, cout, k, stride, pad, dil, (d,h,w), n
     (1, 32, 3, 1, 1, 1, (8, 8, 8), 2),        # U-Net stem (dedicated C_in=1 kernels)
     (1, 32, 3, 1, 1, 1, (9, 20, 33), 1),      # stem, ragged extents
+    (1, 32, 3, 1, 1, 1, (32, 48, 48), 1),     # stem large enough for the K-padded tensor-core path (>= 65536 voxels)
+    (1, 16, 3, 1, 1, 1, (40, 40, 44), 1),     # HighResNet stem (C_out = 16), K-padded
     (1, 16, 5, 1, 2, 1, (8, 8, 12), 1),       # V-Net stem 5x5x5
     (32, 32, 3, 1, 1, 1, (8, 16, 8), 2),      # full-resolution U-Net layer
     (64, 32, 3, 1, 1, 1, (8, 16, 16), 1),     # decoder conv1 (concat input)
@@ -97,6 +99,8 @@ def test_conv3d_fprop_dgrad_wgrad(F, case):
     # which path ran: tcgen05 for stride-1 k in {1,3,5} with 16-aligned channels (wgrad: C_in % 32 == 0)
     if stride == 1 and k in (1, 3, 5) and cin % 16 == 0 and cout % 16 == 0:
         assert F.umma_launch_count() - n0 == (3 if cin % 32 == 0 else 2), "tensor-core path was not taken"
+    elif cin < 16 and stride == 1 and k == 3 and cout % 16 == 0 and n * size[0] * size[1] * size[2] >= 1 << 16:
+        assert F.umma_launch_count() - n0 == 1, "large stem: fprop runs K-padded on the tensor cores"
     else:
         assert F.umma_launch_count() == n0
     close(ncdhw(xd.grad), xr.grad, 8e-3, "dgrad")
