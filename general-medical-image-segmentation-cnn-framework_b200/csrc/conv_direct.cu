@@ -451,6 +451,101 @@ __global__ void __launch_bounds__(256)
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) atomicAdd(&dwp[i], sacc[i]);
 }
 
+// Tiled C_in = 1 weight gradient: a block stages a 4 x 4 x 32 voxel tile of dy (as fp32) and the matching x halo in shared
+// memory; each thread owns 2 taps x 8 output channels = 16 accumulators (14 tap pairs x COUT/8 channel groups active
+// threads per 64-thread stream, 4 streams = 4 z-slices of the tile), so a voxel costs it 2 + 2 shared loads for 16 FMAs
+// instead of the 27 shuffles + 27 FMAs per lane of the warp-broadcast version above.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+    stem_wgrad_k3_tiled_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                               const __nv_bfloat16* __restrict__ dy, int64_t dy_pitch, float* __restrict__ dwp) {
+  constexpr int TZ = 4, TY = 4, TX = 32, CG = COUT / 8;
+  extern __shared__ float smem_f[];
+  float* sdy = smem_f;                                   // [TZ*TY*TX][COUT]
+  float* sx = sdy + TZ * TY * TX * COUT;                 // [TZ+2][TY+2][TX+2]
+  float* sacc = sx + (TZ + 2) * (TY + 2) * (TX + 2);     // [27][COUT]
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sacc[i] = 0.f;
+  const int stream = threadIdx.x >> 6, lt = threadIdx.x & 63;
+  const bool active = lt < 14 * CG;
+  const int tp = lt / CG, cg = lt % CG;
+  const int t0 = 2 * tp, t1 = 2 * tp + 1;
+  const bool has1 = t1 < 27;
+  const int off0 = ((t0 / 9) * (TY + 2) + (t0 / 3) % 3) * (TX + 2) + t0 % 3;
+  const int off1 = has1 ? ((t1 / 9) * (TY + 2) + (t1 / 3) % 3) * (TX + 2) + t1 % 3 : off0;
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
+  const int tz = (g.d + TZ - 1) / TZ, ty = (g.h + TY - 1) / TY, tx = (g.w + TX - 1) / TX;
+  const long long tiles = static_cast<long long>(g.n) * tz * ty * tx;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    long long r = tile;
+    const int x0 = static_cast<int>(r % tx) * TX;
+    r /= tx;
+    const int y0 = static_cast<int>(r % ty) * TY;
+    r /= ty;
+    const int z0 = static_cast<int>(r % tz) * TZ;
+    const int nn = static_cast<int>(r / tz);
+    __syncthreads();   // previous tile fully consumed
+    // dy tile: TZ*TY rows of TX voxels x COUT channels, 8 channels (one 128-bit load) per thread step
+    for (int i = threadIdx.x; i < TZ * TY * TX * CG; i += blockDim.x) {
+      const int c8 = i % CG, v = i / CG;
+      const int xx = v % TX, yy = (v / TX) % TY, zz = v / (TX * TY);
+      const int gz = z0 + zz, gy = y0 + yy, gx = x0 + xx;
+      float f[8];
+      if (gz < g.d && gy < g.h && gx < g.w) {
+        const long long vox = ((static_cast<long long>(nn) * g.d + gz) * g.h + gy) * g.w + gx;
+        unpack8(ld8(dy + vox * dy_pitch + c8 * 8), f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+      float4* dst = reinterpret_cast<float4*>(sdy + v * COUT + c8 * 8);
+      dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+      dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (int i = threadIdx.x; i < (TZ + 2) * (TY + 2) * (TX + 2); i += blockDim.x) {
+      const int xx = i % (TX + 2), yy = (i / (TX + 2)) % (TY + 2), zz = i / ((TX + 2) * (TY + 2));
+      const int gz = z0 - 1 + zz, gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+      float v = 0.f;
+      if (gz >= 0 && gz < g.d && gy >= 0 && gy < g.h && gx >= 0 && gx < g.w)
+        v = __bfloat162float(x[(((static_cast<long long>(nn) * g.d + gz) * g.h + gy) * g.w + gx) * x_pitch]);
+      sx[i] = v;
+    }
+    __syncthreads();
+    if (active) {
+      const float* sxs = sx + stream * (TY + 2) * (TX + 2);
+      const float* sds = sdy + stream * TY * TX * COUT + cg * 8;
+#pragma unroll 1
+      for (int yy = 0; yy < TY; ++yy) {
+#pragma unroll 4
+        for (int xx = 0; xx < TX; ++xx) {
+          const int hb = yy * (TX + 2) + xx;
+          const float xv0 = sxs[hb + off0];
+          const float xv1 = has1 ? sxs[hb + off1] : 0.f;
+          const float4 da = *reinterpret_cast<const float4*>(sds + (yy * TX + xx) * COUT);
+          const float4 db = *reinterpret_cast<const float4*>(sds + (yy * TX + xx) * COUT + 4);
+          const float d8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc0[j] = fmaf(xv0, d8[j], acc0[j]);
+            acc1[j] = fmaf(xv1, d8[j], acc1[j]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sacc[t0 * COUT + cg * 8 + j], acc0[j]);
+      if (has1) atomicAdd(&sacc[t1 * COUT + cg * 8 + j], acc1[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) atomicAdd(&dwp[i], sacc[i]);
+}
+
 static bool is_stem(const ConvGeom& g) {
   return g.cin == 1 && g.stride == 1 && g.dil == 1 && g.k <= 5 && (g.k & 1) && g.pad == (g.k - 1) / 2 &&
          (g.cout == 32 || g.cout == 16);
@@ -519,6 +614,24 @@ int conv_direct_dgrad(const ConvGeom& g, const void* dy, int64_t dy_pitch, const
 
 int conv_direct_wgrad(const ConvGeom& g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, float* dwp,
                       cudaStream_t st) {
+  if (is_stem(g) && g.k == 3 && g.pad == 1 && (g.cout == 32 || g.cout == 16) && dy_pitch % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && static_cast<long long>(g.n) * g.d * g.h * g.w >= (1 << 15)) {
+    const size_t smem = (static_cast<size_t>(4 * 4 * 32) * g.cout + 6 * 6 * 34 + 27 * g.cout) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(stem_wgrad_k3_tiled_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(stem_wgrad_k3_tiled_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr_set = true;
+    }
+    if (g.cout == 32)
+      stem_wgrad_k3_tiled_kernel<32><<<kNumSMs * 3, 256, smem, st>>>(g, static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                                                      static_cast<const __nv_bfloat16*>(dy), dy_pitch, dwp);
+    else
+      stem_wgrad_k3_tiled_kernel<16><<<kNumSMs * 3, 256, smem, st>>>(g, static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                                                      static_cast<const __nv_bfloat16*>(dy), dy_pitch, dwp);
+    B200_CHECK_LAUNCH("stem_wgrad_tiled");
+    return 0;
+  }
   if (is_stem(g) && g.k == 3 && g.cout == 32) {
     stem_wgrad_k3_c32_kernel<<<kNumSMs * 4, 256, 0, st>>>(g, static_cast<const __nv_bfloat16*>(x), x_pitch,
                                                            static_cast<const __nv_bfloat16*>(dy), dy_pitch, dwp);
