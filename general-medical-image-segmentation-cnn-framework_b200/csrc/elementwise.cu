@@ -369,6 +369,84 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_kernel(const __nv_
   }
 }
 
+// Fast path of the backward reduction (128-bit rows, no residual, no PReLU slope gradient, one channel chunk per thread):
+// xhat only enters the second sum linearly, sum(dpre * xhat) = inv_std * sum(dpre * (y - mean)), so the loop keeps just
+// {scale, shift, mean} per channel and folds inv_std in once at the end.  That leaves registers for 4 rows x 2 tensors of
+// 128-bit loads in flight per thread at 3 CTAs/SM (~98 KB outstanding per SM, what B200 needs to stream at HBM speed).
+template <int ACT>
+__global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_fast_kernel(
+    const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch, const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
+    const float* __restrict__ coef, int64_t rows, int C, float act_param, const float* __restrict__ prelu_w,
+    float* __restrict__ sums) {
+  constexpr int V = 8;
+  extern __shared__ float red[];  // [TY][TX][2*V]
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int g = blockIdx.y;
+  const int64_t base = static_cast<int64_t>(g) * rows;
+  const float* cg = coef ? coef + static_cast<size_t>(g) * 4 * C : nullptr;
+  const int ch = threadIdx.x;      // host guarantees C / 8 == blockDim.x
+  float sc[V], sh[V], mu[V], sl[V], s1[V], s2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = ch * V + j;
+    mu[j] = cg ? cg[c] : 0.f;
+    sc[j] = cg ? cg[2 * C + c] : 1.f;
+    sh[j] = cg ? cg[3 * C + c] : 0.f;
+    sl[j] = (ACT == B200SEG_ACT_PRELU) ? prelu_w[c] : act_param;
+    s1[j] = s2[j] = 0.f;
+  }
+  auto fold = [&](const bf16x8& ry, const bf16x8& rd) {
+    float fy[V], fd[V];
+    unpack8(ry, fy);
+    unpack8(rd, fd);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float pre = fy[j] * sc[j] + sh[j];
+      const float dpre = fd[j] * act_bwd(pre, ACT, sl[j]);
+      s1[j] += dpre;
+      s2[j] = fmaf(dpre, fy[j] - mu[j], s2[j]);
+    }
+  };
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * TY;
+  int64_t r = static_cast<int64_t>(blockIdx.x) * TY + threadIdx.y;
+  for (; r + 3 * stride < rows; r += 4 * stride) {
+    bf16x8 ry[4], rd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ry[u] = ld8(y + (base + r + u * stride) * y_pitch + ch * V);
+      rd[u] = ld8(dz + (base + r + u * stride) * dz_pitch + ch * V);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) fold(ry[u], rd[u]);
+  }
+  for (; r < rows; r += stride) fold(ld8(y + (base + r) * y_pitch + ch * V), ld8(dz + (base + r) * dz_pitch + ch * V));
+  float* mine = red + (static_cast<size_t>(threadIdx.y) * TX + threadIdx.x) * (2 * V);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    mine[j] = s1[j];
+    mine[V + j] = s2[j];
+  }
+  __syncthreads();
+  for (int st = TY >> 1; st > 0; st >>= 1) {
+    if (threadIdx.y < st) {
+      const float* other = red + (static_cast<size_t>(threadIdx.y + st) * TX + threadIdx.x) * (2 * V);
+#pragma unroll
+      for (int j = 0; j < 2 * V; ++j) mine[j] += other[j];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.y == 0) {
+    float* out = sums + static_cast<size_t>(g) * 2 * C;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int c = ch * V + j;
+      const float istd = cg ? cg[C + c] : 1.f;
+      atomicAdd(out + c, mine[j]);
+      atomicAdd(out + C + c, mine[V + j] * istd);
+    }
+  }
+}
+
 template <int V, int ACT>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch,
                                           const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
@@ -916,7 +994,13 @@ int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y,
   const auto* yp = static_cast<const __nv_bfloat16*>(y);
   const auto* rp = static_cast<const __nv_bfloat16*>(residual);
   // with dprelu the caller passes sums sized [3][c]; the third row is the slope gradient (== dprelu target)
-  if (vec_ok(c, dz_pitch, y_pitch, residual ? res_pitch : 0)) {
+  if (vec_ok(c, dz_pitch, y_pitch) && residual == nullptr && dprelu == nullptr && c / 8 <= 64 && ((c / 8) & (c / 8 - 1)) == 0 &&
+      ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    dim3 block(c / 8, 256 / (c / 8));
+    dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 3 / (groups > 4 ? 4 : 1)), groups);   // one resident wave
+    B200_ACT_DISPATCH(act, norm_act_bwd_reduce_fast_kernel<A_><<<grid, block, 256 * 16 * sizeof(float), st>>>(
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act_param, prelu_w, sums));
+  } else if (vec_ok(c, dz_pitch, y_pitch, residual ? res_pitch : 0)) {
     dim3 block = reduce_block(c / 8);
     dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
     B200_ACT_DISPATCH(act, norm_act_bwd_reduce_kernel<8, A_><<<grid, block, 256 * 24 * sizeof(float), st>>>(

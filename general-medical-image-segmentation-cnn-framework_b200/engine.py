@@ -31,9 +31,13 @@ class TrainStep:
         for seed in F._SEEDS.values():    # fresh dropout masks every step (device-side counter: graph-replay safe)
             seed.add_(1)
         self.optimizer.zero_grad()
-        out = self.model(x)
-        loss = self.criterion(out, y)
-        loss.backward()
+        F.begin_step(x.device)            # one memset for every small accumulator of the step
+        try:
+            out = self.model(x)
+            loss = self.criterion(out, y)
+            loss.backward()
+        finally:
+            F.end_step()
         return loss.detach(), out.detach()
 
     # ... + gradient all-reduce + Adam.  On one GPU everything is captured.  On several, the SyncBatchNorm exchanges run

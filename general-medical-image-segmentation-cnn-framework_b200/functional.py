@@ -59,6 +59,34 @@ def _call(name, *args, work=0.0, tag=None):
     _PROFILE[0].append((tag or name, work, e0, e1))
 
 
+# Zero-initialised scratch for the many small accumulators of a step (per-layer statistics, backward partial sums):
+# engine.TrainStep clears ONE buffer at the start of the step and the helpers below hand out 256-byte aligned slices of
+# it, instead of launching a fill kernel per accumulator (~60 per U-Net step).  Outside a step (or when it is full)
+# they fall back to torch.zeros.
+_SCRATCH = {"buf": None, "pos": 0, "active": False}
+
+
+def begin_step(device, nbytes=4 << 20):
+    if _SCRATCH["buf"] is None or _SCRATCH["buf"].device != torch.device(device) or _SCRATCH["buf"].numel() < nbytes // 4:
+        _SCRATCH["buf"] = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+    _SCRATCH["buf"].zero_()
+    _SCRATCH["pos"], _SCRATCH["active"] = 0, True
+
+
+def end_step():
+    _SCRATCH["active"] = False
+
+
+def _zeros_f32(numel, device):
+    if _SCRATCH["active"] and _SCRATCH["buf"].device == torch.device(device):
+        pos = _SCRATCH["pos"]
+        nxt = pos + (numel + 63) // 64 * 64
+        if nxt <= _SCRATCH["buf"].numel():
+            _SCRATCH["pos"] = nxt
+            return _SCRATCH["buf"][pos:pos + numel]
+    return torch.zeros(numel, dtype=torch.float32, device=device)
+
+
 def umma_launch_count():
     from ._lib import load
     return load().b200seg_umma_launch_count()
@@ -161,7 +189,7 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
     else:
         y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
     # flat {sum[C], sumsq[C], (count)}: the spare float lets the cross-GPU exchange carry the element count
-    stats = torch.zeros(2 * cout + 1, dtype=torch.float32, device=x.device) if want_stats else None
+    stats = _zeros_f32(2 * cout + 1, x.device) if want_stats else None
     b = bias.detach().float() if bias is not None else None
     # Stem layers (C_in = 1..8, e.g. unet3d.py:80): zero-pad the K dimension to 16 channels so the convolution runs on the
     # tensor cores (the geometry handed back for the backward pass stays the original one)
@@ -230,9 +258,9 @@ def channel_stats(x, groups=1, spare=0):
     rows = n * d * h * w // groups
     if spare:
         assert groups == 1
-        stats = torch.zeros(2 * c + spare, dtype=torch.float32, device=x.device)
+        stats = _zeros_f32(2 * c + spare, x.device)
     else:
-        stats = torch.zeros((groups, 2, c), dtype=torch.float32, device=x.device)
+        stats = _zeros_f32(groups * 2 * c, x.device).view(groups, 2, c)
     _call("b200seg_channel_stats", _ptr(x), xp, rows, groups, c, _ptr(stats), _stream())
     return stats
 
@@ -314,7 +342,7 @@ def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dre
     use_batch_stats = spec.kind == "instance" or (spec.kind == "batch" and spec.training)
     sums = None
     if use_batch_stats or nrow == 3 or (spec.kind == "batch" and coef is not None):
-        sums = torch.zeros((groups, nrow, c), dtype=torch.float32, device=y.device)
+        sums = _zeros_f32(groups * nrow * c, y.device).view(groups, nrow, c)
         dprelu = sums[0, 2] if nrow == 3 else None
         _call("b200seg_norm_act_bwd_reduce", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), rows, groups, c, spec.act,
               spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(sums), _ptr(dprelu), _stream())
@@ -426,7 +454,7 @@ class _ConvNormAct(torch.autograd.Function):
         if has_bias and need[3]:
             if spec.kind is not None and (spec.training or spec.kind == "instance"):
                 # a bias in front of batch/instance statistics has an analytically zero gradient
-                db = torch.zeros(g.cout, dtype=torch.float32, device=dz.device)
+                db = _zeros_f32(g.cout, dz.device)
             else:
                 db = channel_stats(dy, 1)[0, 0]
         return dx, dx2, dw, db, dgamma, dbeta, dprelu, dres, None, None, None
@@ -609,8 +637,8 @@ class _Head(torch.autograd.Function):
         classes = w2.shape[0]
         dl = dl.contiguous().float()
         dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=x.device)
-        gw = torch.zeros((classes, cin), dtype=torch.float32, device=x.device)
-        gb = torch.zeros(classes, dtype=torch.float32, device=x.device)
+        gw = _zeros_f32(classes * cin, x.device).view(classes, cin)
+        gb = _zeros_f32(classes, x.device)
         _call("b200seg_head_conv1x1_bwd", _ptr(dl), _ptr(x), xp, _ptr(w2), _ptr(dx), cin, _ptr(gw), _ptr(gb), n,
               d * h * w, cin, classes, _stream())
         return dx, gw.reshape(ctx.wshape), (gb if ctx.has_bias else None)
