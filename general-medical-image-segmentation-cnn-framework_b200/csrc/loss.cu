@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  __shared__ float sgw[kMaxClasses * 128], sgb[kMaxClasses];
+  __shared__ float sgw[kMaxClasses * 512], sgb[kMaxClasses];
   for (int i = threadIdx.x; i < classes * cin; i += blockDim.x) sgw[i] = 0.f;
   if (threadIdx.x < kMaxClasses) sgb[threadIdx.x] = 0.f;
   __syncthreads();
@@ -470,7 +470,7 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
   B200_CHECK_ARG(dlogits && x && w && dx && grad_w && grad_b && n > 0 && spatial > 0 && cin > 0,
                  "head_conv1x1_bwd: bad arguments");
   B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "head_conv1x1_bwd: classes must be in [1,%d]", kMaxClasses);
-  B200_CHECK_ARG(cin <= 128, "head_conv1x1_bwd: at most 128 input channels");
+  B200_CHECK_ARG(cin <= 128 || (cin <= 512 && classes <= 4), "head_conv1x1_bwd: at most 128 input channels (512 for <= 4 classes)");
   auto st = static_cast<cudaStream_t>(stream);
   const auto* xp = static_cast<const __nv_bfloat16*>(x);
   auto* dxp = static_cast<__nv_bfloat16*>(dx);
@@ -493,7 +493,9 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
   if (classes <= 2 && cpl == 1) B200_HEAD_BWD(2, 1);
   else if (classes <= 4 && cpl == 1) B200_HEAD_BWD(4, 1);
   else if (classes <= 4 && cpl <= 2) B200_HEAD_BWD(4, 2);
-  else B200_HEAD_BWD(8, 4);
+  else if (cpl <= 4) B200_HEAD_BWD(8, 4);
+  else if (cpl <= 8) B200_HEAD_BWD(4, 8);      // deep-supervision heads of the residual U-Net (256 -> classes)
+  else B200_HEAD_BWD(4, 16);
 #undef B200_HEAD_BWD
   B200_CHECK_LAUNCH("head_conv1x1_bwd");
   return 0;

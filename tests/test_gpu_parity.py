@@ -456,3 +456,27 @@ def test_graph_captured_train_step_matches_eager():
     for k, tol in (("encoder1.enc1conv1.weight", 2e-2), ("decoder1.dec1conv2.weight", 2e-2), ("conv.weight", 2e-2),
                    ("encoder2.enc2norm1.running_var", 2e-2), ("bottleneck.bottleneckconv1.weight", 0.3)):
         close(p1[k].float().cpu(), p0[k].float().cpu(), tol, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,classes", [(32, 2), (16, 2), (64, 1), (24, 3), (256, 2), (128, 4)])
+def test_head_conv1x1_forward_backward(F, cin, classes):
+    """1x1x1 class head (unet3d.py:46-48; residual_unet3d.py:60-66 deep-supervision heads up to 256 channels): fp32 NCDHW
+    logits out, gradients w.r.t. features / weight / bias against torch conv3d on the same bf16 features."""
+    g = torch.Generator().manual_seed(cin * 10 + classes)
+    x = bf(torch.randn(2, cin, 6, 10, 12, generator=g))
+    w = torch.randn(classes, cin, 1, 1, 1, generator=g) * 0.2
+    b = torch.randn(classes, generator=g) * 0.1
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.conv3d(xr, wr, br)
+    dl = torch.randn(ref.shape, generator=g)
+    ref.backward(dl)
+    xd = ndhwc(x).requires_grad_(True)
+    wd, bd = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    out = F.head_conv1x1(xd, wd, bd)
+    assert out.dtype == torch.float32 and tuple(out.shape) == tuple(ref.shape)
+    close(out.cpu(), ref.detach(), 1e-5, "logits")
+    out.backward(dl.to(DEV))
+    close(ncdhw(xd.grad), xr.grad, 8e-3, "dx")       # dx is stored in bf16
+    close(wd.grad.cpu(), wr.grad, 1e-4, "dw")
+    close(bd.grad.cpu(), br.grad, 1e-4, "db")
