@@ -20,6 +20,10 @@ sys.path.insert(0, ROOT)
 PATCH = 128
 FEATURES = 32
 BATCH = 2
+# DRAM bytes of the fprop + dgrad conv launches of one step (ncu, profiles/r01_step3_final_launch_list.md) and their
+# algorithmic in + out + weight bytes (3.68 GB per forward, about the same for the data gradients)
+NCU_CONV_TRAFFIC_BYTES_PER_STEP = 5.58e9
+CONV_ALGORITHMIC_BYTES_PER_STEP = 7.3e9
 TRAIN_GFLOP_PER_PATCH = 2850.4  # fwd 951.3 + wgrad 951.3 + dgrad (951.3 - 3.6 first layer): BASELINE.md section 3
 
 
@@ -238,7 +242,7 @@ def run_b200(args):
         ms_step = ms_total / args.steps
         patches = BATCH * world
         value = patches / (ms_step * 1e-3)
-        tc = [v for k, v in prof.items() if k in ("conv_fprop_tc", "conv_dgrad", "conv_wgrad")]
+        tc = [v for k, v in prof.items() if k in ("conv_fprop_tc", "conv_fprop_stem_tc", "conv_dgrad", "conv_wgrad")]
         main = prof.get("conv_fprop_tc", {"ms": 0.0, "work": 0.0, "launches": 0})
         dg = prof.get("conv_dgrad", {"ms": 0.0, "work": 0.0, "launches": 0})
         tc_ms = main["ms"] + dg["ms"]
@@ -261,10 +265,16 @@ def run_b200(args):
             "e2e": {"value": patches / (ms_e2e / args.steps * 1e-3), "unit": "patches/s",
                     "h2d_bytes_per_step": x_host.numel() * 4 + lab_host.numel(), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "tcgen05_launches": umma_launches,
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (fprop + dgrad launches)",
+            # dominant kernel family: the tcgen05 implicit-GEMM convolutions (conv_umma_roll / conv_umma_plane), all 34
+            # forward + data-gradient launches of the step; achieved = their algorithmic FLOPs / their CUDA-event time.
+            # traffic = DRAM read + write bytes of the same launches in the committed ncu launch list
+            # (profiles/r01_step3_final_launch_list.md), per step like `achieved`.
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_plane_kernel (34 fprop + dgrad "
+                                                      "launches per step)",
                          "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " sustained",
-                         "traffic": None, "launches_per_step": (main["launches"] + dg["launches"]) // 2,
+                         "traffic": NCU_CONV_TRAFFIC_BYTES_PER_STEP, "algorithmic_bytes": CONV_ALGORITHMIC_BYTES_PER_STEP,
+                         "launches_per_step": (main["launches"] + dg["launches"]) // 2,
                          "kernel_ms_per_step": tc_ms / 2,
                          "all_conv_ms_per_step": all_conv_ms / 2,
                          "all_conv_tflops": all_conv_work / (all_conv_ms * 1e-3) / 1e12 if all_conv_ms else 0.0,
