@@ -24,6 +24,8 @@ BATCH = 2
 # algorithmic in + out + weight bytes (3.68 GB per forward, about the same for the data gradients)
 NCU_CONV_TRAFFIC_BYTES_PER_STEP = 5.58e9
 CONV_ALGORITHMIC_BYTES_PER_STEP = 7.3e9
+WORKLOAD = ("UNet3D(1,2,32) train step, batch 2x1x128^3 per GPU, Dice+CE, BatchNorm (SyncBatchNorm across ranks when "
+            "N > 1), Adam (BASELINE.json configs[1])")
 TRAIN_GFLOP_PER_PATCH = 2850.4  # fwd 951.3 + wgrad 951.3 + dgrad (951.3 - 3.6 first layer): BASELINE.md section 3
 
 
@@ -138,7 +140,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train_patches_per_s_128cubed", "value": value, "unit": "patches/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "UNet3D(1,2,32) train step, Dice+CE, Adam, synthetic 128^3 patches (config 2)",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * args.gpus, "parallelism": "dp%d" % args.gpus,
                        "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
                              "sample": "oracle port of the reference modules, fp32 torch CPU, %d threads; each step = "
@@ -256,9 +258,7 @@ def run_b200(args):
             "metric": "train_patches_per_s_128cubed", "value": value, "unit": "patches/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "UNet3D(1,2,32) train step, batch 2x1x128^3 per GPU, Dice+CE, %s, fused Adam "
-                                   "(BASELINE.json configs[1])" % ("SyncBatchNorm" if world > 1 else "BatchNorm"),
-                       "global_batch": patches, "parallelism": "dp%d" % world,
+            "config": {"workload": WORKLOAD, "global_batch": patches, "parallelism": "dp%d" % world,
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "l2": "no flush needed: each step streams >10 GB of activations, far larger than the 126 MB L2"},
             "voxels_per_s": value * vox,
