@@ -423,6 +423,21 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   p.stages = (getenv("B200SEG_SINGLE_STAGE") && mmas_per_acc >= 256 && p.NT >= 64) ? 1 : 2;
   int pmax = std::min(8, (p.stages == 1 ? 512 : kStageCols) / p.NT);
   while (pmax > 1 && pmax / 2 >= a.od) pmax /= 2;
+  // Wave quantisation: tiles are dealt to 148 persistent CTAs, so the kernel takes ceil(tiles / 148) rounds of P planes
+  // each.  Small volumes (16^3: 64 tiles at P = 2) leave SMs idle; halving P doubles the tile count for free.
+  {
+    const long long per_plane = static_cast<long long>(a.n) * ((a.oh + 15) / 16) * ((a.ow + 7) / 8) * p.n_ntiles;
+    long long best_cost = -1;
+    int best_p = pmax;
+    // (only when the grid is short of tiles: with many rounds the larger P wins through its smaller d halo)
+    const bool starved = per_plane * ((a.od + pmax - 1) / pmax) < 2LL * kNumSMs;
+    for (int cand = pmax; cand >= 1 && starved; cand /= 2) {
+      const long long tiles = per_plane * ((a.od + cand - 1) / cand);
+      const long long cost = ((tiles + kNumSMs - 1) / kNumSMs) * cand;
+      if (best_cost < 0 || cost < best_cost) best_cost = cost, best_p = cand;   // ties keep the larger P (less weight traffic)
+    }
+    pmax = best_p;
+  }
   const size_t budget = 225 * 1024;
   P = 0;
   for (int cand = pmax; cand >= 1 && !P; cand /= 2) {
