@@ -46,8 +46,11 @@ int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g) {
 }
 
 size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g) {
-  (void)g;
-  return 0;  // neither back end needs scratch memory at present
+  // only the weight gradient uses scratch memory: split-K partial tiles (0 = not needed / atomics path)
+  if (!g || g->stride != 1) return 0;
+  UmmaWgradArgs a{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, g->cin, g->cout, g->k, g->pad, g->dil,
+                  nullptr, g->cin, nullptr, g->cout, nullptr, 0, nullptr, 0};
+  return wgrad_umma_plane_workspace_bytes(a);
 }
 
 int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
@@ -79,13 +82,12 @@ int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_
 
 int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch,
                          float* dw_packed, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (int rc = check_geom(g, "conv3d_wgrad")) return rc;
   B200_CHECK_ARG(x && dy && dw_packed && x_pitch >= g->cin && dy_pitch >= g->cout, "conv3d_wgrad: bad buffers");
   auto st = static_cast<cudaStream_t>(stream);
   if (g->stride == 1) {
     UmmaWgradArgs a{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, g->cin, g->cout, g->k, g->pad, g->dil,
-                    x, x_pitch, dy, dy_pitch, dw_packed, 0};
+                    x, x_pitch, dy, dy_pitch, dw_packed, 0, static_cast<float*>(workspace), workspace_bytes};
     if (wgrad_umma_supported(a)) return wgrad_umma_run(a, st);
   }
   return conv_direct_wgrad(*g, x, x_pitch, dy, dy_pitch, dw_packed, st);
@@ -150,7 +152,8 @@ int b200seg_convt_k2s2_wgrad(const void* x, int64_t x_pitch, const void* dy, int
   // S wgrad: dW_S[tap][cin_S = cout_T][cout_S = cin_T] = sum x_S(*)dy_S with x_S = dy_T, dy_S = x_T.
   const b200seg_conv_geom g = convt_as_conv(n, d, h, w, cin, cout);
   {
-    UmmaWgradArgs a{g.n, g.d, g.h, g.w, g.od, g.oh, g.ow, g.cin, g.cout, 2, 0, 1, dy, dy_pitch, x, x_pitch, dw_packed, 1};
+    UmmaWgradArgs a{g.n, g.d, g.h, g.w, g.od, g.oh, g.ow, g.cin, g.cout, 2, 0, 1, dy, dy_pitch, x, x_pitch, dw_packed, 1,
+                    nullptr, 0};
     if (wgrad_umma_supported(a)) return wgrad_umma_run(a, static_cast<cudaStream_t>(stream));
   }
   return conv_direct_wgrad(g, dy, dy_pitch, x, x_pitch, dw_packed, static_cast<cudaStream_t>(stream));

@@ -58,11 +58,17 @@ struct UmmaWgradArgs {
   // ConvTranspose3d(k2,s2) weight gradient: x is the FINE grid [n,2od,2oh,2ow,cin] (the up-sampled gradient), dy the
   // coarse grid [n,od,oh,ow,cout]; tap abe pairs coarse voxel v with fine voxel 2v+abe.  k must be 2, pad 0.
   int gather2;
+  // Optional split-K workspace: when non-null (and large enough, see wgrad_umma_plane_workspace_bytes) every CTA stores
+  // its partial tile with plain vector stores into slice `split` of the workspace and a second kernel sums the slices
+  // into dwp, instead of every CTA adding its tile to dwp with fp32 atomics.
+  float* partial;
+  size_t partial_bytes;
 };
 bool wgrad_umma_supported(const UmmaWgradArgs& a);
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st);
 // persistent plane-mode kernel with tap blocks on both operands (wgrad_umma_p.cu)
 bool wgrad_umma_plane_supported(const UmmaWgradArgs& a);
+size_t wgrad_umma_plane_workspace_bytes(const UmmaWgradArgs& a);
 int wgrad_umma_plane_run(const UmmaWgradArgs& a, cudaStream_t st);
 
 }  // namespace b200

@@ -492,7 +492,10 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
     if (p.WB > 256 || p.HB > 256) return false;
     const int plane_rows = p.WB * p.HB;
     const int maxoff = halo * (plane_rows + p.WB + 1);
+    // Among the depths per CTA that fit, take the one with the fewest rounds x accumulators: these are the small, K-heavy
+    // layers (8^3 bottleneck), where the largest box leaves most of the 148 SMs without a tile.
     int best_dt = 0, best_p = 0;
+    long long best_cost = -1;
     for (int DT = std::min(a.od, 256 - halo); DT >= 1; --DT) {
       const int P = (DT * plane_rows + 127) / 128;
       if (P * p.NT > 512) continue;
@@ -500,10 +503,13 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
       const size_t loaded = static_cast<size_t>(DT + halo) * plane_rows * p.rowbytes;
       if (loaded > slot) continue;
       const int S = p.nchunks > 1 ? 2 : 1;
-      if (fixed + S * slot <= kSmemBudget) {
+      if (fixed + S * slot > kSmemBudget) continue;
+      const long long ctas = static_cast<long long>(a.n) * ((a.od + DT - 1) / DT) * p.n_ntiles;
+      const long long cost = ((ctas + kNumSMs - 1) / kNumSMs) * P;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
         best_dt = DT;
         best_p = P;
-        break;
       }
     }
     if (!best_dt) return false;

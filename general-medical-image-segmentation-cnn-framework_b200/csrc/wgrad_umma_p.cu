@@ -51,6 +51,8 @@ struct WgradPParams {
   WgradPGroup groups[6];
   unsigned slotX, slotY, bytesX, bytesY, rowbytesA, rowbytesB, swzA, swzB, tmem_cols;
   float* dwp;
+  float* partial;          // split-K workspace [splits][k^3][cin][cout] (null: atomics into dwp)
+  long long slice;         // floats per workspace slice
 };
 
 constexpr int kWgradPThreads = 192;
@@ -243,14 +245,18 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
       }
       umma_commit_pred(accFull, leader);
     }
-  } else if (s0 < s1) {
-    // =========================== epilogue: TMEM -> red.global.add.f32 ===========================
+  } else if (s0 < s1 || p.partial != nullptr) {
+    // =========================== epilogue: TMEM -> workspace slice (vector stores) or red.global.add.f32 ===========
     const int q4 = warp & 3;            // warps 2..5 -> lane quadrants 2,3,0,1
     const int m = q4 * 32 + lane;       // M row = block * KC + ci
     const int blk = m / p.KC, ci = chunk * p.KC + (m % p.KC);
-    mbar_wait(accFull, 0);
-    tc_fence_after();
+    const bool have = s0 < s1;          // a split without steps still has to zero its workspace slice
+    if (have) {
+      mbar_wait(accFull, 0);
+      tc_fence_after();
+    }
     const uint32_t NTOT = p.NBLK * p.NT;
+    float* base = p.partial ? p.partial + static_cast<size_t>(split) * p.slice : p.dwp;
     for (int g = 0; g < NG; ++g) {
       const int b = p.bsplit > 1 ? bsel : p.groups[g].b;
       const int e = p.groups[g].e0 + blk;
@@ -260,12 +266,23 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
         const int tap = (a * p.k + b) * p.k + e;
         for (int cc = 0; cc < p.NT; cc += 16) {
           uint32_t raw[16];
-          tmem_ld_32x16(tbase + (static_cast<uint32_t>(q4 * 32) << 16) + g * NTOT + i * p.NT + cc, raw);
-          tmem_ld_wait();
-          if (row_ok) {
-            float* dst = p.dwp + (static_cast<size_t>(tap) * p.cin + ci) * p.cout + nt * p.NT + cc;
+          if (have) {
+            tmem_ld_32x16(tbase + (static_cast<uint32_t>(q4 * 32) << 16) + g * NTOT + i * p.NT + cc, raw);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(raw[j]));
+            for (int j = 0; j < 16; ++j) raw[j] = 0u;
+          }
+          if (row_ok) {
+            float* dst = base + (static_cast<size_t>(tap) * p.cin + ci) * p.cout + nt * p.NT + cc;
+            if (p.partial) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4*>(dst + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(raw[j]));
+            }
           }
         }
       }
@@ -276,6 +293,24 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tbase, p.tmem_cols);
+  }
+}
+
+// dwp[i] += sum over splits of partial[s][i]   (coalesced: consecutive threads, consecutive elements of every slice)
+__global__ void wgrad_reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ dwp, long long numel,
+                                             int splits) {
+  const long long nvec = numel / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(dwp)[i];
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(partial + static_cast<size_t>(s) * numel)[i];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dwp)[i] = acc;
   }
 }
 
@@ -370,6 +405,15 @@ bool wgrad_umma_plane_supported(const UmmaWgradArgs& a) {
   return plan_wgrad_plane(a, p, smem);
 }
 
+size_t wgrad_umma_plane_workspace_bytes(const UmmaWgradArgs& a) {
+  WgradPParams p;
+  size_t smem;
+  if (!plan_wgrad_plane(a, p, smem) || p.splits < 2) return 0;
+  const size_t numel = static_cast<size_t>(a.k) * a.k * a.k * a.cin * a.cout;
+  if (numel % 4) return 0;
+  return static_cast<size_t>(p.splits) * numel * sizeof(float);
+}
+
 template <int NG>
 static int launch_wgrad_plane(const CUtensorMap& tmX, const CUtensorMap& tmY, const WgradPParams& p, size_t smem,
                               int ctas, cudaStream_t st) {
@@ -399,6 +443,13 @@ int wgrad_umma_plane_run(const UmmaWgradArgs& a, cudaStream_t st) {
     set_error("wgrad_umma_plane_run: buffers must be 16-byte aligned");
     return B200SEG_ERR_INVALID;
   }
+  const long long numel = static_cast<long long>(a.k) * a.k * a.k * a.cin * a.cout;
+  const size_t need = wgrad_umma_plane_workspace_bytes(a);
+  p.partial = nullptr;
+  p.slice = numel;
+  if (need && a.partial && a.partial_bytes >= need && (reinterpret_cast<uintptr_t>(a.partial) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(a.dwp) & 15) == 0)
+    p.partial = a.partial;
   CUtensorMap tmX, tmY;
   {
     const uint64_t dims[5] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.w), static_cast<uint64_t>(a.h),
@@ -424,6 +475,10 @@ int wgrad_umma_plane_run(const UmmaWgradArgs& a, cudaStream_t st) {
     case 3: rc = launch_wgrad_plane<3>(tmX, tmY, p, smem, ctas, st); break;
     case 6: rc = launch_wgrad_plane<6>(tmX, tmY, p, smem, ctas, st); break;
     default: set_error("wgrad_umma_plane_run: unsupported group count"); break;
+  }
+  if (rc == 0 && p.partial) {
+    wgrad_reduce_partials_kernel<<<grid_for(numel / 4, 256, kNumSMs * 8), 256, 0, st>>>(p.partial, a.dwp, numel, p.splits);
+    B200_CHECK_LAUNCH("wgrad_reduce_partials");
   }
   if (rc == 0) ++g_umma_launches;
   return rc;

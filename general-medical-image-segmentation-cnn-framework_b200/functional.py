@@ -240,7 +240,10 @@ def conv3d_wgrad_raw(g, x, dy, weight_shape, weight=None):
     direct = dwp is not None
     if not direct:
         dwp = torch.zeros(k3 * g.cin * g.cout, dtype=torch.float32, device=x.device)
-    _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), None, 0, _stream(),
+    from ._lib import load
+    ws_bytes = load().b200seg_conv3d_workspace_bytes(ctypes.byref(g))      # split-K partial tiles (0: atomics path)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+    _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), _ptr(ws), ws_bytes, _stream(),
           work=_conv_flops(g), tag="conv_wgrad")
     if direct:
         _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(grad), g.cout, g.cin, g.k, 0, g.cin, 1, _stream())

@@ -80,7 +80,9 @@ int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pi
 /* dx = conv_transpose(dy, w).  w_packed from b200seg_pack_conv_weight(dgrad=1).  g describes the FORWARD conv. */
 int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_pitch, const void* w_packed_dgrad,
                          void* dx, int64_t dx_pitch, void* workspace, size_t workspace_bytes, void* stream);
-/* dw_packed[k^3][cin][cout] (fp32, accumulated into; caller zeroes) = sum_voxels x (*) dy. */
+/* dw_packed[k^3][cin][cout] (fp32, accumulated into; caller zeroes) = sum_voxels x (*) dy.  With a workspace of
+ * b200seg_conv3d_workspace_bytes(g) bytes the split-K partial tiles are stored there and summed by a second kernel
+ * (deterministic, no atomics); without one every CTA adds its tile to dw_packed with fp32 atomics. */
 int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* dy,
                          int64_t dy_pitch, float* dw_packed, void* workspace, size_t workspace_bytes, void* stream);
 
