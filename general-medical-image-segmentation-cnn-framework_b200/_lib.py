@@ -21,7 +21,8 @@ SIGNATURES = {
     "b200seg_ncdhw_f32_to_ndhwc_bf16": "ppiilp",
     "b200seg_ndhwc_bf16_to_ncdhw_f32": "ppiilp",
     "b200seg_pack_conv_weight": "ppiiiiiip",
-    "b200seg_pack_weights_batched": "pppip",
+    "b200seg_pack_weights_batched": "pppiiip",
+    "b200seg_unpack_wgrads_batched": "pppiiip",
     "b200seg_pad_channels": "plipilp",
     "b200seg_unpack_conv_wgrad": "ppiiiiiip",
     "b200seg_conv3d_fprop": "gplppplppzp",

@@ -1,6 +1,8 @@
 // Direct (CUDA-core) convolution path: every geometry the tensor-core path does not take -- C_in = 1 stems, class
 // heads, channel counts that are not multiples of 16, strided (k2s2 / k3s2) convolutions and their transposes.
 // bf16 operands, fp32 accumulation.  Also weight packing / gradient unpacking shared with the tcgen05 path.
+#include <algorithm>
+
 #include "common.cuh"
 #include "conv_impl.h"
 
@@ -73,6 +75,87 @@ __global__ void pack_weights_batched_kernel(const float* __restrict__ arena, __n
       ci = static_cast<int>((i / d.cout) % d.cin);
       t = static_cast<int>(i / (static_cast<int64_t>(d.cin) * d.cout));
       p[i] = __float2bfloat16(w[(static_cast<int64_t>(co) * d.cin + ci) * d.k3 + (d.k3 - 1 - t)]);
+    }
+  }
+}
+
+// Tiled versions of the two layout changes for MANY tensors in one launch (blockIdx.y = descriptor).  A block moves a
+// 32 (co) x 8 (ci) x k3 brick through shared memory so that both the torch side ([co][ci][k3], k3 fastest) and the packed
+// side ([k3][co][ci] or [k3][ci][co]) are accessed in runs of consecutive addresses.
+constexpr int kTileCo = 32, kTileCi = 8;
+
+__global__ void __launch_bounds__(256)
+    pack_weights_tiled_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ packs,
+                              const PackDesc* __restrict__ descs, int ndesc, int total_tiles) {
+  extern __shared__ float tile[];   // [kTileCo][kTileCi * k3 + 1]
+  // bricks of all tensors form one list dealt round-robin to the blocks (tensor sizes differ by four orders of magnitude)
+  for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+    int di = 0, tix = gt;
+    for (; di < ndesc; ++di) {
+      const int nt = ((descs[di].cin + kTileCi - 1) / kTileCi) * ((descs[di].cout + kTileCo - 1) / kTileCo);
+      if (tix < nt) break;
+      tix -= nt;
+    }
+    const PackDesc d = descs[di];
+    const float* w = arena + d.src;
+    __nv_bfloat16* p = packs + d.dst;
+    const int k3 = d.k3, cout = d.cout, cin = d.cin;
+    const int tiles_ci = (cin + kTileCi - 1) / kTileCi;
+    const int row = kTileCi * k3 + 1;
+    const int co0 = (tix / tiles_ci) * kTileCo, ci0 = (tix % tiles_ci) * kTileCi;
+    const int nci = min(kTileCi, cin - ci0), nco = min(kTileCo, cout - co0);
+    __syncthreads();
+    // torch layout: for each co a run of nci * k3 consecutive floats
+    for (int i = threadIdx.x; i < nco * nci * k3; i += blockDim.x) {
+      const int co = i / (nci * k3), r = i % (nci * k3);
+      tile[co * row + r] = w[(static_cast<int64_t>(co0 + co) * cin + ci0) * k3 + r];
+    }
+    __syncthreads();
+    if (!d.dgrad) {   // p[t][co][ci]: runs of nci
+      for (int i = threadIdx.x; i < k3 * nco * nci; i += blockDim.x) {
+        const int ci = i % nci, co = (i / nci) % nco, t = i / (nci * nco);
+        p[(static_cast<int64_t>(t) * cout + co0 + co) * cin + ci0 + ci] = __float2bfloat16(tile[co * row + ci * k3 + t]);
+      }
+    } else {          // p[t][ci][co] with the taps flipped: runs of nco
+      for (int i = threadIdx.x; i < k3 * nci * nco; i += blockDim.x) {
+        const int co = i % nco, ci = (i / nco) % nci, t = i / (nco * nci);
+        p[(static_cast<int64_t>(t) * cin + ci0 + ci) * cout + co0 + co] =
+            __float2bfloat16(tile[co * row + ci * k3 + (k3 - 1 - t)]);
+      }
+    }
+  }
+}
+
+// grad[co][ci][t] += dwp[t][ci][co] for many tensors: desc.src = float offset of dwp in `packed`, desc.dst = float offset of
+// the gradient in `grads` (cout, cin, k3 as above; dgrad unused).
+__global__ void __launch_bounds__(256)
+    unpack_wgrads_tiled_kernel(const float* __restrict__ packed, float* __restrict__ grads,
+                               const PackDesc* __restrict__ descs, int ndesc, int total_tiles) {
+  extern __shared__ float tile[];   // [kTileCo][kTileCi * k3 + 1]
+  for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+    int di = 0, tix = gt;
+    for (; di < ndesc; ++di) {
+      const int nt = ((descs[di].cin + kTileCi - 1) / kTileCi) * ((descs[di].cout + kTileCo - 1) / kTileCo);
+      if (tix < nt) break;
+      tix -= nt;
+    }
+    const PackDesc d = descs[di];
+    const float* src = packed + d.src;
+    float* dst = grads + d.dst;
+    const int k3 = d.k3, cout = d.cout, cin = d.cin;
+    const int tiles_ci = (cin + kTileCi - 1) / kTileCi;
+    const int row = kTileCi * k3 + 1;
+    const int co0 = (tix / tiles_ci) * kTileCo, ci0 = (tix % tiles_ci) * kTileCi;
+    const int nci = min(kTileCi, cin - ci0), nco = min(kTileCo, cout - co0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < k3 * nci * nco; i += blockDim.x) {   // packed side: runs of nco
+      const int co = i % nco, ci = (i / nco) % nci, t = i / (nco * nci);
+      tile[co * row + ci * k3 + t] = src[(static_cast<int64_t>(t) * cin + ci0 + ci) * cout + co0 + co];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nco * nci * k3; i += blockDim.x) {   // torch side: runs of nci * k3
+      const int co = i / (nci * k3), r = i % (nci * k3);
+      dst[(static_cast<int64_t>(co0 + co) * cin + ci0) * k3 + r] += tile[co * row + r];
     }
   }
 }
@@ -673,13 +756,39 @@ int b200seg_pad_channels(const void* x, int64_t x_pitch, int c, void* y, int cpa
   return 0;
 }
 
-int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, void* stream) {
-  B200_CHECK_ARG(arena && packs && descs && ndesc > 0 && ndesc <= 65535, "pack_weights_batched: bad arguments");
+int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, int max_k3,
+                                 int total_tiles, void* stream) {
+  B200_CHECK_ARG(arena && packs && descs && ndesc > 0 && ndesc <= 65535 && max_k3 >= 1 && max_k3 <= 125,
+                 "pack_weights_batched: bad arguments");
   static_assert(sizeof(b200::PackDesc) == 32, "descriptor layout is part of the ABI");
-  dim3 grid(96, ndesc);
-  b200::pack_weights_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      arena, static_cast<__nv_bfloat16*>(packs), static_cast<const b200::PackDesc*>(descs));
+  // brick of 32 x 8 x k3 floats in shared memory, sized for the largest kernel in the table (k3 <= 125 = 5x5x5)
+  const size_t smem = static_cast<size_t>(b200::kTileCo) * (b200::kTileCi * max_k3 + 1) * sizeof(float);
+  const size_t smem_max = static_cast<size_t>(b200::kTileCo) * (b200::kTileCi * 125 + 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(b200::pack_weights_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max));
+    attr = true;
+  }
+  b200::pack_weights_tiled_kernel<<<std::min(total_tiles, b200::kNumSMs * 6), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      arena, static_cast<__nv_bfloat16*>(packs), static_cast<const b200::PackDesc*>(descs), ndesc, total_tiles);
   B200_CHECK_LAUNCH("pack_weights_batched");
+  return 0;
+}
+
+int b200seg_unpack_wgrads_batched(const float* packed, float* grads, const void* descs, int ndesc, int max_k3,
+                                  int total_tiles, void* stream) {
+  B200_CHECK_ARG(packed && grads && descs && ndesc > 0 && ndesc <= 65535 && max_k3 >= 1 && max_k3 <= 125,
+                 "unpack_wgrads_batched: bad arguments");
+  const size_t smem = static_cast<size_t>(b200::kTileCo) * (b200::kTileCi * max_k3 + 1) * sizeof(float);
+  const size_t smem_max = static_cast<size_t>(b200::kTileCo) * (b200::kTileCi * 125 + 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(b200::unpack_wgrads_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max));
+    attr = true;
+  }
+  b200::unpack_wgrads_tiled_kernel<<<std::min(total_tiles, b200::kNumSMs * 6), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      packed, grads, static_cast<const b200::PackDesc*>(descs), ndesc, total_tiles);
+  B200_CHECK_LAUNCH("unpack_wgrads_batched");
   return 0;
 }
 

@@ -219,16 +219,15 @@ def conv3d_dgrad_raw(g, dy, weight):
 
 
 def _grad_target(param):
-    """(packed fp32 accumulator, gradient tensor) of a parameter managed by optim.FusedAdam, else (None, None).
-    The accumulator is a slice of an arena that FusedAdam.zero_grad clears together with the gradients, the gradient is
-    the parameter's view into the flat gradient arena: weight gradients then need no zero-fill, no temporary and no
-    autograd accumulation kernel."""
+    """Packed fp32 accumulator ([tap][C_in][C_out]) of a conv weight managed by optim.FusedAdam, else None.  The
+    accumulator is a slice of an arena that FusedAdam.zero_grad clears together with the gradients; the optimiser
+    transposes ALL accumulators into the gradient arena with one launch (FusedAdam.finalize_grads) before the all-reduce /
+    update, so a weight gradient needs no zero-fill, no temporary, no per-layer unpack and no autograd accumulation --
+    and a weight used twice in one step (residual_unet3d.py:126-128) simply accumulates twice."""
     if param is None or not getattr(param, "_b200_direct_grad", False) or param.grad is None:
-        return None, None
-    if param._b200_dwp_used[0]:      # second use of a shared weight in one step (residual_unet3d.py:126-128)
-        return None, None
-    param._b200_dwp_used[0] = True   # cleared by FusedAdam.zero_grad together with the accumulator itself
-    return param._b200_dwp, param.grad
+        return None
+    param._b200_pending[0] = True
+    return param._b200_dwp
 
 
 def conv3d_wgrad_raw(g, x, dy, weight_shape, weight=None):
@@ -236,7 +235,7 @@ def conv3d_wgrad_raw(g, x, dy, weight_shape, weight=None):
     x, xp = _as_rows(x)
     dy, dyp = _as_rows(dy)
     k3 = g.k ** 3
-    dwp, grad = _grad_target(weight)
+    dwp = _grad_target(weight)
     direct = dwp is not None
     if not direct:
         dwp = torch.zeros(k3 * g.cin * g.cout, dtype=torch.float32, device=x.device)
@@ -246,7 +245,6 @@ def conv3d_wgrad_raw(g, x, dy, weight_shape, weight=None):
     _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), _ptr(ws), ws_bytes, _stream(),
           work=_conv_flops(g), tag="conv_wgrad")
     if direct:
-        _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(grad), g.cout, g.cin, g.k, 0, g.cin, 1, _stream())
         return None
     gw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
     _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(gw), g.cout, g.cin, g.k, 0, g.cin, 0, _stream())
@@ -593,15 +591,13 @@ class _ConvT2(torch.autograd.Function):
             dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=x.device)
             _call("b200seg_convt_k2s2_dgrad", _ptr(dy), dyp, _ptr(wd), _ptr(dx), cin, n, d, h, w, cin, cout, _stream())
         if ctx.needs_input_grad[1]:
-            dwp, grad = _grad_target(weight)
+            dwp = _grad_target(weight)
             direct = dwp is not None
             if not direct:
                 dwp = torch.zeros(8 * cin * cout, dtype=torch.float32, device=x.device)
             _call("b200seg_convt_k2s2_wgrad", _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), n, d, h, w, cin, cout, _stream())
             # packed [8][cout_T][cin_T] is the strided conv's [k^3][cin_S][cout_S]: unpack with cout_S=cin_T, cin_S=cout_T
-            if direct:
-                _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(grad), cin, cout, 2, 0, cout, 1, _stream())
-            else:
+            if not direct:
                 dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
                 _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(dw), cin, cout, 2, 0, cout, 0, _stream())
         if ctx.has_bias and ctx.needs_input_grad[2]:

@@ -31,7 +31,7 @@ class FusedAdam:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.dw_arena = self._zeroed[total:]       # see functional._grad_target
-        self._dwp_flags = []
+        self._pending = [False]                    # some packed weight gradient has not been transposed yet
         for p, off in zip(self.params, self.offsets):
             view = self.param_arena[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
@@ -39,24 +39,27 @@ class FusedAdam:
             p.grad = self.grad_arena[off:off + p.numel()].view_as(p)
             if p.dim() == 5:      # Conv3d / ConvTranspose3d weights: backward accumulates straight into p.grad
                 p._b200_dwp = self.dw_arena[off:off + p.numel()]
-                p._b200_dwp_used = [False]
+                p._b200_pending = self._pending
                 p._b200_direct_grad = True
-                self._dwp_flags.append(p._b200_dwp_used)
         self._build_pack_table()
         self.refresh_packs()
 
     # ---- bf16 weight packs for the conv kernels, refreshed by ONE launch after every update -------------------------
     def _build_pack_table(self):
         import struct
-        recs, total = [], 0
+        recs, urecs, total = [], [], 0
+        self._max_k3, self._tiles = 1, 0
         self._packed = []
         for p, off in zip(self.params, self.offsets):
             if p.dim() != 5 or p.shape[2] != p.shape[3] or p.shape[3] != p.shape[4]:
                 continue
             a, b, k3 = p.shape[0], p.shape[1], p.shape[2] ** 3     # Conv3d [cout][cin][k^3]; ConvTranspose3d alike
             n = p.numel()
+            self._max_k3 = max(self._max_k3, k3)
+            self._tiles += ((a + 31) // 32) * ((b + 7) // 8)
             recs.append(struct.pack("<qqiiii", off, total, a, b, k3, 0))
             recs.append(struct.pack("<qqiiii", off, total + n, a, b, k3, 1))
+            urecs.append(struct.pack("<qqiiii", off, off, a, b, k3, 0))     # dw_arena[off] -> grad_arena[off]
             self._packed.append((p, total, n))
             total += 2 * n
         if not recs:
@@ -66,6 +69,8 @@ class FusedAdam:
         self._pack_arena = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self._pack_desc = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
         self._npack = len(recs)
+        self._unpack_desc = torch.frombuffer(bytearray(b"".join(urecs)), dtype=torch.uint8).to(dev)
+        self._nunpack = len(urecs)
         for p, o, n in self._packed:
             p._b200_pack0 = self._pack_arena[o:o + n]            # fprop layout [k^3][cout][cin]
             p._b200_pack1 = self._pack_arena[o + n:o + 2 * n]    # dgrad layout [k^3 flipped][cin][cout]
@@ -75,14 +80,21 @@ class FusedAdam:
         if self._pack_desc is None:
             return
         _call("b200seg_pack_weights_batched", _ptr(self.param_arena), _ptr(self._pack_arena), _ptr(self._pack_desc),
-              self._npack, _stream())
+              self._npack, self._max_k3, 2 * self._tiles, _stream())
         for p, _, _ in self._packed:
             p._b200_pack_ver = p._version
 
+    def finalize_grads(self):
+        """The conv kernels leave their weight gradients in the packed [tap][C_in][C_out] accumulators of dw_arena; one
+        launch transposes all of them into the torch-layout gradient arena.  Runs before the all-reduce / the update."""
+        if self._pending[0] and self._pack_desc is not None:
+            _call("b200seg_unpack_wgrads_batched", _ptr(self.dw_arena), _ptr(self.grad_arena), _ptr(self._unpack_desc),
+                  self._nunpack, self._max_k3, self._tiles, _stream())
+        self._pending[0] = False
+
     def zero_grad(self, set_to_none=False):
         self._zeroed.zero_()
-        for flag in self._dwp_flags:
-            flag[0] = False
+        self._pending[0] = False
         for p, off in zip(self.params, self.offsets):   # autograd accumulates in place into these views
             if p.grad is None or p.grad.data_ptr() != self.grad_arena.data_ptr() + 4 * off:
                 p.grad = self.grad_arena[off:off + p.numel()].view_as(p)
@@ -96,6 +108,7 @@ class FusedAdam:
     def all_reduce_grads(self, group=None):
         """Data-parallel gradient averaging (what DDP does inside accelerator.backward, train.py:211).  Returns the
         factor the summed gradients still have to be scaled by (folded into the Adam kernel)."""
+        self.finalize_grads()
         if getattr(self, "reducer", None) is not None and self.reducer.enabled:
             return self.reducer.finish()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -119,6 +132,7 @@ class FusedAdam:
             self._hyper_host = want
 
     def step(self, grad_scale=1.0):
+        self.finalize_grads()
         self._sync_hyper(grad_scale)
         self.step_count += 1
         _call("b200seg_adam_step_dev", _ptr(self.param_arena), _ptr(self.grad_arena), _ptr(self.exp_avg),

@@ -61,8 +61,15 @@ int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, in
  * input to 16 channels so that the stem convolution (unet3d.py:80, C_in = 1) runs on the tensor-core path. */
 int b200seg_pad_channels(const void* x, int64_t x_pitch, int c, void* y, int cpad, int64_t rows, void* stream);
 /* Both packs of many weight tensors in one launch.  descs: DEVICE array of ndesc 32-byte records
- * {int64 src (float offset into arena), int64 dst (bf16 element offset into packs), int32 cout, cin, k^3, dgrad}. */
-int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, void* stream);
+ * {int64 src (float offset into arena), int64 dst (bf16 element offset into packs), int32 cout, cin, k^3, dgrad};
+ * max_k3 = the largest k^3 in the table (sizes the shared-memory brick); total_tiles = sum over the records of
+ * ceil(cout / 32) * ceil(cin / 8), the number of 32 x 8 x k^3 bricks dealt round-robin to the thread blocks. */
+int b200seg_pack_weights_batched(const float* arena, void* packs, const void* descs, int ndesc, int max_k3,
+                                 int total_tiles, void* stream);
+/* The reverse for the weight gradients of many layers in one launch: grads[dst + (co*cin + ci)*k^3 + t] +=
+ * packed[src + (t*cin + ci)*cout + co]; same 32-byte records (dgrad ignored), k^3 <= 125. */
+int b200seg_unpack_wgrads_batched(const float* packed, float* grads, const void* descs, int ndesc, int max_k3,
+                                  int total_tiles, void* stream);
 /* wgrad result [k^3][cin_cnt][cout] fp32 -> torch-layout grad [cout][cin][k^3] fp32 slice.  accumulate bit 0: add to
  * grad_w instead of overwriting; bit 1: clear dw_packed while reading it (a persistent, always-zero accumulator needs no
  * memset between steps; dw_packed is written in that case despite the const). */
