@@ -26,7 +26,7 @@ SIGNATURES = {
     "b200seg_pad_channels": "plipilp",
     "b200seg_unpack_conv_wgrad": "ppiiiiiip",
     "b200seg_conv3d_fprop": "gplppplppzp",
-    "b200seg_conv3d_dgrad": "gplpplpzp",
+    "b200seg_conv3d_dgrad": "gplpplppzp",
     "b200seg_conv3d_wgrad": "gplplppzp",
     "b200seg_pack_convt_weight": "ppiiip",
     "b200seg_convt_k2s2_fwd": "plpp" + "pl" + "iiiiii" + "p",
@@ -49,7 +49,7 @@ SIGNATURES = {
     "b200seg_head_conv1x1_fwd": "plppp" + "ilii" + "p",
     "b200seg_head_conv1x1_bwd": "ppl" + "p" + "pl" + "pp" + "ilii" + "p",
     "b200seg_argmax_labels": "pp" + "ili" + "p",
-    "b200seg_loss_reduce": "pp" + "ili" + "pp",
+    "b200seg_loss_reduce": "pp" + "ilii" + "pp",
     "b200seg_loss_grad": "pp" + "ili" + "p" + "ffff" + "p" + "pp",
     "b200seg_seg_counts": "ppl" + "pp",
     "b200seg_window_accumulate_crop": "ppp" + "l" + "iiiiiii" + "p" + "iii" + "p",

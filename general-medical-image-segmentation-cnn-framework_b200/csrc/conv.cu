@@ -27,11 +27,11 @@ static UmmaConvArgs fprop_args(const b200seg_conv_geom* g, const void* x, int64_
   return a;
 }
 static UmmaConvArgs dgrad_args(const b200seg_conv_geom* g, const void* dy, int64_t dyp, const void* wd, void* dx,
-                               int64_t dxp) {
+                               int64_t dxp, float* stats) {
   UmmaConvArgs a{};
   a.n = g->n; a.d = g->od; a.h = g->oh; a.w = g->ow; a.od = g->d; a.oh = g->h; a.ow = g->w;
   a.cin = g->cout; a.cout = g->cin; a.k = g->k; a.pad = g->dil * (g->k - 1) - g->pad; a.dil = g->dil;
-  a.in = dy; a.in_pitch = dyp; a.wpack = wd; a.bias = nullptr; a.out = dx; a.out_pitch = dxp; a.stats = nullptr;
+  a.in = dy; a.in_pitch = dyp; a.wpack = wd; a.bias = nullptr; a.out = dx; a.out_pitch = dxp; a.stats = stats;
   return a;
 }
 
@@ -68,16 +68,21 @@ int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pi
 }
 
 int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_pitch, const void* w_packed_dgrad,
-                         void* dx, int64_t dx_pitch, void* workspace, size_t workspace_bytes, void* stream) {
+                         void* dx, int64_t dx_pitch, float* stats, void* workspace, size_t workspace_bytes,
+                         void* stream) {
   (void)workspace; (void)workspace_bytes;
   if (int rc = check_geom(g, "conv3d_dgrad")) return rc;
   B200_CHECK_ARG(dy && w_packed_dgrad && dx && dy_pitch >= g->cout && dx_pitch >= g->cin, "conv3d_dgrad: bad buffers");
   auto st = static_cast<cudaStream_t>(stream);
   if (g->stride == 1 && g->dil * (g->k - 1) - g->pad >= 0) {
-    UmmaConvArgs a = dgrad_args(g, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch);
+    UmmaConvArgs a = dgrad_args(g, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch, stats);
     if (conv_umma_supported(a)) return conv_umma_run(a, st);
   }
-  return conv_direct_dgrad(*g, dy, dy_pitch, w_packed_dgrad, nullptr, dx, dx_pitch, st);
+  if (int rc = conv_direct_dgrad(*g, dy, dy_pitch, w_packed_dgrad, nullptr, dx, dx_pitch, st)) return rc;
+  // the direct kernels have no statistics epilogue: one extra pass over dx
+  if (stats)
+    return b200seg_channel_stats(dx, dx_pitch, static_cast<int64_t>(g->n) * g->d * g->h * g->w, 1, g->cin, stats, stream);
+  return 0;
 }
 
 int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch,

@@ -37,7 +37,8 @@ constexpr int kRollRing = 5;       // accumulators in TMEM
 constexpr int kRollEpiWarps = 8;
 
 struct RollParams {
-  int n, d, od, oh, ow, cout, pad;
+  int n, d, od, oh, ow, cout, pad;   // cout = channels of the whole output tensor
+  int halves;                        // 1, or 2: C_out = 64 handled as two independent 32-channel halves (CTA parity)
   long long out_pitch;
   int KC, NTOT;                    // channels per row (= C_in), N = 3 * C_out
   int WB, HB, S;                   // plane box and ring slots
@@ -55,6 +56,7 @@ struct RollItem {
 
 __device__ __forceinline__ RollItem roll_decode(const RollParams& p, long long it) {
   RollItem r;
+  it /= p.halves;   // the half is the CTA's parity (grid and item count are even), not part of the item
   const int seg = static_cast<int>(it % p.segs);
   it /= p.segs;
   r.w0 = static_cast<int>(it % p.tiles_w) * 8;
@@ -83,6 +85,9 @@ __global__ void __launch_bounds__(kRollThreads, 1)
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);      // [CO]
   float* s_stats = s_bias + CO;                                // [2][CO]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // C_out = 64: even CTAs produce channels [0, 32), odd CTAs [32, 64) of the same tile columns at the same time (the
+  // partner's input planes are L2 hits); each keeps only its own half of the weights resident.
+  const int co_base = p.halves == 2 ? static_cast<int>(blockIdx.x & 1) * CO : 0;
 
   if (tid == 0) {
     for (int i = 0; i < p.S; ++i) {
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     mbar_init(wFull, 1);
     fence_mbar_init();
   }
-  if (tid < CO) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
+  if (tid < CO) s_bias[tid] = p.bias ? p.bias[co_base + tid] : 0.f;
   if (tid < 2 * CO) s_stats[tid] = 0.f;
   if (warp == 3) {
     tmem_alloc(tmem_ptr, 512);
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
       mbar_arrive_expect_tx(wFull, 27u * p.wblock_bytes);
       for (int be = 0; be < 9; ++be)
         for (int a = 0; a < 3; ++a)    // packed weights are [tap = (a*3+kh)*3+kw][C_out][C_in]
-          tma_load_3d(sW + be * p.wtile_bytes + a * p.wblock_bytes, &tmB, wFull, 0, 0, a * 9 + be);
+          tma_load_3d(sW + be * p.wtile_bytes + a * p.wblock_bytes, &tmB, wFull, 0, co_base, a * 9 + be);
       int s = 0;
       uint32_t ph = 0;
       for (long long it = first; it < p.items; it += stride) {
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
               }
             }
             const long long vox = ((static_cast<long long>(r.nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
-            __nv_bfloat16* optr = p.out + vox * p.out_pitch + half * CH;
+            __nv_bfloat16* optr = p.out + vox * p.out_pitch + co_base + half * CH;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               float t8[8];
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     }
   }
   __syncthreads();
-  if (p.stats != nullptr && tid < 2 * CO) atomicAdd(&p.stats[tid], s_stats[tid]);
+  if (p.stats != nullptr && tid < 2 * CO) atomicAdd(&p.stats[(tid / CO) * p.cout + co_base + tid % CO], s_stats[tid]);
   if (warp == 3) {
     tc_fence_after();
     tmem_dealloc(tbase, 512);
@@ -278,23 +283,26 @@ __global__ void __launch_bounds__(kRollThreads, 1)
 static bool plan_roll(const UmmaConvArgs& a, RollParams& p, size_t& smem_bytes) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_ROLL")) return false;
   if (a.k != 3 || a.dil != 1 || a.pad < 0 || a.scatter_cout || a.gather2) return false;
-  if (!(a.cout == 16 || a.cout == 32)) return false;
+  if (!(a.cout == 16 || a.cout == 32 || a.cout == 64) || (getenv("B200SEG_DISABLE_ROLL_HALVES") && a.cout == 64)) return false;
   if (!(a.cin == 16 || a.cin == 32 || a.cin == 64)) return false;
+  const int halves = a.cout == 64 ? 2 : 1;   // two N = 96 instructions beat three N = 64 ones (61 vs 54.6 cycles each)
+  const int CO = a.cout / halves;
   if (a.in_pitch % 8 || a.out_pitch % 8) return false;
   if (a.od != a.d + 2 * a.pad - 2 || a.oh != a.h + 2 * a.pad - 2 || a.ow != a.w + 2 * a.pad - 2) return false;
   if (!(a.oh >= 16 && a.ow >= 8) || a.od < 4) return false;
   p = RollParams{};
   p.n = a.n; p.d = a.d; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.pad = a.pad;
   p.out_pitch = a.out_pitch;
+  p.halves = halves;
   p.KC = a.cin;
-  p.NTOT = 3 * a.cout;
+  p.NTOT = 3 * CO;
   p.rowbytes = p.KC * 2;
   p.swz = p.KC == 64 ? SWZ_128B : (p.KC == 32 ? SWZ_64B : SWZ_32B);
   p.WB = 10;
   p.HB = 18;
   p.bytesA = static_cast<unsigned>(p.WB * p.HB) * p.rowbytes;
   p.slotA = (p.bytesA + 1023) & ~1023u;
-  p.wblock_bytes = static_cast<unsigned>(a.cout) * p.rowbytes;      // one kd tap: C_out rows
+  p.wblock_bytes = static_cast<unsigned>(CO) * p.rowbytes;          // one kd tap: C_out rows (of this half)
   p.wtile_bytes = 3u * p.wblock_bytes;                              // one (kh, kw): 3 * C_out rows, contiguous
   if (p.wblock_bytes % 1024) return false;                          // blocks must start on a swizzle-atom boundary
   const size_t fixed = 9u * p.wtile_bytes + 2048 + 1024;
@@ -304,7 +312,7 @@ static bool plan_roll(const UmmaConvArgs& a, RollParams& p, size_t& smem_bytes) 
   p.tiles_w = (a.ow + 7) / 8;
   p.tiles_h = (a.oh + 15) / 16;
   // segment length: as long as possible (2 halo planes are recomputed per segment) while keeping >= ~4 items per SM
-  const long long cols = static_cast<long long>(a.n) * p.tiles_h * p.tiles_w;
+  const long long cols = static_cast<long long>(a.n) * p.tiles_h * p.tiles_w * halves;
   int L = a.od;
   while (L > 8 && cols * ((a.od + L - 1) / L) < 4LL * kNumSMs) L = (L + 1) / 2;
   p.L = L;
@@ -363,18 +371,20 @@ int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.cout), 27ull};
     const uint64_t str[2] = {static_cast<uint64_t>(a.cin) * 2, static_cast<uint64_t>(a.cin) * a.cout * 2};
-    const uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(a.cout), 1u};
+    const uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(a.cout / p.halves), 1u};
     if (!encode_bf16_map(&tmB, a.wpack, 3, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
   }
-  const int ctas = static_cast<int>(std::min<long long>(kNumSMs, p.items));
+  int ctas = static_cast<int>(std::min<long long>(kNumSMs, p.items));
+  if (p.halves == 2) ctas &= ~1;   // CTA parity selects the half: the stride over the items must be even
   const int KS = a.cin / 16;
+  const int co = a.cout / p.halves;
   int rc = B200SEG_ERR_INVALID;
-  if (a.cout == 32 && KS == 1) rc = launch_roll<1, 32>(tmA, tmB, p, smem, ctas, st);
-  else if (a.cout == 32 && KS == 2) rc = launch_roll<2, 32>(tmA, tmB, p, smem, ctas, st);
-  else if (a.cout == 32 && KS == 4) rc = launch_roll<4, 32>(tmA, tmB, p, smem, ctas, st);
-  else if (a.cout == 16 && KS == 1) rc = launch_roll<1, 16>(tmA, tmB, p, smem, ctas, st);
-  else if (a.cout == 16 && KS == 2) rc = launch_roll<2, 16>(tmA, tmB, p, smem, ctas, st);
-  else if (a.cout == 16 && KS == 4) rc = launch_roll<4, 16>(tmA, tmB, p, smem, ctas, st);
+  if (co == 32 && KS == 1) rc = launch_roll<1, 32>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 32 && KS == 2) rc = launch_roll<2, 32>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 32 && KS == 4) rc = launch_roll<4, 32>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 1) rc = launch_roll<1, 16>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 2) rc = launch_roll<2, 16>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 4) rc = launch_roll<4, 16>(tmA, tmB, p, smem, ctas, st);
   if (rc == 0) ++g_umma_launches;
   return rc;
 }

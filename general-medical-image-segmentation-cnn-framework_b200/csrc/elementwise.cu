@@ -919,9 +919,10 @@ static inline int ew_grid(int64_t total_items, int cv) {
   return blocks;
 }
 // Blocks of a column reduction: every block ends with a shared-memory tree and 2-3 atomics per channel, so a block must
-// own enough rows (>= 32 per thread row) to amortise that -- small tensors get few blocks, not 592 idle ones.
+// own a few rows per thread row (>= 8: two 4-row batches) to amortise that -- but not more: the 16^3 / 8^3 layers are
+// latency-bound (8 blocks walking 32 dependent rows each took 27 us for 2 MB), so small tensors still spread over the SMs.
 static inline int reduce_grid(int64_t rows, int ty, int cap) {
-  int64_t b = (rows + static_cast<int64_t>(ty) * 32 - 1) / (static_cast<int64_t>(ty) * 32);
+  int64_t b = (rows + static_cast<int64_t>(ty) * 8 - 1) / (static_cast<int64_t>(ty) * 8);
   if (b < 1) b = 1;
   if (b > cap) b = cap;
   return static_cast<int>(b);

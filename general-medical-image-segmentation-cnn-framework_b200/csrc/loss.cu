@@ -1,6 +1,8 @@
 // Head (1x1x1 conv to class logits), fused softmax + Dice + CE (+ sigmoid-Dice, BCE) reduction and gradient,
 // arg-max label maps, segmentation counts (Dice/IoU metric) and the sliding-window aggregator.
 // All HBM-bound: one pass over their inputs, 128-bit loads where the layout allows.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int64_t dx_pitch,
                         float* __restrict__ grad_w, float* __restrict__ grad_b, int n, int64_t spatial, int classes) {
   constexpr int CIN = LPV * 8;
+  constexpr int U = 4;                              // voxels in flight per thread
   __shared__ float sgw[2 * CIN + 2];
   for (int i = threadIdx.x; i < 2 * CIN + 2; i += blockDim.x) sgw[i] = 0.f;
   __syncthreads();
@@ -142,27 +145,43 @@ __global__ void __launch_bounds__(256)
     w1[j] = classes > 1 ? w[CIN + c0 + j] : 0.f;
     gw0[j] = gw1[j] = 0.f;
   }
-  const int64_t total = static_cast<int64_t>(n) * spatial;
+  (void)n;
+  const int64_t nn = blockIdx.y;                    // one sample per grid row: no per-voxel 64-bit division
+  const float* dl0 = dlogits + nn * classes * spatial;
+  const float* dl1 = classes > 1 ? dl0 + spatial : dl0;
+  const __nv_bfloat16* xs = x + nn * spatial * x_pitch + c0;
+  __nv_bfloat16* dxs = dx + nn * spatial * dx_pitch + c0;
   const int64_t gthread = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t nvox_step = static_cast<int64_t>(gridDim.x) * blockDim.x / LPV;
-  for (int64_t v = gthread / LPV; v < total; v += nvox_step) {
-    const int64_t nn = v / spatial, sp = v - nn * spatial;
-    const float d0 = dlogits[(nn * classes) * spatial + sp];
-    const float d1 = classes > 1 ? dlogits[(nn * classes + 1) * spatial + sp] : 0.f;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x / LPV;
+  auto one = [&](int64_t v, float d0, float d1, const bf16x8& raw) {
     float f[8], o[8];
-    unpack8(ld8(x + v * x_pitch + c0), f);
+    unpack8(raw, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       o[j] = d0 * w0[j] + d1 * w1[j];
       gw0[j] += d0 * f[j];
       gw1[j] += d1 * f[j];
     }
-    st8(dx + v * dx_pitch + c0, pack8(o));
+    st8(dxs + v * dx_pitch, pack8(o));
     if (sub == 0) {
       gb0 += d0;
       gb1 += d1;
     }
+  };
+  int64_t v = gthread / LPV;
+  for (; v + (U - 1) * step < spatial; v += U * step) {
+    float d0[U], d1[U];
+    bf16x8 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      d0[u] = dl0[v + u * step];
+      d1[u] = classes > 1 ? dl1[v + u * step] : 0.f;
+      raw[u] = ld8(xs + (v + u * step) * x_pitch);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(v + u * step, d0[u], d1[u], raw[u]);
   }
+  for (; v < spatial; v += step) one(v, dl0[v], classes > 1 ? dl1[v] : 0.f, ld8(xs + v * x_pitch));
   // fold the lanes that own the same channel group (lane, lane + LPV, lane + 2 LPV, ...)
 #pragma unroll
   for (int off = LPV; off < 32; off <<= 1) {
@@ -336,6 +355,152 @@ __global__ void loss_grad_kernel(const float* __restrict__ logits, const uint8_t
   }
 }
 
+// ---- two-class fast paths (the reference's segmentation setting, train.py:331): four consecutive voxels per thread and
+// iteration (one 128-bit load per class plane, one 32-bit load of labels), one sample per grid row (no per-voxel 64-bit
+// division), two iterations in flight, and only the sums the configured loss needs.  With two classes the soft-max needs
+// ONE exponential: the larger logit has e = 1 and the other e = exp(-|l1 - l0|).
+struct Soft2 {
+  float p0, p1, nll_if0, nll_if1;   // probabilities and -log p_k
+};
+__device__ __forceinline__ Soft2 softmax2(float l0, float l1) {
+  const float m = fmaxf(l0, l1);
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+  const float z = e0 + e1, inv_z = 1.f / z, logz = logf(z);
+  Soft2 r;
+  r.p0 = e0 * inv_z;
+  r.p1 = e1 * inv_z;
+  r.nll_if0 = -(l0 - m - logz);
+  r.nll_if1 = -(l1 - m - logz);
+  return r;
+}
+
+template <bool SOFT, bool SIG>
+__global__ void __launch_bounds__(256)
+    loss_reduce2_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int64_t spatial,
+                        double* __restrict__ partial) {
+  constexpr int NS = 11;   // 1 + 3*2 + 4
+  float acc[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) acc[i] = 0.f;
+  const int64_t nn = blockIdx.y;
+  const float4* l0 = reinterpret_cast<const float4*>(logits + nn * 2 * spatial);
+  const float4* l1 = reinterpret_cast<const float4*>(logits + (nn * 2 + 1) * spatial);
+  const uchar4* lab = reinterpret_cast<const uchar4*>(labels + nn * spatial);
+  const int64_t quads = spatial >> 2;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  auto one = [&](float a, float b, int t) {
+    const float t0 = (t == 0) ? 1.f : 0.f, t1 = (t == 1) ? 1.f : 0.f;
+    if (SOFT) {
+      const Soft2 r = softmax2(a, b);
+      acc[0] += (t == 0) ? r.nll_if0 : ((t == 1) ? r.nll_if1 : 0.f);
+      acc[1] += r.p0 * t0;
+      acc[2] += r.p0 * r.p0;
+      acc[3] += t0;
+      acc[4] += r.p1 * t1;
+      acc[5] += r.p1 * r.p1;
+      acc[6] += t1;
+    }
+    if (SIG) {
+      const float s0 = sigmoidf_(a), s1 = sigmoidf_(b);
+      acc[7] += s0 * t0 + s1 * t1;
+      acc[8] += s0 + s1;
+      acc[9] += t0 + t1;
+      acc[10] += (fmaxf(a, 0.f) - a * t0 + log1pf(expf(-fabsf(a)))) + (fmaxf(b, 0.f) - b * t1 + log1pf(expf(-fabsf(b))));
+    }
+  };
+  auto quad = [&](const float4& a, const float4& b, const uchar4& t) {
+    one(a.x, b.x, t.x);
+    one(a.y, b.y, t.y);
+    one(a.z, b.z, t.z);
+    one(a.w, b.w, t.w);
+  };
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; q + step < quads; q += 2 * step) {
+    const float4 a0 = l0[q], b0 = l1[q], a1 = l0[q + step], b1 = l1[q + step];
+    const uchar4 t0 = lab[q], t1 = lab[q + step];
+    quad(a0, b0, t0);
+    quad(a1, b1, t1);
+  }
+  for (; q < quads; q += step) quad(l0[q], l1[q], lab[q]);
+  __shared__ double red[NS];
+  if (threadIdx.x < NS) red[threadIdx.x] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    if ((i < 7 && !SOFT) || (i >= 7 && !SIG)) continue;
+    const float t = warp_sum(acc[i]);   // <= 32 x (a few hundred) fp32 terms per warp; doubles from here on
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], static_cast<double>(t));
+  }
+  __syncthreads();
+  if (threadIdx.x < NS && ((threadIdx.x < 7) ? SOFT : SIG)) atomicAdd(&partial[threadIdx.x], red[threadIdx.x]);
+}
+
+template <bool SIG>
+__global__ void __launch_bounds__(256)
+    loss_grad2_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int n, int64_t spatial,
+                      const double* __restrict__ partial, float w_ce, float w_dice, float w_sdice, float w_bce,
+                      const float* __restrict__ gscale_p, float* __restrict__ dlogits) {
+  const float gscale = gscale_p ? *gscale_p : 1.f;
+  float ck_t[2], ck_p[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {   // same coefficients as loss_grad_kernel, recomputed per thread (a handful of flops)
+    const double smooth = 1e-5;
+    const double I = partial[1 + 3 * k], Z = partial[2 + 3 * k], Y = partial[3 + 3 * k];
+    const double D = Z + Y + smooth;
+    ck_t[k] = static_cast<float>(-2.0 / D / 2);
+    ck_p[k] = static_cast<float>(2.0 * (2.0 * I + smooth) / (D * D) / 2);
+  }
+  float sd_t = 0.f, sd_c = 0.f;
+  if (SIG) {
+    const double eps = 1e-5;
+    const double I = partial[7], U = partial[8] + partial[9];
+    sd_t = static_cast<float>(-2.0 / (U + eps));
+    sd_c = static_cast<float>(2.0 * (I + eps) / ((U + eps) * (U + eps)));
+  }
+  const float inv_vox = 1.f / static_cast<float>(static_cast<int64_t>(n) * spatial);
+  const float inv_elems = inv_vox / 2;
+  const int64_t nn = blockIdx.y;
+  const float4* l0 = reinterpret_cast<const float4*>(logits + nn * 2 * spatial);
+  const float4* l1 = reinterpret_cast<const float4*>(logits + (nn * 2 + 1) * spatial);
+  float4* g0 = reinterpret_cast<float4*>(dlogits + nn * 2 * spatial);
+  float4* g1 = reinterpret_cast<float4*>(dlogits + (nn * 2 + 1) * spatial);
+  const uchar4* lab = reinterpret_cast<const uchar4*>(labels + nn * spatial);
+  const int64_t quads = spatial >> 2;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  auto one = [&](float a, float b, int t, float& ga, float& gb) {
+    const float t0 = (t == 0) ? 1.f : 0.f, t1 = (t == 1) ? 1.f : 0.f;
+    const Soft2 r = softmax2(a, b);
+    const float a0 = ck_t[0] * t0 + ck_p[0] * r.p0, a1 = ck_t[1] * t1 + ck_p[1] * r.p1;
+    const float dot = a0 * r.p0 + a1 * r.p1;
+    ga = w_ce * (r.p0 - t0) * inv_vox + w_dice * r.p0 * (a0 - dot);
+    gb = w_ce * (r.p1 - t1) * inv_vox + w_dice * r.p1 * (a1 - dot);
+    if (SIG) {
+      const float s0 = sigmoidf_(a), s1 = sigmoidf_(b);
+      ga += w_sdice * (sd_t * t0 + sd_c) * s0 * (1.f - s0) + w_bce * (s0 - t0) * inv_elems;
+      gb += w_sdice * (sd_t * t1 + sd_c) * s1 * (1.f - s1) + w_bce * (s1 - t1) * inv_elems;
+    }
+    ga *= gscale;
+    gb *= gscale;
+  };
+  auto quad = [&](int64_t q, const float4& a, const float4& b, const uchar4& t) {
+    float4 oa, ob;
+    one(a.x, b.x, t.x, oa.x, ob.x);
+    one(a.y, b.y, t.y, oa.y, ob.y);
+    one(a.z, b.z, t.z, oa.z, ob.z);
+    one(a.w, b.w, t.w, oa.w, ob.w);
+    g0[q] = oa;
+    g1[q] = ob;
+  };
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; q + step < quads; q += 2 * step) {
+    const float4 a0 = l0[q], b0 = l1[q], a1 = l0[q + step], b1 = l1[q + step];
+    const uchar4 t0 = lab[q], t1 = lab[q + step];
+    quad(q, a0, b0, t0);
+    quad(q + step, a1, b1, t1);
+  }
+  for (; q < quads; q += step) quad(q, l0[q], l1[q], lab[q]);
+}
+
 // ------------------------------------------------------------------------------------------------ metric
 __global__ void seg_counts_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred, int64_t numel,
                                   unsigned long long* __restrict__ counts) {
@@ -476,7 +641,8 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
   auto* dxp = static_cast<__nv_bfloat16*>(dx);
   if (classes <= 2 && (cin == 16 || cin == 32 || cin == 64) && x_pitch % 8 == 0 && dx_pitch % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
-    const int g = kNumSMs * 8;
+    const int per_sample = std::max(1, kNumSMs * 8 / n);
+    const dim3 g(static_cast<unsigned>(std::min<int64_t>(per_sample, (spatial * (cin / 8) + 255) / 256)), n);
     if (cin == 16)
       head_bwd_vec_kernel<2><<<g, 256, 0, st>>>(dlogits, xp, x_pitch, w, dxp, dx_pitch, grad_w, grad_b, n, spatial, classes);
     else if (cin == 32)
@@ -509,10 +675,22 @@ int b200seg_argmax_labels(const float* logits, uint8_t* labels, int n, int64_t s
   return 0;
 }
 
-int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
+int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes, int terms,
                         double* partial, void* stream) {
   B200_CHECK_ARG(logits && labels && partial && n > 0 && spatial > 0, "loss_reduce: bad arguments");
   B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "loss_reduce: classes must be in [1,%d]", kMaxClasses);
+  B200_CHECK_ARG(terms >= 1 && terms <= 3, "loss_reduce: terms must be a mask of 1 (soft-max sums) | 2 (sigmoid sums)");
+  if (classes == 2 && spatial % 4 == 0 && n <= 65535 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(labels) & 3) == 0) {
+    const int per_sample = std::max(1, kNumSMs * 4 / n);
+    const dim3 grid(static_cast<unsigned>(std::min<int64_t>(per_sample, (spatial / 4 + 511) / 512)), n);
+    auto st = static_cast<cudaStream_t>(stream);
+    if (terms == 1) loss_reduce2_kernel<true, false><<<grid, 256, 0, st>>>(logits, labels, spatial, partial);
+    else if (terms == 2) loss_reduce2_kernel<false, true><<<grid, 256, 0, st>>>(logits, labels, spatial, partial);
+    else loss_reduce2_kernel<true, true><<<grid, 256, 0, st>>>(logits, labels, spatial, partial);
+    B200_CHECK_LAUNCH("loss_reduce");
+    return 0;
+  }
   loss_reduce_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256, kNumSMs * 8), 256, 0,
                        static_cast<cudaStream_t>(stream)>>>(logits, labels, n, spatial, classes, partial);
   B200_CHECK_LAUNCH("loss_reduce");
@@ -524,6 +702,19 @@ int b200seg_loss_grad(const float* logits, const uint8_t* labels, int n, int64_t
                       const float* gscale, float* dlogits, void* stream) {
   B200_CHECK_ARG(logits && labels && partial && dlogits && n > 0 && spatial > 0, "loss_grad: bad arguments");
   B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "loss_grad: classes must be in [1,%d]", kMaxClasses);
+  if (classes == 2 && spatial % 4 == 0 && n <= 65535 &&
+      ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(labels) & 3) == 0) {
+    const int per_sample = std::max(1, kNumSMs * 8 / n);
+    const dim3 grid(static_cast<unsigned>(std::min<int64_t>(per_sample, (spatial / 4 + 511) / 512)), n);
+    auto st = static_cast<cudaStream_t>(stream);
+    if (w_sdice != 0.f || w_bce != 0.f)
+      loss_grad2_kernel<true><<<grid, 256, 0, st>>>(logits, labels, n, spatial, partial, w_ce, w_dice, w_sdice, w_bce, gscale, dlogits);
+    else
+      loss_grad2_kernel<false><<<grid, 256, 0, st>>>(logits, labels, n, spatial, partial, w_ce, w_dice, w_sdice, w_bce, gscale, dlogits);
+    B200_CHECK_LAUNCH("loss_grad");
+    return 0;
+  }
   loss_grad_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, labels, n, spatial, classes, partial, w_ce, w_dice, w_sdice, w_bce, gscale, dlogits);
   B200_CHECK_LAUNCH("loss_grad");

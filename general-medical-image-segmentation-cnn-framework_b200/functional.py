@@ -71,10 +71,12 @@ def begin_step(device, nbytes=4 << 20):
         _SCRATCH["buf"] = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
     _SCRATCH["buf"].zero_()
     _SCRATCH["pos"], _SCRATCH["active"] = 0, True
+    _COLSUMS.clear()
 
 
 def end_step():
     _SCRATCH["active"] = False
+    _COLSUMS.clear()
 
 
 def _zeros_f32(numel, device):
@@ -209,13 +211,33 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
     return y, stats, g
 
 
-def conv3d_dgrad_raw(g, dy, weight):
+def conv3d_dgrad_raw(g, dy, weight, colsum=False):
+    """dx of the conv described by g.  colsum=True also returns {sum[C_in], sumsq[C_in]} of dx over the voxels (fp32,
+    from the same epilogue): the first row is the bias gradient of whatever produced the conv's input."""
     dy, dyp = _as_rows(dy)
     wd = pack_conv_weight(weight, dgrad=True)
     dx = torch.empty((g.n, g.d, g.h, g.w, g.cin), dtype=torch.bfloat16, device=dy.device)
-    _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, None, 0, _stream(),
-          work=_conv_flops(g), tag="conv_dgrad")
-    return dx
+    stats = _zeros_f32(2 * g.cin, dy.device) if colsum else None
+    _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, _ptr(stats), None, 0,
+          _stream(), work=_conv_flops(g), tag="conv_dgrad")
+    return (dx, stats) if colsum else dx
+
+
+# Column sums of gradients that a conv's dgrad epilogue already produced, keyed by the gradient tensor they describe:
+# ConvTranspose3d.backward takes its bias gradient from here instead of re-reading dy (unet3d.py:58-59: the up-conv output
+# is the first half of the decoder conv's input).  Entries hold the tensor, so its memory cannot be recycled under the key.
+_COLSUMS = {}
+
+
+def _publish_colsum(t, sums):
+    if len(_COLSUMS) >= 16:    # nobody took them (the producers were not up-convolutions): do not pin their memory
+        _COLSUMS.clear()
+    _COLSUMS[(t.data_ptr(), tuple(t.shape), tuple(t.stride()))] = (t, sums)
+
+
+def _take_colsum(t):
+    hit = _COLSUMS.pop((t.data_ptr(), tuple(t.shape), tuple(t.stride())), None)
+    return None if hit is None else hit[1]
 
 
 def _grad_target(param):
@@ -445,11 +467,12 @@ class _ConvNormAct(torch.autograd.Function):
                 dprelu = sums[0, 2]
         dx = dx2 = dw = db = None
         if need[0] or (split is not None and need[1]):
-            dxin = conv3d_dgrad_raw(g, dy, weight)
             if split is None:
-                dx = dxin
+                dx = conv3d_dgrad_raw(g, dy, weight)
             else:
+                dxin, colsum = conv3d_dgrad_raw(g, dy, weight, colsum=True)
                 dx, dx2 = dxin[..., :split], dxin[..., split:]
+                _publish_colsum(dx, colsum[:split])
         if need[2]:
             dw = conv3d_wgrad_raw(g, xin, dy, weight.shape, weight)
         if has_bias and need[3]:
@@ -580,6 +603,7 @@ class _ConvT2(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         n, d, h, w, cin = x.shape
         cout = weight.shape[1]
+        dy_in = dy
         dy, dyp = _as_rows(dy)
         x, xp = _as_rows(x)
         dx = dw = db = None
@@ -601,7 +625,9 @@ class _ConvT2(torch.autograd.Function):
                 dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
                 _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(dw), cin, cout, 2, 0, cout, 0, _stream())
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = channel_stats(dy, 1)[0, 0]
+            db = _take_colsum(dy_in)
+            if db is None:
+                db = channel_stats(dy, 1)[0, 0]
         return dx, dw, db, None
 
 
@@ -705,10 +731,11 @@ class _SegLoss(torch.autograd.Function):
         n, classes = logits.shape[0], logits.shape[1]
         spatial = logits[0, 0].numel()
         partial = torch.zeros(1 + 3 * classes + 4, dtype=torch.float64, device=logits.device)
-        _call("b200seg_loss_reduce", _ptr(logits), _ptr(labels), n, spatial, classes, _ptr(partial), _stream())
+        w_ce, w_dice, w_sdice, w_bce = weights
+        terms = (1 if (w_ce or w_dice) else 0) | (2 if (w_sdice or w_bce) else 0)
+        _call("b200seg_loss_reduce", _ptr(logits), _ptr(labels), n, spatial, classes, terms or 1, _ptr(partial), _stream())
         ctx.save_for_backward(logits, labels, partial)
         ctx.weights = weights
-        w_ce, w_dice, w_sdice, w_bce = weights
         vox = float(n * spatial)
         smooth = 1e-5
         loss = partial.new_zeros(())

@@ -84,9 +84,13 @@ size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g);
 int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
                          const float* bias, void* y, int64_t y_pitch, float* stats, void* workspace,
                          size_t workspace_bytes, void* stream);
-/* dx = conv_transpose(dy, w).  w_packed from b200seg_pack_conv_weight(dgrad=1).  g describes the FORWARD conv. */
+/* dx = conv_transpose(dy, w).  w_packed from b200seg_pack_conv_weight(dgrad=1).  g describes the FORWARD conv.
+ * stats (may be NULL): float[2*cin] = {sum, sumsq} of dx per channel, accumulated into (caller zeroes): the column sums
+ * of a decoder conv's input gradient are the bias gradient of the ConvTranspose3d that produced that input
+ * (unet3d.py:58-59), so they come out of the same epilogue instead of a separate pass over dx. */
 int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_pitch, const void* w_packed_dgrad,
-                         void* dx, int64_t dx_pitch, void* workspace, size_t workspace_bytes, void* stream);
+                         void* dx, int64_t dx_pitch, float* stats, void* workspace, size_t workspace_bytes,
+                         void* stream);
 /* dw_packed[k^3][cin][cout] (fp32, accumulated into; caller zeroes) = sum_voxels x (*) dy.  With a workspace of
  * b200seg_conv3d_workspace_bytes(g) bytes the split-K partial tiles are stored there and summed by a second kernel
  * (deterministic, no atomics); without one every CTA adds its tile to dw_packed with fp32 atomics. */
@@ -180,8 +184,9 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
 int b200seg_argmax_labels(const float* logits, uint8_t* labels, int n, int64_t spatial, int classes, void* stream);
 /* One pass over logits (fp32 NCDHW) and labels (uint8): partial[0] += sum CE nll; partial[1+3k..] += per class
  * {sum p*t, sum p*p, sum t}; partial[1+3*classes..] += sigmoid-dice / BCE sums {sum s*t, sum s, sum t, sum bce}.
- * partial: double[1 + 3*classes + 4] (caller zeroes). */
-int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
+ * partial: double[1 + 3*classes + 4] (caller zeroes).  terms: 1 = the soft-max sums (CE, DiceLossss) are needed,
+ * 2 = the sigmoid sums (DiceLoss, BCE), 3 = both; sums that are not requested may be left untouched. */
+int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes, int terms,
                         double* partial, void* stream);
 /* dlogits = w_ce * dCE + w_dice * dDiceLossss(softmax) + w_sdice * dDiceLoss(sigmoid) + w_bce * dBCE, scaled by the
  * upstream gradient *gscale (a device scalar; NULL = 1), using the sums produced by loss_reduce. */

@@ -73,6 +73,42 @@ def test_full_resolution_conv_kernels_agree():
     assert rel(yab, ya.float() + yb.float()) < 8e-3
 
 
+def test_wide_output_roll_halves_agree_with_plane_kernel_and_torch():
+    """C_out = 64 goes through the rolling-accumulator kernel as two 32-channel halves (CTA parity): compare with the
+    generic plane kernel at 2 x 64^3 (U-Net level 2), with torch fp32 at a small size, and check the column sums the
+    dgrad epilogue publishes (the up-convolution's bias gradient) against a separate reduction."""
+    import b200seg.functional as F
+    g = torch.Generator(device=DEV).manual_seed(1)
+    for cin, cout, s in ((32, 64, 64), (64, 64, 64), (64, 64, 24)):
+        x = torch.randn(2, s, s, s, cin, device=DEV, generator=g).bfloat16()
+        w = torch.randn(cout, cin, 3, 3, 3, device=DEV, generator=g) * 0.05
+        b = torch.randn(cout, device=DEV, generator=g) * 0.1
+        dy = torch.randn(2, s, s, s, cout, device=DEV, generator=g).bfloat16()
+        y_r, st_r, geom = F.conv3d_fprop_raw(x, w, b, 3, 1, 1, 1, True)
+        dx_r, cs_r = F.conv3d_dgrad_raw(geom, dy, w, colsum=True)
+        # dgrad of a 64 -> 32 conv produces a 64-channel gradient: the halves path on the dgrad side
+        w_t = torch.randn(32, 64, 3, 3, 3, device=DEV, generator=g) * 0.05
+        dy32 = torch.randn(2, s, s, s, 32, device=DEV, generator=g).bfloat16()
+        x64 = torch.randn(2, s, s, s, 64, device=DEV, generator=g).bfloat16()
+        _, _, geom_t = F.conv3d_fprop_raw(x64, w_t, None, 3, 1, 1, 1, False)
+        dx64_r, cs64_r = F.conv3d_dgrad_raw(geom_t, dy32, w_t, colsum=True)
+        with env(B200SEG_DISABLE_ROLL_HALVES="1"):
+            y_p, st_p, _ = F.conv3d_fprop_raw(x, w, b, 3, 1, 1, 1, True)
+            dx_p = F.conv3d_dgrad_raw(geom, dy, w)
+            dx64_p = F.conv3d_dgrad_raw(geom_t, dy32, w_t)
+        assert rel(y_r, y_p) < 3e-3 and rel(dx_r, dx_p) < 3e-3 and rel(dx64_r, dx64_p) < 3e-3, (cin, cout, s)
+        assert rel(st_r[:2 * cout], st_p[:2 * cout]) < 1e-4
+        sep = F.channel_stats(dx64_r)[0]
+        assert rel(cs64_r[:64], sep[0]) < 5e-3 and rel(cs64_r[64:], sep[1]) < 5e-3
+        sep = F.channel_stats(dx_r)[0]
+        assert rel(cs_r[:cin], sep[0]) < 5e-3
+        if s == 24:
+            ref = torch.nn.functional.conv3d(x.float().permute(0, 4, 1, 2, 3), w.bfloat16().float(), b, padding=1)
+            assert rel(y_r.float().permute(0, 4, 1, 2, 3), ref) < 6e-3
+            refdx = torch.nn.functional.conv_transpose3d(dy.float().permute(0, 4, 1, 2, 3), w.bfloat16().float(), padding=1)
+            assert rel(dx_r.float().permute(0, 4, 1, 2, 3), refdx) < 6e-3
+
+
 def test_full_size_unet_sample_independence_and_pool_routing():
     import b200seg.functional as F
     from b200seg.models.three_d.unet3d import UNet3D
