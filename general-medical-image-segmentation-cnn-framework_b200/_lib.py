@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200seg_p2p_allreduce": "pi" + "p" + "ii" + "p" + "i" + "d" + "pppp" + "ff" + "i" + "p" + "p",
     "b200seg_adam_step": "pppp" + "l" + "fffff" + "i" + "f" + "p",
     "b200seg_adam_step_dev": "pppp" + "l" + "pp" + "p",
+    "b200seg_adam_step_fused": "ppppp" + "pp" + "iii" + "pp" + "i" + "p",
 }
 STRING_FUNCS = ("b200seg_version", "b200seg_last_error")
 SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g", "b200seg_p2p_mailbox_bytes": ""}

@@ -311,10 +311,17 @@ static bool plan_roll(const UmmaConvArgs& a, RollParams& p, size_t& smem_bytes) 
   if (p.S < 3) return false;
   p.tiles_w = (a.ow + 7) / 8;
   p.tiles_h = (a.oh + 15) / 16;
-  // segment length: as long as possible (2 halo planes are recomputed per segment) while keeping >= ~4 items per SM
   const long long cols = static_cast<long long>(a.n) * p.tiles_h * p.tiles_w * halves;
+  // Items are dealt round-robin to the persistent CTAs, so the kernel takes ceil(items / SMs) rounds of (L + 2 halo planes
+  // + ~1 plane of pipeline fill) plane steps: take the segment count with the fewest steps (ties: the longest segments).
   int L = a.od;
-  while (L > 8 && cols * ((a.od + L - 1) / L) < 4LL * kNumSMs) L = (L + 1) / 2;
+  long long best_cost = -1;
+  for (int segs = 1; segs <= std::max(1, a.od / 4); ++segs) {
+    const int cand = (a.od + segs - 1) / segs;
+    const long long items = cols * ((a.od + cand - 1) / cand);
+    const long long cost = ((items + kNumSMs - 1) / kNumSMs) * (cand + 3);
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, L = cand;
+  }
   p.L = L;
   p.segs = (a.od + L - 1) / L;
   p.items = cols * p.segs;

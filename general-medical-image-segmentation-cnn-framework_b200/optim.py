@@ -62,6 +62,7 @@ class FusedAdam:
             urecs.append(struct.pack("<qqiiii", off, off, a, b, k3, 0))     # dw_arena[off] -> grad_arena[off]
             self._packed.append((p, total, n))
             total += 2 * n
+        self._build_adam_table()
         if not recs:
             self._pack_desc = None
             return
@@ -83,6 +84,27 @@ class FusedAdam:
               self._npack, self._max_k3, 2 * self._tiles, _stream())
         for p, _, _ in self._packed:
             p._b200_pack_ver = p._version
+
+    def _build_adam_table(self):
+        """Records of the one-launch optimiser step (b200seg_adam_step_fused): a brick list over the conv weights (Adam +
+        gradient transpose + both packs) and chunk lists over everything else."""
+        import struct
+        self._adam_desc = None
+        if not self._packed:
+            return
+        packed = {id(p): o for p, o, _ in self._packed}
+        tile_ci = 32 if self._max_k3 <= 27 else 8
+        recs, tile0 = [], 0
+        for p, off in zip(self.params, self.offsets):
+            if id(p) in packed:
+                a, b, k3 = p.shape[0], p.shape[1], p.shape[2] ** 3
+                recs.append(struct.pack("<qqiiiiii", off, packed[id(p)], a, b, k3, 0, tile0, 0))
+                tile0 += ((a + 31) // 32) * ((b + tile_ci - 1) // tile_ci)
+            else:
+                recs.append(struct.pack("<qqiiiiii", off, 0, p.numel(), 0, 0, 1, tile0, 0))
+                tile0 += (p.numel() + 4095) // 4096
+        self._adam_desc = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(self.param_arena.device)
+        self._nadam, self._adam_tiles = len(recs), tile0
 
     def finalize_grads(self):
         """The conv kernels leave their weight gradients in the packed [tap][C_in][C_out] accumulators of dw_arena; one
@@ -132,6 +154,19 @@ class FusedAdam:
             self._hyper_host = want
 
     def step(self, grad_scale=1.0):
+        import os
+        if getattr(self, "_adam_desc", None) is not None and not os.environ.get("B200SEG_DISABLE_FUSED_ADAM"):
+            # one launch: packed weight gradients (if backward left any) + Adam + both bf16 packs of every conv weight
+            self._sync_hyper(grad_scale)
+            self.step_count += 1
+            _call("b200seg_adam_step_fused", _ptr(self.param_arena), _ptr(self.grad_arena), _ptr(self.dw_arena),
+                  _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self._pack_arena), _ptr(self._adam_desc), self._nadam,
+                  self._max_k3, self._adam_tiles, _ptr(self._hyper), _ptr(self._state), 1 if self._pending[0] else 0,
+                  _stream())
+            self._pending[0] = False     # consumed; p.grad of the conv weights is NOT materialised on this path
+            for p, _, _ in self._packed:
+                p._b200_pack_ver = p._version
+            return
         self.finalize_grads()
         self._sync_hyper(grad_scale)
         self.step_count += 1

@@ -249,6 +249,17 @@ int b200seg_adam_step(float* param, const float* grad, float* exp_avg, float* ex
  * {completed steps (incremented by the kernel), scratch (must be 0)}. */
 int b200seg_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
                           const float* hyper, int32_t* state, void* stream);
+/* The whole optimiser step of a flat parameter arena in one launch, including the two layout changes around it: the
+ * packed weight gradients dw ([k^3][cin][cout] fp32, what b200seg_conv3d_wgrad accumulates into; added to grad when
+ * use_dw != 0), Adam on param / exp_avg / exp_avg_sq (torch layout), and both bf16 weight packs of every conv weight
+ * (as b200seg_pack_weights_batched).  descs: DEVICE array of ndesc 40-byte records {int64 src (element offset in the
+ * arenas and in dw), int64 dst (bf16 offset of the fprop pack in packs; the dgrad pack follows it), int32 cout, cin, k^3,
+ * kind (0 = cubic conv weight, 1 = plain range of `cout` elements), tile0 (prefix sum of the records' brick counts:
+ * ceil(cout/32)*ceil(cin/T) with T = 32 if max_k3 <= 27 else 8 for kind 0, ceil(cout/4096) for kind 1), pad};
+ * total_tiles = the sum of all brick counts.  hyper / state as in b200seg_adam_step_dev. */
+int b200seg_adam_step_fused(float* param, const float* grad, const float* dw, float* exp_avg, float* exp_avg_sq,
+                            void* packs, const void* descs, int ndesc, int max_k3, int total_tiles, const float* hyper,
+                            int* state, int use_dw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ LAYERS = [  # name, cin, cout, spatial
     ("bott1", 256, 512, 8), ("bott2", 512, 512, 8),
 ]
 only = sys.argv[1:] if len(sys.argv) > 1 else None
-reps = 5
+reps = 20
 for name, cin, cout, s in LAYERS:
     if only and name not in only:
         continue

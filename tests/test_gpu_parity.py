@@ -480,3 +480,58 @@ def test_head_conv1x1_forward_backward(F, cin, classes):
     close(ncdhw(xd.grad), xr.grad, 8e-3, "dx")       # dx is stored in bf16
     close(wd.grad.cpu(), wr.grad, 1e-4, "dw")
     close(bd.grad.cpu(), br.grad, 1e-4, "db")
+
+
+@pytest.mark.gpu
+def test_fused_optimizer_step_is_bit_identical_to_the_three_kernel_path():
+    """b200seg_adam_step_fused (packed weight gradients + Adam + both bf16 packs in one launch) against the separate
+    unpack -> adam_step_dev -> pack_weights_batched launches: bit-identical parameters, moments and packs over several steps,
+    for full 32 x 32 bricks, ragged bricks, k^3 in {1, 8, 27, 125} and plain ranges; and against torch.optim.Adam
+    (train.py:109) within fp32 rounding."""
+    import os
+    from b200seg.optim import FusedAdam
+    dev = torch.device("cuda")
+    for shapes in ([(64, 32, 3, 3, 3), (64,), (32, 1, 3, 3, 3), (48, 40, 3, 3, 3), (48,), (64, 32, 2, 2, 2), (2, 32, 1, 1, 1),
+                    (2,), (96, 64, 3, 3, 3), (7,)],
+                   [(16, 16, 5, 5, 5), (16,), (32, 16, 2, 2, 2), (33, 9, 3, 3, 3)]):
+        runs = []
+        for fused in (True, False):
+            g = torch.Generator(device=dev).manual_seed(11)
+            params = [torch.nn.Parameter(torch.randn(*s, device=dev, generator=g) * 0.1) for s in shapes]
+            ref = [p.detach().clone().requires_grad_(True) for p in params]
+            os.environ.pop("B200SEG_DISABLE_FUSED_ADAM", None)
+            if not fused:
+                os.environ["B200SEG_DISABLE_FUSED_ADAM"] = "1"
+            try:
+                opt = FusedAdam(params, lr=1e-2, weight_decay=0.01)
+                topt = torch.optim.Adam(ref, lr=1e-2, weight_decay=0.01)
+                for it in range(3):
+                    opt.zero_grad()
+                    for p, r in zip(params, ref):
+                        gr = torch.randn(p.shape, device=dev, generator=g)
+                        r.grad = gr.clone()
+                        if p.dim() == 5 and it != 1:
+                            # what the weight-gradient kernels leave behind: [tap][C_in][C_out] in the packed accumulator
+                            a, b = p.shape[0], p.shape[1]
+                            p._b200_dwp.copy_(gr.reshape(a, b, -1).permute(2, 1, 0).reshape(-1))
+                            p._b200_pending[0] = True
+                        else:
+                            p.grad.copy_(gr)     # the autograd-accumulated form (it == 1: also for conv weights)
+                    opt.step()
+                    topt.step()
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("B200SEG_DISABLE_FUSED_ADAM", None)
+            for p, r in zip(params, ref):
+                close(p.detach().float().cpu(), r.detach().float().cpu(), 1e-5, "adam vs torch %s" % (tuple(p.shape),))
+            runs.append((opt.param_arena.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt._pack_arena.clone(),
+                         int(opt.state_dict()["step"])))
+            # the packs are the bf16 transposes of the updated weights
+            for p, o, n in opt._packed:
+                a, b = p.shape[0], p.shape[1]
+                w = p.detach().reshape(a, b, -1)
+                assert torch.equal(opt._pack_arena[o:o + n].view(-1, a, b), w.permute(2, 0, 1).bfloat16())
+                assert torch.equal(opt._pack_arena[o + n:o + 2 * n].view(-1, b, a), w.flip(2).permute(2, 1, 0).bfloat16())
+        for x, y in zip(runs[0][:4], runs[1][:4]):
+            assert torch.equal(x, y)
+        assert runs[0][4] == runs[1][4] == 3
