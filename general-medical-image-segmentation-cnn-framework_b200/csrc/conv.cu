@@ -1,6 +1,8 @@
 // Convolution entry points of the C ABI: validate, pick the back end (tcgen05 implicit GEMM or direct), launch.
 // ConvTranspose3d(k=2,s=2) is the exact transpose of a k=2 s=2 convolution whose weight tensor has the same memory
 // layout ([C_in_T][C_out_T][2][2][2] == [cout][cin][k^3] of the strided conv), so its three passes reuse the conv code.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_impl.h"
 
@@ -35,6 +37,33 @@ static UmmaConvArgs dgrad_args(const b200seg_conv_geom* g, const void* dy, int64
   return a;
 }
 
+// Weight gradient of the C_in = 1 stem (unet3d.py:80) on the tensor cores: im2col of the 27 taps into 32 channels, then
+// the 1x1x1 / 32-channel weight gradient.  Workspace: [xcol bf16 rows x 32][tmp fp32 32 x cout][inner split-K partials].
+struct StemPlan {
+  size_t xcol_bytes, tmp_off, inner_off, inner_bytes, total;
+  int64_t rows;
+};
+static UmmaWgradArgs stem_wgrad_args(const b200seg_conv_geom* g, const void* xcol, const void* dy, int64_t dyp, float* tmp,
+                                     float* inner, size_t inner_bytes) {
+  return UmmaWgradArgs{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, 32, g->cout, 1, 0, 1,
+                       xcol, 32, dy, dyp, tmp, 0, inner, inner_bytes};
+}
+static bool stem_plan(const b200seg_conv_geom* g, StemPlan& sp) {
+  if (getenv("B200SEG_DISABLE_STEM_IM2COL")) return false;
+  if (!(g->cin == 1 && g->k == 3 && g->stride == 1 && g->pad == 1 && g->dil == 1 && g->cout % 16 == 0 && g->cout <= 64))
+    return false;
+  sp.rows = static_cast<int64_t>(g->n) * g->d * g->h * g->w;
+  if (sp.rows < (1 << 16)) return false;     // small volumes: the CUDA-core kernel is launch-bound either way
+  const UmmaWgradArgs a = stem_wgrad_args(g, nullptr, nullptr, g->cout, nullptr, nullptr, 0);
+  if (!wgrad_umma_plane_supported(a)) return false;
+  sp.xcol_bytes = (static_cast<size_t>(sp.rows) * 32 * 2 + 255) & ~size_t(255);
+  sp.tmp_off = sp.xcol_bytes;
+  sp.inner_off = sp.tmp_off + ((static_cast<size_t>(32) * g->cout * sizeof(float) + 255) & ~size_t(255));
+  sp.inner_bytes = wgrad_umma_plane_workspace_bytes(a);
+  sp.total = sp.inner_off + sp.inner_bytes;
+  return true;
+}
+
 extern "C" {
 
 int64_t b200seg_umma_launch_count(void) { return g_umma_launches; }
@@ -46,8 +75,13 @@ int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g) {
 }
 
 size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g) {
-  // only the weight gradient uses scratch memory: split-K partial tiles (0 = not needed / atomics path)
+  // only the weight gradient uses scratch memory: split-K partial tiles (0 = not needed / atomics path), or the
+  // taps-as-channels copy of a single-channel input (stem_plan)
   if (!g || g->stride != 1) return 0;
+  {
+    StemPlan sp;
+    if (stem_plan(g, sp)) return sp.total;
+  }
   UmmaWgradArgs a{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, g->cin, g->cout, g->k, g->pad, g->dil,
                   nullptr, g->cin, nullptr, g->cout, nullptr, 0, nullptr, 0};
   return wgrad_umma_plane_workspace_bytes(a);
@@ -90,6 +124,24 @@ int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pi
   if (int rc = check_geom(g, "conv3d_wgrad")) return rc;
   B200_CHECK_ARG(x && dy && dw_packed && x_pitch >= g->cin && dy_pitch >= g->cout, "conv3d_wgrad: bad buffers");
   auto st = static_cast<cudaStream_t>(stream);
+  {
+    StemPlan sp;
+    if (workspace && stem_plan(g, sp) && workspace_bytes >= sp.total && dy_pitch % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(workspace) & 255) == 0) {
+      uint8_t* ws = static_cast<uint8_t*>(workspace);
+      float* tmp = reinterpret_cast<float*>(ws + sp.tmp_off);
+      if (int rc = stem_im2col_k3(x, x_pitch, ws, g->n, g->d, g->h, g->w, st)) return rc;
+      if (cudaMemsetAsync(tmp, 0, static_cast<size_t>(32) * g->cout * sizeof(float), st) != cudaSuccess) {
+        set_error("conv3d_wgrad: cudaMemsetAsync failed");
+        return B200SEG_ERR_CUDA;
+      }
+      const UmmaWgradArgs a = stem_wgrad_args(g, ws, dy, dy_pitch, tmp, sp.inner_bytes ? reinterpret_cast<float*>(ws + sp.inner_off) : nullptr,
+                                              sp.inner_bytes);
+      if (int rc = wgrad_umma_run(a, st)) return rc;
+      // tmp is [1][32][cout]; its first 27 rows are dW[tap][0][cout], the layout of dw_packed
+      return add_f32(dw_packed, tmp, 27 * g->cout, st);
+    }
+  }
   if (g->stride == 1) {
     UmmaWgradArgs a{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, g->cin, g->cout, g->k, g->pad, g->dil,
                     x, x_pitch, dy, dy_pitch, dw_packed, 0, static_cast<float*>(workspace), workspace_bytes};

@@ -695,6 +695,61 @@ int conv_direct_dgrad(const ConvGeom& g, const void* dy, int64_t dy_pitch, const
   return 0;
 }
 
+// ---- C_in = 1 stem on the tensor cores: im2col in the CHANNEL dimension ----------------------------------------------
+// xcol[v][j] = x[v + tap_j - 1] for the 27 taps j = (a*3 + b)*3 + e of a 3x3x3 / pad 1 kernel (zero outside the volume),
+// channels 27..31 zero: the stem's weight gradient dW[tap][0][co] = sum_v x[v + tap - 1] dy[v][co] then IS the weight
+// gradient of a 1x1x1 convolution with 32 input channels, which the tcgen05 wgrad kernel runs at HBM speed.
+// One thread per voxel: 27 two-byte loads (neighbours hit L1), four 128-bit stores; a warp writes 2 KB contiguously.
+__global__ void __launch_bounds__(256)
+    stem_im2col_k3_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, __nv_bfloat16* __restrict__ xcol, int n,
+                          int d, int h, int w) {
+  const int64_t total = static_cast<int64_t>(n) * d * h * w;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int xw = static_cast<int>(v % w);
+    const int64_t r1 = v / w;
+    const int yh = static_cast<int>(r1 % h);
+    const int64_t r2 = r1 / h;
+    const int zd = static_cast<int>(r2 % d);
+    alignas(16) __nv_bfloat16 row[32];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const int zz = zd + a - 1, yy = yh + b - 1, xx = xw + e - 1;
+          const bool ok = zz >= 0 && zz < d && yy >= 0 && yy < h && xx >= 0 && xx < w;
+          const int64_t off = v + (static_cast<int64_t>(a - 1) * h + (b - 1)) * w + (e - 1);
+          row[(a * 3 + b) * 3 + e] = ok ? x[off * x_pitch] : zero;
+        }
+#pragma unroll
+    for (int j = 27; j < 32; ++j) row[j] = zero;
+    uint4* dst = reinterpret_cast<uint4*>(xcol + v * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(row)[q];
+  }
+}
+
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+int stem_im2col_k3(const void* x, int64_t x_pitch, void* xcol, int n, int d, int h, int w, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(n) * d * h * w;
+  stem_im2col_k3_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(xcol), n, d, h, w);
+  B200_CHECK_LAUNCH("stem_im2col");
+  return 0;
+}
+
+int add_f32(float* dst, const float* src, int n, cudaStream_t st) {
+  add_f32_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(dst, src, n);
+  B200_CHECK_LAUNCH("add_f32");
+  return 0;
+}
+
 int conv_direct_wgrad(const ConvGeom& g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, float* dwp,
                       cudaStream_t st) {
   if (is_stem(g) && g.k == 3 && g.pad == 1 && (g.cout == 32 || g.cout == 16) && dy_pitch % 8 == 0 &&

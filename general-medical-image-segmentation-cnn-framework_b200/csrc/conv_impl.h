@@ -17,6 +17,10 @@ int conv_direct_dgrad(const ConvGeom& g, const void* dy, int64_t dy_pitch, const
 int conv_direct_wgrad(const ConvGeom& g, const void* x, int64_t x_pitch, const void* dy, int64_t dy_pitch, float* dwp,
                       cudaStream_t st);
 
+// C_in = 1 stem helpers (conv_direct.cu): taps-as-channels im2col [v][32] bf16 of a 3x3x3 / pad 1 kernel, dst += src
+int stem_im2col_k3(const void* x, int64_t x_pitch, void* xcol, int n, int d, int h, int w, cudaStream_t st);
+int add_f32(float* dst, const float* src, int n, cudaStream_t st);
+
 // tcgen05 implicit-GEMM path (conv_umma.cu).  "Conv form": out[o][n] = sum_{tap,k} in[o - pad + tap*dil][k] * W[tap][n][k]
 // with stride 1; fprop uses it directly, dgrad uses it with the flipped pack and pad' = dil*(k-1) - pad.
 struct UmmaConvArgs {

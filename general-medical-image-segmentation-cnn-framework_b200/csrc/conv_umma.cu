@@ -448,7 +448,8 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
   p.slotB = (p.NT * p.rowbytes + 1023) & ~1023u;
   p.NB = static_cast<int>(std::min<size_t>(8, std::max<size_t>(3, 32768 / p.slotB)));  // hide the TMA round trip
   p.bytesB = p.NT * p.rowbytes;
-  const size_t fixed = static_cast<size_t>(p.NB) * p.slotB + 2048 + 3 * p.NT * sizeof(float);
+  const size_t fixed_small = 2048 + 3 * p.NT * sizeof(float);
+  size_t fixed = static_cast<size_t>(p.NB) * p.slotB + fixed_small;
   const int k3 = a.k * a.k * a.k;
   (void)k3;
 
@@ -519,6 +520,14 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
     p.UP = best_dt + halo;
     p.S = p.nchunks > 1 ? 2 : 1;
     p.slotA = static_cast<unsigned>(((static_cast<size_t>(p.P) * 128 + maxoff) * p.rowbytes + 1023) & ~size_t(1023));
+    // These are the K-heavy layers with few accumulators: a weight tile is consumed in P x KC/16 MMAs (0.14 us at P = 1),
+    // far less than a TMA round trip, so the weight ring takes all the shared memory the boxes leave (3 slots of 16 KB
+    // measured 26 GB/s per SM: latency-bound).
+    // (only when the grid is a single wave anyway: larger grids keep the footprint that lets two CTAs share an SM)
+    if (static_cast<long long>(a.n) * ((a.od + p.DT - 1) / p.DT) * p.n_ntiles <= kNumSMs)
+      p.NB = std::max(p.NB, static_cast<int>(std::min<size_t>(
+                                8, (kSmemBudget - fixed_small - static_cast<size_t>(p.S) * p.slotA) / p.slotB)));
+    fixed = static_cast<size_t>(p.NB) * p.slotB + fixed_small;
     p.bytesA_unit = static_cast<unsigned>(p.UP) * plane_rows * p.rowbytes;
     p.tiles_w = p.tiles_h = 1;
     p.tiles_d = (a.od + p.DT - 1) / p.DT;

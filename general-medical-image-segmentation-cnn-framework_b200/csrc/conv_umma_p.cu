@@ -442,16 +442,24 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   P = 0;
   for (int cand = pmax; cand >= 1 && !P; cand /= 2) {
     const int U = cand + halo;
-    // weight ring: enough tiles in flight to cover the TMA round trip, within what the planes leave over
-    for (int extra = 3; extra >= 1 && !P; --extra) {
+    // weight ring: enough tiles in flight to cover the TMA round trip, within what the planes leave over.  With one or
+    // two planes per tile a weight tile lasts only 0.14-0.3 us of MMAs (the 16^3 layers: measured weight-latency-bound
+    // with 5 slots), so there the ring gets its 8 slots before the input ring gets spare planes.
+    const int want_nb = cand <= 2 ? 8 : 3;
+    int best_nb = 0, best_extra = 0;
+    for (int extra = 3; extra >= 1; --extra) {
       const size_t a_bytes = static_cast<size_t>(U + extra) * p.slotA;
       if (a_bytes + fixed_small + 2 * p.slotB > budget) continue;
       const int nb = static_cast<int>(std::min<size_t>(8, (budget - a_bytes - fixed_small) / p.slotB));
       if (nb < 2) continue;
+      if (nb > best_nb) best_nb = nb, best_extra = extra;
+      if (nb >= want_nb) break;
+    }
+    if (best_nb) {
       P = cand;
       p.U = U;
-      p.S = U + extra;
-      p.NB = nb;
+      p.S = U + best_extra;
+      p.NB = best_nb;
     }
   }
   if (!P) return false;

@@ -130,13 +130,13 @@ class FusedAdam:
     def all_reduce_grads(self, group=None):
         """Data-parallel gradient averaging (what DDP does inside accelerator.backward, train.py:211).  Returns the
         factor the summed gradients still have to be scaled by (folded into the Adam kernel)."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return 1.0      # single process: the fused step consumes the packed weight gradients where they are
         self.finalize_grads()
         if getattr(self, "reducer", None) is not None and self.reducer.enabled:
             return self.reducer.finish()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad_arena, group=group)
-            return 1.0 / dist.get_world_size(group)
-        return 1.0
+        dist.all_reduce(self.grad_arena, group=group)
+        return 1.0 / dist.get_world_size(group)
 
     def _sync_hyper(self, grad_scale):
         """Hyper-parameters and the step counter live on the device so a CUDA-graph-captured step replays correctly;

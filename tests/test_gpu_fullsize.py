@@ -109,6 +109,30 @@ def test_wide_output_roll_halves_agree_with_plane_kernel_and_torch():
             assert rel(dx_r.float().permute(0, 4, 1, 2, 3), refdx) < 6e-3
 
 
+def test_stem_weight_gradient_tensor_core_path():
+    """C_in = 1 stem weight gradient (unet3d.py:80): taps-as-channels im2col + the tcgen05 1x1x1 weight-gradient kernel
+    against the CUDA-core stem kernel at the full 2 x 128^3 size and against torch fp32 at 2 x 40^3 (ragged tiles:
+    40 is not a multiple of the 16 x 8 tile)."""
+    import b200seg.functional as F
+    g = torch.Generator(device=DEV).manual_seed(2)
+    for s, cout in ((128, 32), (40, 32), (40, 16)):
+        x = torch.randn(2, s, s, s, 1, device=DEV, generator=g).bfloat16()
+        w = torch.randn(cout, 1, 3, 3, 3, device=DEV, generator=g) * 0.2
+        dy = torch.randn(2, s, s, s, cout, device=DEV, generator=g).bfloat16()
+        _, _, geom = F.conv3d_fprop_raw(x, w, None, 3, 1, 1, 1, False)
+        k0 = F.umma_launch_count()
+        dw_tc = F.conv3d_wgrad_raw(geom, x, dy, w.shape)
+        assert F.umma_launch_count() == k0 + 1, "stem weight gradient did not take the tensor-core path"
+        with env(B200SEG_DISABLE_STEM_IM2COL="1"):
+            dw_cc = F.conv3d_wgrad_raw(geom, x, dy, w.shape)
+        assert rel(dw_tc, dw_cc) < 2e-3, (s, cout, rel(dw_tc, dw_cc))
+        if s == 40:
+            xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(False)
+            wr = w.clone().requires_grad_(True)
+            torch.nn.functional.conv3d(xr, wr, None, padding=1).backward(dy.float().permute(0, 4, 1, 2, 3))
+            assert rel(dw_tc, wr.grad) < 2e-3, (s, cout, rel(dw_tc, wr.grad))
+
+
 def test_full_size_unet_sample_independence_and_pool_routing():
     import b200seg.functional as F
     from b200seg.models.three_d.unet3d import UNet3D
