@@ -35,7 +35,7 @@ SIGNATURES = {
     "b200seg_channel_stats": "pllii" + "pp",
     "b200seg_norm_finalize": "pdii" + "pppp" + "ffi" + "pp",
     "b200seg_norm_act_fwd": "plp" + "lii" + "if" + "p" + "pl" + "pl" + "p",
-    "b200seg_norm_act_bwd_reduce": "plpl" + "p" + "lii" + "if" + "p" + "pl" + "pp" + "p",
+    "b200seg_norm_act_bwd_reduce": "plpl" + "p" + "lii" + "if" + "p" + "pl" + "ppp" + "p",
     "b200seg_norm_act_bwd_apply": "plpl" + "pp" + "d" + "lii" + "if" + "p" + "pl" + "pl" + "pl" + "p",
     "b200seg_maxpool2_fwd": "plplp" + "iiiii" + "p",
     "b200seg_maxpool2_bwd": "plp" + "pl" + "pl" + "iiiii" + "p",

@@ -703,32 +703,38 @@ int conv_direct_dgrad(const ConvGeom& g, const void* dy, int64_t dy_pitch, const
 __global__ void __launch_bounds__(256)
     stem_im2col_k3_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, __nv_bfloat16* __restrict__ xcol, int n,
                           int d, int h, int w) {
-  const int64_t total = static_cast<int64_t>(n) * d * h * w;
-  const __nv_bfloat16 zero = __float2bfloat16(0.f);
-  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
-       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int xw = static_cast<int>(v % w);
-    const int64_t r1 = v / w;
-    const int yh = static_cast<int>(r1 % h);
-    const int64_t r2 = r1 / h;
-    const int zd = static_cast<int>(r2 % d);
-    alignas(16) __nv_bfloat16 row[32];
+  // rows of the (n, d, h) index space are dealt to warps; lanes walk along w, so every tap is one coalesced load per warp
+  const int64_t lines = static_cast<int64_t>(n) * d * h;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (int64_t line = warp0; line < lines; line += nwarps) {
+    const int yh = static_cast<int>(line % h);
+    const int zd = static_cast<int>((line / h) % d);
+    const int64_t v0 = line * w;
+    for (int xw = lane; xw < w; xw += 32) {
+      const int64_t v = v0 + xw;
+      uint32_t pk[16];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+      for (int q = 0; q < 16; ++q) pk[q] = 0u;
 #pragma unroll
-      for (int b = 0; b < 3; ++b)
+      for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          const int zz = zd + a - 1, yy = yh + b - 1, xx = xw + e - 1;
-          const bool ok = zz >= 0 && zz < d && yy >= 0 && yy < h && xx >= 0 && xx < w;
-          const int64_t off = v + (static_cast<int64_t>(a - 1) * h + (b - 1)) * w + (e - 1);
-          row[(a * 3 + b) * 3 + e] = ok ? x[off * x_pitch] : zero;
-        }
+        for (int b = 0; b < 3; ++b)
 #pragma unroll
-    for (int j = 27; j < 32; ++j) row[j] = zero;
-    uint4* dst = reinterpret_cast<uint4*>(xcol + v * 32);
+          for (int e = 0; e < 3; ++e) {
+            const int t = (a * 3 + b) * 3 + e;
+            const int zz = zd + a - 1, yy = yh + b - 1, xx = xw + e - 1;
+            const bool ok = zz >= 0 && zz < d && yy >= 0 && yy < h && xx >= 0 && xx < w;
+            const int64_t off = v + (static_cast<int64_t>(a - 1) * h + (b - 1)) * w + (e - 1);
+            const uint32_t bits = ok ? static_cast<uint32_t>(xs[off * x_pitch]) : 0u;
+            pk[t >> 1] |= (t & 1) ? (bits << 16) : bits;
+          }
+      uint4* dst = reinterpret_cast<uint4*>(xcol + v * 32);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(row)[q];
+      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
   }
 }
 

@@ -119,7 +119,7 @@ __device__ __forceinline__ void cvt_raw(const RawVec<V>& r, float (&f)[V]) {
 // Block = (TX chunk lanes) x (TY row lanes), TX*TY = 256.  NS sums of V channels each are reduced over rows.
 template <int V, int NS, int NT, typename FL, typename FA>
 __device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __restrict__ out_group, int C, FL&& load,
-                                              FA&& accum) {
+                                              FA&& accum, float* __restrict__ affine = nullptr) {
   // load(r, ch, raw[NT]) fetches the NT tensors of row r unconverted; accum(ch, raw[NT], acc) folds one row in.
   extern __shared__ float red[];  // [TY][TX][NS*V]
   const int TX = blockDim.x, TY = blockDim.y;
@@ -163,6 +163,13 @@ __device__ __forceinline__ void column_reduce(int64_t rows, int cv, float* __res
       for (int s = 0; s < NS; ++s)
 #pragma unroll
         for (int i = 0; i < V; ++i) atomicAdd(out_group + static_cast<size_t>(s) * C + ch * V + i, mine[s * V + i]);
+      if (affine != nullptr) {   // {dgamma[C], dbeta[C]} = {row 1, row 0}, straight into the parameter gradients
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          atomicAdd(affine + ch * V + i, mine[1 * V + i]);
+          atomicAdd(affine + C + ch * V + i, mine[0 * V + i]);
+        }
+      }
     }
     __syncthreads();
   }
@@ -307,7 +314,8 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_kernel(const __nv_
                                            const float* __restrict__ coef, int64_t rows, int C, int act_rt,
                                            float act_param, const float* __restrict__ prelu_w,
                                            const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
-                                           float* __restrict__ sums, float* __restrict__ dprelu) {
+                                           float* __restrict__ sums, float* __restrict__ dprelu,
+                                           float* __restrict__ affine) {
   constexpr int act = ACT;
   (void)act_rt;
   const int g = blockIdx.y;
@@ -362,10 +370,10 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_kernel(const __nv_
   if (dprelu) {
     // third running sum = PReLU slope gradient; lands in a scratch row after the two sums of this group
     column_reduce<V, 3, 3>(rows, C / V, sums + static_cast<size_t>(g) * 3 * C, C, load,
-                           [&](int ch, const RawVec<V>(&raw)[3], float(&acc)[3][V]) { accum(ch, raw, acc); });
+                           [&](int ch, const RawVec<V>(&raw)[3], float(&acc)[3][V]) { accum(ch, raw, acc); }, affine);
   } else {
     column_reduce<V, 2, 3>(rows, C / V, sums + static_cast<size_t>(g) * 2 * C, C, load,
-                           [&](int ch, const RawVec<V>(&raw)[3], float(&acc)[2][V]) { accum(ch, raw, acc); });
+                           [&](int ch, const RawVec<V>(&raw)[3], float(&acc)[2][V]) { accum(ch, raw, acc); }, affine);
   }
 }
 
@@ -377,7 +385,7 @@ template <int ACT>
 __global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_fast_kernel(
     const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch, const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
     const float* __restrict__ coef, int64_t rows, int C, float act_param, const float* __restrict__ prelu_w,
-    float* __restrict__ sums) {
+    float* __restrict__ sums, float* __restrict__ affine) {
   constexpr int V = 8;
   extern __shared__ float red[];  // [TY][TX][2*V]
   const int TX = blockDim.x, TY = blockDim.y;
@@ -443,6 +451,10 @@ __global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_fast_kernel(
       const float istd = cg ? cg[C + c] : 1.f;
       atomicAdd(out + c, mine[j]);
       atomicAdd(out + C + c, mine[V + j] * istd);
+      if (affine != nullptr) {   // {dgamma[C], dbeta[C]} straight into the parameter gradients
+        atomicAdd(affine + c, mine[V + j] * istd);
+        atomicAdd(affine + C + c, mine[j]);
+      }
     }
   }
 }
@@ -987,7 +999,7 @@ int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int6
 int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch, const float* coef,
                                 int64_t rows_per_group, int groups, int c, int act, float act_param,
                                 const float* prelu_w, const void* residual, int64_t res_pitch, float* sums,
-                                float* dprelu, void* stream) {
+                                float* dprelu, float* grad_affine, void* stream) {
   B200_CHECK_ARG(dz && y && sums && rows_per_group > 0 && groups > 0 && c > 0, "norm_act_bwd_reduce: bad arguments");
   B200_CHECK_ARG(!dprelu || groups == 1, "norm_act_bwd_reduce: PReLU gradient needs groups == 1");
   auto st = static_cast<cudaStream_t>(stream);
@@ -1000,17 +1012,17 @@ int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y,
     dim3 block(c / 8, 256 / (c / 8));
     dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 3 / (groups > 4 ? 4 : 1)), groups);   // one resident wave
     B200_ACT_DISPATCH(act, norm_act_bwd_reduce_fast_kernel<A_><<<grid, block, 256 * 16 * sizeof(float), st>>>(
-        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act_param, prelu_w, sums));
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act_param, prelu_w, sums, grad_affine));
   } else if (vec_ok(c, dz_pitch, y_pitch, residual ? res_pitch : 0)) {
     dim3 block = reduce_block(c / 8);
     dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
     B200_ACT_DISPATCH(act, norm_act_bwd_reduce_kernel<8, A_><<<grid, block, 256 * 24 * sizeof(float), st>>>(
-        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu));
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu, grad_affine));
   } else {
     dim3 block = reduce_block(c);
     dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 4 / (groups > 4 ? 4 : 1)), groups);
     B200_ACT_DISPATCH(act, norm_act_bwd_reduce_kernel<1, A_><<<grid, block, 256 * 3 * sizeof(float), st>>>(
-        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu));
+        dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act, act_param, prelu_w, rp, res_pitch, sums, dprelu, grad_affine));
   }
   B200_CHECK_LAUNCH("norm_act_bwd_reduce");
   return 0;

@@ -77,6 +77,26 @@ def begin_step(device, nbytes=4 << 20):
 def end_step():
     _SCRATCH["active"] = False
     _COLSUMS.clear()
+    flush_counters()
+
+
+_COUNTERS = []
+
+
+def bump_counter(t):
+    """num_batches_tracked += 1 (what nn.BatchNorm3d.forward does in training mode).  Inside a training step the
+    increments of all norm layers are collected and applied by ONE multi-tensor launch at the end of the step instead of
+    one tiny launch per layer."""
+    if _SCRATCH["active"] and t.is_cuda:
+        _COUNTERS.append(t)
+    else:
+        t += 1
+
+
+def flush_counters():
+    if _COUNTERS:
+        torch._foreach_add_(list(_COUNTERS), 1)
+        _COUNTERS.clear()
 
 
 def _zeros_f32(numel, device):
@@ -240,6 +260,22 @@ def _take_colsum(t):
     return None if hit is None else hit[1]
 
 
+def _arena_managed(param):
+    """The parameter's .grad is a view into optim.FusedAdam's flat gradient arena (zeroed by zero_grad every step)."""
+    return param is not None and getattr(param, "_b200_arena_grad", False) and param.grad is not None
+
+
+def _affine_grad_target(gamma, beta):
+    """Where the backward reduction can add d(gamma) | d(beta) directly: the two gradients are adjacent in the arena
+    (norm.weight is followed by norm.bias in parameters() order).  None: return them to autograd as usual."""
+    if not (_arena_managed(gamma) and _arena_managed(beta)):
+        return None
+    gg, gb = gamma.grad, beta.grad
+    if gg.dtype != torch.float32 or gb.data_ptr() != gg.data_ptr() + 4 * gg.numel() or gb.numel() != gg.numel():
+        return None
+    return gg
+
+
 def _grad_target(param):
     """Packed fp32 accumulator ([tap][C_in][C_out]) of a conv weight managed by optim.FusedAdam, else None.  The
     accumulator is a slice of an arena that FusedAdam.zero_grad clears together with the gradients; the optimiser
@@ -352,7 +388,7 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
     return out, coef, count, groups
 
 
-def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dres):
+def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dres, grad_affine=None):
     """Returns dy (bf16, contiguous), dres, sums ([groups][2 or 3][C] fp32: sum dpre, sum dpre*xhat[, dPReLU])."""
     dz, dzp = _as_rows(dz)
     y, yp = _as_rows(y)
@@ -368,7 +404,7 @@ def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dre
         sums = _zeros_f32(groups * nrow * c, y.device).view(groups, nrow, c)
         dprelu = sums[0, 2] if nrow == 3 else None
         _call("b200seg_norm_act_bwd_reduce", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), rows, groups, c, spec.act,
-              spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(sums), _ptr(dprelu), _stream())
+              spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(sums), _ptr(dprelu), _ptr(grad_affine), _stream())
     red = sums
     if use_batch_stats and spec.kind == "batch" and spec.sync and is_parallel(spec.process_group):
         red = sums.clone()
@@ -447,6 +483,7 @@ class _ConvNormAct(torch.autograd.Function):
         # a plain conv's output is not needed by its own backward (and may be modified in place by a residual sum)
         ctx.save_for_backward(xin, None if plain else y, coef, weight, gamma, prelu_w, residual)
         ctx.cfg = (g, spec, count, groups, None if x2 is None else x.shape[4], bias is not None)
+        ctx.beta_ref, ctx.bias_ref = beta, bias      # parameters (not saved tensors): only their .grad slots are looked at
         return z
 
     @staticmethod
@@ -459,9 +496,10 @@ class _ConvNormAct(torch.autograd.Function):
         if plain:
             dy = dz
         else:
+            affine = _affine_grad_target(gamma, ctx.beta_ref) if (need[4] and need[5]) else None
             dy, dres, sums = _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual,
-                                            residual is not None and need[7])
-            if gamma is not None:
+                                            residual is not None and need[7], grad_affine=affine)
+            if gamma is not None and affine is None:
                 dgamma, dbeta = (sums[0, 1], sums[0, 0]) if groups == 1 else (sums[:, 1].sum(0), sums[:, 0].sum(0))
             if prelu_w is not None:
                 dprelu = sums[0, 2]
@@ -477,8 +515,9 @@ class _ConvNormAct(torch.autograd.Function):
             dw = conv3d_wgrad_raw(g, xin, dy, weight.shape, weight)
         if has_bias and need[3]:
             if spec.kind is not None and (spec.training or spec.kind == "instance"):
-                # a bias in front of batch/instance statistics has an analytically zero gradient
-                db = _zeros_f32(g.cout, dz.device)
+                # a bias in front of batch/instance statistics has an analytically zero gradient: leave the (zeroed)
+                # slot of the gradient arena alone instead of accumulating zeros into it
+                db = None if _arena_managed(ctx.bias_ref) else _zeros_f32(g.cout, dz.device)
             else:
                 db = channel_stats(dy, 1)[0, 0]
         return dx, dx2, dw, db, dgamma, dbeta, dprelu, dres, None, None, None

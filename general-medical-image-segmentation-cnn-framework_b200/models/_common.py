@@ -44,7 +44,11 @@ def norm_spec(F, norm, act="none", act_param=0.0, module_training=True):
     sync = isinstance(norm, (_SynchronizedBatchNorm, nn.SyncBatchNorm))
     training = module_training or not norm.track_running_stats
     if module_training and norm.track_running_stats and norm.num_batches_tracked is not None:
-        norm.num_batches_tracked += 1
+        bump = getattr(F, "bump_counter", None)    # the CUDA backend batches these increments; other backends add now
+        if bump is not None:
+            bump(norm.num_batches_tracked)
+        else:
+            norm.num_batches_tracked += 1
     return F.NormSpec("batch", act, act_param, eps=norm.eps, momentum=0.1 if norm.momentum is None else norm.momentum,
                       training=training, sync=sync, clamp_eps=isinstance(norm, _SynchronizedBatchNorm),
                       process_group=getattr(norm, "process_group", None))

@@ -60,7 +60,7 @@ class UNet3D(nn.Module):
                           clamp_eps=isinstance(norm, _SynchronizedBatchNorm),
                           process_group=getattr(norm, "process_group", None))
         if self.training and norm.track_running_stats and norm.num_batches_tracked is not None:
-            norm.num_batches_tracked += 1
+            F.bump_counter(norm.num_batches_tracked)
         return F.conv_norm_act(x, conv.weight, conv.bias, x2=x2, k=3, stride=1, pad=1, dil=1, spec=spec,
                                gamma=norm.weight, beta=norm.bias, running_mean=norm.running_mean,
                                running_var=norm.running_var, out=out)

@@ -37,6 +37,7 @@ class FusedAdam:
             view.copy_(p.data)
             p.data = view
             p.grad = self.grad_arena[off:off + p.numel()].view_as(p)
+            p._b200_arena_grad = True               # functional._arena_managed: backward may add into the slot directly
             if p.dim() == 5:      # Conv3d / ConvTranspose3d weights: backward accumulates straight into p.grad
                 p._b200_dwp = self.dw_arena[off:off + p.numel()]
                 p._b200_pending = self._pending

@@ -125,11 +125,13 @@ int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int6
                          int c, int act, float act_param, const float* prelu_w, const void* residual,
                          int64_t res_pitch, void* z, int64_t z_pitch, void* stream);
 /* Backward, pass 1: sums[g][2][c] += {sum(dpre), sum(dpre * xhat)}, dpre = dz * act'(pre).  Also accumulates the
- * PReLU slope gradient when dprelu != NULL. */
+ * PReLU slope gradient when dprelu != NULL, and -- when grad_affine != NULL -- adds the same two sums (over all groups)
+ * to grad_affine[0..c) = d(gamma) and grad_affine[c..2c) = d(beta): the affine parameter gradients of the norm layer
+ * (unet3d.py:88,100) land in the optimiser's gradient arena without a separate accumulation launch. */
 int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch,
                                 const float* coef, int64_t rows_per_group, int groups, int c, int act,
                                 float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
-                                float* sums, float* dprelu, void* stream);
+                                float* sums, float* dprelu, float* grad_affine, void* stream);
 /* Backward, pass 2: dy = scale * (dpre - sum_dpre/count - xhat * sum_dpre_xhat/count) (training statistics), or
  * dy = scale * dpre when sums == NULL (eval / no norm).  dres (may be NULL) = dpre (gradient of the residual). */
 int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch, const float* coef,
