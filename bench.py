@@ -222,13 +222,18 @@ def run_b200(args):
         launches = train_step.kernels_per_step * args.steps
         umma_launches = train_step.umma_per_step * args.steps
 
-    # end to end through the public API: pinned host batch -> device, result (loss) read back on the host every step
-    def e2e_step():
-        x = x_host.to(dev, non_blocking=True)
-        lab = lab_host.to(dev, non_blocking=True)
-        return step(x, lab).item()
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    # end to end through the public API (the loop of b200seg/train.py): every step's batch is copied from pinned host memory
+    # inside the timed region -- by data.DevicePrefetcher, one batch ahead on a copy stream -- and every step's result
+    # (the loss) is read back on the host before the next step starts.
+    from b200seg.data import DevicePrefetcher
+
+    def e2e_run(steps):
+        def run():
+            for x, lab in DevicePrefetcher(((x_host, lab_host) for _ in range(steps)), dev):
+                step(x, lab).item()
+        return run
+    e2e_run(2)()
+    ms_e2e = timed(e2e_run(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel timing pass (CUDA events around every launch on the launching stream, eager) -> roofline

@@ -62,6 +62,7 @@ __device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_
   if (use_dw) {
     // packed side: for every (tap, ci) a run of nco consecutive floats
     const float* src = dw + d.src;
+#pragma unroll 8
     for (int i = tid; i < total; i += nthr) {
       const int co = i % nco, r = i / nco;          // r = t * nci + ci
       const int ci = r % nci, t = r / nci;
@@ -76,6 +77,7 @@ __device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_
     const bool vec = (run % 4 == 0) && (co_stride % 4 == 0) && (base % 4 == 0);
     if (vec) {
       const int run4 = run >> 2;
+#pragma unroll 2
       for (int i = tid; i < nco * run4; i += nthr) {
         const int co = i / run4, r = (i - co * run4) << 2;
         const long long idx = base + co * co_stride + r;
@@ -115,6 +117,7 @@ __device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_
   __nv_bfloat16* pd = pf + static_cast<long long>(cout) * cin * k3;              // [k3-1-t][ci][co]
   if (FULL) {
     // two bf16 per store: pairs along ci (fprop pack) / along co (dgrad pack)
+#pragma unroll 4
     for (int i = tid; i < k3 * 32 * 16; i += nthr) {
       const int j = (i & 15) << 1, o = (i >> 4) & 31, t = i >> 9;
       {   // fprop: o = co, j = ci

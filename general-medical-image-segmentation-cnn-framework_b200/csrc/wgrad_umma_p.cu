@@ -296,25 +296,56 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
   }
 }
 
-// dwp[i] += sum over splits of partial[s][i]   (coalesced: consecutive threads, consecutive elements of every slice)
-__global__ void wgrad_reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ dwp, long long numel,
-                                             int splits) {
+// dwp[i] += sum over splits of partial[s][i]   (coalesced: consecutive threads, consecutive elements of every slice).
+// The narrow layers have FEW elements (27 x 32 x 32) in MANY slices (148): one thread per element walking the slices is a
+// chain of dependent-latency loads (measured 42 us for 16 MB), so the slices are also dealt over blockIdx.y -- each thread
+// sums its share with 8 independent loads in flight and adds the result to dwp with one atomic per element.
+__global__ void __launch_bounds__(256)
+    wgrad_reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ dwp, long long numel, int splits) {
   const long long nvec = numel / 4;
+  const int gy = gridDim.y, y = blockIdx.y;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 acc = reinterpret_cast<const float4*>(dwp)[i];
-    for (int s = 0; s < splits; ++s) {
-      const float4 v = reinterpret_cast<const float4*>(partial + static_cast<size_t>(s) * numel)[i];
+    const float4* src = reinterpret_cast<const float4*>(partial) + i;
+    const long long sstride = numel / 4;   // float4s per slice
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = y;
+    for (; s + 7 * gy < splits; s += 8 * gy) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[static_cast<long long>(s + u * gy) * sstride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x += v[u].x;
+        acc.y += v[u].y;
+        acc.z += v[u].z;
+        acc.w += v[u].w;
+      }
+    }
+    for (; s < splits; s += gy) {
+      const float4 v = src[static_cast<long long>(s) * sstride];
       acc.x += v.x;
       acc.y += v.y;
       acc.z += v.z;
       acc.w += v.w;
     }
-    reinterpret_cast<float4*>(dwp)[i] = acc;
+    float* dst = dwp + 4 * i;
+    if (gy == 1) {
+      float4 o = *reinterpret_cast<const float4*>(dst);
+      o.x += acc.x;
+      o.y += acc.y;
+      o.z += acc.z;
+      o.w += acc.w;
+      *reinterpret_cast<float4*>(dst) = o;
+    } else {
+      atomicAdd(dst, acc.x);
+      atomicAdd(dst + 1, acc.y);
+      atomicAdd(dst + 2, acc.z);
+      atomicAdd(dst + 3, acc.w);
+    }
   }
 }
 
-// ------------------------------------------------------------------------------------------------ host side
 static bool plan_wgrad_plane(const UmmaWgradArgs& a, WgradPParams& p, size_t& smem_bytes) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_UMMA_WGRAD") || getenv("B200SEG_DISABLE_PERSISTENT"))
     return false;
@@ -477,7 +508,9 @@ int wgrad_umma_plane_run(const UmmaWgradArgs& a, cudaStream_t st) {
     default: set_error("wgrad_umma_plane_run: unsupported group count"); break;
   }
   if (rc == 0 && p.partial) {
-    wgrad_reduce_partials_kernel<<<grid_for(numel / 4, 256, kNumSMs * 8), 256, 0, st>>>(p.partial, a.dwp, numel, p.splits);
+    const int bx = grid_for(numel / 4, 256, kNumSMs * 8);
+    const int by = std::max(1, std::min(p.splits / 4, 2 * kNumSMs / bx));   // few elements, many slices: split the slices too
+    wgrad_reduce_partials_kernel<<<dim3(bx, by), 256, 0, st>>>(p.partial, a.dwp, numel, p.splits);
     B200_CHECK_LAUNCH("wgrad_reduce_partials");
   }
   if (rc == 0) ++g_umma_launches;

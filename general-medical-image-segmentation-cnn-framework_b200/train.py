@@ -17,7 +17,7 @@ import torch
 
 from . import parallel
 from .config import build_model, compose, weights_init_normal
-from .data import SyntheticPatches
+from .data import DevicePrefetcher, SyntheticPatches
 from .engine import TrainStep
 from .models.sync_batchnorm.batchnorm import convert_model
 from .optim import FusedAdam
@@ -89,9 +89,9 @@ def train(config, model, log=print):
     history = []
     for epoch in range(elapsed_epochs + 1, config.epochs + 1):
         t0, loss_sum, dice_sum, n = time.time(), 0.0, 0.0, 0
-        for i, batch in enumerate(loader):
-            x = batch["source"]["data"].to(dev, non_blocking=True)
-            gt = batch["gt"]["data"].to(dev, non_blocking=True)
+        for i, batch in enumerate(DevicePrefetcher(loader, dev)):   # the copy of batch i+1 overlaps step i
+            x = batch["source"]["data"]
+            gt = batch["gt"]["data"]
             labels = gt.reshape(gt.shape[0], *gt.shape[2:]).to(torch.uint8)   # the one-hot of train.py:191-193, as indices
             loss, pred = step(x, labels)
             mask = F.argmax_labels(pred)                                      # train.py:204

@@ -92,8 +92,9 @@ int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_
                          void* dx, int64_t dx_pitch, float* stats, void* workspace, size_t workspace_bytes,
                          void* stream);
 /* dw_packed[k^3][cin][cout] (fp32, accumulated into; caller zeroes) = sum_voxels x (*) dy.  With a workspace of
- * b200seg_conv3d_workspace_bytes(g) bytes the split-K partial tiles are stored there and summed by a second kernel
- * (deterministic, no atomics); without one every CTA adds its tile to dw_packed with fp32 atomics. */
+ * b200seg_conv3d_workspace_bytes(g) bytes the split-K partial tiles are stored there with vector stores and summed by
+ * a second kernel (one atomic per element and slice group); without one every CTA adds its tile to dw_packed with fp32
+ * atomics.  For a single-channel input (the U-Net stem) the workspace also holds the taps-as-channels copy of x. */
 int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* dy,
                          int64_t dy_pitch, float* dw_packed, void* workspace, size_t workspace_bytes, void* stream);
 
