@@ -404,9 +404,15 @@ bool encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  // A channel SLICE of a wider buffer (the up-convolution's half of a [up | skip] concat gradient: rows of 64 B every
+  // 128 B) must not be promoted to whole 128-byte lines: measured 2x the algorithmic DRAM reads on the memory-bound
+  // ConvTranspose dgrad / wgrad launches.  Contiguous rows keep the 128-byte promotion.
+  const uint64_t row_bytes = dims[0] * 2;
+  const bool sliced = rank > 1 && strides_bytes[0] > row_bytes;
+  const CUtensorMapL2promotion promo = !sliced ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                       : (row_bytes % 64 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return false;

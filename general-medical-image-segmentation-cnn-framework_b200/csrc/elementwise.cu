@@ -3,6 +3,9 @@
 // Roofline for every kernel here is HBM: algorithmic bytes are stated per kernel in DESIGN.md.
 #include <stdarg.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_kernel(const __nv_
 // {scale, shift, mean} per channel and folds inv_std in once at the end.  That leaves registers for 4 rows x 2 tensors of
 // 128-bit loads in flight per thread at 3 CTAs/SM (~98 KB outstanding per SM, what B200 needs to stream at HBM speed).
 template <int ACT>
-__global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_fast_kernel(
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_fast_kernel(
     const __nv_bfloat16* __restrict__ dz, int64_t dz_pitch, const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
     const float* __restrict__ coef, int64_t rows, int C, float act_param, const float* __restrict__ prelu_w,
     float* __restrict__ sums, float* __restrict__ affine) {
@@ -1010,7 +1013,8 @@ int b200seg_norm_act_bwd_reduce(const void* dz, int64_t dz_pitch, const void* y,
   if (vec_ok(c, dz_pitch, y_pitch) && residual == nullptr && dprelu == nullptr && c / 8 <= 64 && ((c / 8) & (c / 8 - 1)) == 0 &&
       ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     dim3 block(c / 8, 256 / (c / 8));
-    dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * 3 / (groups > 4 ? 4 : 1)), groups);   // one resident wave
+    static const int waves = getenv("B200SEG_REDUCE_WAVES") ? std::max(1, atoi(getenv("B200SEG_REDUCE_WAVES"))) : 2;
+    dim3 grid(reduce_grid(rows_per_group, block.y, kNumSMs * waves / (groups > 4 ? 4 : 1)), groups);
     B200_ACT_DISPATCH(act, norm_act_bwd_reduce_fast_kernel<A_><<<grid, block, 256 * 16 * sizeof(float), st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, rows_per_group, c, act_param, prelu_w, sums, grad_affine));
   } else if (vec_ok(c, dz_pitch, y_pitch, residual ? res_pitch : 0)) {

@@ -28,32 +28,39 @@ class DevicePrefetcher:
     issued on a side stream right before batch k is handed out, so it overlaps step k instead of preceding step k+1
     (the reference's loop copies synchronously, train.py:189-196; its Queue prefetches on the host only).
 
+    Two sets of staging tensors are allocated once and alternate (no allocator traffic, no cudaMalloc in the loop); the
+    copy stream waits until the work that was enqueued on the compute stream while a set was handed out has finished
+    before overwriting it.  A batch is therefore valid until the next-but-one `next()`.
     `batches` yields tensors or (nested) tuples / dicts of tensors; the same structure comes back on `device`."""
 
     def __init__(self, batches, device):
         self.it, self.device = iter(batches), torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
-        self._next = self._ready = None
+        self._home = torch.cuda.current_stream(self.device)
+        self._slots = ([], [])             # staging tensors of the two sets, in traversal order
+        self._released = [None, None]      # event after which a set may be overwritten
+        self._k = 0
+        self._next = self._ready = self._out_slot = None
         self._preload()
 
-    def _move(self, obj):
+    def _move(self, obj, bufs, pos):
         if torch.is_tensor(obj):
-            return obj.to(self.device, non_blocking=True)
+            i = pos[0]
+            pos[0] += 1
+            if i == len(bufs):
+                bufs.append(None)
+            if bufs[i] is None or bufs[i].shape != obj.shape or bufs[i].dtype != obj.dtype:
+                # allocated under the CALLER's stream (long-lived, event-guarded by hand): a fresh side stream would miss
+                # the caching allocator's pools and cudaMalloc -- a device-wide synchronisation -- inside the loop
+                with torch.cuda.stream(self._home):
+                    bufs[i] = torch.empty(obj.shape, dtype=obj.dtype, device=self.device)
+            bufs[i].copy_(obj, non_blocking=True)
+            return bufs[i]
         if isinstance(obj, dict):
-            return {k: self._move(v) for k, v in obj.items()}
+            return {k: self._move(v, bufs, pos) for k, v in obj.items()}
         if isinstance(obj, (tuple, list)):
-            return type(obj)(self._move(v) for v in obj)
+            return type(obj)(self._move(v, bufs, pos) for v in obj)
         return obj
-
-    def _record(self, obj, stream):
-        if torch.is_tensor(obj):
-            obj.record_stream(stream)      # allocated on the copy stream, consumed on the compute stream
-        elif isinstance(obj, dict):
-            for v in obj.values():
-                self._record(v, stream)
-        elif isinstance(obj, (tuple, list)):
-            for v in obj:
-                self._record(v, stream)
 
     def _preload(self):
         try:
@@ -61,8 +68,12 @@ class DevicePrefetcher:
         except StopIteration:
             self._next = None
             return
+        slot = self._k & 1
+        self._k += 1
         with torch.cuda.stream(self.stream):
-            self._next = self._move(host)
+            if self._released[slot] is not None:
+                self.stream.wait_event(self._released[slot])
+            self._next = (self._move(host, self._slots[slot], [0]), slot)
             self._ready = torch.cuda.Event()
             self._ready.record(self.stream)
 
@@ -73,9 +84,12 @@ class DevicePrefetcher:
         if self._next is None:
             raise StopIteration
         cur = torch.cuda.current_stream(self.device)
+        if self._out_slot is not None:     # everything that read the previous batch has been enqueued by now
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._released[self._out_slot] = ev
         cur.wait_event(self._ready)
-        batch = self._next
-        self._record(batch, cur)
+        batch, self._out_slot = self._next
         self._preload()
         return batch
 

@@ -24,6 +24,9 @@ z, coef, count, groups = F._norm_forward(y, stats, spec, gamma, beta, rm, rv, No
 t(lambda: F.channel_stats(y), 2, "channel_stats")
 t(lambda: F._norm_forward(y, stats, spec, gamma, beta, rm, rv, None, None, None), 4, "norm_act_fwd(+finalize)")
 t(lambda: F._norm_backward(dz, y, coef, count, groups, spec, None, None, False), 10, "norm_act_bwd(red+apply)")
+sums = torch.zeros(2 * C, device="cuda")
+t(lambda: F._call("b200seg_norm_act_bwd_reduce", F._ptr(dz), C, F._ptr(y), C, F._ptr(coef), 2 * S ** 3, 1, C, spec.act,
+                  spec.act_param, None, None, 0, F._ptr(sums), None, None, F._stream()), 4, "norm_act_bwd_reduce", reps=20)
 t(lambda: F.max_pool2(y), 2.375, "maxpool_fwd")
 w = torch.randn(2, C, 1, 1, 1, device="cuda"); b = torch.zeros(2, device="cuda")
 yy = y.clone().requires_grad_(True); ww = w.clone().requires_grad_(True)
