@@ -54,9 +54,10 @@ struct RollItem {
   int nn, h0, w0, d0, lq;   // lq = output planes in this segment
 };
 
+template <int HV>
 __device__ __forceinline__ RollItem roll_decode(const RollParams& p, long long it) {
   RollItem r;
-  it /= p.halves;   // the half is the CTA's parity (grid and item count are even), not part of the item
+  it /= HV;         // the half is the CTA's parity (grid and item count are even), not part of the item
   const int seg = static_cast<int>(it % p.segs);
   it /= p.segs;
   r.w0 = static_cast<int>(it % p.tiles_w) * 8;
@@ -68,7 +69,9 @@ __device__ __forceinline__ RollItem roll_decode(const RollParams& p, long long i
   return r;
 }
 
-template <int KS, int CO>   // KS = K steps of 16 channels (C_in / 16), CO = C_out
+// KS = K steps of 16 channels (C_in / 16), CO = C_out per CTA, HV = halves of the output tensor (compile-time: the
+// single-half kernel must not pay for the generality -- a run-time `halves` cost the 128^3 layers 20 %)
+template <int KS, int CO, int HV>
 __global__ void __launch_bounds__(kRollThreads, 1)
     conv_umma_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const RollParams p) {
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // C_out = 64: even CTAs produce channels [0, 32), odd CTAs [32, 64) of the same tile columns at the same time (the
   // partner's input planes are L2 hits); each keeps only its own half of the weights resident.
-  const int co_base = p.halves == 2 ? static_cast<int>(blockIdx.x & 1) * CO : 0;
+  const int co_base = HV == 2 ? static_cast<int>(blockIdx.x & 1) * CO : 0;
 
   if (tid == 0) {
     for (int i = 0; i < p.S; ++i) {
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
       int s = 0;
       uint32_t ph = 0;
       for (long long it = first; it < p.items; it += stride) {
-        const RollItem r = roll_decode(p, it);
+        const RollItem r = roll_decode<HV>(p, it);
         for (int t = 0; t < r.lq + 2; ++t) {
           mbar_wait(&emptyA[s], ph ^ 1);
           mbar_arrive_expect_tx(&fullA[s], p.bytesA);
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     int s = 0, acc = 0;
     uint32_t ph = 0, accph = 0;
     for (long long it = first; it < p.items; it += stride) {
-      const RollItem r = roll_decode(p, it);
+      const RollItem r = roll_decode<HV>(p, it);
       for (int t = 0; t < r.lq + 2; ++t) {
         mbar_wait(&accEmpty[acc], accph ^ 1);
         mbar_wait(&fullA[s], ph);
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     int acc = 0;                              // ring slot of the plane about to be waited for
     uint32_t accph = 0;
     for (long long it = first; it < p.items; it += stride) {
-      const RollItem r = roll_decode(p, it);
+      const RollItem r = roll_decode<HV>(p, it);
       const int oh_ = r.h0 + (m >> 3), ow_ = r.w0 + (m & 7);
       const bool hw_ok = oh_ < p.oh && ow_ < p.ow;
       for (int t = 0; t < r.lq + 2; ++t) {
@@ -272,7 +275,8 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     }
   }
   __syncthreads();
-  if (p.stats != nullptr && tid < 2 * CO) atomicAdd(&p.stats[(tid / CO) * p.cout + co_base + tid % CO], s_stats[tid]);
+  if (p.stats != nullptr && tid < 2 * CO)
+    atomicAdd(&p.stats[HV == 1 ? tid : (tid / CO) * p.cout + co_base + tid % CO], s_stats[tid]);
   if (warp == 3) {
     tc_fence_after();
     tmem_dealloc(tbase, 512);
@@ -335,19 +339,19 @@ bool conv_umma_roll_supported(const UmmaConvArgs& a) {
   return plan_roll(a, p, smem);
 }
 
-template <int KS, int CO>
+template <int KS, int CO, int HV>
 static int launch_roll(const CUtensorMap& tmA, const CUtensorMap& tmB, const RollParams& p, size_t smem, int ctas,
                        cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_roll_kernel<KS, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+    if (cudaFuncSetAttribute(conv_umma_roll_kernel<KS, CO, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
       set_error("conv_umma_roll: cannot raise the dynamic shared memory limit");
       return B200SEG_ERR_CUDA;
     }
     attr_set = true;
   }
-  conv_umma_roll_kernel<KS, CO><<<ctas, kRollThreads, smem, st>>>(tmA, tmB, p);
+  conv_umma_roll_kernel<KS, CO, HV><<<ctas, kRollThreads, smem, st>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv_umma_roll");
   return 0;
 }
@@ -386,12 +390,16 @@ int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
   const int KS = a.cin / 16;
   const int co = a.cout / p.halves;
   int rc = B200SEG_ERR_INVALID;
-  if (co == 32 && KS == 1) rc = launch_roll<1, 32>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 32 && KS == 2) rc = launch_roll<2, 32>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 32 && KS == 4) rc = launch_roll<4, 32>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 16 && KS == 1) rc = launch_roll<1, 16>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 16 && KS == 2) rc = launch_roll<2, 16>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 16 && KS == 4) rc = launch_roll<4, 16>(tmA, tmB, p, smem, ctas, st);
+  if (p.halves == 2) {
+    if (KS == 1) rc = launch_roll<1, 32, 2>(tmA, tmB, p, smem, ctas, st);
+    else if (KS == 2) rc = launch_roll<2, 32, 2>(tmA, tmB, p, smem, ctas, st);
+    else if (KS == 4) rc = launch_roll<4, 32, 2>(tmA, tmB, p, smem, ctas, st);
+  } else if (co == 32 && KS == 1) rc = launch_roll<1, 32, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 32 && KS == 2) rc = launch_roll<2, 32, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 32 && KS == 4) rc = launch_roll<4, 32, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 1) rc = launch_roll<1, 16, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 2) rc = launch_roll<2, 16, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 4) rc = launch_roll<4, 16, 1>(tmA, tmB, p, smem, ctas, st);
   if (rc == 0) ++g_umma_launches;
   return rc;
 }
