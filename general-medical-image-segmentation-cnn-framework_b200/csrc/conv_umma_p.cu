@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(kThreadsP, 1)
             if (sl >= p.S) sl -= p.S;
 #pragma unroll
             for (int acc = 0; acc < P; ++acc) {
-              a_lo[acc] = ((sA16 + sl * slotA16) & 0x3FFF) | lo_fixed;
+              // (lane-0 broadcast: warp-uniform hint, keeps the descriptor arithmetic on the uniform datapath)
+              a_lo[acc] = __shfl_sync(0xffffffffu, ((sA16 + sl * slotA16) & 0x3FFF) | lo_fixed, 0);
               if (++sl == p.S) sl = 0;
             }
           }
@@ -269,15 +270,14 @@ __global__ void __launch_bounds__(kThreadsP, 1)
             for (int e = 0; e < k; ++e) {
               mbar_wait(&fullB[bs], bphase);
               tc_fence_after();
-              const uint32_t b_lo = ((sB16 + bs * slotB16) & 0x3FFF) | lo_fixed;
+              const uint32_t b_lo = __shfl_sync(0xffffffffu, ((sB16 + bs * slotB16) & 0x3FFF) | lo_fixed, 0);
               const uint32_t fresh = (c | a | b | e) == 0 ? 0u : 1u;
 #pragma unroll
               for (int acc = 0; acc < P; ++acc) {
 #pragma unroll
                 for (int kk = 0; kk < KS; ++kk) {
-                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo[acc] + tap16 + 2u * kk);
-                  const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk);
-                  umma_f16_pred(d_base + acc * p.NT, ad, bd, idesc, kk == 0 ? fresh : 1u, leader);
+                  umma_f16_pred_lohi(d_base + acc * p.NT, a_lo[acc] + tap16 + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc,
+                                     kk == 0 ? fresh : 1u, leader);
                 }
               }
               umma_commit_pred(&emptyB[bs], leader);

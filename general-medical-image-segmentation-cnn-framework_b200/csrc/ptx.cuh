@@ -139,6 +139,25 @@ __device__ __forceinline__ void umma_f16_pred(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(pred)
       : "memory");
 }
+// Same, with the two 64-bit shared-memory descriptors passed as (low, high) 32-bit halves and assembled inside the PTX
+// block: the issue loops only ever change the low words (start address), and handing ptxas 64-bit C++ values made it
+// strength-reduce the address updates into 64-bit IADD3 / IADD3.X chains through vector registers (21 SASS instructions
+// per MMA in the weight-gradient kernel, which made its single issuing warp the bottleneck).
+__device__ __forceinline__ void umma_f16_pred_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.ne.b32 q, %7, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(pred)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t pred) {
   asm volatile(
       "{\n"

@@ -209,8 +209,10 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
         mbar_wait(&fullX[sx], phx);
         tc_fence_after();
         // (planes that wrapped to slots 0 .. span-2 are read through their mirrors at RY + slot)
-        const uint32_t b_lo0 = ((sY16 + oslot * slotY16) & 0x3FFF) | b_lbo;
-        const uint32_t x_lo0 = (sX16 + sx * slotX16);
+        // lane-0 broadcasts: tell ptxas the two per-step bases are warp-uniform, so the 24 descriptor updates below run on
+        // the uniform datapath instead of one R2UR per descriptor half per MMA
+        const uint32_t b_lo0 = __shfl_sync(0xffffffffu, ((sY16 + oslot * slotY16) & 0x3FFF) | b_lbo, 0);
+        const uint32_t x_lo0 = __shfl_sync(0xffffffffu, sX16 + sx * slotX16, 0);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           uint32_t a_lo = ((x_lo0 + g_off16[g]) & 0x3FFF) | a_lbo;
@@ -218,9 +220,7 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
           const uint32_t d_tmem = tbase + g * NTOT;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
-            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
-            umma_f16_pred(d_tmem, ad, bd, idesc, ks == 0 ? accum : 1u, leader);
+            umma_f16_pred_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, ks == 0 ? accum : 1u, leader);
             a_lo += a_adv16;
             b_lo += b_adv16;
           }
