@@ -27,6 +27,12 @@
 #include "conv_impl.h"
 #include "ptx.cuh"
 
+// 1: MMA descriptors built on the uniform datapath (lane-0 broadcast bases, lo/hi halves) as in the plane and weight-
+// gradient kernels.  Measured A/B on one box (probes/ab_roll.py) before choosing the default.
+#ifndef B200_ROLL_UNIFORM
+#define B200_ROLL_UNIFORM 0
+#endif
+
 namespace b200 {
 
 bool encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -149,7 +155,11 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 16, static_cast<uint32_t>(p.WB) * p.rowbytes, p.swz) >> 32);
     const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 16, 8u * p.rowbytes, p.swz) >> 32);
     const uint32_t lo_fixed = 1u << 16;
+#if B200_ROLL_UNIFORM
     const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = __shfl_sync(0xffffffffu, smem_u32(sW) >> 4, 0);
+#else
+    const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = smem_u32(sW) >> 4;
+#endif
     const uint32_t slotA16 = p.slotA >> 4, wtile16 = p.wtile_bytes >> 4, row16 = p.rowbytes >> 4;
     mbar_wait(wFull, 0);
     tc_fence_after();
@@ -161,8 +171,12 @@ __global__ void __launch_bounds__(kRollThreads, 1)
         mbar_wait(&accEmpty[acc], accph ^ 1);
         mbar_wait(&fullA[s], ph);
         tc_fence_after();
+#if B200_ROLL_UNIFORM
         // lane-0 broadcast: marks the per-step base as warp-uniform so the descriptor arithmetic stays on the uniform datapath
         const uint32_t a_lo0 = __shfl_sync(0xffffffffu, ((sA16 + s * slotA16) & 0x3FFF) | lo_fixed, 0);
+#else
+        const uint32_t a_lo0 = ((sA16 + s * slotA16) & 0x3FFF) | lo_fixed;
+#endif
         const uint32_t d_tmem = tbase + acc * NTOT;
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
@@ -172,7 +186,13 @@ __global__ void __launch_bounds__(kRollThreads, 1)
             const uint32_t b_lo = ((sW16 + (b * 3 + e) * wtile16) & 0x3FFF) | lo_fixed;
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
+#if B200_ROLL_UNIFORM
               umma_f16_pred_lohi(d_tmem, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, (b | e | kk) != 0 ? 1u : 0u, leader);
+#else
+              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * kk);
+              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk);
+              umma_f16_pred(d_tmem, ad, bd, idesc, (b | e | kk) != 0 ? 1u : 0u, leader);
+#endif
             }
           }
         }
