@@ -32,6 +32,7 @@ struct UmmaConvParams {
   long long out_pitch;
   int k, pad, dil;
   int KC, nchunks, NT, n_ntiles, P, flat;
+  int G;                 // weight tiles per ring barrier (the k kw-taps of one (kd, kh) pair, or 1)
   int WB, HB, U, UP, S, NB, DT;
   int tiles_w, tiles_h, tiles_d;
   int scatter_cout, cpm;  // pixel-shuffle epilogue channel count (0 = off); K-chunks per input tensor map
@@ -137,16 +138,21 @@ __global__ void __launch_bounds__(256, 2)
   } else if (warp == 1) {
     // =========================== weight-tile producer ===========================
     if (lane == 0) {
+      // One full/empty barrier pair covers G consecutive weight tiles (G = k: the kw taps of one (kd, kh) pair): the
+      // consumer then waits and commits once per G tiles (measured -12 % on the P = 1 bottleneck layers, which issue
+      // only 4 MMAs per weight tile).
+      const int ngroups = p.NB / p.G;
       int L = 0;
       for (int c = 0; c < p.nchunks; ++c) {
-        for (int t = 0; t < k3; ++t, ++L) {
-          const int s = L % p.NB;
-          const uint32_t ph = (L / p.NB) & 1;
+        for (int t = 0; t < k3; t += p.G, ++L) {
+          const int s = L % ngroups;
+          const uint32_t ph = (L / ngroups) & 1;
           mbar_wait(&emptyB[s], ph ^ 1);
-          mbar_arrive_expect_tx(&fullB[s], p.bytesB);
-          // multi-map (gather) mode: the map index doubles as the weight "tap"
-          tma_load_3d(sB + static_cast<size_t>(s) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT,
-                      p.cpm < p.nchunks ? c / p.cpm : t);
+          mbar_arrive_expect_tx(&fullB[s], p.G * p.bytesB);
+          for (int e = 0; e < p.G; ++e)
+            // multi-map (gather) mode: the map index doubles as the weight "tap"
+            tma_load_3d(sB + static_cast<size_t>(s * p.G + e) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT,
+                        p.cpm < p.nchunks ? c / p.cpm : t + e);
         }
       }
     }
@@ -200,9 +206,12 @@ __global__ void __launch_bounds__(256, 2)
           }
           for (int b = 0; b < k; ++b) {
             for (int e = 0; e < k; ++e) {
-              mbar_wait(&fullB[bs], bphase);
-              tc_fence_after();
-              const uint32_t b_lo = (((sB_addr + bs * p.slotB) >> 4) & 0x3FFF) | lo_fixed;
+              const int ge = p.G == 1 ? 0 : e;          // tile inside the group (groups are whole kw rows)
+              if (ge == 0) {
+                mbar_wait(&fullB[bs], bphase);
+                tc_fence_after();
+              }
+              const uint32_t b_lo = (((sB_addr + (bs * p.G + ge) * p.slotB) >> 4) & 0x3FFF) | lo_fixed;
               const uint32_t tapoff = p.flat
                   ? static_cast<uint32_t>((a * p.dil * p.HB + b * p.dil) * p.WB + e * p.dil) * p.rowbytes
                   : static_cast<uint32_t>((b * p.dil) * p.WB + e * p.dil) * p.rowbytes;
@@ -224,23 +233,29 @@ __global__ void __launch_bounds__(256, 2)
                   }
                 }
               } else {
-                uint32_t a_addr = a_first + tapoff;
+                // flat mode: these are the K-heavy 8^3 layers, where the single issuing thread was the bottleneck (576
+                // cycles per weight tile for 4 MMAs of 55): bases broadcast from lane 0 (uniform datapath), descriptors
+                // as (lo, hi) halves, K steps unrolled
+                uint32_t a_lo = __shfl_sync(0xffffffffu, (((a_first + tapoff) >> 4) & 0x3FFF) | lo_fixed, 0);
+                const uint32_t b_lo_u = __shfl_sync(0xffffffffu, b_lo, 0);
                 uint32_t d_tmem = tbase;
                 for (int acc = 0; acc < p.P; ++acc) {
-                  const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | lo_fixed;
-                  for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * kk);
-                    const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk);
-                    umma_f16_pred(d_tmem, ad, bd, idesc, accum0 | (kk != 0 ? 1u : 0u), leader);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    if (kk < ksteps)
+                      umma_f16_pred_lohi(d_tmem, a_lo + 2u * kk, a_hi, b_lo_u + 2u * kk, b_hi, idesc,
+                                         accum0 | (kk != 0 ? 1u : 0u), leader);
                   }
                   d_tmem += p.NT;
-                  a_addr += acc_stride_flat;
+                  a_lo += acc_stride_flat >> 4;
                 }
               }
-              umma_commit_pred(&emptyB[bs], leader);  // weight tile consumed once these MMAs retire
-              if (++bs == p.NB) {
-                bs = 0;
-                bphase ^= 1;
+              if (ge == p.G - 1) {
+                umma_commit_pred(&emptyB[bs], leader);  // weight tiles of the group consumed once these MMAs retire
+                if (++bs == p.NB / p.G) {
+                  bs = 0;
+                  bphase ^= 1;
+                }
               }
             }
           }
@@ -444,21 +459,39 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
   p.cpm = cin_map / p.KC;
   p.rowbytes = p.KC * 2;
   p.swz = p.KC == 64 ? SWZ_128B : (p.KC == 32 ? SWZ_64B : SWZ_32B);
+  const int k3 = a.k * a.k * a.k;
   // N tile: the whole C_out when it fits one accumulator comfortably, else 128 / 64 / 32 / 16
   if (a.cout <= 128 && !a.scatter_cout) p.NT = a.cout;
   else if (a.cout % 128 == 0) p.NT = 128;
   else if (a.cout % 64 == 0) p.NT = 64;
   else if (a.cout % 32 == 0) p.NT = 32;
   else p.NT = 16;
+  if (!(a.oh >= 16 && a.ow >= 8) && !a.scatter_cout && p.NT == 128) {
+    // Flat mode on the K-heavy 8^3 layers: a CTA streams taps x C_in x NT weights through shared memory for ONE or two
+    // accumulators, so its time is max(MMA issue, weight bytes / ~40 B per clock of L2->SM bandwidth) and N = 128 leaves
+    // most SMs without a tile (bottleneck dgrad: 32 CTAs, 3.5 MB of weights each).  Narrower N tiles cost more MMA
+    // instructions per FLOP (66.5 / 54.6 / 48.6 cycles at N = 128 / 64 / 32) but spread the weight stream over the SMs.
+    const long long rows = static_cast<long long>(a.oh + halo) * (a.ow + halo);
+    const long long accs = (rows + 127) / 128;                       // accumulators per d-plane
+    const double mma_cyc[3] = {66.5, 54.6, 48.6};
+    const int cand[3] = {128, 64, 32};
+    double best = -1;
+    for (int i = 0; i < 3; ++i) {
+      if (a.cout % cand[i]) continue;
+      const long long ctas = static_cast<long long>(a.n) * a.od * (a.cout / cand[i]);
+      const double waves = static_cast<double>((ctas + kNumSMs - 1) / kNumSMs);
+      const double mma = static_cast<double>(k3) * (a.cin / 16) * accs * mma_cyc[i];
+      const double wbytes = static_cast<double>(k3) * a.cin * cand[i] * 2 / 40.0;
+      const double cost = waves * std::max(mma, wbytes);
+      if (best < 0 || cost < best) best = cost, p.NT = cand[i];
+    }
+  }
   p.n_ntiles = a.cout / p.NT;
   p.slotB = (p.NT * p.rowbytes + 1023) & ~1023u;
   p.NB = static_cast<int>(std::min<size_t>(8, std::max<size_t>(3, 32768 / p.slotB)));  // hide the TMA round trip
   p.bytesB = p.NT * p.rowbytes;
   const size_t fixed_small = 2048 + 3 * p.NT * sizeof(float);
   size_t fixed = static_cast<size_t>(p.NB) * p.slotB + fixed_small;
-  const int k3 = a.k * a.k * a.k;
-  (void)k3;
-
   if (a.oh >= 16 && a.ow >= 8) {
     // ---- plane mode
     p.flat = 0;
@@ -532,11 +565,17 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
     // (only when the grid is a single wave anyway: larger grids keep the footprint that lets two CTAs share an SM)
     if (static_cast<long long>(a.n) * ((a.od + p.DT - 1) / p.DT) * p.n_ntiles <= kNumSMs)
       p.NB = std::max(p.NB, static_cast<int>(std::min<size_t>(
-                                8, (kSmemBudget - fixed_small - static_cast<size_t>(p.S) * p.slotA) / p.slotB)));
+                                9, (kSmemBudget - fixed_small - static_cast<size_t>(p.S) * p.slotA) / p.slotB)));
     fixed = static_cast<size_t>(p.NB) * p.slotB + fixed_small;
     p.bytesA_unit = static_cast<unsigned>(p.UP) * plane_rows * p.rowbytes;
     p.tiles_w = p.tiles_h = 1;
     p.tiles_d = (a.od + p.DT - 1) / p.DT;
+  }
+  // weight-ring grouping: whole kw rows per barrier when at least two groups fit (rounds NB down to a multiple of k)
+  p.G = 1;
+  if (a.k > 1 && !a.gather2 && p.NB / a.k >= 2) {
+    p.G = a.k;
+    p.NB = (p.NB / a.k) * a.k;
   }
   unsigned cols = 32;
   while (cols < static_cast<unsigned>(p.P * p.NT)) cols <<= 1;

@@ -36,6 +36,7 @@ struct PlaneParams {
   int k, pad, dil;
   int KC, nchunks, NT, n_ntiles;
   int WB, HB, U, S, NB;
+  int G;                      // weight tiles per ring barrier: k (one kw row) or 1, see conv_umma.cu
   int stages;   // TMEM accumulator stages: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one (K-heavy) tile
   int tiles_w, tiles_h, tiles_d;
   long long tiles;
@@ -205,12 +206,13 @@ __global__ void __launch_bounds__(kThreadsP, 1)
       for (long long t = first; t < p.tiles; t += step) {
         const int nt = static_cast<int>(t % p.n_ntiles);
         for (int c = 0; c < p.nchunks; ++c) {
-          for (int tap = 0; tap < k3; ++tap) {
+          for (int tap = 0; tap < k3; tap += p.G) {     // one barrier pair per group of G tiles (a kw row)
             mbar_wait(&emptyB[s], ph ^ 1);
-            mbar_arrive_expect_tx(&fullB[s], p.bytesB);
-            tma_load_3d(sB + static_cast<size_t>(s) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT,
-                        multimap ? c / p.cpm : tap);
-            if (++s == p.NB) {
+            mbar_arrive_expect_tx(&fullB[s], p.G * p.bytesB);
+            for (int e = 0; e < p.G; ++e)
+              tma_load_3d(sB + static_cast<size_t>(s * p.G + e) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT,
+                          multimap ? c / p.cpm : tap + e);
+            if (++s == p.NB / p.G) {
               s = 0;
               ph ^= 1;
             }
@@ -268,9 +270,12 @@ __global__ void __launch_bounds__(kThreadsP, 1)
           for (int b = 0; b < k; ++b) {
             uint32_t tap16 = tap16_row;
             for (int e = 0; e < k; ++e) {
-              mbar_wait(&fullB[bs], bphase);
-              tc_fence_after();
-              const uint32_t b_lo = __shfl_sync(0xffffffffu, ((sB16 + bs * slotB16) & 0x3FFF) | lo_fixed, 0);
+              const int ge = p.G == 1 ? 0 : e;
+              if (ge == 0) {
+                mbar_wait(&fullB[bs], bphase);
+                tc_fence_after();
+              }
+              const uint32_t b_lo = __shfl_sync(0xffffffffu, ((sB16 + (bs * p.G + ge) * slotB16) & 0x3FFF) | lo_fixed, 0);
               const uint32_t fresh = (c | a | b | e) == 0 ? 0u : 1u;
 #pragma unroll
               for (int acc = 0; acc < P; ++acc) {
@@ -280,10 +285,12 @@ __global__ void __launch_bounds__(kThreadsP, 1)
                                      kk == 0 ? fresh : 1u, leader);
                 }
               }
-              umma_commit_pred(&emptyB[bs], leader);
-              if (++bs == p.NB) {
-                bs = 0;
-                bphase ^= 1;
+              if (ge == p.G - 1) {
+                umma_commit_pred(&emptyB[bs], leader);
+                if (++bs == p.NB / p.G) {
+                  bs = 0;
+                  bphase ^= 1;
+                }
               }
               tap16 += p.dil * row16;
             }
@@ -463,6 +470,12 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
     }
   }
   if (!P) return false;
+  // Weight-ring grouping (few accumulators per tile only: with P x KS >= 8 MMAs per tile the hand-shake is amortised)
+  p.G = 1;
+  if (a.k > 1 && !a.gather2 && P * KS <= 4 && p.NB / a.k >= 2) {
+    p.G = a.k;
+    p.NB = (p.NB / a.k) * a.k;
+  }
   p.tiles_w = (a.ow + 7) / 8;
   p.tiles_h = (a.oh + 15) / 16;
   p.tiles_d = (a.od + P - 1) / P;

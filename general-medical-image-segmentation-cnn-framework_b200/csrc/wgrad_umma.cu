@@ -159,16 +159,15 @@ __global__ void __launch_bounds__(192, 1)
       for (long long it = it0; it < it1; ++it) {
         mbar_wait(&full[s], phase);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+        // (lane-0 broadcast: warp-uniform hint so the descriptor arithmetic below runs on the uniform datapath)
+        const uint32_t st = __shfl_sync(0xffffffffu, smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes), 0);
         const uint32_t y_lo0 = (((st + p.nplanes * p.slotX) >> 4) & 0x3FFF) | (1u << 16);
         for (int g = 0; g < p.ngroups; ++g) {
           uint32_t a_lo = (((st + g_off[g]) >> 4) & 0x3FFF) | g_lbo[g];
           uint32_t y_lo = y_lo0;
           const uint32_t d_tmem = tbase + g * p.NT;
           for (int ks = 0; ks < p.ksteps; ++ks) {
-            const uint64_t ad = (static_cast<uint64_t>(g_hi[g]) << 32) | a_lo;
-            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | y_lo;
-            umma_f16_pred(d_tmem, ad, bd, idesc, accum | (ks != 0 ? 1u : 0u), leader);
+            umma_f16_pred_lohi(d_tmem, a_lo, g_hi[g], y_lo, b_hi, idesc, accum | (ks != 0 ? 1u : 0u), leader);
             a_lo += a_adv16;
             y_lo += b_adv16;
           }
