@@ -22,9 +22,9 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 PATCH = 128
 FEATURES = 32
 BATCH = 2
-# DRAM bytes of the fprop + dgrad conv launches of one step (ncu, profiles/r01_step3_final_launch_list.md) and their
+# DRAM bytes of the fprop + dgrad conv launches of one step (ncu, profiles/r01_step4_final_launch_list.md) and their
 # algorithmic in + out + weight bytes (3.68 GB per forward, about the same for the data gradients)
-NCU_CONV_TRAFFIC_BYTES_PER_STEP = 5.58e9
+NCU_CONV_TRAFFIC_BYTES_PER_STEP = 5.69e9
 CONV_ALGORITHMIC_BYTES_PER_STEP = 7.3e9
 WORKLOAD = ("UNet3D(1,2,32) train step, batch 2x1x128^3 per GPU, Dice+CE, BatchNorm (SyncBatchNorm across ranks when "
             "N > 1), Adam (BASELINE.json configs[1])")
@@ -275,9 +275,9 @@ def run_b200(args):
             # dominant kernel family: the tcgen05 implicit-GEMM convolutions (conv_umma_roll / conv_umma_plane), all 34
             # forward + data-gradient launches of the step; achieved = their algorithmic FLOPs / their CUDA-event time.
             # traffic = DRAM read + write bytes of the same launches in the committed ncu launch list
-            # (profiles/r01_step3_final_launch_list.md), per step like `achieved`.
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_plane_kernel (34 fprop + dgrad "
-                                                      "launches per step)",
+            # (profiles/r01_step4_final_launch_list.md), per step like `achieved`.
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_plane_kernel (the fprop + dgrad "
+                                                      "launches of the step)",
                          "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " sustained",
                          "traffic": NCU_CONV_TRAFFIC_BYTES_PER_STEP, "algorithmic_bytes": CONV_ALGORITHMIC_BYTES_PER_STEP,
