@@ -36,6 +36,7 @@ struct PlaneParams {
   int k, pad, dil;
   int KC, nchunks, NT, n_ntiles;
   int WB, HB, U, S, NB;
+  int wide;                   // output rows allow 256-bit stores (pitch and channel offsets % 16 == 0, base 32-byte aligned)
   int G;                      // weight tiles per ring barrier: k (one kw row) or 1, see conv_umma.cu
   int stages;   // TMEM accumulator stages: 2 = epilogue overlaps the next tile, 1 = all 512 columns for one (K-heavy) tile
   int tiles_w, tiles_h, tiles_d;
@@ -75,7 +76,7 @@ __device__ __forceinline__ TileCoord decode_tile(const PlaneParams& p, long long
 // One 32- or 16-column slab of one accumulator: TMEM -> +bias -> statistics -> bf16 -> global.
 template <int CW>
 __device__ __forceinline__ void epilogue_slab(uint32_t taddr, const float* s_bias_col, bool valid, __nv_bfloat16* optr,
-                                              float (&s1)[CW], float (&s2)[CW], bool want_stats) {
+                                              float (&s1)[CW], float (&s2)[CW], bool want_stats, bool wide) {
   uint32_t raw[CW];
   if constexpr (CW == 32) tmem_ld_32x32(taddr, raw);
   else tmem_ld_32x16(taddr, raw);
@@ -91,12 +92,25 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, const float* s_bia
         s2[j] = fmaf(v[j], v[j], s2[j]);
       }
     }
+    if (wide) {                       // 32-byte aligned rows: 256-bit stores, half the L2 requests
 #pragma unroll
-    for (int j = 0; j < CW; j += 8) {
-      float t8[8];
+      for (int j = 0; j < CW; j += 16) {
+        float t8[8], u8[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t8[i] = v[j + i];
-      st8(optr + j, pack8(t8));
+        for (int i = 0; i < 8; ++i) {
+          t8[i] = v[j + i];
+          u8[i] = v[j + 8 + i];
+        }
+        st16(optr + j, pack8(t8), pack8(u8));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; j += 8) {
+        float t8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = v[j + i];
+        st8(optr + j, pack8(t8));
+      }
     }
   }
 }
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(kThreadsP, 1)
               const long long vox = ((static_cast<long long>(tc.nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
               optr = p.out + vox * p.out_pitch + col0;
             }
-            epilogue_slab<CW>(t_lane + acc * p.NT + c0, s_bias + col0, valid, optr, s1, s2, want_stats);
+            epilogue_slab<CW>(t_lane + acc * p.NT + c0, s_bias + col0, valid, optr, s1, s2, want_stats, p.wide != 0);
           }
           if (want_stats) {
             warp_colsum<CW>(s1, lane);
@@ -519,6 +533,9 @@ int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st) {
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.bias = a.bias;
   p.stats = a.stats;
+  // pixel-shuffle epilogue: column chunk c0 lands at channel c0 % scatter_cout of another voxel -> scatter_cout % 16 too
+  p.wide = (a.out_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0 &&
+            (!a.scatter_cout || a.scatter_cout % 16 == 0) && !getenv("B200SEG_NO_WIDE_STORES")) ? 1 : 0;
   if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.wpack)) & 15) {
     set_error("conv_umma_plane_run: buffers must be 16-byte aligned");
     return B200SEG_ERR_INVALID;

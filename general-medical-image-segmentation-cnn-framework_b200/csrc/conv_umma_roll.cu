@@ -44,6 +44,7 @@ constexpr int kRollEpiWarps = 8;
 
 struct RollParams {
   int n, d, od, oh, ow, cout, pad;   // cout = channels of the whole output tensor
+  int wide;                          // output rows allow 256-bit stores (pitch % 16 == 0, base 32-byte aligned)
   int halves;                        // 1, or 2: C_out = 64 handled as two independent 32-channel halves (CTA parity)
   long long out_pitch;
   int KC, NTOT;                    // channels per row (= C_in), N = 3 * C_out
@@ -258,12 +259,22 @@ __global__ void __launch_bounds__(kRollThreads, 1)
             }
             const long long vox = ((static_cast<long long>(r.nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
             __nv_bfloat16* optr = p.out + vox * p.out_pitch + co_base + half * CH;
+            if (CH == 16 && p.wide) {        // 32-byte aligned rows: one 256-bit store
+              float t8[8], u8[8];
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              float t8[8];
+              for (int i = 0; i < 8; ++i) {
+                t8[i] = v[i];
+                u8[i] = v[8 + i];
+              }
+              st16(optr, pack8(t8), pack8(u8));
+            } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) t8[i] = v[j + i];
-              st8(optr + j, pack8(t8));
+              for (int j = 0; j < CH; j += 8) {
+                float t8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t8[i] = v[j + i];
+                st8(optr + j, pack8(t8));
+              }
             }
           }
         }
@@ -385,6 +396,7 @@ int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.bias = a.bias;
   p.stats = a.stats;
+  p.wide = (a.out_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0 && !getenv("B200SEG_NO_WIDE_STORES")) ? 1 : 0;
   if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.wpack)) & 15) {
     set_error("conv_umma_roll_run: buffers must be 16-byte aligned");
     return B200SEG_ERR_INVALID;
