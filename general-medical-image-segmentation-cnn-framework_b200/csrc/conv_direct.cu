@@ -34,6 +34,17 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
 
 // y[row][0:c] = x[row][0:c], y[row][c:cpad] = 0 (cpad a multiple of 8): widens a 1-4 channel tensor so that it can feed
 // the tensor-core kernels, whose K dimension comes in chunks of 16 channels.
+// C = 1 -> 16 (the U-Net stem input): one thread per voxel, one 256-bit store
+__global__ void pad_1_to_16_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, __nv_bfloat16* __restrict__ y,
+                                   int64_t rows) {
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t v = xs[i * x_pitch], z = 0u;
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %2, %2, %2, %2, %2, %2};" ::"l"(y + i * 16), "r"(v), "r"(z) : "memory");
+  }
+}
+
 __global__ void pad_channels_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, int c,
                                     __nv_bfloat16* __restrict__ y, int cpad, int64_t rows) {
   const int groups = cpad / 8;
@@ -731,9 +742,13 @@ __global__ void __launch_bounds__(256)
             const uint32_t bits = ok ? static_cast<uint32_t>(xs[off * x_pitch]) : 0u;
             pk[t >> 1] |= (t & 1) ? (bits << 16) : bits;
           }
-      uint4* dst = reinterpret_cast<uint4*>(xcol + v * 32);
+      __nv_bfloat16* dst = xcol + v * 32;     // 64-byte rows of a 256-byte aligned workspace: two 256-bit stores
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < 2; ++q)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * q), "r"(pk[8 * q]),
+                     "r"(pk[8 * q + 1]), "r"(pk[8 * q + 2]), "r"(pk[8 * q + 3]), "r"(pk[8 * q + 4]), "r"(pk[8 * q + 5]),
+                     "r"(pk[8 * q + 6]), "r"(pk[8 * q + 7])
+                     : "memory");
     }
   }
 }
@@ -811,8 +826,12 @@ extern "C" {
 
 int b200seg_pad_channels(const void* x, int64_t x_pitch, int c, void* y, int cpad, int64_t rows, void* stream) {
   B200_CHECK_ARG(x && y && c > 0 && cpad >= c && cpad % 8 == 0 && rows > 0 && x_pitch >= c, "pad_channels: bad arguments");
-  b200::pad_channels_kernel<<<grid_for(rows * (cpad / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_pitch, c, static_cast<__nv_bfloat16*>(y), cpad, rows);
+  if (c == 1 && cpad == 16 && (reinterpret_cast<uintptr_t>(y) & 31) == 0)
+    b200::pad_1_to_16_kernel<<<grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), rows);
+  else
+    b200::pad_channels_kernel<<<grid_for(rows * (cpad / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, c, static_cast<__nv_bfloat16*>(y), cpad, rows);
   B200_CHECK_LAUNCH("pad_channels");
   return 0;
 }
