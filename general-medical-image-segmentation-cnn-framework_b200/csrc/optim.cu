@@ -34,6 +34,17 @@ struct AdamCoef {
   float lr_bc1, b1, b2, eps, wd, gscale, bc2_sqrt;
 };
 
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st8f(float* p, const float (&f)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]),
+               "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+               : "memory");
+}
+
 __device__ __forceinline__ float adam_one(float pi, float grad, float& mi, float& vi, const AdamCoef& c) {
   grad *= c.gscale;
   if (c.wd != 0.f) grad += c.wd * pi;
@@ -62,6 +73,20 @@ __device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_
   if (use_dw) {
     // packed side: for every (tap, ci) a run of nco consecutive floats
     const float* src = dw + d.src;
+    if (FULL && (cout & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      // 128-bit loads along C_out (8 per (tap, ci) row of the brick); the four values go to four tile rows
+#pragma unroll 4
+      for (int i = tid; i < total / 4; i += nthr) {
+        const int co4 = (i & 7) << 2, r = i >> 3;     // r = t * 32 + ci
+        const int ci = r & 31, t = r >> 5;
+        const float4 q = *reinterpret_cast<const float4*>(src + (static_cast<long long>(t) * cin + ci0 + ci) * cout + co0 + co4);
+        float* tl = tile + co4 * row + ci * k3 + t;
+        tl[0] = q.x;
+        tl[row] = q.y;
+        tl[2 * row] = q.z;
+        tl[3 * row] = q.w;
+      }
+    } else
 #pragma unroll 8
     for (int i = tid; i < total; i += nthr) {
       const int co = i % nco, r = i / nco;          // r = t * nci + ci
@@ -75,7 +100,30 @@ __device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_
     const long long base = d.src + (static_cast<long long>(co0) * cin + ci0) * k3;
     const long long co_stride = static_cast<long long>(cin) * k3;
     const bool vec = (run % 4 == 0) && (co_stride % 4 == 0) && (base % 4 == 0);
-    if (vec) {
+    const bool vec8 = (run % 8 == 0) && (co_stride % 8 == 0) && (base % 8 == 0);
+    if (vec8) {
+      // 256-bit accesses (sm_100 LDG/STG.256): half the memory requests of the float4 form
+      const int run8 = run >> 3;
+#pragma unroll 2
+      for (int i = tid; i < nco * run8; i += nthr) {
+        const int co = i / run8, r = (i - co * run8) << 3;
+        const long long idx = base + co * co_stride + r;
+        float pv[8], gv[8], mv[8], vv[8], o[8];
+        ld8f(p + idx, pv);
+        ld8f(g + idx, gv);
+        ld8f(m + idx, mv);
+        ld8f(v + idx, vv);
+        float* tl = tile + co * row + r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = adam_one(pv[j], gv[j] + (use_dw ? tl[j] : 0.f), mv[j], vv[j], c);
+          tl[j] = o[j];
+        }
+        st8f(p + idx, o);
+        st8f(m + idx, mv);
+        st8f(v + idx, vv);
+      }
+    } else if (vec) {
       const int run4 = run >> 2;
 #pragma unroll 2
       for (int i = tid; i < nco * run4; i += nthr) {

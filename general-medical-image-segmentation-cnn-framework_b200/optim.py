@@ -26,11 +26,12 @@ class FusedAdam:
         self.numel = total
         self.param_arena = torch.zeros(total, dtype=torch.float32, device=dev)
         # gradients and the conv kernels' packed weight-gradient accumulators share one allocation: one memset clears both
-        self._zeroed = torch.zeros(2 * total, dtype=torch.float32, device=dev)
+        padded = (total + 63) // 64 * 64          # the packed accumulators start 256-byte aligned (128-bit loads of dw)
+        self._zeroed = torch.zeros(padded + total, dtype=torch.float32, device=dev)
         self.grad_arena = self._zeroed[:total]
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.dw_arena = self._zeroed[total:]       # see functional._grad_target
+        self.dw_arena = self._zeroed[padded:]      # see functional._grad_target
         self._pending = [False]                    # some packed weight gradient has not been transposed yet
         for p, off in zip(self.params, self.offsets):
             view = self.param_arena[off:off + p.numel()].view_as(p)
