@@ -338,10 +338,9 @@ __global__ void __launch_bounds__(256)
       o.w += acc.w;
       *reinterpret_cast<float4*>(dst) = o;
     } else {
-      atomicAdd(dst, acc.x);
-      atomicAdd(dst + 1, acc.y);
-      atomicAdd(dst + 2, acc.z);
-      atomicAdd(dst + 3, acc.w);
+      // one 4-wide vector reduction (REDG.E.ADD.F32x4; dwp is 16-byte aligned on this path)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w)
+                   : "memory");
     }
   }
 }
