@@ -281,7 +281,19 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
                 *reinterpret_cast<uint4*>(dst + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(raw[j]));
+              for (int j = 0; j < 16; j += 4) {
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
+                               "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])),
+                               "f"(__uint_as_float(raw[j + 3]))
+                               : "memory");
+                } else {
+                  atomicAdd(dst + j, __uint_as_float(raw[j]));
+                  atomicAdd(dst + j + 1, __uint_as_float(raw[j + 1]));
+                  atomicAdd(dst + j + 2, __uint_as_float(raw[j + 2]));
+                  atomicAdd(dst + j + 3, __uint_as_float(raw[j + 3]));
+                }
+              }
             }
           }
         }
