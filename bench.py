@@ -31,6 +31,29 @@ WORKLOAD = ("UNet3D(1,2,32) train step, batch 2x1x128^3 per GPU, Dice+CE, BatchN
 TRAIN_GFLOP_PER_PATCH = 2850.4  # fwd 951.3 + wgrad 951.3 + dgrad (951.3 - 3.6 first layer): BASELINE.md section 3
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: keep a private duplicate of fd 1 for it and point fd 1 at stderr
+    for the rest of the run, so that whatever a library prints to stdout (NCCL's version banner under NCCL_DEBUG, which
+    ignores NCCL_DEBUG_FILE on this stack) cannot end up in front of the result."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -149,7 +172,7 @@ def run_reference(args):
                                        "fwd+bwd+Adam on one 1x1x64^3 patch, counted as 1/8 of a 128^3 patch" % cores},
             "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ b200 arm
@@ -294,7 +317,7 @@ def run_b200(args):
                                        "of 5 fwd+bwd+Adam steps on one 1x1x64^3 patch = 1/8 of a 128^3 patch" % cores},
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -308,6 +331,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                                                             "the captured CUDA graph of the step")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
