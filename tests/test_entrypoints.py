@@ -84,3 +84,20 @@ def test_predict_entry_matches_oracle_stitching(tmp_path):
             lab = F.argmax_labels(model(data.cuda().float())).cpu().numpy()
             oagg.add_batch(lab, locs.numpy())
     assert np.array_equal(pred, oagg.get_output_tensor())
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: stdout carries ONE JSON line (library chatter such as NCCL's banner is diverted to stderr by
+    duplicating fd 1); the reference arm runs the oracle port on the host cores and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_patches_per_s_128cubed" and d["unit"] == "patches/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference") and d["e2e"]["h2d_bytes_per_step"] == 0
