@@ -49,8 +49,10 @@ SIGNATURES = {
     "b200seg_head_conv1x1_fwd": "plppp" + "ilii" + "p",
     "b200seg_head_conv1x1_bwd": "ppl" + "p" + "pl" + "pp" + "ilii" + "p",
     "b200seg_argmax_labels": "pp" + "ili" + "p",
-    "b200seg_loss_reduce": "pp" + "ilii" + "pp",
-    "b200seg_loss_grad": "pp" + "ili" + "p" + "ffff" + "p" + "pp",
+    "b200seg_loss_reduce": "pp" + "ilii" + "ppp",
+    "b200seg_loss_grad": "pp" + "ili" + "p" + "ffff" + "pp" + "pp",
+    "b200seg_dice_sums": "ppp" + "iil" + "if" + "pp",
+    "b200seg_dice_grad": "ppp" + "iil" + "if" + "ppp" + "pp",
     "b200seg_seg_counts": "ppl" + "pp",
     "b200seg_window_accumulate_crop": "ppp" + "l" + "iiiiiii" + "p" + "iii" + "p",
     "b200seg_window_keys_to_labels": "pp" + "l" + "p",

@@ -240,7 +240,8 @@ __global__ void argmax_kernel(const float* __restrict__ logits, uint8_t* __restr
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 __global__ void loss_reduce_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int n,
-                                   int64_t spatial, int classes, double* __restrict__ partial) {
+                                   int64_t spatial, int classes, const float* __restrict__ ce_weight,
+                                   double* __restrict__ partial) {
   const int nsum = 1 + 3 * classes + 4;
   float acc[1 + 3 * kMaxClasses + 4];
 #pragma unroll
@@ -271,7 +272,7 @@ __global__ void loss_reduce_kernel(const float* __restrict__ logits, const uint8
       if (k < classes) {
         const float p = e[k] * inv_z;
         const float tk = (k == t) ? 1.f : 0.f;
-        if (k == t) acc[0] += -(l[k] - m - logz);
+        if (k == t) acc[0] += -(l[k] - m - logz) * (ce_weight ? ce_weight[k] : 1.f);   // nll_loss(weight=...), :13
         acc[1 + 3 * k + 0] += p * tk;
         acc[1 + 3 * k + 1] += p * p;
         acc[1 + 3 * k + 2] += tk;
@@ -296,9 +297,10 @@ __global__ void loss_reduce_kernel(const float* __restrict__ logits, const uint8
 __global__ void loss_grad_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int n,
                                  int64_t spatial, int classes, const double* __restrict__ partial, float w_ce,
                                  float w_dice, float w_sdice, float w_bce, const float* __restrict__ gscale_p,
-                                 float* __restrict__ dlogits) {
+                                 const float* __restrict__ class_weights, float* __restrict__ dlogits) {
   const float gscale = gscale_p ? *gscale_p : 1.f;
   __shared__ float ck_t[kMaxClasses], ck_p[kMaxClasses];  // dDice/dp_k = ck_t*t_k + ck_p*p_k
+  __shared__ float ce_w[kMaxClasses];                      // class_weights = {ce[classes], dice[classes]} or null
   __shared__ float sd_t, sd_c;
   const int64_t total = static_cast<int64_t>(n) * spatial;
   if (threadIdx.x < classes) {
@@ -307,8 +309,10 @@ __global__ void loss_grad_kernel(const float* __restrict__ logits, const uint8_t
     const double I = partial[1 + 3 * k], Z = partial[2 + 3 * k], Y = partial[3 + 3 * k];
     const double D = Z + Y + smooth;
     // L_k = 1 - (2I+s)/D ; dL_k/dp = -2 t / D + (2I+s) * 2p / D^2 ; averaged over classes
-    ck_t[k] = static_cast<float>(-2.0 / D / classes);
-    ck_p[k] = static_cast<float>(2.0 * (2.0 * I + smooth) / (D * D) / classes);
+    const double wd = class_weights ? class_weights[classes + k] : 1.0;   // loss += dice_k * weight[k], :183
+    ck_t[k] = static_cast<float>(-2.0 / D / classes * wd);
+    ck_p[k] = static_cast<float>(2.0 * (2.0 * I + smooth) / (D * D) / classes * wd);
+    ce_w[k] = class_weights ? class_weights[k] : 1.f;
   }
   if (threadIdx.x == 0) {
     const double eps = 1e-5;
@@ -353,13 +357,71 @@ __global__ void loss_grad_kernel(const float* __restrict__ logits, const uint8_t
     for (int k = 0; k < kMaxClasses; ++k)
       if (k < classes) {
         const float tk = (k == t) ? 1.f : 0.f;
-        float g = w_ce * (p[k] - tk) * inv_vox + w_dice * p[k] * (a[k] - dot);
+        float g = w_ce * ce_w[t < classes ? t : 0] * (p[k] - tk) * inv_vox + w_dice * p[k] * (a[k] - dot);
         if (w_sdice != 0.f || w_bce != 0.f) {
           const float sg = sigmoidf_(l[k]);
           g += w_sdice * (sd_t * tk + sd_c) * sg * (1.f - sg) + w_bce * (sg - tk) * inv_elems;
         }
         dlogits[(nn * classes + k) * spatial + s] = g * gscale;
       }
+  }
+}
+
+// ---- Dice on PROBABILITIES supplied by the caller: BinaryDiceLoss (loss_function.py:61-99, one loss per sample) and
+// DiceLossss without its soft-max (:172-184, one loss per class).  pred is fp32 [N][K][S]; the target is either a float
+// tensor of the same layout or uint8 labels [N][S] (target of class k = (label == k), the comparison of :154-160).
+// Row r of the reduction is the sample (by_class = 0) or the class (by_class = 1): partial[r] = {sum x*t, sum x^p, sum t^p}.
+__device__ __forceinline__ float pow_p(float v, float p) { return p == 2.f ? v * v : (p == 1.f ? v : powf(v, p)); }
+
+__global__ void __launch_bounds__(256) dice_sums_kernel(const float* __restrict__ pred, const float* __restrict__ tf,
+                                                        const uint8_t* __restrict__ tl, int classes, int64_t spatial,
+                                                        int by_class, float p_exp, double* __restrict__ partial) {
+  const int plane = blockIdx.y, nn = plane / classes, k = plane % classes;
+  const float* x = pred + static_cast<int64_t>(plane) * spatial;
+  const float* t_f = tf ? tf + static_cast<int64_t>(plane) * spatial : nullptr;
+  const uint8_t* t_l = tl ? tl + static_cast<int64_t>(nn) * spatial : nullptr;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < spatial;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    const float t = t_f ? t_f[i] : (t_l[i] == k ? 1.f : 0.f);
+    a0 = fmaf(v, t, a0);
+    a1 += pow_p(v, p_exp);
+    a2 += t_f ? pow_p(t, p_exp) : t;
+  }
+  __shared__ double red[3];
+  if (threadIdx.x < 3) red[threadIdx.x] = 0.0;
+  __syncthreads();
+  const double s0 = warp_sum_d(a0), s1 = warp_sum_d(a1), s2 = warp_sum_d(a2);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&red[0], s0);
+    atomicAdd(&red[1], s1);
+    atomicAdd(&red[2], s2);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(&partial[3 * (by_class ? k : nn) + threadIdx.x], red[threadIdx.x]);
+}
+
+// dpred = gscale * (coef_t[r] * t + coef_x[r] * p * x^(p-1))
+__global__ void __launch_bounds__(256) dice_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tf,
+                                                        const uint8_t* __restrict__ tl, int classes, int64_t spatial,
+                                                        int by_class, float p_exp, const float* __restrict__ coef_t,
+                                                        const float* __restrict__ coef_x, const float* __restrict__ gscale_p,
+                                                        float* __restrict__ dpred) {
+  const int plane = blockIdx.y, nn = plane / classes, k = plane % classes;
+  const int r = by_class ? k : nn;
+  const float gs = gscale_p ? *gscale_p : 1.f;
+  const float ct = coef_t[r] * gs, cx = coef_x[r] * gs * p_exp;
+  const float* x = pred + static_cast<int64_t>(plane) * spatial;
+  float* dx = dpred + static_cast<int64_t>(plane) * spatial;
+  const float* t_f = tf ? tf + static_cast<int64_t>(plane) * spatial : nullptr;
+  const uint8_t* t_l = tl ? tl + static_cast<int64_t>(nn) * spatial : nullptr;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < spatial;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    const float t = t_f ? t_f[i] : (t_l[i] == k ? 1.f : 0.f);
+    const float vp = p_exp == 2.f ? v : (p_exp == 1.f ? 1.f : powf(v, p_exp - 1.f));
+    dx[i] = ct * t + cx * vp;
   }
 }
 
@@ -684,11 +746,11 @@ int b200seg_argmax_labels(const float* logits, uint8_t* labels, int n, int64_t s
 }
 
 int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes, int terms,
-                        double* partial, void* stream) {
+                        const float* class_weights, double* partial, void* stream) {
   B200_CHECK_ARG(logits && labels && partial && n > 0 && spatial > 0, "loss_reduce: bad arguments");
   B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "loss_reduce: classes must be in [1,%d]", kMaxClasses);
   B200_CHECK_ARG(terms >= 1 && terms <= 3, "loss_reduce: terms must be a mask of 1 (soft-max sums) | 2 (sigmoid sums)");
-  if (classes == 2 && spatial % 4 == 0 && n <= 65535 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+  if (classes == 2 && !class_weights && spatial % 4 == 0 && n <= 65535 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(labels) & 3) == 0) {
     const int per_sample = std::max(1, kNumSMs * 4 / n);
     const dim3 grid(static_cast<unsigned>(std::min<int64_t>(per_sample, (spatial / 4 + 511) / 512)), n);
@@ -700,17 +762,17 @@ int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64
     return 0;
   }
   loss_reduce_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256, kNumSMs * 8), 256, 0,
-                       static_cast<cudaStream_t>(stream)>>>(logits, labels, n, spatial, classes, partial);
+                       static_cast<cudaStream_t>(stream)>>>(logits, labels, n, spatial, classes, class_weights, partial);
   B200_CHECK_LAUNCH("loss_reduce");
   return 0;
 }
 
 int b200seg_loss_grad(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
                       const double* partial, float w_ce, float w_dice, float w_sdice, float w_bce,
-                      const float* gscale, float* dlogits, void* stream) {
+                      const float* gscale, const float* class_weights, float* dlogits, void* stream) {
   B200_CHECK_ARG(logits && labels && partial && dlogits && n > 0 && spatial > 0, "loss_grad: bad arguments");
   B200_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "loss_grad: classes must be in [1,%d]", kMaxClasses);
-  if (classes == 2 && spatial % 4 == 0 && n <= 65535 &&
+  if (classes == 2 && !class_weights && spatial % 4 == 0 && n <= 65535 &&
       ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(labels) & 3) == 0) {
     const int per_sample = std::max(1, kNumSMs * 8 / n);
@@ -724,8 +786,35 @@ int b200seg_loss_grad(const float* logits, const uint8_t* labels, int n, int64_t
     return 0;
   }
   loss_grad_kernel<<<grid_for(static_cast<int64_t>(n) * spatial, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, labels, n, spatial, classes, partial, w_ce, w_dice, w_sdice, w_bce, gscale, dlogits);
+      logits, labels, n, spatial, classes, partial, w_ce, w_dice, w_sdice, w_bce, gscale, class_weights, dlogits);
   B200_CHECK_LAUNCH("loss_grad");
+  return 0;
+}
+
+int b200seg_dice_sums(const float* pred, const float* target_f, const uint8_t* target_l, int n, int classes, int64_t spatial,
+                      int by_class, float p_exp, double* partial, void* stream) {
+  B200_CHECK_ARG(pred && partial && (target_f != nullptr) != (target_l != nullptr) && n > 0 && classes > 0 && spatial > 0 &&
+                     p_exp > 0.f, "dice_sums: bad arguments (exactly one of the two target forms)");
+  const int64_t planes = static_cast<int64_t>(n) * classes;
+  B200_CHECK_ARG(planes <= 65535, "dice_sums: at most 65535 (sample, class) planes");
+  const int per_plane = static_cast<int>(std::min<int64_t>(std::max<int64_t>(1, kNumSMs * 8 / planes), (spatial + 2047) / 2048));
+  dice_sums_kernel<<<dim3(per_plane, static_cast<unsigned>(planes)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, target_f, target_l, classes, spatial, by_class, p_exp, partial);
+  B200_CHECK_LAUNCH("dice_sums");
+  return 0;
+}
+
+int b200seg_dice_grad(const float* pred, const float* target_f, const uint8_t* target_l, int n, int classes, int64_t spatial,
+                      int by_class, float p_exp, const float* coef_t, const float* coef_x, const float* gscale, float* dpred,
+                      void* stream) {
+  B200_CHECK_ARG(pred && dpred && coef_t && coef_x && (target_f != nullptr) != (target_l != nullptr) && n > 0 && classes > 0 &&
+                     spatial > 0 && p_exp > 0.f, "dice_grad: bad arguments");
+  const int64_t planes = static_cast<int64_t>(n) * classes;
+  B200_CHECK_ARG(planes <= 65535, "dice_grad: at most 65535 (sample, class) planes");
+  const int per_plane = static_cast<int>(std::min<int64_t>(std::max<int64_t>(1, kNumSMs * 8 / planes), (spatial + 1023) / 1024));
+  dice_grad_kernel<<<dim3(per_plane, static_cast<unsigned>(planes)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, target_f, target_l, classes, spatial, by_class, p_exp, coef_t, coef_x, gscale, dpred);
+  B200_CHECK_LAUNCH("dice_grad");
   return 0;
 }
 

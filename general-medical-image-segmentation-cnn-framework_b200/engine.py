@@ -61,8 +61,15 @@ class TrainStep:
         reducer = getattr(self.optimizer, "reducer", None)
         if self._split and reducer is not None:
             reducer.enabled = False           # no NCCL launches from autograd hooks while capturing / replaying
+        self._grad_scale = 1.0
         with torch.cuda.graph(self.graph):
-            self._loss, self._out = (self._fwd_bwd if self._split else self._body)(self._x, self._y)
+            if self._split:
+                # the packed weight gradients are transposed into the gradient arena INSIDE the graph: the host-side
+                # "some packed gradient is pending" flag is only ever set by the Python backward, which a replay skips
+                self._loss, self._out = self._fwd_bwd(self._x, self._y)
+                self.optimizer.finalize_grads()
+            else:
+                self._loss, self._out = self._body(self._x, self._y)
         self.kernels_per_step, self.umma_per_step = F.launches() - k0, F.umma_launch_count() - u0
         torch.cuda.synchronize()
 
@@ -82,6 +89,10 @@ class TrainStep:
             return self._body(x, y)               # odd-sized last batch: run it eagerly
         self._x.copy_(x, non_blocking=True)
         self._y.copy_(y, non_blocking=True)
+        if not self._split:
+            # the captured Adam launch reads lr / betas / eps / weight decay from device memory: push host-side changes
+            # (StepLR, train.py:119-120) before the replay -- a no-op when nothing changed
+            self.optimizer._sync_hyper(self._grad_scale)
         self.graph.replay()
         if self._split:
             self._update()

@@ -762,18 +762,20 @@ def _labels_u8(target, n, spatial_shape):
 
 class _SegLoss(torch.autograd.Function):
     """w_ce*cross_entropy_3D + w_dice*DiceLossss(softmax=True) + w_sdice*DiceLoss(sigmoid) + w_bce*BCEWithLogits,
-    from one reduction pass over the logits (loss_function.py:8-16, 102-130, 148-185; train.py:115)."""
+    from one reduction pass over the logits (loss_function.py:8-16, 102-130, 148-185; train.py:115).  class_weights:
+    None or fp32 [2][K] = per-class {cross-entropy, Dice} weights (loss_function.py:13, 176-183)."""
 
     @staticmethod
-    def forward(ctx, logits, labels, weights):
+    def forward(ctx, logits, labels, weights, class_weights):
         logits = logits.contiguous().float()
         n, classes = logits.shape[0], logits.shape[1]
         spatial = logits[0, 0].numel()
         partial = torch.zeros(1 + 3 * classes + 4, dtype=torch.float64, device=logits.device)
         w_ce, w_dice, w_sdice, w_bce = weights
         terms = (1 if (w_ce or w_dice) else 0) | (2 if (w_sdice or w_bce) else 0)
-        _call("b200seg_loss_reduce", _ptr(logits), _ptr(labels), n, spatial, classes, terms or 1, _ptr(partial), _stream())
-        ctx.save_for_backward(logits, labels, partial)
+        _call("b200seg_loss_reduce", _ptr(logits), _ptr(labels), n, spatial, classes, terms or 1, _ptr(class_weights),
+              _ptr(partial), _stream())
+        ctx.save_for_backward(logits, labels, partial, class_weights)
         ctx.weights = weights
         vox = float(n * spatial)
         smooth = 1e-5
@@ -782,7 +784,10 @@ class _SegLoss(torch.autograd.Function):
             loss = loss + w_ce * partial[0] / vox
         if w_dice:
             pk = partial[1:1 + 3 * classes].view(classes, 3)
-            loss = loss + w_dice * (1 - (2 * pk[:, 0] + smooth) / (pk[:, 1] + pk[:, 2] + smooth)).mean()
+            per_class = 1 - (2 * pk[:, 0] + smooth) / (pk[:, 1] + pk[:, 2] + smooth)
+            if class_weights is not None:
+                per_class = per_class * class_weights[1].double()
+            loss = loss + w_dice * per_class.mean()
         tail = partial[1 + 3 * classes:]
         if w_sdice:
             loss = loss + w_sdice * (1 - 2 * (tail[0] + smooth) / (tail[1] + tail[2] + smooth))
@@ -792,22 +797,76 @@ class _SegLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        logits, labels, partial = ctx.saved_tensors
+        logits, labels, partial, class_weights = ctx.saved_tensors
         n, classes = logits.shape[0], logits.shape[1]
         spatial = logits[0, 0].numel()
         w_ce, w_dice, w_sdice, w_bce = ctx.weights
         dl = torch.empty_like(logits)
         gs = g.reshape(1).to(device=logits.device, dtype=torch.float32)
         _call("b200seg_loss_grad", _ptr(logits), _ptr(labels), n, spatial, classes, _ptr(partial), float(w_ce),
-              float(w_dice), float(w_sdice), float(w_bce), _ptr(gs), _ptr(dl), _stream())
-        return dl, None, None
+              float(w_dice), float(w_sdice), float(w_bce), _ptr(gs), _ptr(class_weights), _ptr(dl), _stream())
+        return dl, None, None, None
 
 
-def seg_loss(logits, target, w_ce=1.0, w_dice=1.0, w_sdice=0.0, w_bce=0.0):
-    """logits: fp32 [N, K, D, H, W]; target: integer class labels [N, D, H, W] or [N, 1, D, H, W]."""
-    n = logits.shape[0]
+def seg_loss(logits, target, w_ce=1.0, w_dice=1.0, w_sdice=0.0, w_bce=0.0, ce_class_weight=None, dice_class_weight=None):
+    """logits: fp32 [N, K, D, H, W]; target: integer class labels [N, D, H, W] or [N, 1, D, H, W].  The optional
+    per-class weights follow nll_loss(weight=...) (sum, then / numel: loss_function.py:13-15) and DiceLossss's `weight`."""
+    n, k = logits.shape[0], logits.shape[1]
     labels = _labels_u8(target, n, logits.shape[2:])
-    return _SegLoss.apply(logits, labels, (w_ce, w_dice, w_sdice, w_bce))
+    cw = None
+    if ce_class_weight is not None or dice_class_weight is not None:
+        def vec(w):
+            if w is None:
+                return torch.ones(k, dtype=torch.float32, device=logits.device)
+            w = torch.as_tensor(w, dtype=torch.float32, device=logits.device).reshape(-1)
+            assert w.numel() == k, "expected one weight per class"
+            return w
+        cw = torch.stack((vec(ce_class_weight), vec(dice_class_weight))).contiguous()
+    return _SegLoss.apply(logits, labels, (w_ce, w_dice, w_sdice, w_bce), cw)
+
+
+class _ProbDice(torch.autograd.Function):
+    """Dice on probabilities the caller supplies (BinaryDiceLoss, DiceLossss(softmax=False)): per-row losses
+    1 - (a*I + smooth) / (X + T + smooth) with I = sum x*t, X = sum x^p, T = sum t^p (b200seg_dice_sums / _dice_grad)."""
+
+    @staticmethod
+    def forward(ctx, pred, target_f, target_l, cfg):
+        by_class, p_exp, smooth, a = cfg
+        pred = pred.contiguous().float()
+        n, k = pred.shape[0], pred.shape[1]
+        spatial = pred[0, 0].numel()
+        rows = k if by_class else n
+        partial = torch.zeros((rows, 3), dtype=torch.float64, device=pred.device)
+        _call("b200seg_dice_sums", _ptr(pred), _ptr(target_f), _ptr(target_l), n, k, spatial, int(by_class), float(p_exp),
+              _ptr(partial), _stream())
+        den = partial[:, 1] + partial[:, 2] + smooth
+        num = a * partial[:, 0] + smooth
+        ctx.save_for_backward(pred, target_f, target_l, num, den)
+        ctx.cfg = cfg
+        return (1 - num / den).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target_f, target_l, num, den = ctx.saved_tensors
+        by_class, p_exp, smooth, a = ctx.cfg
+        n, k = pred.shape[0], pred.shape[1]
+        spatial = pred[0, 0].numel()
+        g = g.double()
+        coef_t = (-a / den * g).float().contiguous()          # d(1 - num/den)/dx = -a*t/den + num * p x^(p-1) / den^2
+        coef_x = (num / (den * den) * g).float().contiguous()
+        dp = torch.empty_like(pred)
+        _call("b200seg_dice_grad", _ptr(pred), _ptr(target_f), _ptr(target_l), n, k, spatial, int(by_class), float(p_exp),
+              _ptr(coef_t), _ptr(coef_x), None, _ptr(dp), _stream())
+        return dp, None, None, None
+
+
+def prob_dice_rows(pred, target=None, labels=None, by_class=False, p=2.0, smooth=1.0, intersect_scale=1.0):
+    """Per-row Dice losses on probabilities: pred [N, K, *]; `target` float of the same shape, or integer `labels`
+    [N, *] compared with the class index.  Rows are samples (by_class=False) or classes (by_class=True)."""
+    n, k = pred.shape[0], pred.shape[1]
+    tf = target.contiguous().float().reshape(pred.shape) if target is not None else None
+    tl = _labels_u8(labels, n, pred.shape[2:]) if labels is not None else None
+    return _ProbDice.apply(pred, tf, tl, (by_class, float(p), float(smooth), float(intersect_scale)))
 
 
 def argmax_labels(logits):

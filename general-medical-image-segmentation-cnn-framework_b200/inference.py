@@ -72,27 +72,44 @@ class GridAggregator:
             if c != 1:
                 raise ValueError("crop mode stitches single-channel label maps")
             patches = batch.to(self.device).to(torch.uint8).contiguous()
-            if self.keys is None:
-                self.keys = torch.zeros((vw, vh, vd), dtype=torch.int32, device=self.device)
+            self._ensure_buffers(1)
+            last = int(patch_ids.max()) if patch_ids is not None and patch_ids.numel() else self._added + b - 1
+            if last >= (1 << 23) - 1 or (patch_ids is not None and patch_ids.numel() and int(patch_ids.min()) < 0):
+                raise ValueError("crop-mode keys hold 23-bit patch indices: patch id %d is out of range" % last)
             ids = patch_ids.to(self.device, torch.int64).contiguous() if patch_ids is not None else None
             _call("b200seg_window_accumulate_crop", _ptr(patches), _ptr(locations), _ptr(ids), self._added, b, pw, ph, pd,
                   ow, oh, od, _ptr(self.keys), vw, vh, vd, _stream())
         else:
             patches = batch.to(self.device).float().contiguous()
-            if self.out is None:
-                self.out = torch.zeros((c, vw, vh, vd), dtype=torch.float32, device=self.device)
-                self.count = torch.zeros((vw, vh, vd), dtype=torch.float32, device=self.device)
+            self._ensure_buffers(c)
+            if self.out.shape[0] != c:
+                raise ValueError("average mode: %d channels, the aggregator holds %d" % (c, self.out.shape[0]))
             _call("b200seg_window_accumulate_average", _ptr(patches), _ptr(locations), b, c, pw, ph, pd, _ptr(self.out),
                   _ptr(self.count), vw, vh, vd, _stream())
         self._added += b
 
-    def all_reduce(self, group=None):
-        """Merge the volumes of ranks that each aggregated a share of the patches (parallel.shard_patches)."""
+    def _ensure_buffers(self, channels):
+        vw, vh, vd = self.sampler.spatial_shape
+        if self.mode == "crop":
+            if self.keys is None:
+                self.keys = torch.zeros((vw, vh, vd), dtype=torch.int32, device=self.device)
+        elif self.out is None:
+            self.out = torch.zeros((channels, vw, vh, vd), dtype=torch.float32, device=self.device)
+            self.count = torch.zeros((vw, vh, vd), dtype=torch.float32, device=self.device)
+
+    def all_reduce(self, group=None, channels=None):
+        """Merge the volumes of ranks that each aggregated a share of the patches (parallel.shard_patches).  EVERY rank
+        joins the collective, also one whose share was empty (more ranks than patches): its volumes are all-zero.
+        channels: class-score channels of the average mode, needed only by a rank that never called add_batch."""
         from . import parallel
         if self.mode == "crop":
-            if self.keys is not None:
-                parallel.reduce_volume(self.keys, group, op="max")
-        elif self.out is not None:
+            self._ensure_buffers(1)
+            parallel.reduce_volume(self.keys, group, op="max")
+        else:
+            if self.out is None:
+                if channels is None:
+                    raise ValueError("all_reduce on an empty average-mode aggregator needs the channel count")
+                self._ensure_buffers(channels)
             parallel.reduce_volume(self.out, group)
             parallel.reduce_volume(self.count, group)
 
@@ -107,6 +124,15 @@ class GridAggregator:
         _call("b200seg_window_finalize", _ptr(acc), _ptr(self.count), acc.shape[0], self.count.numel(), _ptr(labels),
               _stream())
         return (acc, labels.unsqueeze(0)) if return_labels else acc
+
+
+def _out_channels(model):
+    """Class-score channels of a segmentation model = output channels of its last convolution."""
+    last = None
+    for m in model.modules():
+        if isinstance(m, torch.nn.Conv3d):
+            last = m
+    return last.out_channels if last is not None else None
 
 
 @torch.no_grad()
@@ -134,7 +160,7 @@ def sliding_window_predict(model, volume, patch_size, patch_overlap, batch_size=
             agg.add_batch(F.argmax_labels(logits), locs, patch_ids=ids)
         else:
             agg.add_batch(logits, locs)
-    agg.all_reduce(group)
+    agg.all_reduce(group, channels=getattr(model, "out_channels", None) or _out_channels(model))
     model.train(was_training)
     if overlap_mode == "crop":
         return agg.get_output_tensor()

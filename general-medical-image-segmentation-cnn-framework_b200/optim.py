@@ -177,15 +177,59 @@ class FusedAdam:
         self.refresh_packs()
 
     def state_dict(self):
+        """torch.optim.Adam's schema ({"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]}), so
+        that a checkpoint written here resumes under the reference's `optimizer.load_state_dict` (train.py:128) and
+        vice versa.  The moments are views into the flat arenas (torch.save writes them out as tensors)."""
         if getattr(self, "_state", None) is not None:
             self.step_count = int(self._state[0].item())   # graph replays advance the device counter only
-        return {"step": self.step_count, "lr": self.lr, "betas": self.betas, "eps": self.eps,
-                "weight_decay": self.weight_decay, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+        state = {}
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[off:off + p.numel()].view_as(p),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + p.numel()].view_as(p)}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.step_count, self.lr = sd["step"], sd["lr"]
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        """Accepts torch.optim.Adam's state dict (a reference checkpoint; per-parameter state is matched by position in
+        parameters() order and checked by shape) and the flat round-1 form {"step", "lr", "exp_avg", "exp_avg_sq"}."""
+        if "param_groups" in sd:
+            group = sd["param_groups"][0]
+            if len(sd["param_groups"]) != 1 or len(group["params"]) != len(self.params):
+                raise ValueError("FusedAdam.load_state_dict: expected one parameter group of %d tensors, got %s"
+                                 % (len(self.params), [len(g["params"]) for g in sd["param_groups"]]))
+            if group.get("amsgrad") or group.get("maximize"):
+                raise ValueError("FusedAdam.load_state_dict: amsgrad / maximize are not supported")
+            self.lr, self.betas = float(group["lr"]), tuple(float(b) for b in group["betas"])
+            self.eps, self.weight_decay = float(group["eps"]), float(group["weight_decay"])
+            steps = set()
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            for key, p, off in zip(group["params"], self.params, self.offsets):
+                st = sd["state"].get(key)
+                if st is None:        # a parameter that never received a gradient has no entry in torch's state
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError("FusedAdam.load_state_dict: state %r has shape %s, parameter has %s"
+                                     % (key, tuple(st["exp_avg"].shape), tuple(p.shape)))
+                self.exp_avg[off:off + p.numel()].view_as(p).copy_(st["exp_avg"])
+                self.exp_avg_sq[off:off + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+            if len(steps) > 1:
+                raise ValueError("FusedAdam.load_state_dict: per-parameter step counts differ (%s); the fused kernel keeps "
+                                 "one counter" % sorted(steps))
+            self.step_count = steps.pop() if steps else 0
+        else:
+            if sd["exp_avg"].numel() != self.numel:
+                raise ValueError("FusedAdam.load_state_dict: arena of %d elements, checkpoint has %d"
+                                 % (self.numel, sd["exp_avg"].numel()))
+            self.step_count, self.lr = sd["step"], sd["lr"]
+            self.betas = tuple(sd.get("betas", self.betas))
+            self.eps, self.weight_decay = sd.get("eps", self.eps), sd.get("weight_decay", self.weight_decay)
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self._hyper_host = None
         if getattr(self, "_state", None) is not None:
             self._state[0] = self.step_count

@@ -39,10 +39,14 @@ class StepLR:
         return [self.optimizer.lr]
 
     def state_dict(self):
-        return {"step_size": self.step_size, "gamma": self.gamma, "base_lr": self.base_lr, "last_epoch": self.last_epoch}
+        """Same keys as torch.optim.lr_scheduler.StepLR.state_dict() (what the reference checkpoints, train.py:288-294)."""
+        return {"step_size": self.step_size, "gamma": self.gamma, "base_lrs": [self.base_lr], "last_epoch": self.last_epoch,
+                "_step_count": self.last_epoch + 1, "_last_lr": [self.optimizer.lr]}
 
     def load_state_dict(self, sd):
-        self.step_size, self.gamma, self.base_lr, self.last_epoch = sd["step_size"], sd["gamma"], sd["base_lr"], sd["last_epoch"]
+        """Accepts torch's StepLR state ({"base_lrs": [..], ...}, a reference checkpoint) and the round-1 form."""
+        self.step_size, self.gamma, self.last_epoch = sd["step_size"], sd["gamma"], sd["last_epoch"]
+        self.base_lr = sd["base_lrs"][0] if "base_lrs" in sd else sd["base_lr"]
         self.optimizer.lr = self.base_lr * self.gamma ** (self.last_epoch // self.step_size)
 
 

@@ -14,10 +14,9 @@ def _labels_from(target, logits):
 
 
 def cross_entropy_3D(input, target, weight=None, size_average=True):
-    """loss_function.py:8-16.  `weight` (per-class) is not on the reference's path and is rejected."""
-    if weight is not None:
-        raise NotImplementedError("cross_entropy_3D: per-class weights are not supported by the fused kernel")
-    loss = F.seg_loss(input, target, w_ce=1.0, w_dice=0.0)
+    """loss_function.py:8-16: nll_loss(log_softmax, weight, sum) / numel -- with class weights the divisor stays the voxel
+    count (not the weight sum F.cross_entropy(reduction='mean') would use)."""
+    loss = F.seg_loss(input, target, w_ce=1.0, w_dice=0.0, ce_class_weight=weight)
     if not size_average:
         loss = loss * float(target.numel())
     return loss
@@ -42,7 +41,8 @@ def make_one_hot(input, num_classes):
 
 
 class BinaryDiceLoss(nn.Module):
-    """loss_function.py:61-99.  Operates on probabilities supplied by the caller; tiny per-sample reductions."""
+    """loss_function.py:61-99: per-sample 1 - (sum x*t + smooth) / (sum x^p + sum t^p + smooth) on probabilities supplied
+    by the caller, reduced over the batch ('mean' | 'sum' | 'none').  One reduction and one gradient kernel."""
 
     def __init__(self, smooth=1, p=2, reduction='mean'):
         super(BinaryDiceLoss, self).__init__()
@@ -50,11 +50,9 @@ class BinaryDiceLoss(nn.Module):
 
     def forward(self, predict, target):
         assert predict.shape[0] == target.shape[0], "predict & target batch size don't match"
-        predict = predict.contiguous().view(predict.shape[0], -1)
-        target = target.contiguous().view(target.shape[0], -1)
-        num = torch.sum(torch.mul(predict, target), dim=1) + self.smooth
-        den = torch.sum(predict.pow(self.p) + target.pow(self.p), dim=1) + self.smooth
-        loss = 1 - num / den
+        n = predict.shape[0]
+        loss = F.prob_dice_rows(predict.reshape(n, 1, -1), target=target.reshape(n, 1, -1), by_class=False, p=self.p,
+                                smooth=self.smooth, intersect_scale=1.0)
         if self.reduction == 'mean':
             return loss.mean()
         elif self.reduction == 'sum':
@@ -84,13 +82,14 @@ class DiceLossss(nn.Module):
         self.n_classes = n_classes
 
     def forward(self, inputs, target, weight=None, softmax=False):
-        if weight is not None:
-            raise NotImplementedError("DiceLossss: per-class weights are not supported by the fused kernel")
-        if not softmax:
-            raise NotImplementedError("DiceLossss(softmax=False) expects probabilities; the fused kernel takes logits "
-                                      "(call with softmax=True)")
         assert inputs.shape[1] == self.n_classes, 'predict & target shape do not match'
-        return F.seg_loss(inputs, target, w_ce=0.0, w_dice=1.0)
+        if softmax:       # logits: soft-max, per-class sums and (weighted) class average in one fused pass
+            return F.seg_loss(inputs, target, w_ce=0.0, w_dice=1.0, dice_class_weight=weight)
+        # the reference's default: `inputs` already are probabilities (:172-184)
+        per_class = F.prob_dice_rows(inputs, labels=target, by_class=True, p=2.0, smooth=1e-5, intersect_scale=2.0)
+        if weight is not None:
+            per_class = per_class * torch.as_tensor(weight, dtype=per_class.dtype, device=per_class.device)
+        return per_class.sum() / self.n_classes
 
 
 class DiceCELoss(nn.Module):

@@ -185,17 +185,29 @@ int b200seg_head_conv1x1_bwd(const float* dlogits, const void* x, int64_t x_pitc
                              int classes, void* stream);
 /* argmax over classes, ties -> lowest index; labels uint8 [n][spatial]. */
 int b200seg_argmax_labels(const float* logits, uint8_t* labels, int n, int64_t spatial, int classes, void* stream);
-/* One pass over logits (fp32 NCDHW) and labels (uint8): partial[0] += sum CE nll; partial[1+3k..] += per class
+/* class_weights (may be NULL): float[2*classes] = {cross-entropy weight per class (nll_loss(weight=), loss_function.py:13),
+ * Dice weight per class (DiceLossss.forward(weight=), loss_function.py:176-183)}.
+ * One pass over logits (fp32 NCDHW) and labels (uint8): partial[0] += sum CE nll (times the label's CE weight); partial[1+3k..] += per class
  * {sum p*t, sum p*p, sum t}; partial[1+3*classes..] += sigmoid-dice / BCE sums {sum s*t, sum s, sum t, sum bce}.
  * partial: double[1 + 3*classes + 4] (caller zeroes).  terms: 1 = the soft-max sums (CE, DiceLossss) are needed,
  * 2 = the sigmoid sums (DiceLoss, BCE), 3 = both; sums that are not requested may be left untouched. */
 int b200seg_loss_reduce(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes, int terms,
-                        double* partial, void* stream);
+                        const float* class_weights, double* partial, void* stream);
 /* dlogits = w_ce * dCE + w_dice * dDiceLossss(softmax) + w_sdice * dDiceLoss(sigmoid) + w_bce * dBCE, scaled by the
  * upstream gradient *gscale (a device scalar; NULL = 1), using the sums produced by loss_reduce. */
 int b200seg_loss_grad(const float* logits, const uint8_t* labels, int n, int64_t spatial, int classes,
                       const double* partial, float w_ce, float w_dice, float w_sdice, float w_bce,
-                      const float* gscale, float* dlogits, void* stream);
+                      const float* gscale, const float* class_weights, float* dlogits, void* stream);
+/* Dice on caller-supplied PROBABILITIES: BinaryDiceLoss (loss_function.py:61-99; one loss per sample, by_class = 0) and
+ * DiceLossss(softmax=False) (loss_function.py:172-184; one loss per class, by_class = 1).  pred: fp32 [n][classes][spatial];
+ * the target is EITHER target_f (fp32, same layout) OR target_l (uint8 labels [n][spatial]; target of class k is
+ * label == k, loss_function.py:154-160).  partial: double[rows][3] += {sum x*t, sum x^p, sum t^p}, rows = n or classes. */
+int b200seg_dice_sums(const float* pred, const float* target_f, const uint8_t* target_l, int n, int classes, int64_t spatial,
+                      int by_class, float p_exp, double* partial, void* stream);
+/* dpred = *gscale * (coef_t[row] * t + coef_x[row] * p * x^(p-1)); coefficients computed by the caller from dice_sums. */
+int b200seg_dice_grad(const float* pred, const float* target_f, const uint8_t* target_l, int n, int classes, int64_t spatial,
+                      int by_class, float p_exp, const float* coef_t, const float* coef_x, const float* gscale, float* dpred,
+                      void* stream);
 
 /* ---- metric (metric.py:20-75) ---------------------------------------------------------------------------------- */
 /* counts: uint64[4] += {sum gt, sum pred, |gt & pred| nonzero, |gt | pred| nonzero} over uint8 label volumes. */

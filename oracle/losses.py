@@ -3,11 +3,15 @@ import torch
 import torch.nn.functional as F
 
 
-def cross_entropy_3d(logits, target):
-    """cross_entropy_3D (loss_function.py:8-16): log_softmax over channels, NLL summed then / numel."""
+def cross_entropy_3d(logits, target, weight=None, size_average=True):
+    """cross_entropy_3D (loss_function.py:8-16): log_softmax over channels, NLL (times the label's class weight) summed,
+    then / numel -- the voxel count, also when weights are given."""
     logp = F.log_softmax(logits, dim=1)
     t = target.reshape(target.shape[0], 1, *logits.shape[2:]).long()
-    return -(logp.gather(1, t)).sum() / float(t.numel())
+    nll = -(logp.gather(1, t))
+    if weight is not None:
+        nll = nll * torch.as_tensor(weight, dtype=nll.dtype)[t]
+    return nll.sum() / float(t.numel()) if size_average else nll.sum()
 
 
 def dice_loss_sigmoid(logits, onehot, eps=1e-5):

@@ -90,6 +90,22 @@ def loss_case():
     rec("BinaryDiceLoss", lambda: BinaryDiceLoss()(torch.sigmoid(pred[:, 1]), onehot[:, 1]))
     rec("BCEWithLogits", lambda: torch.nn.BCEWithLogitsLoss()(pred, onehot))
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **fix)
+    # round 2: the weighted / non-default variants of the same functions (loss_function.py:8-16, 61-99, 172-184),
+    # in a separate file so that losses.npz stays byte-identical
+    fix = {"pred": pred.detach().numpy(), "lab": lab.numpy(), "ce_weight": np.float32([0.3, 1.7]),
+           "dice_weight": np.float32([0.4, 1.6])}
+    probs = lambda: torch.softmax(pred, dim=1)   # noqa: E731
+    rec("cross_entropy_3D_weighted", lambda: cross_entropy_3D(pred, lab, weight=torch.tensor([0.3, 1.7])))
+    rec("cross_entropy_3D_sum", lambda: cross_entropy_3D(pred, lab, size_average=False))
+    rec("DiceLossss_softmax_weighted", lambda: DiceLossss(2)(pred, lab, weight=[0.4, 1.6], softmax=True))
+    rec("DiceLossss_raw_weighted", lambda: DiceLossss(2)(pred, lab, weight=[0.4, 1.6], softmax=False))
+    rec("DiceLossss_raw_on_probs", lambda: DiceLossss(2)(probs(), lab, softmax=False))
+    rec("BinaryDiceLoss_sum", lambda: BinaryDiceLoss(reduction="sum")(torch.sigmoid(pred[:, 1]), onehot[:, 1]))
+    rec("BinaryDiceLoss_p1_smooth", lambda: BinaryDiceLoss(smooth=0.5, p=1)(torch.sigmoid(pred), onehot))
+    rec("BinaryDiceLoss_p3", lambda: BinaryDiceLoss(p=3)(torch.sigmoid(pred), onehot))
+    none = BinaryDiceLoss(reduction="none")(torch.sigmoid(pred[:, 1]), onehot[:, 1])
+    fix["BinaryDiceLoss_none"] = none.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "losses_extra.npz"), **fix)
     print("losses", {k: float(v) for k, v in fix.items() if v.ndim == 0})
 
 
@@ -147,6 +163,10 @@ def pool_case():
                         logits=lg.numpy(), argmax=lg.argmax(1, keepdim=True).numpy())
     print("pool ok")
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "losses":
+    loss_case()
+    sys.exit(0)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pool":

@@ -50,7 +50,7 @@ def test_train_entry_learns_checkpoints_and_resumes(tmp_path):
     assert len(hist) == 3 and hist[-1][1] < hist[0][1], hist            # the loss goes down
     ckpt = torch.load(os.path.join(str(tmp_path), "latest_checkpoint.pt"), map_location="cpu")
     assert set(ckpt) == {"model", "optim", "scheduler", "epoch"} and ckpt["epoch"] == 3
-    assert len(ckpt["model"]) == 136 and ckpt["optim"]["step"] == 24
+    assert len(ckpt["model"]) == 136 and int(ckpt["optim"]["state"][0]["step"]) == 24
     assert os.path.exists(os.path.join(str(tmp_path), "checkpoint_0002.pt"))
     hist2 = T.main(args[:-1] + ["config.epochs=4", "config.load_mode=1",
                                 "config.ckpt=%s" % os.path.join(str(tmp_path), "latest_checkpoint.pt")])

@@ -277,8 +277,58 @@ def test_reference_named_loss_classes(golden):
     assert abs(Binary_Loss()(pred, onehot).item() - float(gz["BCEWithLogits"])) < 2e-6
     both = float(gz["cross_entropy_3D"]) + float(gz["DiceLossss_softmax"])
     assert abs(DiceCELoss(2)(pred, lab).item() - both) < 4e-6
-    with pytest.raises(NotImplementedError):
-        DiceLossss(2)(pred, lab, softmax=False)
+
+
+def test_nondefault_loss_variants_match_reference_golden(golden):
+    """DiceLossss(softmax=False) -- the reference's default --, per-class weights, cross_entropy_3D(weight=, size_average=)
+    and BinaryDiceLoss (p, smooth, reduction) through the fused kernels, values and gradients against the reference's own
+    outputs (tests/golden/losses.npz, losses_extra.npz; loss_function.py:8-16, 61-99, 172-184)."""
+    from b200seg.utils.loss_function import BinaryDiceLoss, DiceLossss, cross_entropy_3D
+    g0, g = golden("losses"), golden("losses_extra")
+    lab = torch.from_numpy(g["lab"]).to(DEV)
+    onehot = torch.stack([(lab == 0), (lab == 1)], 1).float()
+    cw, dw = g["ce_weight"].tolist(), g["dice_weight"].tolist()
+    cases = [
+        (g0, "DiceLossss_raw", lambda p: DiceLossss(2)(p, lab, softmax=False)),
+        (g0, "BinaryDiceLoss", lambda p: BinaryDiceLoss()(torch.sigmoid(p[:, 1]), onehot[:, 1])),
+        (g, "cross_entropy_3D_weighted", lambda p: cross_entropy_3D(p, lab, weight=torch.tensor(cw))),
+        (g, "cross_entropy_3D_sum", lambda p: cross_entropy_3D(p, lab, size_average=False)),
+        (g, "DiceLossss_softmax_weighted", lambda p: DiceLossss(2)(p, lab, weight=dw, softmax=True)),
+        (g, "DiceLossss_raw_weighted", lambda p: DiceLossss(2)(p, lab, weight=dw, softmax=False)),
+        (g, "DiceLossss_raw_on_probs", lambda p: DiceLossss(2)(torch.softmax(p, 1), lab, softmax=False)),
+        (g, "BinaryDiceLoss_sum", lambda p: BinaryDiceLoss(reduction="sum")(torch.sigmoid(p[:, 1]), onehot[:, 1])),
+        (g, "BinaryDiceLoss_p1_smooth", lambda p: BinaryDiceLoss(smooth=0.5, p=1)(torch.sigmoid(p), onehot)),
+        (g, "BinaryDiceLoss_p3", lambda p: BinaryDiceLoss(p=3)(torch.sigmoid(p), onehot)),
+    ]
+    for gz, name, fn in cases:
+        p = torch.from_numpy(gz["pred"]).to(DEV).requires_grad_(True)
+        v = fn(p)
+        v.backward()
+        want = float(gz[name])
+        assert abs(v.item() - want) < 2e-6 * max(1.0, abs(want)), (name, v.item(), want)
+        assert torch.allclose(p.grad.cpu(), torch.from_numpy(gz[name + ".grad"]), rtol=3e-4, atol=1e-8), name
+    none = BinaryDiceLoss(reduction="none")(torch.sigmoid(torch.from_numpy(g["pred"]).to(DEV)[:, 1]), onehot[:, 1])
+    assert torch.allclose(none.cpu(), torch.from_numpy(g["BinaryDiceLoss_none"]), rtol=1e-6)
+    with pytest.raises(Exception):
+        BinaryDiceLoss(reduction="bogus")(torch.sigmoid(p[:, 1]), onehot[:, 1])
+    # more than two classes takes the generic (non two-class) kernels: compare with the oracle on the CPU
+    gen = torch.Generator().manual_seed(4)
+    pr = torch.randn(2, 3, 6, 5, 7, generator=gen)
+    lb = torch.randint(0, 3, (2, 6, 5, 7), generator=gen)
+    w3 = [0.5, 1.0, 2.0]
+    for fn_o, fn_d in (
+            (lambda p: olosses.cross_entropy_3d(p, lb, weight=w3), lambda p: cross_entropy_3D(p, lb.to(DEV), weight=w3)),
+            (lambda p: olosses.dice_loss_per_class(p, lb, 3, softmax=True, weight=w3),
+             lambda p: DiceLossss(3)(p, lb.to(DEV), weight=w3, softmax=True)),
+            (lambda p: olosses.dice_loss_per_class(torch.softmax(p, 1), lb, 3, weight=w3),
+             lambda p: DiceLossss(3)(torch.softmax(p, 1), lb.to(DEV), weight=w3))):
+        po = pr.clone().requires_grad_(True)
+        vo = fn_o(po)
+        vo.backward()
+        pd = pr.to(DEV).requires_grad_(True)
+        vd = fn_d(pd)
+        vd.backward()
+        assert abs(vd.item() - vo.item()) < 3e-6 and torch.allclose(pd.grad.cpu(), po.grad, rtol=3e-4, atol=1e-8)
 
 
 def test_argmax_and_metric_bit_exact(F, golden):
@@ -447,7 +497,7 @@ def test_graph_captured_train_step_matches_eager():
         assert (step.graph is not None) == use_graph
         if use_graph:
             assert step.kernels_per_step > 100 and step.umma_per_step > 20
-        assert opt.state_dict()["step"] == 6
+        assert int(opt.state_dict()["state"][0]["step"]) == 6
         results.append((losses, {k: v.clone() for k, v in net.state_dict().items()}))
     (l0, p0), (l1, p1) = results
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 6e-3, (l0, l1)
@@ -526,7 +576,7 @@ def test_fused_optimizer_step_is_bit_identical_to_the_three_kernel_path():
             for p, r in zip(params, ref):
                 close(p.detach().float().cpu(), r.detach().float().cpu(), 1e-5, "adam vs torch %s" % (tuple(p.shape),))
             runs.append((opt.param_arena.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt._pack_arena.clone(),
-                         int(opt.state_dict()["step"])))
+                         int(opt.state_dict()["state"][0]["step"])))
             # the packs are the bf16 transposes of the updated weights
             for p, o, n in opt._packed:
                 a, b = p.shape[0], p.shape[1]

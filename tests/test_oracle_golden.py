@@ -60,6 +60,27 @@ def test_losses_match_reference(golden):
         v.backward()
         assert abs(float(v) - float(g[name])) < 2e-6, name
         assert torch.allclose(p.grad, T(g[name + ".grad"]), rtol=1e-4, atol=1e-8), name
+    # weighted / non-default variants (losses_extra.npz, produced by the same reference functions)
+    g = golden("losses_extra")
+    cw, dw = g["ce_weight"].tolist(), g["dice_weight"].tolist()
+    cases = {
+        "cross_entropy_3D_weighted": lambda p: losses.cross_entropy_3d(p, lab, weight=cw),
+        "cross_entropy_3D_sum": lambda p: losses.cross_entropy_3d(p, lab, size_average=False),
+        "DiceLossss_softmax_weighted": lambda p: losses.dice_loss_per_class(p, lab, 2, softmax=True, weight=dw),
+        "DiceLossss_raw_weighted": lambda p: losses.dice_loss_per_class(p, lab, 2, softmax=False, weight=dw),
+        "DiceLossss_raw_on_probs": lambda p: losses.dice_loss_per_class(torch.softmax(p, 1), lab, 2, softmax=False),
+        "BinaryDiceLoss_sum": lambda p: losses.binary_dice_loss(torch.sigmoid(p[:, 1]), onehot[:, 1], reduction="sum"),
+        "BinaryDiceLoss_p1_smooth": lambda p: losses.binary_dice_loss(torch.sigmoid(p), onehot, smooth=0.5, p=1),
+        "BinaryDiceLoss_p3": lambda p: losses.binary_dice_loss(torch.sigmoid(p), onehot, p=3),
+    }
+    for name, fn in cases.items():
+        p = T(g["pred"]).clone().requires_grad_(True)
+        v = fn(p)
+        v.backward()
+        assert abs(float(v) - float(g[name])) < 2e-6 * max(1.0, abs(float(g[name]))), name
+        assert torch.allclose(p.grad, T(g[name + ".grad"]), rtol=1e-4, atol=1e-8), name
+    none = losses.binary_dice_loss(torch.sigmoid(T(g["pred"])[:, 1]), onehot[:, 1], reduction="none")
+    assert torch.allclose(none, T(g["BinaryDiceLoss_none"]), rtol=1e-6)
 
 
 def test_metric_matches_reference(golden):
