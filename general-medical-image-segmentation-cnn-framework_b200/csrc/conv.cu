@@ -64,12 +64,126 @@ static bool stem_plan(const b200seg_conv_geom* g, StemPlan& sp) {
   return true;
 }
 
+// ---- Conv3d(k=2, s=2, p=0) (V-Net down-convolutions, vnet3d.py:65) on the tensor cores: the same three GEMMs as
+// ConvTranspose3d(k2,s2), with the roles of the passes exchanged (see the ConvT entry points below).
+static bool is_k2s2(const b200seg_conv_geom* g) {
+  return g->k == 2 && g->stride == 2 && g->pad == 0 && g->dil == 1 && g->d == 2 * g->od && g->h == 2 * g->oh &&
+         g->w == 2 * g->ow && !getenv("B200SEG_DISABLE_K2S2_UMMA");
+}
+// fprop: K runs over (tap abe, C_in); K-chunk group abe reads the sub-lattice x[2v + abe] through its own strided tensor
+// map; the fprop pack [abe][C_out][C_in] is the K-major weight matrix.
+static UmmaConvArgs k2s2_fprop_args(const b200seg_conv_geom* g, const void* x, int64_t xp, const void* w, const float* bias,
+                                    void* y, int64_t yp, float* stats) {
+  UmmaConvArgs a{};
+  a.n = g->n; a.d = g->od; a.h = g->oh; a.w = g->ow; a.od = g->od; a.oh = g->oh; a.ow = g->ow;
+  a.cin = 8 * g->cin; a.cout = g->cout; a.k = 1; a.pad = 0; a.dil = 1;
+  a.in = x; a.in_pitch = xp; a.wpack = w; a.bias = bias; a.out = y; a.out_pitch = yp; a.stats = stats;
+  a.scatter_cout = 0; a.gather2 = 1;
+  return a;
+}
+// dgrad: pointwise GEMM [coarse voxels x C_out] . [C_out x 8*C_in] with the pixel-shuffle scatter epilogue; the dgrad pack
+// [7 - abe][C_in][C_out] is an [8*C_in][C_out] K-major matrix.
+static UmmaConvArgs k2s2_dgrad_args(const b200seg_conv_geom* g, const void* dy, int64_t dyp, const void* wd, void* dx,
+                                    int64_t dxp) {
+  UmmaConvArgs a{};
+  a.n = g->n; a.d = g->od; a.h = g->oh; a.w = g->ow; a.od = g->od; a.oh = g->oh; a.ow = g->ow;
+  a.cin = g->cout; a.cout = 8 * g->cin; a.k = 1; a.pad = 0; a.dil = 1;
+  a.in = dy; a.in_pitch = dyp; a.wpack = wd; a.bias = nullptr; a.out = dx; a.out_pitch = dxp; a.stats = nullptr;
+  a.scatter_cout = g->cin; a.gather2 = 0;
+  return a;
+}
+static UmmaWgradArgs k2s2_wgrad_args(const b200seg_conv_geom* g, const void* x, int64_t xp, const void* dy, int64_t dyp,
+                                     float* dwp) {
+  return UmmaWgradArgs{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, g->cin, g->cout, 2, 0, 1, x, xp, dy, dyp, dwp, 1,
+                       nullptr, 0};
+}
+
+// ---- Conv3d(k=3, s=2, p=1) (residual U-Net context down-steps, residual_unet3d.py:29-44) on the tensor cores.
+// Input coordinate i = 2o - 1 + t: tap t = 1 reads the EVEN sub-lattice at index o, taps t = 0 / 2 read the ODD
+// sub-lattice at indices o - 1 / o.  Per dimension the parity r of the sub-lattice therefore fixes which taps exist, and
+// on every sub-lattice the convolution has stride 1 -- "2x2x2 shifted taps, some absent" (UmmaConvArgs::tapmode):
+//   forward: ONE launch; K runs over (parity class, C_in), each class reads its sub-lattice through a strided tensor map;
+//   data gradient: one launch per OUTPUT parity class (dx[2m + r] gathers dy[m] (t = 1 | 2) and dy[m + 1] (t = 0));
+//   weight gradient: one launch per INPUT parity class of the first-generation kernel with a (1|2)^3 tap table.
+static bool is_k3s2(const b200seg_conv_geom* g) {
+  return g->k == 3 && g->stride == 2 && g->pad == 1 && g->dil == 1 && g->cin % 16 == 0 && g->cout % 16 == 0 &&
+         !getenv("B200SEG_DISABLE_K3S2_UMMA");
+}
+static UmmaConvArgs k3s2_fprop_args(const b200seg_conv_geom* g, const void* x, int64_t xp, const void* w, const float* bias,
+                                    void* y, int64_t yp, float* stats) {
+  UmmaConvArgs a{};
+  a.n = g->n; a.d = g->od; a.h = g->oh; a.w = g->ow; a.od = g->od; a.oh = g->oh; a.ow = g->ow;
+  a.cin = 8 * g->cin; a.cout = g->cout; a.k = 2; a.pad = 1; a.dil = 1;
+  a.in = x; a.in_pitch = xp; a.wpack = w; a.bias = bias; a.out = y; a.out_pitch = yp; a.stats = stats;
+  a.tapmode = 1; a.in_sub = 1; a.wtaps = 27; a.fd = g->d; a.fh = g->h; a.fw = g->w;
+  for (int cls = 0; cls < 8; ++cls)
+    for (int sh = 0; sh < 8; ++sh) {
+      const int r[3] = {cls >> 2, (cls >> 1) & 1, cls & 1}, sft[3] = {sh >> 2, (sh >> 1) & 1, sh & 1};
+      int t[3];
+      bool ok = true;
+      for (int i = 0; i < 3; ++i) {
+        ok = ok && (r[i] == 1 || sft[i] == 1);      // even lattice: only the shift that lands on index o
+        t[i] = r[i] ? 2 * sft[i] : 1;
+      }
+      a.tapw[cls][sh] = ok ? static_cast<unsigned char>((t[0] * 3 + t[1]) * 3 + t[2]) : 0xFF;
+    }
+  return a;
+}
+static UmmaConvArgs k3s2_dgrad_args(const b200seg_conv_geom* g, int cls, const void* dy, int64_t dyp, const void* wd, void* dx,
+                                    int64_t dxp, float* stats) {
+  const int r[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
+  UmmaConvArgs a{};
+  a.n = g->n; a.d = g->od; a.h = g->oh; a.w = g->ow;
+  a.od = (g->d - r[0] + 1) / 2; a.oh = (g->h - r[1] + 1) / 2; a.ow = (g->w - r[2] + 1) / 2;
+  a.cin = g->cout; a.cout = g->cin; a.k = 2; a.pad = 0; a.dil = 1;
+  a.in = dy; a.in_pitch = dyp; a.wpack = wd; a.bias = nullptr; a.out = dx; a.out_pitch = dxp; a.stats = stats;
+  a.tapmode = 1; a.out_sub = 1; a.cls = cls; a.wtaps = 27; a.fd = g->d; a.fh = g->h; a.fw = g->w;
+  for (int c2 = 0; c2 < 8; ++c2)
+    for (int sh = 0; sh < 8; ++sh) a.tapw[c2][sh] = 0xFF;
+  for (int sh = 0; sh < 8; ++sh) {
+    const int j[3] = {sh >> 2, (sh >> 1) & 1, sh & 1};
+    int t[3];
+    bool ok = true;
+    for (int i = 0; i < 3; ++i) {
+      ok = ok && (r[i] == 1 || j[i] == 0);
+      t[i] = r[i] ? 2 - 2 * j[i] : 1;
+    }
+    // the data-gradient pack is [26 - tap][C_in][C_out]
+    if (ok) a.tapw[cls & 7][sh] = static_cast<unsigned char>(26 - ((t[0] * 3 + t[1]) * 3 + t[2]));
+  }
+  return a;
+}
+static UmmaWgradArgs k3s2_wgrad_args(const b200seg_conv_geom* g, int cls, const void* x, int64_t xp, const void* dy,
+                                     int64_t dyp, float* dwp) {
+  const int r[3] = {cls >> 2, (cls >> 1) & 1, cls & 1};
+  UmmaWgradArgs a{};
+  a.n = g->n; a.d = (g->d - r[0] + 1) / 2; a.h = (g->h - r[1] + 1) / 2; a.w = (g->w - r[2] + 1) / 2;
+  a.od = g->od; a.oh = g->oh; a.ow = g->ow; a.cin = g->cin; a.cout = g->cout; a.k = 2; a.pad = 0; a.dil = 1;
+  a.x = x; a.x_pitch = xp; a.dy = dy; a.dy_pitch = dyp; a.dwp = dwp;
+  a.sub = 1; a.cls = cls; a.fd = g->d; a.fh = g->h; a.fw = g->w;
+  a.kd = 1 + r[0]; a.kh = 1 + r[1]; a.kw = 1 + r[2];     // odd sub-lattice: taps 0 and 2 at indices o - 1 and o
+  a.pd = r[0]; a.ph = r[1]; a.pw = r[2];
+  for (int ta = 0; ta < a.kd; ++ta)
+    for (int tb = 0; tb < a.kh; ++tb)
+      for (int te = 0; te < a.kw; ++te) {
+        const int t0 = r[0] ? 2 * ta : 1, t1 = r[1] ? 2 * tb : 1, t2 = r[2] ? 2 * te : 1;
+        a.tapmap[(ta * a.kh + tb) * a.kw + te] = (t0 * 3 + t1) * 3 + t2;
+      }
+  return a;
+}
+static bool k3s2_class_empty(const b200seg_conv_geom* g, int cls) {
+  return (g->d - (cls >> 2) + 1) / 2 == 0 || (g->h - ((cls >> 1) & 1) + 1) / 2 == 0 || (g->w - (cls & 1) + 1) / 2 == 0;
+}
+
 extern "C" {
 
 int64_t b200seg_umma_launch_count(void) { return g_umma_launches; }
 
 int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g) {
-  if (!g || g->stride != 1) return 0;
+  if (!g) return 0;
+  if (is_k2s2(g)) return conv_umma_supported(k2s2_fprop_args(g, nullptr, g->cin, nullptr, nullptr, nullptr, g->cout, nullptr)) ? 1 : 0;
+  if (is_k3s2(g)) return conv_umma_supported(k3s2_fprop_args(g, nullptr, g->cin, nullptr, nullptr, nullptr, g->cout, nullptr)) ? 1 : 0;
+  if (g->stride != 1) return 0;
   UmmaConvArgs a = fprop_args(g, nullptr, g->cin, nullptr, nullptr, nullptr, g->cout, nullptr);
   return conv_umma_supported(a) ? 1 : 0;
 }
@@ -97,6 +211,12 @@ int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pi
   if (g->stride == 1) {
     UmmaConvArgs a = fprop_args(g, x, x_pitch, w_packed, bias, y, y_pitch, stats);
     if (conv_umma_supported(a)) return conv_umma_run(a, st);
+  } else if (is_k2s2(g)) {
+    UmmaConvArgs a = k2s2_fprop_args(g, x, x_pitch, w_packed, bias, y, y_pitch, stats);
+    if (conv_umma_supported(a)) return conv_umma_run(a, st);
+  } else if (is_k3s2(g)) {
+    UmmaConvArgs a = k3s2_fprop_args(g, x, x_pitch, w_packed, bias, y, y_pitch, stats);
+    if (conv_umma_supported(a)) return conv_umma_run(a, st);
   }
   return conv_direct_fprop(*g, x, x_pitch, w_packed, bias, y, y_pitch, stats, st);
 }
@@ -111,6 +231,25 @@ int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_
   if (g->stride == 1 && g->dil * (g->k - 1) - g->pad >= 0) {
     UmmaConvArgs a = dgrad_args(g, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch, stats);
     if (conv_umma_supported(a)) return conv_umma_run(a, st);
+  } else if (is_k2s2(g)) {
+    UmmaConvArgs a = k2s2_dgrad_args(g, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch);
+    if (conv_umma_supported(a)) {
+      if (int rc = conv_umma_run(a, st)) return rc;
+      if (stats)   // the pixel-shuffle epilogue has no statistics: one extra pass over dx
+        return b200seg_channel_stats(dx, dx_pitch, static_cast<int64_t>(g->n) * g->d * g->h * g->w, 1, g->cin, stats, stream);
+      return 0;
+    }
+  } else if (is_k3s2(g) && conv_umma_supported(k3s2_dgrad_args(g, 7, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch, stats))) {
+    for (int cls = 0; cls < 8; ++cls) {     // one launch per parity class of dx; the statistics add up over the launches
+      if (k3s2_class_empty(g, cls)) continue;
+      const UmmaConvArgs a = k3s2_dgrad_args(g, cls, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch, stats);
+      if (!conv_umma_supported(a)) {
+        set_error("conv3d_dgrad: stride-2 class %d is not supported by the tensor-core path", cls);
+        return B200SEG_ERR_INVALID;
+      }
+      if (int rc = conv_umma_run(a, st)) return rc;
+    }
+    return 0;
   }
   if (int rc = conv_direct_dgrad(*g, dy, dy_pitch, w_packed_dgrad, nullptr, dx, dx_pitch, st)) return rc;
   // the direct kernels have no statistics epilogue: one extra pass over dx
@@ -146,6 +285,21 @@ int b200seg_conv3d_wgrad(const b200seg_conv_geom* g, const void* x, int64_t x_pi
     UmmaWgradArgs a{g->n, g->d, g->h, g->w, g->od, g->oh, g->ow, g->cin, g->cout, g->k, g->pad, g->dil,
                     x, x_pitch, dy, dy_pitch, dw_packed, 0, static_cast<float*>(workspace), workspace_bytes};
     if (wgrad_umma_supported(a)) return wgrad_umma_run(a, st);
+  } else if (is_k2s2(g)) {
+    UmmaWgradArgs a = k2s2_wgrad_args(g, x, x_pitch, dy, dy_pitch, dw_packed);
+    if (wgrad_umma_supported(a)) return wgrad_umma_run(a, st);
+  } else if (is_k3s2(g) && wgrad_umma_supported(k3s2_wgrad_args(g, 7, x, x_pitch, dy, dy_pitch, dw_packed)) &&
+             wgrad_umma_supported(k3s2_wgrad_args(g, 0, x, x_pitch, dy, dy_pitch, dw_packed))) {
+    for (int cls = 0; cls < 8; ++cls) {     // one launch per parity class of x; every tap belongs to exactly one class
+      if (k3s2_class_empty(g, cls)) continue;
+      const UmmaWgradArgs a = k3s2_wgrad_args(g, cls, x, x_pitch, dy, dy_pitch, dw_packed);
+      if (!wgrad_umma_supported(a)) {
+        set_error("conv3d_wgrad: stride-2 class %d is not supported by the tensor-core path", cls);
+        return B200SEG_ERR_INVALID;
+      }
+      if (int rc = wgrad_umma_run(a, st)) return rc;
+    }
+    return 0;
   }
   return conv_direct_wgrad(*g, x, x_pitch, dy, dy_pitch, dw_packed, st);
 }

@@ -41,6 +41,16 @@ struct UmmaConvArgs {
   // ConvTranspose3d(k2,s2) backward-data as a pointwise GEMM with K = 8*cin_each: K-chunk group g reads the strided
   // sub-lattice (2v + abe_g) of `in` through its own tensor map.  0 = single input map.
   int gather2;           // 1 = `in` is [n,2d,2h,2w,cin/8] and K runs over (abe, channel)
+  // Stride-2 decompositions of a 3x3x3 / pad 1 convolution (conv.cu: k3s2_*; residual_unet3d.py:29-44).  tapmode = 1:
+  // the kernel is 2x2x2 SHIFTED taps (k must be 2, dil 1, `pad` = front padding only) of which only some exist per
+  // class; tapw[class][a*4 + b*2 + e] is the index of the weight tile (in a pack of `wtaps` tiles) or 0xFF.
+  //   in_sub = 1 (forward): `in` is the fine grid [n, fd, fh, fw, cin/8]; K-chunk group g (class g) reads the sub-lattice
+  //       of parity bits g = (d<<2 | h<<1 | w) through its own strided tensor map; d, h, w are the output extents.
+  //   out_sub = 1 (data gradient, one launch per class): `out` is the sub-lattice of parity bits `cls` of the fine grid
+  //       [n, fd, fh, fw, cout]; od, oh, ow are that sub-lattice's extents and class `cls` selects the row of tapw.
+  int tapmode, in_sub, out_sub, cls, wtaps;
+  int fd, fh, fw;
+  unsigned char tapw[8][8];
 };
 extern long long g_umma_launches;
 bool conv_umma_supported(const UmmaConvArgs& a);
@@ -67,6 +77,12 @@ struct UmmaWgradArgs {
   // into dwp, instead of every CTA adding its tile to dwp with fp32 atomics.
   float* partial;
   size_t partial_bytes;
+  // Stride-2 3x3x3 / pad 1 weight gradient, one launch per input-parity class (conv.cu: k3s2_wgrad): sub = 1 means x is
+  // the sub-lattice `cls` (parity bits d<<2 | h<<1 | w) of the fine grid [n, fd, fh, fw, cin]; d, h, w are that
+  // sub-lattice's extents.  The class sees a (kd, kh, kw) in {1,2}^3 kernel with front padding (pd, ph, pw) only;
+  // tapmap[(a*kh + b)*kw + e] is the tap index inside dwp ([27][cin][cout]).
+  int sub, cls, fd, fh, fw, kd, kh, kw, pd, ph, pw;
+  int tapmap[8];
 };
 bool wgrad_umma_supported(const UmmaWgradArgs& a);
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st);

@@ -451,7 +451,7 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
   p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.out_pitch = a.out_pitch;
   p.k = a.k; p.pad = a.pad; p.dil = a.dil;
   p.scatter_cout = a.scatter_cout;
-  if (a.scatter_cout && (a.scatter_cout % 32 || a.cout != 8 * a.scatter_cout || a.k != 1 || a.stats)) return false;
+  if (a.scatter_cout && (a.scatter_cout % 16 || a.cout != 8 * a.scatter_cout || a.k != 1 || a.stats)) return false;
   const int cin_map = a.gather2 ? a.cin / 8 : a.cin;   // channels behind one input tensor map
   if (a.gather2 && (a.cin % 8 || a.k != 1 || cin_map % 16)) return false;
   p.KC = cin_map % 64 == 0 ? 64 : (cin_map % 32 == 0 ? 32 : 16);

@@ -46,6 +46,11 @@ struct PlaneParams {
   __nv_bfloat16* out;
   const float* bias;
   float* stats;
+  // TAP kernels only (stride-2 decompositions, see UmmaConvArgs::tapmode): weight tile per (class, shifted tap), the class
+  // of a single-map launch, and explicit output strides (elements) so that `out` may be a sub-lattice of a finer grid
+  int cls;
+  long long osn, osd, osh, osw;
+  unsigned char tapw[8][8];
 };
 
 struct TensorMaps8P {
@@ -135,7 +140,7 @@ __device__ __forceinline__ void warp_colsum(float (&v)[CW], int lane) {
   }
 }
 
-template <int P, int KS>
+template <int P, int KS, bool TAP>
 __global__ void __launch_bounds__(kThreadsP, 1)
     conv_umma_plane_kernel(const __grid_constant__ TensorMaps8P tmAs, const __grid_constant__ CUtensorMap tmB,
                            const PlaneParams p) {
@@ -220,15 +225,31 @@ __global__ void __launch_bounds__(kThreadsP, 1)
       for (long long t = first; t < p.tiles; t += step) {
         const int nt = static_cast<int>(t % p.n_ntiles);
         for (int c = 0; c < p.nchunks; ++c) {
-          for (int tap = 0; tap < k3; tap += p.G) {     // one barrier pair per group of G tiles (a kw row)
-            mbar_wait(&emptyB[s], ph ^ 1);
-            mbar_arrive_expect_tx(&fullB[s], p.G * p.bytesB);
-            for (int e = 0; e < p.G; ++e)
-              tma_load_3d(sB + static_cast<size_t>(s * p.G + e) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT,
-                          multimap ? c / p.cpm : tap + e);
-            if (++s == p.NB / p.G) {
-              s = 0;
-              ph ^= 1;
+          if constexpr (TAP) {
+            // shifted-tap mode: the taps that exist for this chunk's class, in the issuer's (a, b, e) order; G == 1
+            const int cls = multimap ? c / p.cpm : p.cls;
+            for (int sh = 0; sh < 8; ++sh) {
+              const int wt = p.tapw[cls][sh];
+              if (wt == 0xFF) continue;
+              mbar_wait(&emptyB[s], ph ^ 1);
+              mbar_arrive_expect_tx(&fullB[s], p.bytesB);
+              tma_load_3d(sB + static_cast<size_t>(s) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT, wt);
+              if (++s == p.NB) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+          } else {
+            for (int tap = 0; tap < k3; tap += p.G) {     // one barrier pair per group of G tiles (a kw row)
+              mbar_wait(&emptyB[s], ph ^ 1);
+              mbar_arrive_expect_tx(&fullB[s], p.G * p.bytesB);
+              for (int e = 0; e < p.G; ++e)
+                tma_load_3d(sB + static_cast<size_t>(s * p.G + e) * p.slotB, &tmB, &fullB[s], (c % p.cpm) * p.KC, nt * p.NT,
+                            multimap ? c / p.cpm : tap + e);
+              if (++s == p.NB / p.G) {
+                s = 0;
+                ph ^= 1;
+              }
             }
           }
         }
@@ -255,6 +276,7 @@ __global__ void __launch_bounds__(kThreadsP, 1)
       mbar_wait(&accEmpty[stage], (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_base = tbase + stage * kStageCols;
+      uint32_t started = 0;     // TAP: becomes 1 after the first issued tap of this tile
       for (int c = 0; c < p.nchunks; ++c) {
         int waited = 0, wslot = unit0;
         uint32_t wphase = unit0_phase;
@@ -284,13 +306,20 @@ __global__ void __launch_bounds__(kThreadsP, 1)
           for (int b = 0; b < k; ++b) {
             uint32_t tap16 = tap16_row;
             for (int e = 0; e < k; ++e) {
+              if constexpr (TAP) {
+                if (p.tapw[p.cpm < p.nchunks ? c / p.cpm : p.cls][a * 4 + b * 2 + e] == 0xFF) {   // tap absent for this class
+                  tap16 += p.dil * row16;
+                  continue;
+                }
+              }
               const int ge = p.G == 1 ? 0 : e;
               if (ge == 0) {
                 mbar_wait(&fullB[bs], bphase);
                 tc_fence_after();
               }
               const uint32_t b_lo = __shfl_sync(0xffffffffu, ((sB16 + (bs * p.G + ge) * slotB16) & 0x3FFF) | lo_fixed, 0);
-              const uint32_t fresh = (c | a | b | e) == 0 ? 0u : 1u;
+              const uint32_t fresh = TAP ? started : ((c | a | b | e) == 0 ? 0u : 1u);
+              started = 1;
 #pragma unroll
               for (int acc = 0; acc < P; ++acc) {
 #pragma unroll
@@ -363,6 +392,8 @@ __global__ void __launch_bounds__(kThreadsP, 1)
               const long long ovox = ((static_cast<long long>(tc.nn) * 2 * p.od + 2 * od_ + (abe >> 2)) * 2 * p.oh +
                                       2 * oh_ + ((abe >> 1) & 1)) * 2 * p.ow + 2 * ow_ + (abe & 1);
               optr = p.out + ovox * p.out_pitch + co0;
+            } else if constexpr (TAP) {
+              optr = p.out + tc.nn * p.osn + od_ * p.osd + oh_ * p.osh + ow_ * p.osw + col0;
             } else {
               const long long vox = ((static_cast<long long>(tc.nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
               optr = p.out + vox * p.out_pitch + col0;
@@ -379,7 +410,8 @@ __global__ void __launch_bounds__(kThreadsP, 1)
           }
         }
       };
-      if ((p.NT & 31) == 0) slabs(std::integral_constant<int, 32>{});
+      // (a 32-column slab must lie inside one pixel-shuffle offset: scatter_cout % 32, else 16-column slabs)
+      if ((p.NT & 31) == 0 && (p.scatter_cout & 31) == 0) slabs(std::integral_constant<int, 32>{});
       else slabs(std::integral_constant<int, 16>{});
       tc_fence_before();
       __syncwarp();
@@ -403,18 +435,26 @@ __global__ void __launch_bounds__(kThreadsP, 1)
 static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, size_t& smem_bytes) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_PERSISTENT")) return false;
   if (a.cin % 16 || a.cout % 16) return false;
-  if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
   if (a.in_pitch % 8 || a.out_pitch % 8) return false;
   const int halo = (a.k - 1) * a.dil;
-  if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
-  if (!(a.oh >= 16 && a.ow >= 8)) return false;
+  if (a.tapmode) {
+    // 2x2x2 shifted taps (stride-2 decompositions): the caller vouches for the extents; short tiles are masked, so the
+    // small deep levels (8^3 outputs) run here too instead of needing a flat-mode variant
+    if (a.k != 2 || a.dil != 1 || a.pad < 0 || a.pad > 1 || a.scatter_cout || a.gather2 || (a.in_sub && a.out_sub)) return false;
+    if (!(a.oh >= 4 && a.ow >= 4)) return false;
+  } else {
+    if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
+    if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
+    if (!(a.oh >= 16 && a.ow >= 8)) return false;
+  }
   p = PlaneParams{};
   p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.out_pitch = a.out_pitch;
   p.k = a.k; p.pad = a.pad; p.dil = a.dil;
   p.scatter_cout = a.scatter_cout;
-  if (a.scatter_cout && (a.scatter_cout % 32 || a.cout != 8 * a.scatter_cout || a.k != 1 || a.stats)) return false;
-  const int cin_map = a.gather2 ? a.cin / 8 : a.cin;
+  if (a.scatter_cout && (a.scatter_cout % 16 || a.cout != 8 * a.scatter_cout || a.k != 1 || a.stats)) return false;
+  const int cin_map = (a.gather2 || a.in_sub) ? a.cin / 8 : a.cin;
   if (a.gather2 && (a.cin % 8 || a.k != 1 || cin_map % 16)) return false;
+  if (a.in_sub && (a.cin % 8 || cin_map % 16)) return false;
   p.KC = cin_map % 64 == 0 ? 64 : (cin_map % 32 == 0 ? 32 : 16);
   KS = p.KC / 16;
   p.nchunks = a.cin / p.KC;
@@ -486,7 +526,7 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   if (!P) return false;
   // Weight-ring grouping (few accumulators per tile only: with P x KS >= 8 MMAs per tile the hand-shake is amortised)
   p.G = 1;
-  if (a.k > 1 && !a.gather2 && P * KS <= 4 && p.NB / a.k >= 2) {
+  if (a.k > 1 && !a.gather2 && !a.tapmode && P * KS <= 4 && p.NB / a.k >= 2) {
     p.G = a.k;
     p.NB = (p.NB / a.k) * a.k;
   }
@@ -505,19 +545,19 @@ bool conv_umma_plane_supported(const UmmaConvArgs& a) {
   return plan_plane(a, p, P, KS, smem);
 }
 
-template <int P, int KS>
+template <int P, int KS, bool TAP>
 static int launch_plane(const TensorMaps8P& tmAs, const CUtensorMap& tmB, const PlaneParams& p, size_t smem, int ctas,
                         cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_plane_kernel<P, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+    if (cudaFuncSetAttribute(conv_umma_plane_kernel<P, KS, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
       set_error("conv_umma_plane: cannot raise the dynamic shared memory limit");
       return B200SEG_ERR_CUDA;
     }
     attr_set = true;
   }
-  conv_umma_plane_kernel<P, KS><<<ctas, kThreadsP, smem, st>>>(tmAs, tmB, p);
+  conv_umma_plane_kernel<P, KS, TAP><<<ctas, kThreadsP, smem, st>>>(tmAs, tmB, p);
   B200_CHECK_LAUNCH("conv_umma_plane");
   return 0;
 }
@@ -543,7 +583,43 @@ int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st) {
   TensorMaps8P tmAs;
   CUtensorMap tmB;
   const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB), 1u, 1u};
-  if (!a.gather2) {
+  if (a.tapmode) {
+    p.cls = a.cls;
+    for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < 8; ++j) p.tapw[i][j] = a.tapw[i][j];
+    if (a.out_sub) {
+      // `out` = sub-lattice `cls` of the fine grid [n, fd, fh, fw, cout]
+      const long long pit = a.out_pitch;
+      p.osw = 2 * pit;
+      p.osh = 2 * pit * a.fw;
+      p.osd = 2 * pit * a.fw * a.fh;
+      p.osn = pit * a.fw * a.fh * a.fd;
+      p.out += ((static_cast<long long>(a.cls >> 2) * a.fh + ((a.cls >> 1) & 1)) * a.fw + (a.cls & 1)) * pit;
+      p.wide = 0;
+      if (a.out_pitch % 8) return B200SEG_ERR_INVALID;
+    } else {
+      p.osw = a.out_pitch;
+      p.osh = p.osw * a.ow;
+      p.osd = p.osh * a.oh;
+      p.osn = p.osd * a.od;
+    }
+  }
+  if (a.in_sub) {
+    // class g = parity bits (d<<2 | h<<1 | w) of the fine grid `in` [n, fd, fh, fw, cin/8]: extent ceil((f - r) / 2)
+    const int cm = a.cin / 8;
+    const uint64_t pb = static_cast<uint64_t>(a.in_pitch) * 2;
+    for (int g = 0; g < 8; ++g) {
+      const int rd = g >> 2, rh = (g >> 1) & 1, rw = g & 1;
+      const uint64_t off = ((static_cast<uint64_t>(rd) * a.fh + rh) * a.fw + rw) * pb;
+      const uint64_t dims[5] = {static_cast<uint64_t>(cm), static_cast<uint64_t>((a.fw - rw + 1) / 2),
+                                static_cast<uint64_t>((a.fh - rh + 1) / 2), static_cast<uint64_t>((a.fd - rd + 1) / 2),
+                                static_cast<uint64_t>(a.n)};
+      if (dims[1] == 0 || dims[2] == 0 || dims[3] == 0) return B200SEG_ERR_INVALID;
+      const uint64_t str[4] = {2 * pb, 2 * pb * a.fw, 2 * pb * a.fw * a.fh, pb * a.fw * a.fh * a.fd};
+      if (!encode_bf16_map(&tmAs.m[g], static_cast<const uint8_t*>(a.in) + off, 5, dims, str, box, p.KC))
+        return B200SEG_ERR_CUDA;
+    }
+  } else if (!a.gather2) {
     const uint64_t dims[5] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.w), static_cast<uint64_t>(a.h),
                               static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.n)};
     const uint64_t pb = static_cast<uint64_t>(a.in_pitch) * 2;
@@ -564,8 +640,8 @@ int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st) {
     }
   }
   {
-    const int k3 = a.gather2 ? 8 : a.k * a.k * a.k;
-    const uint64_t cin_w = a.gather2 ? a.cin / 8 : a.cin;
+    const int k3 = a.tapmode ? a.wtaps : (a.gather2 ? 8 : a.k * a.k * a.k);
+    const uint64_t cin_w = (a.gather2 || a.in_sub) ? a.cin / 8 : a.cin;
     const uint64_t dims[3] = {cin_w, static_cast<uint64_t>(a.cout), static_cast<uint64_t>(k3)};
     const uint64_t str[2] = {cin_w * 2, cin_w * a.cout * 2};
     const uint32_t boxb[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.NT), 1u};
@@ -573,8 +649,10 @@ int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st) {
   }
   const int ctas = static_cast<int>(std::min<long long>(kNumSMs, p.tiles));
   int rc = B200SEG_ERR_INVALID;
-#define B200_PLANE_CASE(PP, KK) \
-  if (P == PP && KS == KK) rc = launch_plane<PP, KK>(tmAs, tmB, p, smem, ctas, st);
+#define B200_PLANE_CASE(PP, KK)                                                                 \
+  if (P == PP && KS == KK)                                                                      \
+    rc = a.tapmode ? launch_plane<PP, KK, true>(tmAs, tmB, p, smem, ctas, st)                   \
+                   : launch_plane<PP, KK, false>(tmAs, tmB, p, smem, ctas, st);
   B200_PLANE_CASE(8, 1) B200_PLANE_CASE(8, 2) B200_PLANE_CASE(8, 4)
   B200_PLANE_CASE(4, 1) B200_PLANE_CASE(4, 2) B200_PLANE_CASE(4, 4)
   B200_PLANE_CASE(2, 1) B200_PLANE_CASE(2, 2) B200_PLANE_CASE(2, 4)

@@ -52,6 +52,7 @@ struct WgradParams {
   int splits;                  // CTAs sharing one (asplit, chunk, ntile) combination
   int nchunks, n_ntiles, asplit;
   int stages, gather2;
+  int padd, padh, padw;        // front padding per dimension (== pad except for the stride-2 class launches)
   unsigned slotX, slotY, stage_bytes, rowbytesA, rowbytesB, swzA, swzB, bytesX, bytesY, tmem_cols;
   float* dwp;
 };
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(192, 1)
           if (p.gather2)   // sub-lattice j of the fine grid, no halo
             tma_load_5d(st + static_cast<size_t>(j) * p.slotX, &tmXs.m[j], &full[s], chunk * p.KC, w0, h0, d0, nn);
           else
-            tma_load_5d(st + static_cast<size_t>(j) * p.slotX, &tmXs.m[0], &full[s], chunk * p.KC, w0 - p.pad,
-                        h0 - p.pad, d0 - p.pad + (p.flat ? 0 : a * p.dil), nn);
+            tma_load_5d(st + static_cast<size_t>(j) * p.slotX, &tmXs.m[0], &full[s], chunk * p.KC, w0 - p.padw,
+                        h0 - p.padh, d0 - p.padd + (p.flat ? 0 : a * p.dil), nn);
         }
         tma_load_5d(st + static_cast<size_t>(p.nplanes) * p.slotX, &tmY, &full[s], nt * p.NT, w0, h0, d0, nn);
       }
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(192, 1)
           for (int j = 16; j < 32; ++j) raw[j] = 0u;
         }
         tmem_ld_wait();
-        if (tap >= 0) {
+        if (tap >= 0 && ci < p.cin) {
           float* dst = p.dwp + (static_cast<size_t>(tap) * p.cin + ci) * p.cout + nt * p.NT + cc;
           if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (ncol & 3) == 0) {
             // 4-wide vector reductions (REDG.E.ADD.F32x4): a quarter of the L2 atomic operations
@@ -304,10 +305,12 @@ static bool encode5_strided(CUtensorMap* tm, const void* base, int c, int w, int
 
 static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_bytes) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_UMMA_WGRAD")) return false;
-  if (a.cin % 32 || a.cout % 16) return false;
+  if (a.cin % 16 || a.cout % 16) return false;   // ragged last 32-channel chunk: TMA zero fill + masked epilogue rows
   if (a.x_pitch % 8 || a.dy_pitch % 8) return false;
   const int halo = a.gather2 ? 0 : (a.k - 1) * a.dil;
-  if (a.gather2) {
+  if (a.sub) {
+    if (a.gather2 || a.dil != 1 || a.kd < 1 || a.kd > 2 || a.kh < 1 || a.kh > 2 || a.kw < 1 || a.kw > 2) return false;
+  } else if (a.gather2) {
     if (a.k != 2 || a.pad != 0 || a.dil != 1 || a.d != 2 * a.od || a.h != 2 * a.oh || a.w != 2 * a.ow) return false;
   } else {
     if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
@@ -317,9 +320,12 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
   p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cin = a.cin; p.cout = a.cout;
   p.k = a.k; p.pad = a.pad; p.dil = a.dil;
   p.gather2 = a.gather2;
+  p.padd = a.sub ? a.pd : a.pad;
+  p.padh = a.sub ? a.ph : a.pad;
+  p.padw = a.sub ? a.pw : a.pad;
   p.KC = (a.cin % 64 == 0 && !a.gather2) ? 64 : 32;   // gather mode keeps 8 boxes per stage: use the narrow chunk
   p.MB = 128 / p.KC;
-  p.nchunks = a.cin / p.KC;
+  p.nchunks = (a.cin + p.KC - 1) / p.KC;
   p.NT = a.cout % 64 == 0 ? 64 : (a.cout % 32 == 0 ? 32 : 16);
   p.n_ntiles = a.cout / p.NT;
   p.rowbytesA = p.KC * 2;
@@ -328,10 +334,11 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
   p.swzB = p.NT == 64 ? SWZ_128B : (p.NT == 32 ? SWZ_64B : SWZ_32B);
   const int k = a.k;
 
-  p.flat = !(a.oh >= 16 && a.ow >= 8);
+  // (class launches always tile planes: rows past a short extent are zero-filled dy rows and contribute nothing)
+  p.flat = !(a.oh >= 16 && a.ow >= 8) && !a.sub;
   if (!p.flat) {
-    p.WB = 8 + halo;
-    p.HB = 16 + halo;
+    p.WB = 8 + (a.sub ? a.kw - 1 : halo);
+    p.HB = 16 + (a.sub ? a.kh - 1 : halo);
     p.DT = 1;
     p.UPX = 1;
     p.tiles_w = (a.ow + 7) / 8;
@@ -354,18 +361,19 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
   struct G2 { int base, lbo, tap[8]; };
   G2 per_plane[16];
   int gpp = 0;
+  const int kh_ = a.sub ? a.kh : k, kw_ = a.sub ? a.kw : k, kd_ = a.sub ? a.kd : k;   // taps per dimension
   if (a.gather2) {
     // filled in below: groups are runs of MB consecutive sub-lattice boxes (LBO = one box)
   } else if (p.KC == 64) {
-    for (int i = 0; i < k * k; i += 2) {
+    for (int i = 0; i < kh_ * kw_; i += 2) {
       G2 g{};
       for (int j = 0; j < 8; ++j) g.tap[j] = -1;
-      const int b0 = i / k, e0 = i % k;
+      const int b0 = i / kw_, e0 = i % kw_;
       g.base = (b0 * a.dil) * p.WB + e0 * a.dil;
       g.tap[0] = i;
       g.lbo = 1;
-      if (i + 1 < k * k) {
-        const int b1 = (i + 1) / k, e1 = (i + 1) % k;
+      if (i + 1 < kh_ * kw_) {
+        const int b1 = (i + 1) / kw_, e1 = (i + 1) % kw_;
         g.lbo = (b1 * a.dil) * p.WB + e1 * a.dil - g.base;
         g.tap[1] = i + 1;
       }
@@ -373,20 +381,21 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
       per_plane[gpp++] = g;
     }
   } else {
-    for (int b = 0; b < k; ++b)
-      for (int e0 = 0; e0 < k; e0 += 4) {
+    for (int b = 0; b < kh_; ++b)
+      for (int e0 = 0; e0 < kw_; e0 += 4) {
         G2 g{};
         for (int j = 0; j < 8; ++j) g.tap[j] = -1;
         g.base = (b * a.dil) * p.WB + e0 * a.dil;
         g.lbo = a.dil;
-        for (int j = 0; j < 4 && e0 + j < k; ++j) g.tap[j] = b * k + e0 + j;
+        for (int j = 0; j < 4 && e0 + j < kw_; ++j) g.tap[j] = b * kw_ + e0 + j;
         if (gpp >= 16) return false;
         per_plane[gpp++] = g;
       }
   }
-  p.asplit = a.gather2 ? 1 : ((k * gpp * p.NT <= 512 && k * gpp <= kMaxGroups) ? 1 : k);
+  p.asplit = (a.gather2 || a.sub) ? 1 : ((k * gpp * p.NT <= 512 && k * gpp <= kMaxGroups) ? 1 : k);
   if (gpp * p.NT > 512 || gpp > kMaxGroups) return false;
-  const int planes_in_cta = a.gather2 ? 0 : (p.asplit == 1 ? k : 1);
+  if (a.sub && (kd_ * gpp * p.NT > 512 || kd_ * gpp > kMaxGroups)) return false;
+  const int planes_in_cta = a.gather2 ? 0 : (p.asplit == 1 ? kd_ : 1);
   p.ngroups = 0;
   for (int pa = 0; pa < planes_in_cta; ++pa)
     for (int gi = 0; gi < gpp; ++gi) {
@@ -394,8 +403,10 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
       G.plane = p.flat ? 0 : pa;
       G.base_rows = per_plane[gi].base + (p.flat ? pa * a.dil * plane_rows : 0);
       G.lbo_rows = per_plane[gi].lbo;
-      for (int j = 0; j < 8; ++j)
-        G.tap[j] = per_plane[gi].tap[j] < 0 ? -1 : (p.asplit == 1 ? pa * k * k : 0) + per_plane[gi].tap[j];
+      for (int j = 0; j < 8; ++j) {
+        const int local = per_plane[gi].tap[j] < 0 ? -1 : (p.asplit == 1 ? pa * kh_ * kw_ : 0) + per_plane[gi].tap[j];
+        G.tap[j] = (a.sub && local >= 0) ? a.tapmap[local] : local;   // class launches: straight to the 27-tap index
+      }
     }
   for (int pa = 0; pa < 8; ++pa) p.plane_a[pa] = pa;
   unsigned cols = 32;
@@ -465,14 +476,14 @@ static bool plan_wgrad(const UmmaWgradArgs& a, WgradParams& p, size_t& smem_byte
 }
 
 bool wgrad_umma_supported(const UmmaWgradArgs& a) {
-  if (wgrad_umma_plane_supported(a)) return true;
+  if (!a.sub && wgrad_umma_plane_supported(a)) return true;
   WgradParams p;
   size_t smem;
   return plan_wgrad(a, p, smem);
 }
 
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st) {
-  if (wgrad_umma_plane_supported(a)) return wgrad_umma_plane_run(a, st);   // wgrad_umma_p.cu
+  if (!a.sub && wgrad_umma_plane_supported(a)) return wgrad_umma_plane_run(a, st);   // wgrad_umma_p.cu
   WgradParams p;
   size_t smem;
   if (!plan_wgrad(a, p, smem)) {
@@ -486,7 +497,15 @@ int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st) {
   }
   TensorMaps8W tmXs;
   CUtensorMap tmY;
-  if (!a.gather2) {
+  if (a.sub) {
+    // x = sub-lattice `cls` of the fine grid: its own extents, doubled strides, shifted base
+    const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB), 1u, 1u};
+    const long long off = ((static_cast<long long>(a.cls >> 2) * a.fh + ((a.cls >> 1) & 1)) * a.fw + (a.cls & 1)) * a.x_pitch;
+    if (!encode5_strided(&tmXs.m[0], static_cast<const __nv_bfloat16*>(a.x) + off, a.cin, a.w, a.h, a.d, a.n, a.x_pitch,
+                         a.fw, a.fh, a.fd, box, p.KC))
+      return B200SEG_ERR_CUDA;
+    for (int i = 1; i < 8; ++i) tmXs.m[i] = tmXs.m[0];
+  } else if (!a.gather2) {
     const uint32_t box[5] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.WB), static_cast<uint32_t>(p.HB),
                              static_cast<uint32_t>(p.UPX), 1u};
     if (!encode5(&tmXs.m[0], a.x, a.cin, a.w, a.h, a.d, a.n, a.x_pitch, box, p.KC)) return B200SEG_ERR_CUDA;

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kWgradPThreads, 1)
     for (int g = 0; g < NG; ++g) {
       const int b = p.bsplit > 1 ? bsel : p.groups[g].b;
       const int e = p.groups[g].e0 + blk;
-      const bool row_ok = blk < p.groups[g].nblk;
+      const bool row_ok = blk < p.groups[g].nblk && ci < p.cin;   // ci >= cin: zero-filled rows of a ragged last chunk
       for (int i = 0; i < p.NBLK; ++i) {
         const int a = p.k - 1 - i;      // N block i holds dy plane dx + pad - (k-1-i)*dil
         const int tap = (a * p.k + b) * p.k + e;
@@ -361,7 +361,9 @@ static bool plan_wgrad_plane(const UmmaWgradArgs& a, WgradPParams& p, size_t& sm
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_UMMA_WGRAD") || getenv("B200SEG_DISABLE_PERSISTENT"))
     return false;
   if (a.gather2) return false;
-  if (a.cin % 32 || a.cout % 16) return false;
+  // C_in only has to be a multiple of 16 (HighRes3DNet's 16-channel layers, highresnet.py:40-59): the last 32-channel
+  // chunk then reaches past the tensor, TMA fills those channels with zeros and the epilogue skips their rows
+  if (a.cin % 16 || a.cout % 16) return false;
   if (a.x_pitch % 8 || a.dy_pitch % 8) return false;
   if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
   const int halo = (a.k - 1) * a.dil;
@@ -375,7 +377,7 @@ static bool plan_wgrad_plane(const UmmaWgradArgs& a, WgradPParams& p, size_t& sm
   // narrow outputs use 32-channel rows (chunks become the CTA classes): same MMA count, 2.4x less L2 traffic.
   p.KC = (a.cin % 64 == 0 && a.cout > 32) ? 64 : 32;
   const int MB = 128 / p.KC;
-  p.nchunks = a.cin / p.KC;
+  p.nchunks = (a.cin + p.KC - 1) / p.KC;
   p.NBLK = a.k;
   const int egroups = (a.k + MB - 1) / MB;
   // dy channels per N block: N = k*NT <= 256, and the accumulators of one CTA must fit 512 TMEM columns

@@ -62,6 +62,8 @@ class TrainStep:
         if self._split and reducer is not None:
             reducer.enabled = False           # no NCCL launches from autograd hooks while capturing / replaying
         self._grad_scale = 1.0
+        if not self._split:
+            self.optimizer._sync_hyper(self._grad_scale)   # a scheduler may have moved lr since the last eager step
         with torch.cuda.graph(self.graph):
             if self._split:
                 # the packed weight gradients are transposed into the gradient arena INSIDE the graph: the host-side

@@ -71,6 +71,15 @@ CONV_CASES = [
     (128, 128, 3, 1, 1, 1, (4, 16, 16), 1),   # two K chunks in plane mode
     (512, 256, 3, 1, 1, 1, (4, 4, 4), 1),     # 8 K chunks, 2 N tiles, flat mode
     (32, 32, 3, 1, 1, 1, (5, 17, 11), 1),     # ragged extents: masked rows in the last tiles
+    # round 2: stride-2 / 16-channel geometries of the other model families on the tensor cores
+    (32, 64, 3, 2, 1, 1, (32, 32, 32), 1),    # residual U-Net down-step: parity-class decomposition, 16^3 output
+    (64, 128, 3, 2, 1, 1, (16, 16, 16), 2),   # ... 8^3 output (short tiles), batch 2
+    (32, 64, 3, 2, 1, 1, (18, 34, 22), 1),    # ... ragged tiles
+    (32, 32, 3, 2, 1, 1, (17, 33, 19), 1),    # ... odd extents: the parity classes have different sizes
+    (16, 32, 2, 2, 0, 1, (32, 32, 32), 1),    # V-Net down conv as gather GEMM / pixel-shuffle GEMM
+    (128, 256, 2, 2, 0, 1, (8, 16, 16), 1),   # V-Net deep down conv
+    (16, 16, 3, 1, 1, 1, (16, 32, 16), 1),    # HighRes3DNet: C_in = 16 weight gradient (zero-filled half chunk)
+    (48, 32, 3, 1, 1, 1, (8, 16, 16), 1),     # ragged last C_in chunk in the weight gradient
 ]
 
 
@@ -96,9 +105,12 @@ def test_conv3d_fprop_dgrad_wgrad(F, case):
     y = F.conv_norm_act(xd, wd, bd, k=k, stride=stride, pad=pad, dil=dil)
     close(ncdhw(y), y_ref.detach(), 8e-3, "fprop")
     y.backward(ndhwc(dy))
-    # which path ran: tcgen05 for stride-1 k in {1,3,5} with 16-aligned channels (wgrad: C_in % 32 == 0)
+    # which path ran: tcgen05 for stride-1 k in {1,3,5} with 16-aligned channels
     if stride == 1 and k in (1, 3, 5) and cin % 16 == 0 and cout % 16 == 0:
-        assert F.umma_launch_count() - n0 == (3 if cin % 32 == 0 else 2), "tensor-core path was not taken"
+        assert F.umma_launch_count() - n0 == 3, "tensor-core path was not taken"
+    elif stride == 2 and cin % 16 == 0 and cout % 16 == 0 and min(size) >= 8:
+        # k3s2: 1 forward + 8 data-gradient + 8 weight-gradient class launches; k2s2: one launch per pass
+        assert F.umma_launch_count() - n0 == (17 if k == 3 else 3), "strided tensor-core path was not taken"
     elif cin < 16 and stride == 1 and k == 3 and cout % 16 == 0 and n * size[0] * size[1] * size[2] >= 1 << 16:
         # large stem: fprop runs K-padded on the tensor cores; with C_in = 1 the weight gradient does too (taps as channels)
         assert F.umma_launch_count() - n0 == (2 if cin == 1 else 1), "large stem: tensor-core path was not taken"
