@@ -60,6 +60,7 @@ bool conv_umma_roll_supported(const UmmaConvArgs& a);
 int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st);
 // persistent plane-mode kernel (conv_umma_p.cu); conv_umma_run dispatches to it when the geometry allows
 bool conv_umma_plane_supported(const UmmaConvArgs& a);
+bool conv_umma_plane_relaxed_supported(const UmmaConvArgs& a);   // short planes (masked tile rows): last resort
 int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st);
 
 struct UmmaWgradArgs {
@@ -88,6 +89,7 @@ bool wgrad_umma_supported(const UmmaWgradArgs& a);
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st);
 // persistent plane-mode kernel with tap blocks on both operands (wgrad_umma_p.cu)
 bool wgrad_umma_plane_supported(const UmmaWgradArgs& a);
+bool wgrad_umma_plane_relaxed_supported(const UmmaWgradArgs& a);
 size_t wgrad_umma_plane_workspace_bytes(const UmmaWgradArgs& a);
 int wgrad_umma_plane_run(const UmmaWgradArgs& a, cudaStream_t st);
 

@@ -591,7 +591,7 @@ bool conv_umma_supported(const UmmaConvArgs& a) {
   if (conv_umma_roll_supported(a) || conv_umma_plane_supported(a)) return true;
   UmmaConvParams p;
   size_t smem;
-  return plan(a, p, smem);
+  return plan(a, p, smem) || conv_umma_plane_relaxed_supported(a);
 }
 
 int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
@@ -600,6 +600,8 @@ int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
   UmmaConvParams p;
   size_t smem;
   if (!plan(a, p, smem)) {
+    // small planes with a halo too large for the flat kernel's whole-box slot (5x5x5 at 8^3, vnet3d.py:25)
+    if (conv_umma_plane_relaxed_supported(a)) return conv_umma_plane_run(a, st);
     set_error("conv_umma_run: unsupported geometry");
     return B200SEG_ERR_INVALID;
   }

@@ -432,7 +432,9 @@ __global__ void __launch_bounds__(kThreadsP, 1)
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, size_t& smem_bytes) {
+// kc_cap: largest K chunk (channels per shared-memory row) to try; relaxed: accept short planes (H_out, W_out >= 4; the
+// rows of a 16 x 8 tile that fall outside are masked) -- the last resort for geometries no other kernel takes.
+static bool plan_plane_kc(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, size_t& smem_bytes, int kc_cap, bool relaxed) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_PERSISTENT")) return false;
   if (a.cin % 16 || a.cout % 16) return false;
   if (a.in_pitch % 8 || a.out_pitch % 8) return false;
@@ -445,7 +447,7 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   } else {
     if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
     if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
-    if (!(a.oh >= 16 && a.ow >= 8)) return false;
+    if (relaxed ? !(a.oh >= 4 && a.ow >= 4) : !(a.oh >= 16 && a.ow >= 8)) return false;
   }
   p = PlaneParams{};
   p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.out_pitch = a.out_pitch;
@@ -455,7 +457,7 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   const int cin_map = (a.gather2 || a.in_sub) ? a.cin / 8 : a.cin;
   if (a.gather2 && (a.cin % 8 || a.k != 1 || cin_map % 16)) return false;
   if (a.in_sub && (a.cin % 8 || cin_map % 16)) return false;
-  p.KC = cin_map % 64 == 0 ? 64 : (cin_map % 32 == 0 ? 32 : 16);
+  p.KC = (cin_map % 64 == 0 && kc_cap >= 64) ? 64 : ((cin_map % 32 == 0 && kc_cap >= 32) ? 32 : 16);
   KS = p.KC / 16;
   p.nchunks = a.cin / p.KC;
   p.cpm = cin_map / p.KC;
@@ -483,6 +485,7 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   const long long mmas_per_acc = static_cast<long long>(p.nchunks) * a.k * a.k * a.k * KS;
   p.stages = (getenv("B200SEG_SINGLE_STAGE") && mmas_per_acc >= 256 && p.NT >= 64) ? 1 : 2;
   int pmax = std::min(8, (p.stages == 1 ? 512 : kStageCols) / p.NT);
+  while (pmax & (pmax - 1)) pmax &= pmax - 1;      // power of two (N tiles of 48, 80, ... channels: 5 -> 4, 3 -> 2)
   while (pmax > 1 && pmax / 2 >= a.od) pmax /= 2;
   // Wave quantisation: tiles are dealt to 148 persistent CTAs, so the kernel takes ceil(tiles / 148) rounds of P planes
   // each.  Small volumes (16^3: 64 tiles at P = 2) leave SMs idle; halving P doubles the tile count for free.
@@ -538,11 +541,25 @@ static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, s
   return smem_bytes <= 227 * 1024;
 }
 
+// Widest K chunk whose input-plane ring fits shared memory: large halos (dilation 4: 16 x 24-voxel planes, 12 of them per
+// tile; 5x5x5 kernels) need narrower rows (highresnet.py:62-84 runs 64-channel layers at dilation 4).
+static bool plan_plane(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS, size_t& smem_bytes, bool relaxed = false) {
+  for (int cap : {64, 32, 16})
+    if (plan_plane_kc(a, p, P, KS, smem_bytes, cap, relaxed)) return true;
+  return false;
+}
+
 bool conv_umma_plane_supported(const UmmaConvArgs& a) {
   PlaneParams p;
   int P, KS;
   size_t smem;
   return plan_plane(a, p, P, KS, smem);
+}
+bool conv_umma_plane_relaxed_supported(const UmmaConvArgs& a) {
+  PlaneParams p;
+  int P, KS;
+  size_t smem;
+  return plan_plane(a, p, P, KS, smem, true);
 }
 
 template <int P, int KS, bool TAP>
@@ -566,7 +583,7 @@ int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st) {
   PlaneParams p;
   int P, KS;
   size_t smem;
-  if (!plan_plane(a, p, P, KS, smem)) {
+  if (!plan_plane(a, p, P, KS, smem) && !plan_plane(a, p, P, KS, smem, true)) {
     set_error("conv_umma_plane_run: unsupported geometry");
     return B200SEG_ERR_INVALID;
   }
@@ -658,6 +675,7 @@ int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st) {
   B200_PLANE_CASE(2, 1) B200_PLANE_CASE(2, 2) B200_PLANE_CASE(2, 4)
   B200_PLANE_CASE(1, 1) B200_PLANE_CASE(1, 2) B200_PLANE_CASE(1, 4)
 #undef B200_PLANE_CASE
+  if (rc == B200SEG_ERR_INVALID) set_error("conv_umma_plane_run: no kernel instance for P = %d, KS = %d", P, KS);
   if (rc == 0) ++g_umma_launches;
   return rc;
 }

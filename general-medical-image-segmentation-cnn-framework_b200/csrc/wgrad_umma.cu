@@ -479,7 +479,7 @@ bool wgrad_umma_supported(const UmmaWgradArgs& a) {
   if (!a.sub && wgrad_umma_plane_supported(a)) return true;
   WgradParams p;
   size_t smem;
-  return plan_wgrad(a, p, smem);
+  return plan_wgrad(a, p, smem) || (!a.sub && !a.gather2 && wgrad_umma_plane_relaxed_supported(a));
 }
 
 int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st) {
@@ -487,6 +487,7 @@ int wgrad_umma_run(const UmmaWgradArgs& a, cudaStream_t st) {
   WgradParams p;
   size_t smem;
   if (!plan_wgrad(a, p, smem)) {
+    if (!a.sub && !a.gather2 && wgrad_umma_plane_relaxed_supported(a)) return wgrad_umma_plane_run(a, st);
     set_error("wgrad_umma_run: unsupported geometry");
     return B200SEG_ERR_INVALID;
   }

@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-static bool plan_wgrad_plane(const UmmaWgradArgs& a, WgradPParams& p, size_t& smem_bytes) {
+// relaxed: accept short planes (H_out, W_out >= 4): rows of the 16 x 8 dy tile outside the tensor arrive as TMA zero fill
+// and contribute nothing -- the last resort for small planes whose halo is too large for the flat kernel (5x5x5 at 8^3)
+static bool plan_wgrad_plane(const UmmaWgradArgs& a, WgradPParams& p, size_t& smem_bytes, bool relaxed = false) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_UMMA_WGRAD") || getenv("B200SEG_DISABLE_PERSISTENT"))
     return false;
   if (a.gather2) return false;
@@ -368,7 +370,7 @@ static bool plan_wgrad_plane(const UmmaWgradArgs& a, WgradPParams& p, size_t& sm
   if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
   const int halo = (a.k - 1) * a.dil;
   if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
-  if (!(a.oh >= 16 && a.ow >= 8)) return false;
+  if (relaxed ? !(a.oh >= 4 && a.ow >= 4) : !(a.oh >= 16 && a.ow >= 8)) return false;
   p = WgradPParams{};
   p.n = a.n; p.d = a.d; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cin = a.cin; p.cout = a.cout;
   p.k = a.k; p.pad = a.pad; p.dil = a.dil;
@@ -448,6 +450,11 @@ bool wgrad_umma_plane_supported(const UmmaWgradArgs& a) {
   size_t smem;
   return plan_wgrad_plane(a, p, smem);
 }
+bool wgrad_umma_plane_relaxed_supported(const UmmaWgradArgs& a) {
+  WgradPParams p;
+  size_t smem;
+  return plan_wgrad_plane(a, p, smem, true);
+}
 
 size_t wgrad_umma_plane_workspace_bytes(const UmmaWgradArgs& a) {
   WgradPParams p;
@@ -478,7 +485,7 @@ static int launch_wgrad_plane(const CUtensorMap& tmX, const CUtensorMap& tmY, co
 int wgrad_umma_plane_run(const UmmaWgradArgs& a, cudaStream_t st) {
   WgradPParams p;
   size_t smem;
-  if (!plan_wgrad_plane(a, p, smem)) {
+  if (!plan_wgrad_plane(a, p, smem) && !plan_wgrad_plane(a, p, smem, true)) {
     set_error("wgrad_umma_plane_run: unsupported geometry");
     return B200SEG_ERR_INVALID;
   }

@@ -200,11 +200,86 @@ def pack_conv_weight(weight, cin_off=0, cin_cnt=None, dgrad=False):
 
 
 # ------------------------------------------------------------------------------------------------ raw op helpers
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def _padded_geom(g):
+    return ConvGeom(g.n, g.d, g.h, g.w, _pad16(g.cin), g.od, g.oh, g.ow, _pad16(g.cout), g.k, g.stride, g.pad, g.dil)
+
+
+def _use_padded(g):
+    """Channel counts that are not multiples of 16 (C_in = 1 stems, DenseVoxelNet's 12-channel growth and 16+12i inputs,
+    V-Net's 32 -> 2 output conv: densevoxelnet3d.py:22, vnet3d.py:47,111) reach the tensor cores zero-padded: the weights
+    get zero rows / columns, activations and gradients a zero-filled copy.  Only where it pays (large volumes)."""
+    if g.cin % 16 == 0 and g.cout % 16 == 0:
+        return False
+    if g.n * g.od * g.oh * g.ow < (1 << 16) and _conv_flops(g) < 2e8:     # tiny: the direct kernels are launch-bound
+        return False
+    return conv_uses_tensor_cores(_padded_geom(g))
+
+
+def _pad_channels(x, c_pad):
+    """[N,D,H,W,C] -> contiguous [N,D,H,W,c_pad] with zero-filled extra channels."""
+    x, xp = _as_rows(x) if (x.dim() == 5 and x.stride(4) == 1 and _pitched(x)) else (x.contiguous(), x.shape[4])
+    n, d, h, w, c = x.shape
+    if c == c_pad and xp == c:
+        return x
+    out = torch.empty((n, d, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
+    _call("b200seg_pad_channels", _ptr(x), xp, c, _ptr(out), c_pad, n * d * h * w, _stream())
+    return out
+
+
+def _padded_weight(weight, cin_p, cout_p):
+    w = weight.detach()
+    cout, cin = w.shape[0], w.shape[1]
+    if (cout, cin) == (cout_p, cin_p):
+        return w
+    wp = w.new_zeros((cout_p, cin_p) + tuple(w.shape[2:]))
+    wp[:cout, :cin] = w
+    return wp
+
+
+def _pack_fresh(w, dgrad):
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    packed = torch.empty(k ** 3 * cout * cin, dtype=torch.bfloat16, device=w.device)
+    _call("b200seg_pack_conv_weight", _ptr(w), _ptr(packed), cout, cin, k, 0, cin, int(dgrad), _stream())
+    return packed
+
+
+def _unpad_stats(stats_p, c, c_pad, spare):
+    if c == c_pad:
+        return stats_p
+    parts = [stats_p[:c], stats_p[c_pad:c_pad + c]]
+    if spare:
+        parts.append(stats_p[2 * c_pad:2 * c_pad + spare])
+    return torch.cat(parts)
+
+
 def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=None):
     x, xp = _as_rows(x)
     cout, cin = weight.shape[0], weight.shape[1]
     assert x.shape[4] == cin, "input has %d channels, weight expects %d" % (x.shape[4], cin)
     g = _geom(x.shape, cin, cout, k, stride, pad, dil)
+    b = bias.detach().float() if bias is not None else None
+    if _use_padded(g):
+        gp = _padded_geom(g)
+        x_p = _pad_channels(x, gp.cin)
+        if gp.cout == cout:     # only K is padded (stems): the pack kernel zero-fills the extra input channels itself
+            wp = torch.empty(k ** 3 * cout * gp.cin, dtype=torch.bfloat16, device=x.device)
+            _call("b200seg_pack_conv_weight", _ptr(weight.detach()), _ptr(wp), cout, cin, k, 0, gp.cin, 0, _stream())
+        else:
+            wp = _pack_fresh(_padded_weight(weight, gp.cin, gp.cout), False)
+        b_p = b
+        if b is not None and gp.cout != cout:
+            b_p = b.new_zeros(gp.cout)
+            b_p[:cout] = b
+        y_p = torch.empty((g.n, g.od, g.oh, g.ow, gp.cout), dtype=torch.bfloat16, device=x.device)
+        stats_p = _zeros_f32(2 * gp.cout + 1, x.device) if want_stats else None
+        _call("b200seg_conv3d_fprop", ctypes.byref(gp), _ptr(x_p), gp.cin, _ptr(wp), _ptr(b_p), _ptr(y_p), gp.cout,
+              _ptr(stats_p), None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_padded_tc")
+        y = y_p[..., :cout] if gp.cout != cout else y_p
+        return y, (_unpad_stats(stats_p, cout, gp.cout, 1) if want_stats else None), g
     if y_out is not None and _pitched(y_out) and tuple(y_out.shape) == (g.n, g.od, g.oh, g.ow, cout) \
             and y_out.data_ptr() % 16 == 0 and y_out.stride(3) % 8 == 0:
         y = y_out
@@ -212,19 +287,6 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
         y = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
     # flat {sum[C], sumsq[C], (count)}: the spare float lets the cross-GPU exchange carry the element count
     stats = _zeros_f32(2 * cout + 1, x.device) if want_stats else None
-    b = bias.detach().float() if bias is not None else None
-    # Stem layers (C_in = 1..8, e.g. unet3d.py:80): zero-pad the K dimension to 16 channels so the convolution runs on the
-    # tensor cores (the geometry handed back for the backward pass stays the original one)
-    gp = _geom(x.shape, 16, cout, k, stride, pad, dil) if (cin < 16 and stride == 1) else None
-    if gp is not None and conv_uses_tensor_cores(gp) and g.n * g.od * g.oh * g.ow >= (1 << 16):
-        rows = g.n * g.d * g.h * g.w
-        x16 = torch.empty((g.n, g.d, g.h, g.w, 16), dtype=torch.bfloat16, device=x.device)
-        _call("b200seg_pad_channels", _ptr(x), xp, cin, _ptr(x16), 16, rows, _stream())
-        wp = torch.empty(k ** 3 * cout * 16, dtype=torch.bfloat16, device=x.device)
-        _call("b200seg_pack_conv_weight", _ptr(weight.detach()), _ptr(wp), cout, cin, k, 0, 16, 0, _stream())
-        _call("b200seg_conv3d_fprop", ctypes.byref(gp), _ptr(x16), 16, _ptr(wp), _ptr(b), _ptr(y), y.stride(3),
-              _ptr(stats), None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_stem_tc")
-        return y, stats, g
     wp = pack_conv_weight(weight)
     _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), y.stride(3), _ptr(stats),
           None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_tc" if conv_uses_tensor_cores(g) else "conv_fprop_direct")
@@ -234,6 +296,16 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
 def conv3d_dgrad_raw(g, dy, weight, colsum=False):
     """dx of the conv described by g.  colsum=True also returns {sum[C_in], sumsq[C_in]} of dx over the voxels (fp32,
     from the same epilogue): the first row is the bias gradient of whatever produced the conv's input."""
+    if _use_padded(g):
+        gp = _padded_geom(g)
+        dy_p = _pad_channels(dy, gp.cout)
+        wd = _pack_fresh(_padded_weight(weight, gp.cin, gp.cout), True)
+        dx_p = torch.empty((g.n, g.d, g.h, g.w, gp.cin), dtype=torch.bfloat16, device=dy.device)
+        stats_p = _zeros_f32(2 * gp.cin, dy.device) if colsum else None
+        _call("b200seg_conv3d_dgrad", ctypes.byref(gp), _ptr(dy_p), gp.cout, _ptr(wd), _ptr(dx_p), gp.cin, _ptr(stats_p),
+              None, 0, _stream(), work=_conv_flops(g), tag="conv_dgrad_padded")
+        dx = dx_p[..., :g.cin] if gp.cin != g.cin else dx_p
+        return (dx, _unpad_stats(stats_p, g.cin, gp.cin, 0)) if colsum else dx
     dy, dyp = _as_rows(dy)
     wd = pack_conv_weight(weight, dgrad=True)
     dx = torch.empty((g.n, g.d, g.h, g.w, g.cin), dtype=torch.bfloat16, device=dy.device)
@@ -290,6 +362,19 @@ def _grad_target(param):
 
 def conv3d_wgrad_raw(g, x, dy, weight_shape, weight=None):
     """Returns the weight gradient, or None when it was accumulated straight into weight.grad (FusedAdam arena)."""
+    from ._lib import load
+    if _use_padded(g) and not (g.cin == 1 and g.k == 3 and g.stride == 1 and load().b200seg_conv3d_workspace_bytes(ctypes.byref(g))):
+        # (the C_in = 1 3x3x3 stem keeps its taps-as-channels weight gradient, conv.cu: stem_plan)
+        gp = _padded_geom(g)
+        x_p, dy_p = _pad_channels(x, gp.cin), _pad_channels(dy, gp.cout)
+        dwp_p = torch.zeros(g.k ** 3 * gp.cin * gp.cout, dtype=torch.float32, device=x_p.device)
+        ws_bytes = load().b200seg_conv3d_workspace_bytes(ctypes.byref(gp))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x_p.device) if ws_bytes else None
+        _call("b200seg_conv3d_wgrad", ctypes.byref(gp), _ptr(x_p), gp.cin, _ptr(dy_p), gp.cout, _ptr(dwp_p), _ptr(ws), ws_bytes,
+              _stream(), work=_conv_flops(g), tag="conv_wgrad_padded")
+        gw_p = torch.empty((gp.cout, gp.cin) + tuple(weight_shape[2:]), dtype=torch.float32, device=x_p.device)
+        _call("b200seg_unpack_conv_wgrad", _ptr(dwp_p), _ptr(gw_p), gp.cout, gp.cin, g.k, 0, gp.cin, 0, _stream())
+        return gw_p[:g.cout, :g.cin].contiguous()
     x, xp = _as_rows(x)
     dy, dyp = _as_rows(dy)
     k3 = g.k ** 3
@@ -297,7 +382,6 @@ def conv3d_wgrad_raw(g, x, dy, weight_shape, weight=None):
     direct = dwp is not None
     if not direct:
         dwp = torch.zeros(k3 * g.cin * g.cout, dtype=torch.float32, device=x.device)
-    from ._lib import load
     ws_bytes = load().b200seg_conv3d_workspace_bytes(ctypes.byref(g))      # split-K partial tiles (0: atomics path)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     _call("b200seg_conv3d_wgrad", ctypes.byref(g), _ptr(x), xp, _ptr(dy), dyp, _ptr(dwp), _ptr(ws), ws_bytes, _stream(),

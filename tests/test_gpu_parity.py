@@ -80,6 +80,16 @@ CONV_CASES = [
     (128, 256, 2, 2, 0, 1, (8, 16, 16), 1),   # V-Net deep down conv
     (16, 16, 3, 1, 1, 1, (16, 32, 16), 1),    # HighRes3DNet: C_in = 16 weight gradient (zero-filled half chunk)
     (48, 32, 3, 1, 1, 1, (8, 16, 16), 1),     # ragged last C_in chunk in the weight gradient
+    (64, 64, 3, 1, 4, 4, (12, 24, 16), 1),    # HighRes3DNet dilation 4: narrow K chunk so that the 12-plane ring fits
+    (32, 64, 3, 1, 4, 4, (10, 16, 24), 2),
+    (64, 64, 5, 1, 2, 1, (8, 8, 8), 1),       # V-Net 5x5x5 at 8^3: short planes (masked tile rows)
+    (128, 128, 5, 1, 2, 1, (4, 4, 4), 2),
+    # channel counts that are not multiples of 16, zero-padded onto the tensor cores (>= 65536 voxels)
+    (28, 12, 3, 1, 1, 1, (40, 40, 44), 1),    # DenseVoxelNet growth conv
+    (32, 2, 5, 1, 2, 1, (40, 40, 44), 1),     # V-Net output conv 5x5x5 to 2 classes
+    (1, 16, 5, 1, 2, 1, (40, 40, 44), 1),     # V-Net stem 5x5x5
+    (64, 2, 1, 1, 0, 1, (40, 40, 44), 1),     # HighRes3DNet classifier
+    (24, 40, 3, 2, 1, 1, (64, 64, 64), 1),    # stride 2 with padded channels
 ]
 
 
@@ -111,9 +121,10 @@ def test_conv3d_fprop_dgrad_wgrad(F, case):
     elif stride == 2 and cin % 16 == 0 and cout % 16 == 0 and min(size) >= 8:
         # k3s2: 1 forward + 8 data-gradient + 8 weight-gradient class launches; k2s2: one launch per pass
         assert F.umma_launch_count() - n0 == (17 if k == 3 else 3), "strided tensor-core path was not taken"
-    elif cin < 16 and stride == 1 and k == 3 and cout % 16 == 0 and n * size[0] * size[1] * size[2] >= 1 << 16:
-        # large stem: fprop runs K-padded on the tensor cores; with C_in = 1 the weight gradient does too (taps as channels)
-        assert F.umma_launch_count() - n0 == (2 if cin == 1 else 1), "large stem: tensor-core path was not taken"
+    elif y_ref.numel() // cout >= 1 << 16 or 2.0 * (y_ref.numel() // cout) * cout * cin * k ** 3 >= 2e8:
+        # large volume with odd channel counts: zero-padded channels, every pass on the tensor cores (the C_in = 1 3x3x3
+        # stem's weight gradient through its taps-as-channels copy)
+        assert F.umma_launch_count() - n0 >= 3, "padded tensor-core path was not taken"
     else:
         assert F.umma_launch_count() == n0
     close(ncdhw(xd.grad), xr.grad, 8e-3, "dgrad")
