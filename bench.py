@@ -1,12 +1,16 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: 3D U-Net(1,2,32) training step on synthetic 128^3 single-channel patches.
+"""Benchmark of the hot path (BASELINE.json configs[1]): 3D U-Net(1,2,32) training on synthetic 128^3 single-channel patches.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|predict] [--sustain S]
 
-One "step" = host/HBM batch 2x1x128^3 per GPU -> forward -> Dice+CE -> backward -> (gradient all-reduce) -> Adam.
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+train   : one "step" = batch 2x1x128^3 per GPU -> forward -> Dice+CE -> backward -> (gradient all-reduce) -> Adam.
+predict : one "step" = sliding-window inference of one synthetic 512x512x256 volume (BASELINE configs[4]: 128^3 patches,
+          50 % overlap = 147 patches, batch 16, eval-mode U-Net -> argmax -> crop-mode stitch).
+Prints ONE JSON line (rank 0).  DESIGN.md section 6 says how every field is obtained.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -22,14 +26,15 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 PATCH = 128
 FEATURES = 32
 BATCH = 2
-# DRAM bytes of the fprop + dgrad conv launches of one step (ncu, profiles/r01_step4_final_launch_list.md) and their
-# algorithmic in + out + weight bytes (3.68 GB per forward, about the same for the data gradients)
-NCU_CONV_TRAFFIC_BYTES_PER_STEP = 5.69e9
-CONV_ALGORITHMIC_BYTES_PER_STEP = 7.3e9
 WORKLOAD = ("UNet3D(1,2,32) train step, batch 2x1x128^3 per GPU, Dice+CE, BatchNorm (SyncBatchNorm across ranks when "
             "N > 1), Adam (BASELINE.json configs[1])")
-TRAIN_GFLOP_PER_PATCH = 2850.4  # fwd 951.3 + wgrad 951.3 + dgrad (951.3 - 3.6 first layer): BASELINE.md section 3
-
+PREDICT_WORKLOAD = ("predict.py sliding window: eval UNet3D(1,2,32) on a synthetic 1x512x512x256 volume, 128^3 patches, "
+                    "overlap 64 (147 patches), batch 16, argmax + crop-mode stitch (BASELINE.json configs[4])")
+TRAIN_GFLOP_PER_PATCH = 2850.4   # fwd 951.3 + wgrad 951.3 + dgrad (951.3 - 3.6 first layer): SURVEY.md appendix A
+FWD_GFLOP_PER_PATCH = 951.3
+VOLUME = (512, 512, 256)
+OVERLAP = (64, 64, 64)
+TRAFFIC_PROFILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
 
 _RESULT_FD = None
 
@@ -60,11 +65,51 @@ def load_peaks():
         d = json.load(open(path))
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
                 "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    # fallback stated by /opt/skills/guides/B200_PROFILING.md
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def kernel_stamp():
+    """Hash of the CUDA sources: a committed ncu profile is only quoted while it describes THIS build."""
+    h = hashlib.sha256()
+    pkg = os.path.join(ROOT, "general-medical-image-segmentation-cnn-framework_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(pkg, "*.cu")) + glob.glob(os.path.join(pkg, "*.cuh")) + glob.glob(os.path.join(pkg, "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_traffic(key):
+    """DRAM bytes per step of a kernel family from the committed ncu launch list (profiles/r02_traffic.json, written by
+    probes/make_traffic_json.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`).  None (and a loud note
+    on stderr) when the profile is missing or was taken from different kernel sources."""
+    if not os.path.exists(TRAFFIC_PROFILE):
+        print("[bench] no committed traffic profile (%s): roofline.traffic = null" % TRAFFIC_PROFILE, file=sys.stderr)
+        return None, "no profile"
+    d = json.load(open(TRAFFIC_PROFILE))
+    if d.get("kernel_stamp") != kernel_stamp():
+        print("[bench] STALE traffic profile: %s was captured for kernel sources %s, this build is %s -- re-run "
+              "probes/make_traffic_json.py; roofline.traffic = null" % (TRAFFIC_PROFILE, d.get("kernel_stamp"), kernel_stamp()),
+              file=sys.stderr)
+        return None, "stale profile (kernel sources changed since the ncu capture)"
+    fam = d.get("families", {}).get(key)
+    return (fam["dram_bytes_per_step"] if fam else None), d.get("source", TRAFFIC_PROFILE)
+
+
+def unet_conv_algorithmic_bytes():
+    """bf16 input + output + weight bytes, each touched once, of the 18 fprop and 17 dgrad 3x3x3 launches of one
+    UNet3D(1,2,32) step at batch 2x1x128^3 (the first layer has no data gradient)."""
+    f, s = FEATURES, PATCH
+    layers = [(1, f, s), (f, f, s), (f, 2 * f, s // 2), (2 * f, 2 * f, s // 2), (2 * f, 4 * f, s // 4), (4 * f, 4 * f, s // 4),
+              (4 * f, 8 * f, s // 8), (8 * f, 8 * f, s // 8), (8 * f, 16 * f, s // 16), (16 * f, 16 * f, s // 16),
+              (16 * f, 8 * f, s // 8), (8 * f, 8 * f, s // 8), (8 * f, 4 * f, s // 4), (4 * f, 4 * f, s // 4),
+              (4 * f, 2 * f, s // 2), (2 * f, 2 * f, s // 2), (2 * f, f, s), (f, f, s)]
+    fwd = sum((BATCH * e ** 3 * (ci + co) + 27 * ci * co) * 2 for ci, co, e in layers)
+    return fwd + fwd - (BATCH * s ** 3 * (1 + f) + 27 * f) * 2
+
+
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """nvidia-smi clock / throttle-reason samples during a timed region."""
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
@@ -80,6 +125,7 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -108,19 +154,41 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def oracle_step_factory(size, batch=1):
-    """The reference's CPU implementation of the path (oracle port: same torch.nn arithmetic, fp32, all host cores)."""
+# ------------------------------------------------------------------------------------------------ the reference on the CPU
+def _reference_available():
+    from oracle import build_ref
+    return build_ref.import_ref()
+
+
+def cpu_step_factory(size, batch=1):
+    """One training step of the reference's CPU path: its own UNet3D / cross_entropy_3D / DiceLossss modules (oracle/_ref,
+    vendored unmodified by oracle/build_ref.py) when they travelled to this box, else the oracle port of the same
+    arithmetic; fp32, torch CPU, all host threads.  Returns (step, kind)."""
     import torch
-    from oracle import losses as olosses
-    from oracle import unet3d as ounet
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
+    x = torch.randn(batch, 1, size, size, size)
+    lab = (torch.rand(batch, size, size, size) > 0.9).long()
+    if _reference_available():
+        from models.three_d.unet3d import UNet3D as RefUNet3D
+        from utils.loss_function import DiceLossss, cross_entropy_3D
+        net = RefUNet3D(in_channels=1, out_channels=2, init_features=FEATURES).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        dice = DiceLossss(2)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            out = net(x)
+            loss = cross_entropy_3D(out, lab) + dice(out, lab, softmax=True)
+            loss.backward()
+            opt.step()
+            return float(loss)
+        return step, "reference"
+    from oracle import losses as olosses
+    from oracle import unet3d as ounet
     sd = ounet.init_state_dict(1, 2, FEATURES, seed=0)
     params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
     opt = torch.optim.Adam(list(params.values()), lr=1e-3)
-    x = torch.randn(batch, 1, size, size, size)
-    lab = (torch.rand(batch, size, size, size) > 0.9).long()
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -132,50 +200,152 @@ def oracle_step_factory(size, batch=1):
         for k, v in stats.items():
             sd[k] = v
         return float(loss)
-    return step
+    return step, "port"
 
 
-def time_cpu(size, iters, warmup=1):
-    step = oracle_step_factory(size)
-    for _ in range(warmup):
-        step()
+def time_cpu_sample(size=64, iters=3):
+    """cpu_baseline of the GPU arm: median of `iters` steps on one 1x1x64^3 patch (1/8 of a 128^3 patch), ~10 s."""
+    step, kind = cpu_step_factory(size)
+    step()
     ts = []
     for _ in range(iters):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
     ts.sort()
-    return ts[len(ts) // 2]
+    return ts[len(ts) // 2], kind
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the step on the box's host cores (rank 0 only).
+
+    Each step is ONE full 1x1x128^3 patch of the named configuration (half the per-GPU batch: the work per patch is what
+    the metric counts) through the reference's own modules.  If the first step shows that K + W such steps would not end
+    within ~4 minutes on this host, the sample per step drops to one 64^3 patch (1/8 of a patch) and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    size = 64  # bounded sample: one 1x1x64^3 patch per step = 1/8 of a 128^3 patch
-    step = oracle_step_factory(size)
-    for _ in range(max(args.warmup, 1)):
+    budget_s = 240.0
+    size = PATCH
+    step, kind = cpu_step_factory(size)
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    done_warm = 1
+    if first * (args.steps + max(args.warmup, 1)) > budget_s:
+        size = 64
+        step, kind = cpu_step_factory(size)
+        done_warm = 0
+    for _ in range(max(args.warmup - done_warm, 0 if done_warm else 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    value = (size / PATCH) ** 3 / dt
+    patches_per_step = (size / PATCH) ** 3
+    value = patches_per_step / dt
     cores = os.cpu_count() or 1
+    what = ("the reference's own UNet3D + cross_entropy_3D + DiceLossss modules (oracle/_ref, unmodified)" if kind == "reference"
+            else "oracle port of the reference modules")
+    sample = ("%s, fp32 torch CPU, %d threads; each step = fwd + Dice/CE + bwd + Adam on one 1x1x%d^3 patch%s"
+              % (what, cores, size, "" if size == PATCH else " = 1/8 of a 128^3 patch (a full patch took %.0f s on this host)" % first))
     line = {"impl": "reference", "metric": "train_patches_per_s_128cubed", "value": value, "unit": "patches/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH * args.gpus, "parallelism": "dp%d" % args.gpus,
-                       "l2": "n/a (CPU)"},
-            "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
-                             "sample": "oracle port of the reference modules, fp32 torch CPU, %d threads; each step = "
-                                       "fwd+bwd+Adam on one 1x1x64^3 patch, counted as 1/8 of a 128^3 patch" % cores},
+                       "l2": "n/a (CPU)", "patches_per_step": patches_per_step, "same_patch_size": size == PATCH},
+            "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-# ------------------------------------------------------------------------------------------------ b200 arm
+# ------------------------------------------------------------------------------------------------ helpers of the GPU arm
+def library_bar(dev, steps=6):
+    """The UNMODIFIED reference UNet3D (oracle/_ref) under stock PyTorch/cuDNN on this GPU, bf16 autocast + channels_last_3d
+    + cudnn.benchmark (its strongest library configuration), same batch, Dice+CE, torch.optim.Adam: the library yardstick
+    SURVEY section 0 names as the real bar.  Not the product; reported beside it."""
+    import torch
+    if not _reference_available():
+        return {"unavailable": "oracle/_ref not on this box"}
+    from models.three_d.unet3d import UNet3D as RefUNet3D
+    from utils.loss_function import DiceLossss, cross_entropy_3D
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        torch.manual_seed(0)
+        net = RefUNet3D(in_channels=1, out_channels=2, init_features=FEATURES).to(dev).to(memory_format=torch.channels_last_3d).train()
+        x = torch.randn(BATCH, 1, PATCH, PATCH, PATCH, device=dev).contiguous(memory_format=torch.channels_last_3d)
+        lab = (torch.rand(BATCH, PATCH, PATCH, PATCH, device=dev) > 0.9).long()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        dice = DiceLossss(2)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = net(x)
+            out = out.float()
+            loss = cross_entropy_3D(out, lab) + dice(out, lab, softmax=True)
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del net, opt
+        torch.cuda.empty_cache()
+        return {"value": BATCH / ms * 1e3, "unit": "patches/s", "ms_per_step": ms,
+                "what": "unmodified reference UNet3D (oracle/_ref) on this GPU: torch %s / cuDNN %s, bf16 autocast, "
+                        "channels_last_3d, cudnn.benchmark, eager; 1 GPU" % (torch.__version__, torch.backends.cudnn.version())}
+    except Exception as e:   # the yardstick must never take the benchmark down
+        return {"unavailable": repr(e)[:200]}
+    finally:
+        torch.backends.cudnn.benchmark = old
+
+
+def parity_block(net, dev, rank, world):
+    """N > 1: (1) every rank must hold bit-identical parameters after the timed steps (max cross-rank difference of the
+    flattened parameters, must be 0); (2) SynchronizedBatchNorm3d statistics of a fresh layer on per-rank shards against
+    single-process batch norm over the gathered batch (batchnorm.py:48-125)."""
+    import torch
+    import torch.distributed as dist
+    from b200seg.models.sync_batchnorm.batchnorm import SynchronizedBatchNorm3d
+    flat = torch.cat([p.detach().float().flatten() for p in net.parameters()])
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    param_diff = float((hi - lo).abs().max())
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    c = 32
+    x = (torch.randn(2, c, 8, 16, 16, device=dev, generator=g) * (1 + 0.25 * rank) + 0.1 * rank).bfloat16().float()
+    bn = SynchronizedBatchNorm3d(c).to(dev).train()
+    out = bn(x)
+    shards = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(shards, x)
+    full = torch.cat(shards)
+    mean = full.mean((0, 2, 3, 4))
+    var_b = full.var((0, 2, 3, 4), unbiased=False)
+    var_u = full.var((0, 2, 3, 4), unbiased=True)
+    ref_out = (x - mean.view(1, -1, 1, 1, 1)) * var_b.clamp(1e-5).rsqrt().view(1, -1, 1, 1, 1)
+
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+    errs = torch.tensor([rel(out.detach(), ref_out), rel(bn.running_mean, 0.1 * mean), rel(bn.running_var, 0.9 + 0.1 * var_u)],
+                        device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    return {"param_max_cross_rank_diff": param_diff,
+            "syncbn_vs_gathered_batch": {"out_rel_err": errs[0].item(), "running_mean_rel_err": errs[1].item(),
+                                         "running_var_rel_err": errs[2].item(), "tolerance": "out 1e-2 (bf16 output), stats 1e-4"},
+            "ok": bool(param_diff == 0.0 and errs[0].item() < 1e-2 and errs[1].item() < 1e-4 and errs[2].item() < 1e-4)}
+
+
+# ------------------------------------------------------------------------------------------------ b200 arm: training
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -196,11 +366,11 @@ def run_b200(args):
     net = UNet3D(1, 2, FEATURES).to(dev)
     if world > 1:
         parallel.broadcast_parameters(net)
-        convert_model(net)       # nn.BatchNorm3d -> SynchronizedBatchNorm3d (statistics all-reduced over NCCL)
+        convert_model(net)       # nn.BatchNorm3d -> SynchronizedBatchNorm3d (statistics exchanged over NVLink peer memory)
     net.train()
     opt = FusedAdam(net.parameters(), lr=1e-3)
     if world > 1:
-        opt.attach_reducer()     # bucketed gradient all-reduce on a side stream, overlapped with backward
+        opt.attach_reducer()     # bucketed gradient all-reduce on a side stream, overlapped with backward (eager mode)
     crit = DiceCELoss(2)
     vox = PATCH ** 3
     x_host = torch.randn(BATCH, 1, PATCH, PATCH, PATCH).pin_memory()
@@ -231,13 +401,12 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(args.warmup, 3) + 2):   # TrainStep runs 3 eager steps, captures, then replays
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup + 2):   # TrainStep runs 3 eager steps, captures, then replays
         step(x_dev, lab_dev)
     barrier()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local).start() if rank == 0 else None
     F.reset_launches()
     umma0 = F.umma_launch_count()
     ms_total = timed(lambda: step(x_dev, lab_dev), args.steps)
@@ -261,6 +430,19 @@ def run_b200(args):
     ms_e2e = timed(e2e_run(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # sustained leg: the same step back to back for >= args.sustain seconds (power / clock equilibrium), own clock samples
+    ms_step = ms_total / args.steps
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(args.steps, int(args.sustain * 1e3 / ms_step) + 1)
+        sampler2 = ClockSampler(local).start() if rank == 0 else None
+        ms_sus = timed(lambda: step(x_dev, lab_dev), n_sus)
+        clocks2 = sampler2.stop() if rank == 0 else None
+        sustained = {"value": BATCH * world / (ms_sus / n_sus * 1e-3), "unit": "patches/s", "steps": n_sus,
+                     "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus, "clocks": clocks2}
+
+    parity = parity_block(net, dev, rank, world) if world > 1 else None
+
     # per-kernel timing pass (CUDA events around every launch on the launching stream, eager) -> roofline
     eager = TrainStep(net, crit, opt, use_graph=False)
     eager(x_dev, lab_dev)
@@ -271,50 +453,154 @@ def run_b200(args):
 
     if rank == 0:
         peaks = load_peaks()
-        ms_step = ms_total / args.steps
         patches = BATCH * world
         value = patches / (ms_step * 1e-3)
-        tc = [v for k, v in prof.items() if k in ("conv_fprop_tc", "conv_fprop_stem_tc", "conv_dgrad", "conv_wgrad")]
-        main = prof.get("conv_fprop_tc", {"ms": 0.0, "work": 0.0, "launches": 0})
-        dg = prof.get("conv_dgrad", {"ms": 0.0, "work": 0.0, "launches": 0})
+        zero = {"ms": 0.0, "work": 0.0, "launches": 0}
+        main, dg = prof.get("conv_fprop_tc", zero), prof.get("conv_dgrad", zero)
         tc_ms = main["ms"] + dg["ms"]
         tc_work = main["work"] + dg["work"]
         achieved = tc_work / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        all_conv_ms = sum(v["ms"] for v in tc) + prof.get("conv_fprop_direct", {"ms": 0})["ms"]
-        all_conv_work = sum(v["work"] for v in prof.values())
-        cpu_t = time_cpu(64, iters=5, warmup=1)
+        conv_tags = [k for k in prof if k.startswith("conv_")]
+        all_conv_ms = sum(prof[k]["ms"] for k in conv_tags)
+        all_conv_work = sum(prof[k]["work"] for k in conv_tags)
+        all_conv = all_conv_work / (all_conv_ms * 1e-3) / 1e12 if all_conv_ms else 0.0
+        traffic, traffic_src = load_traffic("conv_fprop_dgrad")
+        cpu_t, cpu_kind = time_cpu_sample(64, iters=3)
         cores = os.cpu_count() or 1
         line = {
             "metric": "train_patches_per_s_128cubed", "value": value, "unit": "patches/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": patches, "parallelism": "dp%d" % world,
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "l2": "no flush needed: each step streams >10 GB of activations, far larger than the 126 MB L2"},
             "voxels_per_s": value * vox,
+            # the same loop run for >= 5 s: the figure a training job sees once power and clocks have settled
+            "value_sustained": sustained["value"] if sustained else None, "sustained": sustained,
             "e2e": {"value": patches / (ms_e2e / args.steps * 1e-3), "unit": "patches/s",
                     "h2d_bytes_per_step": x_host.numel() * 4 + lab_host.numel(), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "tcgen05_launches": umma_launches,
-            # dominant kernel family: the tcgen05 implicit-GEMM convolutions (conv_umma_roll / conv_umma_plane), all 34
-            # forward + data-gradient launches of the step; achieved = their algorithmic FLOPs / their CUDA-event time.
-            # traffic = DRAM read + write bytes of the same launches in the committed ncu launch list
-            # (profiles/r01_step4_final_launch_list.md), per step like `achieved`.
+            # dominant kernel family: the tcgen05 implicit-GEMM convolutions (conv_umma_roll / conv_umma_plane), the 17 fprop +
+            # 17 dgrad launches of the step; achieved = their algorithmic FLOPs / their CUDA-event time in a burst (eager)
+            # pass, so the peak is the BURST cuBLAS figure; frac_of_sustained_peak is given beside it.
             "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_plane_kernel (the fprop + dgrad "
                                                       "launches of the step)",
-                         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " sustained",
-                         "traffic": NCU_CONV_TRAFFIC_BYTES_PER_STEP, "algorithmic_bytes": CONV_ALGORITHMIC_BYTES_PER_STEP,
+                         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst (bf16_tflops)",
+                         "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": unet_conv_algorithmic_bytes(),
                          "launches_per_step": (main["launches"] + dg["launches"]) // 2,
                          "kernel_ms_per_step": tc_ms / 2,
-                         "all_conv_ms_per_step": all_conv_ms / 2,
-                         "all_conv_tflops": all_conv_work / (all_conv_ms * 1e-3) / 1e12 if all_conv_ms else 0.0,
+                         "all_conv_ms_per_step": all_conv_ms / 2, "all_conv_tflops": all_conv,
+                         "all_conv_frac": all_conv / peaks["bf16_tflops"],
                          "per_kernel": {k: {"ms_per_step": v["ms"] / 2, "launches_per_step": v["launches"] // 2,
                                             "tflops": v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else 0.0}
                                         for k, v in prof.items()}},
-            "model_tflops": patches * TRAIN_GFLOP_PER_PATCH / ms_step / 1e3,
-            "cpu_baseline": {"value": (64 / PATCH) ** 3 / cpu_t, "unit": "patches/s", "cores": cores, "kind": "port",
-                             "sample": "oracle port (reference modules' torch CPU arithmetic, fp32, %d threads): median "
-                                       "of 5 fwd+bwd+Adam steps on one 1x1x64^3 patch = 1/8 of a 128^3 patch" % cores},
+            "model_tflops": patches * TRAIN_GFLOP_PER_PATCH / ms_step,     # GFLOP / ms = TFLOP/s, whole step
+            "library_bar": library_bar(dev) if world == 1 else None,
+            "cpu_baseline": {"value": (64 / PATCH) ** 3 / cpu_t, "unit": "patches/s", "cores": cores, "kind": cpu_kind,
+                             "sample": "%s, fp32 torch CPU, %d threads: median of 3 fwd+bwd+Adam steps on one 1x1x64^3 patch "
+                                       "= 1/8 of a 128^3 patch" % ("reference modules (oracle/_ref)" if cpu_kind == "reference"
+                                                                   else "oracle port", cores)},
+            "parity": parity,
+            "clocks": clocks,
+        }
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ b200 arm: sliding-window inference
+def run_predict(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    import b200seg.functional as F
+    from b200seg import parallel
+    from b200seg.inference import GridSampler, sliding_window_predict
+    from b200seg.models.three_d.unet3d import UNet3D
+    rank, local, world = parallel.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.manual_seed(1234)
+    net = UNet3D(1, 2, FEATURES).to(dev).eval()
+    if world > 1:
+        parallel.broadcast_parameters(net)
+    vol_host = torch.randn((1,) + VOLUME).pin_memory()
+    vol_dev = vol_host.to(dev)
+    npatch = len(GridSampler(VOLUME, (PATCH,) * 3, OVERLAP))
+
+    def one(vol):
+        return sliding_window_predict(net, vol, (PATCH,) * 3, OVERLAP, batch_size=16, overlap_mode="crop")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        one(vol_dev)
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    F.reset_launches()
+    umma0 = F.umma_launch_count()
+    ms = timed(lambda: one(vol_dev), args.steps) / args.steps
+    launches, umma_launches = F.launches(), F.umma_launch_count() - umma0
+    out_host = torch.empty((1,) + VOLUME, dtype=torch.uint8).pin_memory()
+
+    def e2e():
+        out_host.copy_(one(vol_host.to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e()
+    ms_e2e = timed(e2e, args.steps) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    F.profile_begin()
+    one(vol_dev)
+    prof = F.profile_end()
+    if rank == 0:
+        peaks = load_peaks()
+        zero = {"ms": 0.0, "work": 0.0, "launches": 0}
+        fp = prof.get("conv_fprop_tc", zero)
+        achieved = fp["work"] / (fp["ms"] * 1e-3) / 1e12 if fp["ms"] else 0.0
+        total_ms = sum(v["ms"] for v in prof.values())
+        traffic, traffic_src = load_traffic("predict_conv_fprop")
+        line = {
+            "metric": "predict_volumes_per_s_512x512x256", "value": 1e3 / ms, "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": PREDICT_WORKLOAD, "patches_per_volume": npatch, "batch": 16, "parallelism": "patches dealt "
+                       "round-robin to %d rank(s), volumes merged by one all-reduce" % world,
+                       "l2": "no flush needed: one volume streams > 100 GB of activations"},
+            "patches_per_s": npatch * 1e3 / ms, "voxels_per_s": VOLUME[0] * VOLUME[1] * VOLUME[2] * 1e3 / ms,
+            "e2e": {"value": 1e3 / ms_e2e, "unit": "volumes/s", "h2d_bytes_per_step": vol_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel()},
+            "gpu_launches": launches, "tcgen05_launches": umma_launches,
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_plane_kernel (the forward conv launches "
+                                                      "of one volume, eval-mode BatchNorm + ReLU in the epilogue)",
+                         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst (bf16_tflops)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel_ms_per_step": fp["ms"], "all_kernels_ms_per_step": total_ms,
+                         "per_kernel": {k: {"ms_per_step": v["ms"], "launches_per_step": v["launches"],
+                                            "tflops": v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] and v["work"] else 0.0}
+                                        for k, v in prof.items()}},
+            "model_tflops": npatch * FWD_GFLOP_PER_PATCH / ms,
+            "cpu_baseline": None,
             "clocks": clocks,
         }
         emit(line)
@@ -328,6 +614,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "predict"])
+    ap.add_argument("--sustain", type=float, default=5.0, help="seconds of the sustained leg (0 = skip)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                                                             "the captured CUDA graph of the step")
     args = ap.parse_args()
@@ -340,9 +628,13 @@ def main():
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus",
-               str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload,
+               "--sustain", str(args.sustain)] + (["--no-graph"] if args.no_graph else [])
         sys.exit(subprocess.call(cmd))
-    run_b200(args)
+    if args.workload == "predict":
+        run_predict(args)
+    else:
+        run_b200(args)
 
 
 if __name__ == "__main__":

@@ -26,6 +26,8 @@ SIGNATURES = {
     "b200seg_pad_channels": "plipilp",
     "b200seg_unpack_conv_wgrad": "ppiiiiiip",
     "b200seg_conv3d_fprop": "gplppplppzp",
+    "b200seg_conv3d_fprop_act_supported": "g",
+    "b200seg_conv3d_fprop_act": "gplp" + "pp" + "if" + "pl" + "p",
     "b200seg_conv3d_dgrad": "gplpplppzp",
     "b200seg_conv3d_wgrad": "gplplppzp",
     "b200seg_pack_convt_weight": "ppiiip",
@@ -34,6 +36,7 @@ SIGNATURES = {
     "b200seg_convt_k2s2_wgrad": "plpl" + "p" + "iiiiii" + "p",
     "b200seg_channel_stats": "pllii" + "pp",
     "b200seg_norm_finalize": "pdii" + "pppp" + "ffi" + "pp",
+    "b200seg_norm_eval_coef": "ppppp" + "fi" + "pp",
     "b200seg_norm_act_fwd": "plp" + "lii" + "if" + "p" + "pl" + "pl" + "p",
     "b200seg_norm_act_bwd_reduce": "plpl" + "p" + "lii" + "if" + "p" + "pl" + "ppp" + "p",
     "b200seg_norm_act_bwd_apply": "plpl" + "pp" + "d" + "lii" + "if" + "p" + "pl" + "pl" + "pl" + "p",

@@ -221,6 +221,33 @@ int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pi
   return conv_direct_fprop(*g, x, x_pitch, w_packed, bias, y, y_pitch, stats, st);
 }
 
+int b200seg_conv3d_fprop_act_supported(const b200seg_conv_geom* g) {
+  if (!g || g->stride != 1 || getenv("B200SEG_DISABLE_FUSED_ACT")) return 0;
+  static const float one = 1.f;
+  UmmaConvArgs a = fprop_args(g, nullptr, g->cin, nullptr, nullptr, nullptr, g->cout, nullptr);
+  a.scale = &one;      // only its presence matters for the support query
+  return conv_umma_supported(a) ? 1 : 0;
+}
+
+int b200seg_conv3d_fprop_act(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
+                             const float* scale, const float* shift, int act, float slope, void* y, int64_t y_pitch,
+                             void* stream) {
+  if (int rc = check_geom(g, "conv3d_fprop_act")) return rc;
+  B200_CHECK_ARG(x && w_packed && y && scale && shift && x_pitch >= g->cin && y_pitch >= g->cout, "conv3d_fprop_act: bad buffers");
+  B200_CHECK_ARG(act == B200SEG_ACT_NONE || act == B200SEG_ACT_RELU || act == B200SEG_ACT_LEAKY,
+                 "conv3d_fprop_act: the fused epilogue takes no activation, ReLU or LeakyReLU");
+  B200_CHECK_ARG(g->stride == 1, "conv3d_fprop_act: stride-1 convolutions only");
+  UmmaConvArgs a = fprop_args(g, x, x_pitch, w_packed, shift, y, y_pitch, nullptr);
+  a.scale = scale;
+  a.act = act;
+  a.slope = slope;
+  if (!conv_umma_supported(a)) {
+    set_error("conv3d_fprop_act: geometry not supported by the fused tensor-core path (query conv3d_fprop_act_supported)");
+    return B200SEG_ERR_INVALID;
+  }
+  return conv_umma_run(a, static_cast<cudaStream_t>(stream));
+}
+
 int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_pitch, const void* w_packed_dgrad,
                          void* dx, int64_t dx_pitch, float* stats, void* workspace, size_t workspace_bytes,
                          void* stream) {

@@ -48,6 +48,12 @@ struct UmmaConvArgs {
   //       of parity bits g = (d<<2 | h<<1 | w) through its own strided tensor map; d, h, w are the output extents.
   //   out_sub = 1 (data gradient, one launch per class): `out` is the sub-lattice of parity bits `cls` of the fine grid
   //       [n, fd, fh, fw, cout]; od, oh, ow are that sub-lattice's extents and class `cls` selects the row of tapw.
+  // Fused epilogue (inference: eval-mode BatchNorm folded into the convolution, unet3d.py:80-101 in eval()):
+  //   out = act(scale[c] * conv + bias[c]) with act in {none, ReLU, LeakyReLU(slope)}; `bias` then carries the folded
+  //   shift (beta - mean*scale + scale*conv_bias).  scale == nullptr: plain conv + bias.  Not combined with `stats`.
+  const float* scale;
+  int act;
+  float slope;
   int tapmode, in_sub, out_sub, cls, wtaps;
   int fd, fh, fw;
   unsigned char tapw[8][8];

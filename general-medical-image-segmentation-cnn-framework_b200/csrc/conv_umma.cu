@@ -589,6 +589,7 @@ static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
 
 bool conv_umma_supported(const UmmaConvArgs& a) {
   if (conv_umma_roll_supported(a) || conv_umma_plane_supported(a)) return true;
+  if (a.scale) return conv_umma_plane_relaxed_supported(a);   // the flat kernel has no fused scale / activation epilogue
   UmmaConvParams p;
   size_t smem;
   return plan(a, p, smem) || conv_umma_plane_relaxed_supported(a);
@@ -599,7 +600,7 @@ int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
   if (conv_umma_plane_supported(a)) return conv_umma_plane_run(a, st);   // persistent kernel (conv_umma_p.cu)
   UmmaConvParams p;
   size_t smem;
-  if (!plan(a, p, smem)) {
+  if (a.scale || !plan(a, p, smem)) {
     // small planes with a halo too large for the flat kernel's whole-box slot (5x5x5 at 8^3, vnet3d.py:25)
     if (conv_umma_plane_relaxed_supported(a)) return conv_umma_plane_run(a, st);
     set_error("conv_umma_run: unsupported geometry");

@@ -51,6 +51,10 @@ struct PlaneParams {
   int cls;
   long long osn, osd, osh, osw;
   unsigned char tapw[8][8];
+  // fused epilogue out = act(scale * conv + bias) (UmmaConvArgs::scale); scale == nullptr: conv + bias
+  const float* scale;
+  int act;
+  float slope;
 };
 
 struct TensorMaps8P {
@@ -81,15 +85,24 @@ __device__ __forceinline__ TileCoord decode_tile(const PlaneParams& p, long long
 // One 32- or 16-column slab of one accumulator: TMEM -> +bias -> statistics -> bf16 -> global.
 template <int CW>
 __device__ __forceinline__ void epilogue_slab(uint32_t taddr, const float* s_bias_col, bool valid, __nv_bfloat16* optr,
-                                              float (&s1)[CW], float (&s2)[CW], bool want_stats, bool wide) {
+                                              float (&s1)[CW], float (&s2)[CW], bool want_stats, bool wide,
+                                              const float* scale_col = nullptr, int act = 0, float slope = 0.f) {
   uint32_t raw[CW];
   if constexpr (CW == 32) tmem_ld_32x32(taddr, raw);
   else tmem_ld_32x16(taddr, raw);
   tmem_ld_wait();
   if (valid) {
     float v[CW];
+    if (scale_col != nullptr) {       // inference: folded BatchNorm scale / shift + activation
 #pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(raw[j]) + s_bias_col[j];
+      for (int j = 0; j < CW; ++j) {
+        const float z = fmaf(__uint_as_float(raw[j]), __ldg(scale_col + j), s_bias_col[j]);
+        v[j] = act == B200SEG_ACT_NONE ? z : (z > 0.f ? z : (act == B200SEG_ACT_RELU ? 0.f : slope * z));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(raw[j]) + s_bias_col[j];
+    }
     if (want_stats) {
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
@@ -398,7 +411,8 @@ __global__ void __launch_bounds__(kThreadsP, 1)
               const long long vox = ((static_cast<long long>(tc.nn) * p.od + od_) * p.oh + oh_) * p.ow + ow_;
               optr = p.out + vox * p.out_pitch + col0;
             }
-            epilogue_slab<CW>(t_lane + acc * p.NT + c0, s_bias + col0, valid, optr, s1, s2, want_stats, p.wide != 0);
+            epilogue_slab<CW>(t_lane + acc * p.NT + c0, s_bias + col0, valid, optr, s1, s2, want_stats, p.wide != 0,
+                              p.scale ? p.scale + col0 : nullptr, p.act, p.slope);
           }
           if (want_stats) {
             warp_colsum<CW>(s1, lane);
@@ -590,6 +604,13 @@ int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st) {
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.bias = a.bias;
   p.stats = a.stats;
+  p.scale = a.scale;
+  p.act = a.act;
+  p.slope = a.slope;
+  if (a.scale && (a.scatter_cout || a.stats)) {
+    set_error("conv_umma_plane_run: the fused scale/activation epilogue excludes the pixel-shuffle and statistics epilogues");
+    return B200SEG_ERR_INVALID;
+  }
   // pixel-shuffle epilogue: column chunk c0 lands at channel c0 % scatter_cout of another voxel -> scatter_cout % 16 too
   p.wide = (a.out_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0 &&
             (!a.scatter_cout || a.scatter_cout % 16 == 0) && !getenv("B200SEG_NO_WIDE_STORES")) ? 1 : 0;

@@ -44,6 +44,9 @@ constexpr int kRollEpiWarps = 8;
 
 struct RollParams {
   int n, d, od, oh, ow, cout, pad;   // cout = channels of the whole output tensor
+  const float* scale;                // AFF kernels: out = act(scale * conv + bias), see UmmaConvArgs::scale
+  int act;
+  float slope;
   int wide;                          // output rows allow 256-bit stores (pitch % 16 == 0, base 32-byte aligned)
   int halves;                        // 1, or 2: C_out = 64 handled as two independent 32-channel halves (CTA parity)
   long long out_pitch;
@@ -78,7 +81,7 @@ __device__ __forceinline__ RollItem roll_decode(const RollParams& p, long long i
 
 // KS = K steps of 16 channels (C_in / 16), CO = C_out per CTA, HV = halves of the output tensor (compile-time: the
 // single-half kernel must not pay for the generality -- a run-time `halves` cost the 128^3 layers 20 %)
-template <int KS, int CO, int HV>
+template <int KS, int CO, int HV, bool AFF>
 __global__ void __launch_bounds__(kRollThreads, 1)
     conv_umma_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const RollParams p) {
@@ -217,10 +220,12 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     const int m = q4 * 32 + lane;
     const bool want_stats = p.stats != nullptr;
     float s1[CH], s2[CH], bias_r[CH];
+    float scale_r[AFF ? CH : 1];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       s1[j] = s2[j] = 0.f;
       bias_r[j] = s_bias[half * CH + j];
+      if constexpr (AFF) scale_r[j] = p.scale[co_base + half * CH + j];
     }
     const uint32_t t_lane = tbase + (static_cast<uint32_t>(q4 * 32) << 16) + half * CH;
     int acc = 0;                              // ring slot of the plane about to be waited for
@@ -251,7 +256,13 @@ __global__ void __launch_bounds__(kRollThreads, 1)
             float v[CH];
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
-              v[j] = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + (__uint_as_float(r2[j]) + bias_r[j]);
+              if constexpr (AFF) {
+                const float acc3 = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+                const float z = fmaf(acc3, scale_r[j], bias_r[j]);
+                v[j] = p.act == B200SEG_ACT_NONE ? z : (z > 0.f ? z : (p.act == B200SEG_ACT_RELU ? 0.f : p.slope * z));
+              } else {
+                v[j] = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + (__uint_as_float(r2[j]) + bias_r[j]);
+              }
               if (want_stats) {
                 s1[j] += v[j];
                 s2[j] = fmaf(v[j], v[j], s2[j]);
@@ -369,21 +380,27 @@ bool conv_umma_roll_supported(const UmmaConvArgs& a) {
   return plan_roll(a, p, smem);
 }
 
-template <int KS, int CO, int HV>
-static int launch_roll(const CUtensorMap& tmA, const CUtensorMap& tmB, const RollParams& p, size_t smem, int ctas,
+template <int KS, int CO, int HV, bool AFF>
+static int launch_roll_(const CUtensorMap& tmA, const CUtensorMap& tmB, const RollParams& p, size_t smem, int ctas,
                        cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_roll_kernel<KS, CO, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+    if (cudaFuncSetAttribute(conv_umma_roll_kernel<KS, CO, HV, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
       set_error("conv_umma_roll: cannot raise the dynamic shared memory limit");
       return B200SEG_ERR_CUDA;
     }
     attr_set = true;
   }
-  conv_umma_roll_kernel<KS, CO, HV><<<ctas, kRollThreads, smem, st>>>(tmA, tmB, p);
+  conv_umma_roll_kernel<KS, CO, HV, AFF><<<ctas, kRollThreads, smem, st>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv_umma_roll");
   return 0;
+}
+template <int KS, int CO, int HV>
+static int launch_roll(const CUtensorMap& tmA, const CUtensorMap& tmB, const RollParams& p, size_t smem, int ctas,
+                       cudaStream_t st) {
+  return p.scale ? launch_roll_<KS, CO, HV, true>(tmA, tmB, p, smem, ctas, st)
+                 : launch_roll_<KS, CO, HV, false>(tmA, tmB, p, smem, ctas, st);
 }
 
 int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
@@ -396,6 +413,9 @@ int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.bias = a.bias;
   p.stats = a.stats;
+  p.scale = a.scale;
+  p.act = a.act;
+  p.slope = a.slope;
   p.wide = (a.out_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0 && !getenv("B200SEG_NO_WIDE_STORES")) ? 1 : 0;
   if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.wpack)) & 15) {
     set_error("conv_umma_roll_run: buffers must be 16-byte aligned");

@@ -247,6 +247,25 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, double cou
   o[3 * C + c] = static_cast<float>(be - mean * ga * inv_std);
 }
 
+// Inference-mode BatchNorm constants from the running statistics (F.batch_norm(training=False)): rows {mean, inv_std,
+// scale = gamma * inv_std, shift = beta - mean * scale [+ scale * conv_bias]} -- the optional conv bias is folded into the
+// shift so that the convolution's epilogue can apply scale / shift / activation to the raw accumulator.
+__global__ void norm_eval_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      const float* __restrict__ conv_bias, float eps, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = running_mean[c];
+  const float inv_std = 1.f / sqrtf(running_var[c] + eps);
+  const float scale = (gamma ? gamma[c] : 1.f) * inv_std;
+  float shift = (beta ? beta[c] : 0.f) - mean * scale;
+  if (conv_bias) shift = fmaf(scale, conv_bias[c], shift);
+  out[0 * C + c] = mean;
+  out[1 * C + c] = inv_std;
+  out[2 * C + c] = scale;
+  out[3 * C + c] = shift;
+}
+
 template <int V, int ACT>
 __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, int64_t y_pitch,
                                     const float* __restrict__ coef, int64_t rows_per_group, int groups, int C, int act_rt,
@@ -1000,6 +1019,15 @@ int b200seg_norm_finalize(const float* stats, double count, int groups, int c, c
   norm_finalize_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       stats, count, groups, c, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps, out);
   B200_CHECK_LAUNCH("norm_finalize");
+  return 0;
+}
+
+int b200seg_norm_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                           const float* conv_bias, float eps, int c, float* out, void* stream) {
+  B200_CHECK_ARG(running_mean && running_var && out && c > 0, "norm_eval_coef: bad arguments");
+  norm_eval_coef_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, running_mean, running_var,
+                                                                                       conv_bias, eps, c, out);
+  B200_CHECK_LAUNCH("norm_eval_coef");
   return 0;
 }
 

@@ -415,12 +415,41 @@ def _norm_coef(stats, count, groups, c, gamma, beta, running_mean, running_var, 
     return coef
 
 
-def _eval_coef(gamma, beta, running_mean, running_var, eps, c, device):
-    """Inference-mode normalisation constants from the running statistics (C-element vectors)."""
-    inv_std = torch.rsqrt(running_var.float() + eps)
-    scale = inv_std * gamma.float() if gamma is not None else inv_std
-    shift = (beta.float() if beta is not None else torch.zeros(c, device=device)) - running_mean.float() * scale
-    return torch.stack((running_mean.float(), inv_std, scale, shift)).unsqueeze(0).contiguous()
+def _eval_coef(gamma, beta, running_mean, running_var, eps, c, device, conv_bias=None):
+    """Inference-mode normalisation constants [1][4][C] = {mean, inv_std, scale, shift} from the running statistics;
+    a convolution bias in front of the norm is folded into the shift (for the fused conv epilogue)."""
+    coef = torch.empty((1, 4, c), dtype=torch.float32, device=device)
+    f32 = lambda t: None if t is None else t.detach().float().contiguous()   # noqa: E731
+    g_, b_, rm, rv, cb = f32(gamma), f32(beta), f32(running_mean), f32(running_var), f32(conv_bias)
+    _call("b200seg_norm_eval_coef", _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), _ptr(cb), float(eps), c, _ptr(coef), _stream())
+    return coef
+
+
+def conv_fused_eval_supported(g):
+    from ._lib import load
+    return bool(load().b200seg_conv3d_fprop_act_supported(ctypes.byref(g)))
+
+
+def conv3d_fprop_eval_fused(x, weight, bias, k, pad, dil, spec, gamma, beta, running_mean, running_var, out=None):
+    """Inference: conv -> eval-mode BatchNorm -> {none, ReLU, LeakyReLU} in ONE kernel (scale / shift / activation in the conv
+    epilogue).  Returns None when the geometry is not on the fused tensor-core path (the caller then runs the two passes)."""
+    x, xp = _as_rows(x)
+    cout, cin = weight.shape[0], weight.shape[1]
+    g = _geom(x.shape, cin, cout, k, 1, pad, dil)
+    if cin % 16 or cout % 16 or not conv_fused_eval_supported(g):
+        return None
+    coef = _eval_coef(gamma, beta, running_mean, running_var, spec.eps, cout, x.device, conv_bias=bias)
+    if out is not None and _pitched(out) and tuple(out.shape) == (g.n, g.od, g.oh, g.ow, cout) and out.data_ptr() % 16 == 0 \
+            and out.stride(3) % 8 == 0:
+        z = out
+    else:
+        z = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
+    _call("b200seg_conv3d_fprop_act", ctypes.byref(g), _ptr(x), xp, _ptr(pack_conv_weight(weight)), _ptr(coef[0, 2]),
+          _ptr(coef[0, 3]), spec.act, spec.act_param, _ptr(z), z.stride(3), _stream(), work=_conv_flops(g), tag="conv_fprop_tc")
+    if out is not None and z is not out:
+        out.copy_(z)
+        z = out
+    return z
 
 
 class NormSpec:
@@ -553,6 +582,12 @@ class _ConvNormAct(torch.autograd.Function):
     def forward(ctx, x, x2, weight, bias, gamma, beta, prelu_w, residual, running_mean, running_var, cfg):
         k, stride, pad, dil, spec, out = cfg
         xin = x if x2 is None else merge_channels(x, x2)
+        if (spec.kind == "batch" and not spec.training and residual is None and stride == 1 and not torch.is_grad_enabled()
+                and spec.act in (ACT["none"], ACT["relu"], ACT["leaky_relu"]) and running_mean is not None):
+            # inference: BatchNorm scale / shift + activation in the convolution's epilogue, no separate pass
+            z = conv3d_fprop_eval_fused(xin, weight, bias, k, pad, dil, spec, gamma, beta, running_mean, running_var, out)
+            if z is not None:
+                return z
         fused_stats = spec.kind == "batch" and spec.training
         plain = spec.kind is None and spec.act == 0 and residual is None
         y, stats, g = conv3d_fprop_raw(xin, weight, bias, k, stride, pad, dil, fused_stats, y_out=out if plain else None)

@@ -84,6 +84,15 @@ size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g);
 int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
                          const float* bias, void* y, int64_t y_pitch, float* stats, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* Inference: convolution with the eval-mode BatchNorm scale / shift and the activation applied in the epilogue
+ * (unet3d.py:80-101 under model.eval(); north-star "scale-shift and ReLU fused into the epilogue"):
+ *   y = act(scale[c] * conv(x, w)[c] + shift[c]),  act in {B200SEG_ACT_NONE, _RELU, _LEAKY(slope)}.
+ * scale / shift: fp32 [cout] (rows 2 and 3 of b200seg_norm_eval_coef, which folds the conv bias into the shift).
+ * Tensor-core geometries only: ask b200seg_conv3d_fprop_act_supported first (1 = supported). */
+int b200seg_conv3d_fprop_act_supported(const b200seg_conv_geom* g);
+int b200seg_conv3d_fprop_act(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
+                             const float* scale, const float* shift, int act, float slope, void* y, int64_t y_pitch,
+                             void* stream);
 /* dx = conv_transpose(dy, w).  w_packed from b200seg_pack_conv_weight(dgrad=1).  g describes the FORWARD conv.
  * stats (may be NULL): float[2*cin] = {sum, sumsq} of dx per channel, accumulated into (caller zeroes): the column sums
  * of a decoder conv's input gradient are the bias gradient of the ConvTranspose3d that produced that input
@@ -120,6 +129,10 @@ int b200seg_channel_stats(const void* x, int64_t pitch, int64_t rows_per_group, 
 int b200seg_norm_finalize(const float* stats, double count, int groups, int c, const float* gamma,
                           const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                           int clamp_eps, float* out, void* stream);
+/* F.batch_norm(training=False) constants from the running statistics: out = float[4][c] = {mean, inv_std,
+ * scale = gamma*inv_std, shift = beta - mean*scale (+ scale*conv_bias when conv_bias != NULL)}; gamma/beta may be NULL. */
+int b200seg_norm_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                           const float* conv_bias, float eps, int c, float* out, void* stream);
 /* z = act(y*scale + shift [+ residual]).  coef = the [groups][4][c] block from norm_finalize (NULL: identity).
  * act_param: leaky slope (scalar, host) ; prelu_w: per-channel slope (device) for B200SEG_ACT_PRELU. */
 int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int64_t rows_per_group, int groups,

@@ -207,6 +207,36 @@ def test_batchnorm_eval_mode(F):
     close(ncdhw(z), ref, 1e-2, "eval bn")
 
 
+@pytest.mark.parametrize("cin,cout,size,act", [(32, 32, (8, 16, 8), "relu"), (64, 128, (4, 16, 16), "leaky_relu"),
+                                               (32, 64, (8, 16, 16), "none"), (256, 256, (4, 4, 4), "relu"),
+                                               (16, 16, (6, 32, 24), "relu")])
+def test_eval_mode_conv_bn_act_fused_epilogue(F, cin, cout, size, act):
+    """Inference: conv -> BatchNorm(eval) -> activation as ONE launch (scale / shift / activation in the conv epilogue) against
+    the oracle's three separate ops, and against our own unfused two-pass path."""
+    g = torch.Generator().manual_seed(cin + cout)
+    x = bf(torch.randn(2, cin, *size, generator=g))
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) * (2.0 / (cin * 27)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.3
+    rm, rv = torch.randn(cout, generator=g) * 0.2, torch.rand(cout, generator=g) + 0.5
+    h = oops.batch_norm_eval(oops.conv3d(x, bf(w), b, 1, 1, 1), gamma, beta, rm, rv)
+    ref = oops.ACTIVATIONS[act](h, None) if act != "none" else h
+    if act == "leaky_relu":
+        ref = torch.nn.functional.leaky_relu(h, 0.01)
+    spec = F.NormSpec("batch", act, act_param=0.01, training=False)
+    args = dict(k=3, stride=1, pad=1, dil=1, spec=spec, gamma=gamma.to(DEV), beta=beta.to(DEV), running_mean=rm.to(DEV),
+                running_var=rv.to(DEV))
+    with torch.no_grad():
+        k0, u0 = F.launches(), F.umma_launch_count()
+        z = F.conv_norm_act(ndhwc(x), w.to(DEV), b.to(DEV), **args)
+        fused_launches = F.launches() - k0
+        assert F.umma_launch_count() - u0 == 1 and fused_launches <= 3, fused_launches   # (pack +) coefficients + conv
+    close(ncdhw(z), ref, 1e-2, "fused eval conv+bn+act")
+    z2 = F.conv_norm_act(ndhwc(x).requires_grad_(True), w.to(DEV), b.to(DEV), **args)   # grad mode: the unfused passes
+    close(ncdhw(z2), ref, 1.2e-2, "unfused eval path")
+    assert rel_err(ncdhw(z), ncdhw(z2)) < 8e-3
+
+
 def test_maxpool_indices_bit_exact_with_ties_and_nan(F, golden):
     gz = golden("pool_argmax")
     x = torch.from_numpy(gz["x"])
