@@ -80,8 +80,11 @@ def build_model(config):
     if net == "highresnet":   # not wired into the reference's train.py; BASELINE.json config 4 names it
         from .models.three_d.highresnet import HighRes3DNet
         return HighRes3DNet(config.in_classes, config.out_classes)
+    if net == "csrnet":       # train.py:366-369 (init_features defaults to 64 there)
+        from .models.three_d.csrnet import CSRNet
+        return CSRNet(in_channels=config.in_classes, out_channels=config.out_classes)
     raise ValueError("network %r is not on the b200seg path (supported: unet, res_unet, vnet, densevoxelnet, "
-                     "highresnet)" % net)
+                     "highresnet, csrnet)" % net)
 
 
 def weights_init_normal(init_type):

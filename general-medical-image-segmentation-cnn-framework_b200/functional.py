@@ -794,6 +794,66 @@ def conv_transpose_k2s2(x, weight, bias=None, out=None):
     return _ConvT2.apply(x, weight, bias, out)
 
 
+class _ConvTS(torch.autograd.Function):
+    """nn.ConvTranspose3d(kernel_size = stride = s, padding 0): non-overlapping up-convolution for any s (csrnet.py:137-149
+    uses s = 4).  It is the exact transpose of the strided convolution S: [n, s*d, s*h, s*w, C_out] -> [n, d, h, w, C_in]
+    with the same weight memory, so the three passes are S's data-gradient / forward / weight-gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cfg):
+        s, out = cfg
+        x, xp = _as_rows(x)
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[1]
+        assert weight.shape[0] == cin and tuple(weight.shape[2:]) == (s, s, s)
+        gs = ConvGeom(n, s * d, s * h, s * w, cout, d, h, w, cin, s, s, 0, 1)
+        if out is None:
+            out = torch.empty((n, s * d, s * h, s * w, cout), dtype=torch.bfloat16, device=x.device)
+        assert _pitched(out) and tuple(out.shape) == (n, s * d, s * h, s * w, cout)
+        wd = torch.empty(s ** 3 * cin * cout, dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_pack_conv_weight", _ptr(weight.detach()), _ptr(wd), cin, cout, s, 0, cout, 1, _stream())
+        _call("b200seg_conv3d_dgrad", ctypes.byref(gs), _ptr(x), xp, _ptr(wd), _ptr(out), out.stride(3), None, None, 0, _stream())
+        if bias is not None:      # + bias: one scale-shift pass with scale 1
+            coef = torch.zeros((1, 4, cout), dtype=torch.float32, device=x.device)
+            coef[0, 2] = 1.0
+            coef[0, 3] = bias.detach().float()
+            _call("b200seg_norm_act_fwd", _ptr(out), out.stride(3), _ptr(coef), n * d * h * w * s ** 3, 1, cout, 0, 0.0, None,
+                  None, 0, _ptr(out), out.stride(3), _stream())
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (s, gs, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        s, gs, has_bias = ctx.cfg
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[1]
+        dy, dyp = _as_rows(dy)
+        x, xp = _as_rows(x)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wf = torch.empty(s ** 3 * cin * cout, dtype=torch.bfloat16, device=x.device)
+            _call("b200seg_pack_conv_weight", _ptr(weight.detach()), _ptr(wf), cin, cout, s, 0, cout, 0, _stream())
+            dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=x.device)
+            _call("b200seg_conv3d_fprop", ctypes.byref(gs), _ptr(dy), dyp, _ptr(wf), None, _ptr(dx), cin, None, None, 0, _stream())
+        if ctx.needs_input_grad[1]:
+            dwp = torch.zeros(s ** 3 * cin * cout, dtype=torch.float32, device=x.device)   # [k^3][cin_S = cout][cout_S = cin]
+            _call("b200seg_conv3d_wgrad", ctypes.byref(gs), _ptr(dy), dyp, _ptr(x), xp, _ptr(dwp), None, 0, _stream())
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            _call("b200seg_unpack_conv_wgrad", _ptr(dwp), _ptr(dw), cin, cout, s, 0, cout, 0, _stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            db = channel_stats(dy, 1)[0, 0]
+        return dx, dw, db, None
+
+
+def conv_transpose_kxsx(x, weight, bias=None, stride=2, out=None):
+    """nn.ConvTranspose3d(kernel_size = stride).  stride 2 takes the dedicated tensor-core path (conv_transpose_k2s2)."""
+    if stride == 2:
+        return _ConvT2.apply(x, weight, bias, out)
+    return _ConvTS.apply(x, weight, bias, (int(stride), out))
+
+
 class _Head(torch.autograd.Function):
     """1x1x1 convolution to class logits, returned as fp32 NCDHW like the reference model's output (unet3d.py:70)."""
 
@@ -856,21 +916,27 @@ def upsample_nearest2(x):
 
 class _Add(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, out):
         a, ap = _as_rows(a)
         b, bp = _as_rows(b)
         n, d, h, w, c = a.shape
-        out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=a.device)
-        _call("b200seg_add", _ptr(a), ap, _ptr(b), bp, _ptr(out), c, n * d * h * w, c, _stream())
+        if out is None:
+            out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=a.device)
+        else:
+            assert _pitched(out) and out.shape == a.shape
+            if out.data_ptr() == a.data_ptr() or out.data_ptr() == b.data_ptr():
+                ctx.mark_dirty(out)
+        _call("b200seg_add", _ptr(a), ap, _ptr(b), bp, _ptr(out), out.stride(3), n * d * h * w, c, _stream())
         return out
 
     @staticmethod
     def backward(ctx, g):
-        return g, g
+        return g, g, None
 
 
-def add(a, b):
-    return _Add.apply(a, b)
+def add(a, b, out=None):
+    """a + b (element-wise); `out` may be a channel slice of a concat buffer, or alias `a` (in-place sum)."""
+    return _Add.apply(a, b, out)
 
 
 # ------------------------------------------------------------------------------------------------ losses / metrics

@@ -151,11 +151,19 @@ def conv_transpose_k2s2(x, weight, bias=None, out=None):
     return _ra(TF.conv_transpose3d(x, _rw(weight), bias, stride=2))
 
 
+def conv_transpose_kxsx(x, weight, bias=None, stride=2, out=None):
+    return _ra(TF.conv_transpose3d(x, _rw(weight), bias, stride=stride))
+
+
+def max_pool2_skip(x):
+    return TF.max_pool3d(x, 2, 2), x
+
+
 def upsample_nearest2(x):
     return TF.interpolate(x, scale_factor=2, mode="nearest")
 
 
-def add(a, b):
+def add(a, b, out=None):
     return _ra(a + b)
 
 

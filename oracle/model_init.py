@@ -41,6 +41,7 @@ MODEL_CASES = {
     "resunet8": ("models.three_d.residual_unet3d", "UNet", dict(in_channels=1, n_classes=2, base_n_filter=8), 64, 1),
     "highres3d": ("models.three_d.highresnet", "HighRes3DNet", dict(in_channels=1, out_channels=2), 24, 1),
     "densevoxel": ("models.three_d.densevoxelnet3d", "DenseVoxelNet", dict(in_channels=1, classes=2), 32, 2),
+    "csrnet": ("models.three_d.csrnet", "CSRNet", dict(in_channels=1, out_channels=2, init_features=8), 32, 2),
 }
 
 

@@ -90,6 +90,7 @@ CONV_CASES = [
     (1, 16, 5, 1, 2, 1, (40, 40, 44), 1),     # V-Net stem 5x5x5
     (64, 2, 1, 1, 0, 1, (40, 40, 44), 1),     # HighRes3DNet classifier
     (24, 40, 3, 2, 1, 1, (64, 64, 64), 1),    # stride 2 with padded channels
+    (32, 64, 3, 4, 0, 1, (16, 16, 20), 2),    # CSRNet cross-scale branch: stride 4, no padding (generic strided kernels)
 ]
 
 
@@ -276,6 +277,26 @@ def test_conv_transpose_k2s2(F):
         close(ncdhw(xd.grad), xr.grad, 8e-3, "convT dgrad")
         close(wd.grad.cpu(), wr.grad, 8e-3, "convT wgrad")
         close(bd.grad.cpu(), dy.sum((0, 2, 3, 4)), 8e-3, "convT bias grad")
+
+
+def test_conv_transpose_k4s4(F):
+    """nn.ConvTranspose3d(kernel 4, stride 4) (csrnet.py:137-149) through the strided convolution's three passes."""
+    g = torch.Generator().manual_seed(6)
+    for cin, cout, size in [(32, 16, (2, 3, 4)), (64, 8, (2, 2, 2))]:
+        x = bf(torch.randn(2, cin, *size, generator=g))
+        w = torch.randn(cin, cout, 4, 4, 4, generator=g) * 0.1
+        b = torch.randn(cout, generator=g) * 0.1
+        xr, wr = x.clone().requires_grad_(True), bf(w).requires_grad_(True)
+        y_ref = torch.nn.functional.conv_transpose3d(xr, wr, b, stride=4)
+        dy = bf(torch.randn(y_ref.shape, generator=g))
+        y_ref.backward(dy)
+        xd, wd, bd = ndhwc(x).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        y = F.conv_transpose_kxsx(xd, wd, bd, stride=4)
+        close(ncdhw(y), y_ref.detach(), 8e-3, "convT k4s4 fwd")
+        y.backward(ndhwc(dy))
+        close(ncdhw(xd.grad), xr.grad, 8e-3, "convT k4s4 dgrad")
+        close(wd.grad.cpu(), wr.grad, 8e-3, "convT k4s4 wgrad")
+        close(bd.grad.cpu(), dy.sum((0, 2, 3, 4)), 8e-3, "convT k4s4 bias grad")
 
 
 def test_concat_free_decoder_input_equals_torch_cat(F):
