@@ -57,6 +57,9 @@ SIGNATURES = {
     "b200seg_dice_sums": "ppp" + "iil" + "if" + "pp",
     "b200seg_dice_grad": "ppp" + "iil" + "if" + "ppp" + "pp",
     "b200seg_seg_counts": "ppl" + "pp",
+    "b200seg_volume_stats": "plpp",
+    "b200seg_znorm_finalize": "plpp",
+    "b200seg_crop_patch": "pi" + "iiii" + "iii" + "iii" + "ppp",
     "b200seg_window_accumulate_crop": "ppp" + "l" + "iiiiiii" + "p" + "iii" + "p",
     "b200seg_window_keys_to_labels": "pp" + "l" + "p",
     "b200seg_window_accumulate_average": "pp" + "iiiii" + "pp" + "iii" + "p",

@@ -94,6 +94,75 @@ class DevicePrefetcher:
         return batch
 
 
+class GpuPatchSampler:
+    """Training batches cut on the GPU from volumes that stay resident in HBM: torchio's ZNormalization +
+    UniformSampler(patch_size) + Queue(samples_per_volume) (dataloader.py:52-67) without the host in the loop.
+
+    volumes: list of fp32 [C, W, H, D] tensors (host or device); labels: list of [1, W, H, D] label maps.  Each volume is
+    uploaded once and its z-normalisation constants (mean, unbiased std over all voxels) are computed once on the device;
+    an epoch draws `samples_per_volume` uniformly placed patches per volume (start index uniform in [0, size - patch]
+    per axis), shuffles them like the Queue does, and yields the reference's batch dict
+    {"source": {"data": fp32 [B, C, pw, ph, pd]}, "gt": {"data": [B, 1, pw, ph, pd]}} -- already on the device, normalised
+    inside the cropping kernel.  drop_last like the reference's DataLoader (train.py:158)."""
+
+    def __init__(self, volumes, labels, patch_size, batch_size, samples_per_volume=10, device="cuda", seed=0, shuffle=True):
+        from .functional import _call, _ptr, _stream
+        assert len(volumes) == len(labels) and len(volumes) > 0
+        self.device = torch.device(device)
+        self.patch_size, self.batch_size = tuple(int(p) for p in patch_size), int(batch_size)
+        self.samples_per_volume, self.shuffle = int(samples_per_volume), shuffle
+        self.gen = torch.Generator().manual_seed(seed)
+        self.volumes, self.labels, self.norms = [], [], []
+        for v, lab in zip(volumes, labels):
+            v = v.to(self.device, torch.float32).contiguous()
+            lab = lab.to(self.device).to(torch.uint8).contiguous()
+            if v.dim() != 4 or lab.dim() != 4 or tuple(lab.shape[1:]) != tuple(v.shape[1:]):
+                raise ValueError("expected [C, W, H, D] images and [1, W, H, D] label maps of the same extent")
+            if any(p > s for p, s in zip(self.patch_size, v.shape[1:])):
+                raise ValueError("patch size %s is larger than a volume of extent %s" % (self.patch_size, tuple(v.shape[1:])))
+            sums = torch.zeros(2, dtype=torch.float64, device=self.device)
+            norm = torch.empty(2, dtype=torch.float32, device=self.device)
+            _call("b200seg_volume_stats", _ptr(v), v.numel(), _ptr(sums), _stream())
+            _call("b200seg_znorm_finalize", _ptr(sums), v.numel(), _ptr(norm), _stream())
+            self.volumes.append(v)
+            self.labels.append(lab)
+            self.norms.append(norm)
+
+    def __len__(self):
+        return len(self.volumes) * self.samples_per_volume // self.batch_size
+
+    def draw_locations(self):
+        """[(volume index, x0, y0, z0)] of one epoch: samples_per_volume uniform locations per volume, shuffled."""
+        locs = []
+        for vi, v in enumerate(self.volumes):
+            for _ in range(self.samples_per_volume):
+                locs.append((vi,) + tuple(int(torch.randint(0, s - p + 1, (1,), generator=self.gen))
+                                          for s, p in zip(v.shape[1:], self.patch_size)))
+        if self.shuffle:
+            order = torch.randperm(len(locs), generator=self.gen).tolist()
+            locs = [locs[i] for i in order]
+        return locs
+
+    def crop(self, picks):
+        from .functional import _call, _ptr, _stream
+        c = self.volumes[0].shape[0]
+        pw, ph, pd = self.patch_size
+        x = torch.empty((len(picks), c, pw, ph, pd), dtype=torch.float32, device=self.device)
+        gt = torch.empty((len(picks), 1, pw, ph, pd), dtype=torch.uint8, device=self.device)
+        for b, (vi, x0, y0, z0) in enumerate(picks):
+            v, lab = self.volumes[vi], self.labels[vi]
+            _call("b200seg_crop_patch", _ptr(v), 0, v.shape[0], v.shape[1], v.shape[2], v.shape[3], x0, y0, z0, pw, ph, pd,
+                  _ptr(self.norms[vi]), _ptr(x[b]), _stream())
+            _call("b200seg_crop_patch", _ptr(lab), 1, 1, v.shape[1], v.shape[2], v.shape[3], x0, y0, z0, pw, ph, pd, None,
+                  _ptr(gt[b]), _stream())
+        return {"source": {"data": x}, "gt": {"data": gt}}
+
+    def __iter__(self):
+        locs = self.draw_locations()
+        for s in range(0, len(locs) - self.batch_size + 1, self.batch_size):
+            yield self.crop(locs[s:s + self.batch_size])
+
+
 def synthetic_volume(size, in_channels=1, seed=0):
     g = torch.Generator().manual_seed(seed)
     vol = torch.randn((in_channels,) + tuple(size), generator=g)

@@ -17,7 +17,7 @@ import torch
 
 from . import parallel
 from .config import build_model, compose, weights_init_normal
-from .data import DevicePrefetcher, SyntheticPatches
+from .data import DevicePrefetcher, GpuPatchSampler, SyntheticPatches, synthetic_volume
 from .engine import TrainStep
 from .models.sync_batchnorm.batchnorm import convert_model
 from .optim import FusedAdam
@@ -87,13 +87,21 @@ def train(config, model, log=print):
         elapsed_epochs = ckpt["epoch"]
     model.train()
     step = TrainStep(model, criterion, optimizer, use_graph=bool(config.cuda_graph))
-    loader = SyntheticPatches(config.patch_size, config.batch_size, config.iters_per_epoch, config.in_classes,
-                              seed=config.seed + rank)
+    if str(config.get("data", "synthetic")) == "volumes":
+        # device-resident volumes: z-normalisation + uniform patch crop on the GPU (dataloader.py:52-67)
+        vols = [synthetic_volume(config.volume_size, config.in_classes, seed=config.seed + 17 * rank + i)
+                for i in range(int(config.get("num_volumes", 2)))]
+        loader = GpuPatchSampler([v for v, _ in vols], [g for _, g in vols], config.patch_size, config.batch_size,
+                                 int(config.get("samples_per_volume", 10)), device=dev, seed=config.seed + rank)
+    else:
+        loader = SyntheticPatches(config.patch_size, config.batch_size, config.iters_per_epoch, config.in_classes,
+                                  seed=config.seed + rank)
     os.makedirs(config.hydra_path, exist_ok=True)
     history = []
     for epoch in range(elapsed_epochs + 1, config.epochs + 1):
         t0, loss_sum, dice_sum, n = time.time(), 0.0, 0.0, 0
-        for i, batch in enumerate(DevicePrefetcher(loader, dev)):   # the copy of batch i+1 overlaps step i
+        batches = loader if isinstance(loader, GpuPatchSampler) else DevicePrefetcher(loader, dev)
+        for i, batch in enumerate(batches):                         # host batches: the copy of batch i+1 overlaps step i
             x = batch["source"]["data"]
             gt = batch["gt"]["data"]
             labels = gt.reshape(gt.shape[0], *gt.shape[2:]).to(torch.uint8)   # the one-hot of train.py:191-193, as indices

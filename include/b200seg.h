@@ -222,6 +222,16 @@ int b200seg_dice_grad(const float* pred, const float* target_f, const uint8_t* t
                       int by_class, float p_exp, const float* coef_t, const float* coef_x, const float* gscale, float* dpred,
                       void* stream);
 
+/* ---- training data path (dataloader.py:52-67: torchio ZNormalization + UniformSampler) ------------------------- */
+/* sums: double[2] += {sum x, sum x^2} over n floats (a whole image, all channels: ZNormalization without a mask). */
+int b200seg_volume_stats(const float* x, int64_t n, double* sums, void* stream);
+/* mean_inv_std: float[2] = {mean, 1 / unbiased std} (torch.std semantics, like torchio's ZNormalization.znorm). */
+int b200seg_znorm_finalize(const double* sums, int64_t n, float* mean_inv_std, void* stream);
+/* One patch of a device-resident volume [c][w][h][d] starting at (x0,y0,z0): fp32 images are written z-normalised
+ * ((v - mean) * inv_std; mean_inv_std may be NULL = copy), uint8 label maps (is_label = 1) are copied.  out: [c][pw][ph][pd]. */
+int b200seg_crop_patch(const void* vol, int is_label, int c, int w, int h, int d, int x0, int y0, int z0, int pw, int ph, int pd,
+                       const float* mean_inv_std, void* out, void* stream);
+
 /* ---- metric (metric.py:20-75) ---------------------------------------------------------------------------------- */
 /* counts: uint64[4] += {sum gt, sum pred, |gt & pred| nonzero, |gt | pred| nonzero} over uint8 label volumes. */
 int b200seg_seg_counts(const uint8_t* gt, const uint8_t* pred, int64_t numel, unsigned long long* counts,
