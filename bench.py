@@ -368,9 +368,11 @@ def run_b200(args):
         parallel.broadcast_parameters(net)
         convert_model(net)       # nn.BatchNorm3d -> SynchronizedBatchNorm3d (statistics exchanged over NVLink peer memory)
     net.train()
-    opt = FusedAdam(net.parameters(), lr=1e-3)
-    if world > 1:
-        opt.attach_reducer()     # bucketed gradient all-reduce on a side stream, overlapped with backward (eager mode)
+    # N > 1: gradients are summed over NVLink peer memory INSIDE the captured step (optim.PeerGradExchange);
+    # B200SEG_GRADS=nccl selects the bucketed NCCL all-reduce (overlapped with backward in eager mode) instead
+    opt = FusedAdam(net.parameters(), lr=1e-3, peer_grads=world > 1)
+    if world > 1 and not opt.peer_grads:
+        opt.attach_reducer()
     crit = DiceCELoss(2)
     vox = PATCH ** 3
     x_host = torch.randn(BATCH, 1, PATCH, PATCH, PATCH).pin_memory()
@@ -473,6 +475,8 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": patches, "parallelism": "dp%d" % world,
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
+                       "gradient_exchange": None if world == 1 else ("NVLink peer-memory reduce-scatter + all-gather inside the "
+                                                                     "graph" if opt.peer_grads else "NCCL all-reduce after the graph"),
                        "l2": "no flush needed: each step streams >10 GB of activations, far larger than the 126 MB L2"},
             "voxels_per_s": value * vox,
             # the same loop run for >= 5 s: the figure a training job sees once power and clocks have settled

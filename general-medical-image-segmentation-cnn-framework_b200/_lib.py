@@ -65,6 +65,8 @@ SIGNATURES = {
     "b200seg_window_accumulate_average": "pp" + "iiiii" + "pp" + "iii" + "p",
     "b200seg_window_finalize": "pp" + "il" + "pp",
     "b200seg_p2p_alloc": "pp",
+    "b200seg_p2p_alloc_bytes": "zpp",
+    "b200seg_p2p_grad_allreduce": "pppp" + "iii" + "pp",
     "b200seg_p2p_open": "pp",
     "b200seg_p2p_close": "pi",
     "b200seg_p2p_allreduce": "pi" + "p" + "ii" + "p" + "i" + "d" + "pppp" + "ff" + "i" + "p" + "p",

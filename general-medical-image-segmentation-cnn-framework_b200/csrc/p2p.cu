@@ -104,6 +104,90 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Gradient all-reduce over NVLink peer memory, capturable in the training step's CUDA graph (train.py:211: the all-reduce
+// DDP performs inside accelerator.backward).  Every rank's gradient buffer (optim.FusedAdam's zeroed arena: torch-layout
+// gradients followed by the conv kernels' packed weight-gradient accumulators), a staging buffer and a small flag block
+// live in cudaMalloc'ed memory that all peers map through CUDA IPC.  Only the 64-float chunks that ever receive a gradient
+// are exchanged (`live`: sorted chunk indices, identical on every rank).  Four launches, all stream-ordered:
+//   1. signal A: "my gradients of exchange `seq` are complete" -> every peer's flag block (release, system scope);
+//   2. reduce-scatter: wait for A from everybody; rank r sums ITS share of the live chunks over all ranks' buffers in rank
+//      order (peer loads over NVLink; the same order everywhere) into its staging buffer;
+//   3. signal B: "my share is reduced";
+//   4. all-gather: wait for B from everybody; copy every share from its owner's staging buffer into the local gradient
+//      buffer.  All ranks end with bit-identical sums.
+// Hazards: a peer's buffer is only overwritten (by its own all-gather, or by the next step's backward) after it has seen B
+// from every rank, i.e. after every rank has finished reading it; staging buffers are rewritten only after A of the next
+// exchange, which every rank sends after its all-gather.  `seq` lives in device memory and is advanced by launch 1, so a
+// captured sequence replays correctly.
+constexpr int kGradChunk = 64;   // floats
+
+struct GradPeers {
+  float* buf[kP2PMaxWorld];
+  float* red[kP2PMaxWorld];
+  unsigned int* flags[kP2PMaxWorld];   // [2][kP2PMaxWorld] per rank
+};
+
+__global__ void p2p_grad_signal_kernel(GradPeers peers, int which, int rank, int world, unsigned int* __restrict__ seq_ptr,
+                                       int bump) {
+  __shared__ unsigned int seq;
+  if (threadIdx.x == 0) {
+    seq = *seq_ptr + (bump ? 1u : 0u);
+    if (bump) *seq_ptr = seq;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) st_release_sys(&peers.flags[threadIdx.x][which * kP2PMaxWorld + rank], seq);
+}
+
+__device__ __forceinline__ void grad_wait(const unsigned int* mine, int which, int world, unsigned int seq) {
+  if (threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine[which * kP2PMaxWorld + threadIdx.x]) < seq) {
+      if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a peer never arrived
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) p2p_grad_reduce_scatter_kernel(GradPeers peers, const int* __restrict__ live, int n_live,
+                                                                      int rank, int world, const unsigned int* __restrict__ seq_ptr) {
+  grad_wait(peers.flags[rank], 0, world, *seq_ptr);
+  const int per = (n_live + world - 1) / world;
+  const int lo = rank * per, hi = min(n_live, lo + per);
+  float* out = peers.red[rank];
+  const long long items = static_cast<long long>(max(hi - lo, 0)) * (kGradChunk / 4);
+  for (long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; w < items;
+       w += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int li = lo + static_cast<int>(w / (kGradChunk / 4)), q = static_cast<int>(w % (kGradChunk / 4));
+    const long long off = static_cast<long long>(live[li]) * kGradChunk + q * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.buf[r] + off));
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + static_cast<long long>(li - lo) * kGradChunk + q * 4) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) p2p_grad_all_gather_kernel(GradPeers peers, const int* __restrict__ live, int n_live, int rank,
+                                                                  int world, const unsigned int* __restrict__ seq_ptr) {
+  grad_wait(peers.flags[rank], 1, world, *seq_ptr);
+  const int per = (n_live + world - 1) / world;
+  float* dst = peers.buf[rank];
+  const long long items = static_cast<long long>(n_live) * (kGradChunk / 4);
+  for (long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; w < items;
+       w += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int li = static_cast<int>(w / (kGradChunk / 4)), q = static_cast<int>(w % (kGradChunk / 4));
+    const int owner = li / per;
+    const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.red[owner] + static_cast<long long>(li - owner * per) * kGradChunk + q * 4));
+    *reinterpret_cast<float4*>(dst + static_cast<long long>(live[li]) * kGradChunk + q * 4) = v;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -126,6 +210,46 @@ int b200seg_p2p_alloc(void** dev_ptr, void* ipc_handle_out) {
   }
   memcpy(ipc_handle_out, &h, sizeof(h));
   *dev_ptr = p;
+  return 0;
+}
+
+int b200seg_p2p_alloc_bytes(size_t bytes, void** dev_ptr, void* ipc_handle_out) {
+  B200_CHECK_ARG(dev_ptr && ipc_handle_out && bytes > 0, "p2p_alloc_bytes: bad arguments");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    set_error("p2p_alloc_bytes: %s", cudaGetErrorString(e));
+    if (p) cudaFree(p);
+    return B200SEG_ERR_CUDA;
+  }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return 0;
+}
+
+int b200seg_p2p_grad_allreduce(const void* const* bufs, const void* const* reds, const void* const* flags, const int32_t* live,
+                               int n_live, int rank, int world, uint32_t* seq, void* stream) {
+  B200_CHECK_ARG(bufs && reds && flags && live && seq && n_live > 0, "p2p_grad_allreduce: bad arguments");
+  B200_CHECK_ARG(world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, "p2p_grad_allreduce: bad rank / world");
+  GradPeers peers{};
+  for (int r = 0; r < world; ++r) {
+    B200_CHECK_ARG(bufs[r] && reds[r] && flags[r], "p2p_grad_allreduce: null peer pointer for rank %d", r);
+    peers.buf[r] = static_cast<float*>(const_cast<void*>(bufs[r]));
+    peers.red[r] = static_cast<float*>(const_cast<void*>(reds[r]));
+    peers.flags[r] = static_cast<unsigned int*>(const_cast<void*>(flags[r]));
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  const int per = (n_live + world - 1) / world;
+  const int g_rs = grid_for(static_cast<int64_t>(per) * (kGradChunk / 4), 256, kNumSMs * 4);
+  const int g_ag = grid_for(static_cast<int64_t>(n_live) * (kGradChunk / 4), 256, kNumSMs * 4);
+  p2p_grad_signal_kernel<<<1, 32, 0, st>>>(peers, 0, rank, world, seq, 1);
+  p2p_grad_reduce_scatter_kernel<<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, world, seq);
+  p2p_grad_signal_kernel<<<1, 32, 0, st>>>(peers, 1, rank, world, seq, 0);
+  p2p_grad_all_gather_kernel<<<g_ag, 256, 0, st>>>(peers, live, n_live, rank, world, seq);
+  B200_CHECK_LAUNCH("p2p_grad_allreduce");
   return 0;
 }
 

@@ -57,11 +57,14 @@ class TrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         k0, u0 = F.launches(), F.umma_launch_count()
-        self._split = parallel.is_parallel()
+        # several GPUs: everything is captured when the optimiser exchanges gradients over NVLink peer memory
+        # (optim.PeerGradExchange); with NCCL the exchange and the update follow the replay eagerly ("split")
+        peer = getattr(self.optimizer, "peer_grads", False)
+        self._split = parallel.is_parallel() and not peer
         reducer = getattr(self.optimizer, "reducer", None)
         if self._split and reducer is not None:
             reducer.enabled = False           # no NCCL launches from autograd hooks while capturing / replaying
-        self._grad_scale = 1.0
+        self._grad_scale = 1.0 / parallel.world_size() if (peer and parallel.is_parallel()) else 1.0
         if not self._split:
             self.optimizer._sync_hyper(self._grad_scale)   # a scheduler may have moved lr since the last eager step
         with torch.cuda.graph(self.graph):

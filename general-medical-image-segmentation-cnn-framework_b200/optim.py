@@ -11,8 +11,68 @@ import torch.distributed as dist
 from .functional import _call, _ptr, _stream
 
 
+class _RawDeviceBuffer:
+    """A cudaMalloc'ed float buffer exposed through __cuda_array_interface__ (zero-copy view for torch.as_tensor)."""
+
+    def __init__(self, ptr, numel):
+        self.ptr, self.numel = ptr, numel
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerGradExchange:
+    """Gradient all-reduce over NVLink peer memory (csrc/p2p.cu: b200seg_p2p_grad_allreduce), capturable in the training
+    step's CUDA graph -- what NCCL's all-reduce is not on this stack.  Owns the IPC-shareable allocation that FusedAdam
+    uses as its zeroed gradient arena, a staging buffer and the flag block, and the peers' mappings of all three."""
+
+    def __init__(self, numel, group=None):
+        from ._lib import call
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.numel = numel
+        dev = torch.device("cuda", torch.cuda.current_device())
+        chunks = (numel + 63) // 64
+        sizes = {"buf": chunks * 64 * 4, "red": ((chunks + self.world - 1) // self.world) * 64 * 4, "flags": 256}
+        self._own, handles = {}, {}
+        for name, nbytes in sizes.items():
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            call("b200seg_p2p_alloc_bytes", nbytes, ctypes.byref(ptr), handle)
+            self._own[name], handles[name] = ptr.value, handle.raw
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=group)
+        self._tables = {}
+        for name in sizes:
+            ptrs = []
+            for r, hs in enumerate(gathered):
+                if r == self.rank:
+                    ptrs.append(self._own[name])
+                else:
+                    q = ctypes.c_void_p()
+                    call("b200seg_p2p_open", ctypes.create_string_buffer(hs[name], 64), ctypes.byref(q))
+                    ptrs.append(q.value)
+            self._tables[name] = (ctypes.c_void_p * self.world)(*ptrs)
+        self.arena = torch.as_tensor(_RawDeviceBuffer(self._own["buf"], chunks * 64), device=dev)
+        self.seq = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.live, self.live_mask, self.detections = None, None, 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)      # every buffer is mapped and zeroed before anybody's first exchange
+
+    def set_live_chunks(self, mask):
+        """mask: bool tensor over the 64-float chunks of the arena (True = receives gradients on some rank)."""
+        m = mask.to(torch.int32)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)      # identical list on every rank
+        self.live = torch.nonzero(m, as_tuple=False).flatten().to(torch.int32).contiguous()
+        return int(self.live.numel())
+
+    def all_reduce_(self):
+        assert self.live is not None and self.live.numel() > 0
+        _call("b200seg_p2p_grad_allreduce", self._tables["buf"], self._tables["red"], self._tables["flags"], _ptr(self.live),
+              int(self.live.numel()), self.rank, self.world, _ptr(self.seq), _stream())
+
+
 class FusedAdam:
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, peer_grads=False, group=None):
+        """peer_grads=True (multi-GPU): the gradient arena lives in CUDA-IPC shareable memory and `all_reduce_grads` sums
+        it over NVLink peer memory inside the stream (CUDA-graph capturable) instead of calling NCCL."""
         self.params = [p for p in params if p.requires_grad]
         assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -27,7 +87,15 @@ class FusedAdam:
         self.param_arena = torch.zeros(total, dtype=torch.float32, device=dev)
         # gradients and the conv kernels' packed weight-gradient accumulators share one allocation: one memset clears both
         padded = (total + 63) // 64 * 64          # the packed accumulators start 256-byte aligned (128-bit loads of dw)
-        self._zeroed = torch.zeros(padded + total, dtype=torch.float32, device=dev)
+        self._padded = padded
+        self.peer = None
+        import os
+        if peer_grads and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
+                and os.environ.get("B200SEG_GRADS", "p2p") != "nccl":
+            self.peer = PeerGradExchange(padded + total, group)
+            self._zeroed = self.peer.arena[:padded + total]
+        else:
+            self._zeroed = torch.zeros(padded + total, dtype=torch.float32, device=dev)
         self.grad_arena = self._zeroed[:total]
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -134,11 +202,41 @@ class FusedAdam:
         factor the summed gradients still have to be scaled by (folded into the Adam kernel)."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return 1.0      # single process: the fused step consumes the packed weight gradients where they are
+        if self.peer is not None:
+            # NVLink peer-memory exchange of both arenas as they are (torch-layout gradients and the packed conv weight
+            # gradients): no transpose pass, no NCCL call, capturable; the fused Adam kernel consumes both afterwards
+            if torch.cuda.is_current_stream_capturing():
+                if self.peer.live is None:
+                    raise RuntimeError("FusedAdam: the first gradient exchange must run eagerly (it records which chunks "
+                                       "of the arena receive gradients)")
+            elif self.peer.detections < 3:
+                # the first eager steps record (and accumulate) which chunks receive gradients; fixed afterwards
+                mask = self._live_chunk_mask()
+                if self.peer.live_mask is not None:
+                    mask = mask | self.peer.live_mask
+                self.peer.live_mask = mask
+                self.peer.set_live_chunks(mask)
+                self.peer.detections += 1
+            self.peer.all_reduce_()
+            return 1.0 / dist.get_world_size(group)
         self.finalize_grads()
         if getattr(self, "reducer", None) is not None and self.reducer.enabled:
             return self.reducer.finish()
         dist.all_reduce(self.grad_arena, group=group)
         return 1.0 / dist.get_world_size(group)
+
+    def _live_chunk_mask(self):
+        """Which 64-float chunks of [gradient arena | packed weight-gradient arena] hold a gradient after this backward:
+        a conv weight's gradient sits in the packed arena (direct accumulation) or the torch-layout one (autograd), never
+        both; biases in front of batch statistics get none at all.  Decided from the data once, in an eager step."""
+        z = self._zeroed
+        n = (z.numel() + 63) // 64 * 64
+        buf = self.peer.arena[:n] if self.peer is not None else torch.nn.functional.pad(z, (0, n - z.numel()))
+        return buf.view(-1, 64).ne(0).any(dim=1)
+
+    @property
+    def peer_grads(self):
+        return self.peer is not None
 
     def _sync_hyper(self, grad_scale):
         """Hyper-parameters and the step counter live on the device so a CUDA-graph-captured step replays correctly;

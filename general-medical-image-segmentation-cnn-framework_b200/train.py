@@ -72,8 +72,8 @@ def train(config, model, log=print):
         parallel.broadcast_parameters(model)
         if config.sync_bn:
             convert_model(model)
-    optimizer = FusedAdam(model.parameters(), lr=config.init_lr)
-    if world > 1:
+    optimizer = FusedAdam(model.parameters(), lr=config.init_lr, peer_grads=world > 1)
+    if world > 1 and not optimizer.peer_grads:
         optimizer.attach_reducer()
     criterion = make_criterion(config.criterion, config.out_classes)
     scheduler = StepLR(optimizer, config.scheduler_step_size, config.scheduler_gamma) if config.use_scheduler else None

@@ -257,6 +257,16 @@ int b200seg_window_accumulate_average(const float* patches, const int64_t* locat
 int b200seg_window_finalize(float* acc, const float* count, int c, int64_t voxels, uint8_t* labels, void* stream);
 
 /* ---- cross-GPU exchange over NVLink peer memory (models/sync_batchnorm/batchnorm.py:90-111, comm.py:56-137) ------ */
+/* cudaMalloc'ed, zeroed buffer of `bytes` bytes plus its CUDA IPC handle (64 bytes): peers map it with b200seg_p2p_open. */
+int b200seg_p2p_alloc_bytes(size_t bytes, void** dev_ptr, void* ipc_handle_out);
+/* In-place SUM over ranks of the `live` 64-float chunks of a gradient buffer, over NVLink peer memory, capturable in a CUDA
+ * graph (replaces the DDP gradient all-reduce of accelerator.backward, train.py:211).  bufs / reds / flags: `world` device
+ * pointers each (this rank's own allocation and its peers' IPC mappings, indexed by rank): the gradient buffer, a staging
+ * buffer of >= ceil(n_live / world) * 64 floats, and a zero-initialised block of 16 uint32 flags.  live: sorted chunk indices
+ * (int32, device), identical on all ranks.  seq: device uint32, zero-initialised, owned by the library afterwards.  Every
+ * rank must issue the same sequence of calls; all ranks end with bit-identical sums (rank-ordered addition). */
+int b200seg_p2p_grad_allreduce(const void* const* bufs, const void* const* reds, const void* const* flags, const int32_t* live,
+                               int n_live, int rank, int world, uint32_t* seq, void* stream);
 /* Every rank allocates one mailbox (b200seg_p2p_alloc: cudaMalloc + CUDA-IPC handle, 64 bytes), ships the handle to its
  * peers (any side channel; the Python layer uses torch.distributed.all_gather_object) and maps theirs
  * (b200seg_p2p_open).  b200seg_p2p_close(ptr, opened): opened=1 unmaps a peer's mailbox, 0 frees one's own. */

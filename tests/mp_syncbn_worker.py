@@ -68,32 +68,42 @@ def main():
     data = [(torch.randn(2, 1, 32, 32, 32, device=dev), (torch.rand(2, 32, 32, 32, device=dev) > 0.8).to(torch.uint8))
             for _ in range(7)]
     results = []
-    for use_graph in (False, True):
+    # (eager, NCCL bucket reducer) is the yardstick; (graph, NCCL after the replay) and (graph / eager, NVLink peer-memory
+    # exchange inside the stream) must follow it
+    for use_graph, peer in ((False, False), (True, False), (True, True), (False, True)):
         net = UNet3D(1, 2, 16).to(dev)
         net.load_state_dict(sd)
         convert_model(net)
         net.train()
-        opt = FusedAdam(net.parameters(), lr=1e-3)
-        opt.attach_reducer()
+        opt = FusedAdam(net.parameters(), lr=1e-3, peer_grads=peer)
+        assert opt.peer_grads == peer
+        if not peer:
+            opt.attach_reducer()
         step = TrainStep(net, DiceCELoss(2), opt, use_graph=use_graph, warmup=2)
         losses = [float(step(xb, yb)[0]) for xb, yb in data]
         assert (step.graph is not None) == use_graph
+        if use_graph:
+            assert step._split == (not peer)
         torch.cuda.synchronize()
         results.append((losses, {k: v.detach().clone() for k, v in net.state_dict().items()}))
         # data-parallel invariant: every rank holds the same parameters, bit for bit
         flat = torch.cat([v.flatten().float() for v in net.parameters()])
         other = flat.clone()
         dist.broadcast(other, 0)
-        assert torch.equal(flat, other), "ranks diverged (graph=%s): max diff %g" % (use_graph, float((flat - other).abs().max()))
-    (l0, p0), (l1, p1) = results
-    assert max(abs(a - b) for a, b in zip(l0, l1)) < 6e-3, (l0, l1)
-    for k, tol in (("encoder1.enc1conv1.weight", 2e-2), ("decoder1.dec1conv2.weight", 2e-2), ("conv.weight", 2e-2),
-                   ("upconv1.weight", 2e-2), ("encoder2.enc2norm1.running_var", 2e-2)):
-        e = rel(p1[k].float().cpu(), p0[k].float().cpu())
-        assert e < tol, (k, e)
-    # the conv weights really moved in the replayed steps (the weight gradients were not dropped after the first replay)
-    moved = rel(p1["decoder1.dec1conv2.weight"].cpu(), sd["decoder1.dec1conv2.weight"])
-    assert moved > 1e-3, moved
+        assert torch.equal(flat, other), "ranks diverged (graph=%s peer=%s): max diff %g" % (use_graph, peer,
+                                                                                             float((flat - other).abs().max()))
+        if hasattr(opt, "reducer"):
+            opt.reducer.remove()
+    l0, p0 = results[0]
+    for (l1, p1), what in zip(results[1:], ("graph+nccl", "graph+peer", "eager+peer")):
+        assert max(abs(a - b) for a, b in zip(l0, l1)) < 6e-3, (what, l0, l1)
+        for k, tol in (("encoder1.enc1conv1.weight", 2e-2), ("decoder1.dec1conv2.weight", 2e-2), ("conv.weight", 2e-2),
+                       ("upconv1.weight", 2e-2), ("encoder2.enc2norm1.running_var", 2e-2)):
+            e = rel(p1[k].float().cpu(), p0[k].float().cpu())
+            assert e < tol, (what, k, e)
+        # the conv weights really moved in the replayed steps (the weight gradients were not dropped after the first replay)
+        moved = rel(p1["decoder1.dec1conv2.weight"].cpu(), sd["decoder1.dec1conv2.weight"])
+        assert moved > 1e-3, (what, moved)
     dist.barrier()
     if rank == 0:
         print("MP_SYNCBN_OK", flush=True)
