@@ -70,10 +70,11 @@ def load_peaks():
 
 
 def kernel_stamp():
-    """Hash of the CUDA sources: a committed ncu profile is only quoted while it describes THIS build."""
+    """Hash of the convolution kernels' sources (csrc/conv*.cu, conv_impl.h, ptx.cuh, common.cuh): a committed ncu profile
+    of the conv family is only quoted while it describes THIS build of those kernels."""
     h = hashlib.sha256()
     pkg = os.path.join(ROOT, "general-medical-image-segmentation-cnn-framework_b200", "csrc")
-    for f in sorted(glob.glob(os.path.join(pkg, "*.cu")) + glob.glob(os.path.join(pkg, "*.cuh")) + glob.glob(os.path.join(pkg, "*.h"))):
+    for f in sorted(glob.glob(os.path.join(pkg, "conv*.cu")) + glob.glob(os.path.join(pkg, "*.cuh")) + glob.glob(os.path.join(pkg, "conv*.h"))):
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())
     return h.hexdigest()[:16]
