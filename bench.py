@@ -624,18 +624,18 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                                                             "the captured CUDA graph of the step")
     args = ap.parse_args()
-    claim_stdout()
-    if args.impl == "reference":
-        run_reference(args)
-        return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus > 1 and world == 1:
-        # convenience: re-launch under torchrun when called directly with --gpus N
+    if args.impl == "b200" and args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N (the children print the line)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus",
                str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload,
                "--sustain", str(args.sustain)] + (["--no-graph"] if args.no_graph else [])
         sys.exit(subprocess.call(cmd))
+    claim_stdout()
+    if args.impl == "reference":
+        run_reference(args)
+        return
     if args.workload == "predict":
         run_predict(args)
     else:

@@ -69,7 +69,7 @@ SIGNATURES = {
     "b200seg_p2p_grad_allreduce": "pppp" + "iii" + "pp",
     "b200seg_p2p_open": "pp",
     "b200seg_p2p_close": "pi",
-    "b200seg_p2p_allreduce": "pi" + "p" + "ii" + "p" + "i" + "d" + "pppp" + "ff" + "i" + "p" + "p",
+    "b200seg_p2p_allreduce": "pi" + "p" + "ii" + "p" + "ii" + "d" + "pppp" + "ff" + "i" + "p" + "p",
     "b200seg_adam_step": "pppp" + "l" + "fffff" + "i" + "f" + "p",
     "b200seg_adam_step_dev": "pppp" + "l" + "pp" + "p",
     "b200seg_adam_step_fused": "ppppp" + "pp" + "iii" + "pp" + "i" + "p",

@@ -44,27 +44,32 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 
 // vec: n floats, reduced in place.  finalize != 0: vec = {sum[C], sumsq[C], count} and coef / running stats are produced
 // exactly like norm_finalize_kernel does from the reduced sums.
+// phase: 0 = the whole exchange in one launch; 1 = steps 1-2 only (send: returns as soon as the vector is on its way);
+// 2 = steps 3-4 only (receive).  Launching 1, then unrelated kernels, then 2 hides the NVLink round trip behind them.
 __global__ void __launch_bounds__(512) p2p_allreduce_kernel(float* __restrict__ vec, int n, P2PPeers peers, int rank,
-                                                            int world, unsigned int* __restrict__ seq_ptr, int finalize,
+                                                            int world, unsigned int* __restrict__ seq_ptr, int phase, int finalize,
                                                             float local_count, int C, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ running_mean,
                                                             float* __restrict__ running_var, float momentum, float eps,
                                                             int clamp_eps, float* __restrict__ coef) {
   const unsigned int seq = *seq_ptr + 1;
   const int slot = seq % kP2PSlots;
-  if (finalize) {   // the element count travels with the sums (sum_size in batchnorm.py:58-62)
-    if (threadIdx.x == 0) vec[2 * C] = local_count;
+  if (phase != 2) {
+    if (finalize) {   // the element count travels with the sums (sum_size in batchnorm.py:58-62)
+      if (threadIdx.x == 0) vec[2 * C] = local_count;
+      __syncthreads();
+    }
+    // 1. scatter my vector into every rank's mailbox (my own included)
+    for (int r = 0; r < world; ++r) {
+      float* dst = peers.box[r]->data[slot][rank];
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vec[i];
+    }
+    __threadfence_system();
     __syncthreads();
+    // 2. publish
+    if (threadIdx.x < world) st_release_sys(&peers.box[threadIdx.x]->flags[slot][rank], seq);
+    if (phase == 1) return;
   }
-  // 1. scatter my vector into every rank's mailbox (my own included)
-  for (int r = 0; r < world; ++r) {
-    float* dst = peers.box[r]->data[slot][rank];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vec[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  // 2. publish
-  if (threadIdx.x < world) st_release_sys(&peers.box[threadIdx.x]->flags[slot][rank], seq);
   // 3. wait for everybody
   P2PMailbox* mine = peers.box[rank];
   if (threadIdx.x < world) {
@@ -274,11 +279,12 @@ int b200seg_p2p_close(void* dev_ptr, int opened) {
   return 0;
 }
 
-int b200seg_p2p_allreduce(float* vec, int n, const void* const* mailboxes, int rank, int world, uint32_t* seq,
+int b200seg_p2p_allreduce(float* vec, int n, const void* const* mailboxes, int rank, int world, uint32_t* seq, int phase,
                           int finalize_channels, double local_count, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float momentum, float eps, int clamp_eps, float* coef, void* stream) {
   B200_CHECK_ARG(vec && mailboxes && seq && n > 0 && n <= kP2PMaxFloats, "p2p_allreduce: at most %d floats", kP2PMaxFloats);
   B200_CHECK_ARG(world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, "p2p_allreduce: bad rank / world");
+  B200_CHECK_ARG(phase >= 0 && phase <= 2, "p2p_allreduce: phase must be 0 (whole exchange), 1 (send) or 2 (receive)");
   B200_CHECK_ARG(finalize_channels == 0 || (coef && n == 2 * finalize_channels + 1), "p2p_allreduce: finalize needs "
                  "{sum[C], sumsq[C], count} and a coefficient buffer");
   P2PPeers peers{};
@@ -287,7 +293,7 @@ int b200seg_p2p_allreduce(float* vec, int n, const void* const* mailboxes, int r
     peers.box[r] = static_cast<P2PMailbox*>(const_cast<void*>(mailboxes[r]));
   }
   p2p_allreduce_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(
-      vec, n, peers, rank, world, seq, finalize_channels > 0, static_cast<float>(local_count), finalize_channels, gamma, beta, running_mean, running_var,
+      vec, n, peers, rank, world, seq, phase, finalize_channels > 0, static_cast<float>(local_count), finalize_channels, gamma, beta, running_mean, running_var,
       momentum, eps, clamp_eps, coef);
   B200_CHECK_LAUNCH("p2p_allreduce");
   return 0;

@@ -75,9 +75,23 @@ def begin_step(device, nbytes=4 << 20):
 
 
 def end_step():
+    flush_deferred()
     _SCRATCH["active"] = False
     _COLSUMS.clear()
     flush_counters()
+
+
+# Weight-gradient launches that were postponed by one layer (multi-GPU SyncBatchNorm only): the backward statistics
+# exchange of the NEXT layer in backward order is a send launch and a receive launch (parallel.PeerExchange.
+# all_reduce_split_), and the postponed weight gradient -- which nothing in that chain depends on -- runs in between, so
+# the NVLink round trip and the wait for the slowest rank cost nothing.  Only inside a training step (begin_step ...
+# end_step flushes the last one) and only for weights whose gradient is accumulated directly into the optimiser's arena.
+_DEFERRED = []
+
+
+def flush_deferred():
+    while _DEFERRED:
+        _DEFERRED.pop(0)()
 
 
 _COUNTERS = []
@@ -521,7 +535,7 @@ def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dre
     red = sums
     if use_batch_stats and spec.kind == "batch" and spec.sync and is_parallel(spec.process_group):
         red = sums.clone()
-        all_reduce_stats(red, spec.process_group)
+        all_reduce_stats(red, spec.process_group, between=flush_deferred if _DEFERRED else None)
     dy = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device)
     dres = torch.empty_like(dy) if want_dres else None
     _call("b200seg_norm_act_bwd_apply", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), _ptr(red if use_batch_stats else None),
@@ -631,7 +645,12 @@ class _ConvNormAct(torch.autograd.Function):
                 dx, dx2 = dxin[..., :split], dxin[..., split:]
                 _publish_colsum(dx, colsum[:split])
         if need[2]:
-            dw = conv3d_wgrad_raw(g, xin, dy, weight.shape, weight)
+            if (_SCRATCH["active"] and spec.kind == "batch" and spec.sync and spec.training and is_parallel(spec.process_group)
+                    and _arena_managed(weight) and getattr(weight, "_b200_direct_grad", False) and not _use_padded(g)):
+                # postponed to the middle of the next layer's statistics exchange (see _DEFERRED)
+                _DEFERRED.append(lambda g=g, xin=xin, dy=dy, weight=weight: conv3d_wgrad_raw(g, xin, dy, weight.shape, weight))
+            else:
+                dw = conv3d_wgrad_raw(g, xin, dy, weight.shape, weight)
         if has_bias and need[3]:
             if spec.kind is not None and (spec.training or spec.kind == "instance"):
                 # a bias in front of batch/instance statistics has an analytically zero gradient: leave the (zeroed)

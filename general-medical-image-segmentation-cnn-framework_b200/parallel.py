@@ -90,10 +90,10 @@ class PeerExchange:
         dist.barrier(group=group)     # every mailbox is mapped (and zeroed) before anybody's first exchange
 
     def _call(self, vec, n, finalize_c=0, count=0.0, gamma=None, beta=None, running_mean=None, running_var=None,
-              momentum=0.1, eps=1e-5, clamp_eps=False, coef=None):
+              momentum=0.1, eps=1e-5, clamp_eps=False, coef=None, phase=0):
         import ctypes
         from .functional import _call, _ptr, _stream
-        _call("b200seg_p2p_allreduce", _ptr(vec), int(n), self.boxes, self.rank, self.world, _ptr(self.seq),
+        _call("b200seg_p2p_allreduce", _ptr(vec), int(n), self.boxes, self.rank, self.world, _ptr(self.seq), int(phase),
               int(finalize_c), float(count), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
               float(momentum), float(eps), int(clamp_eps), _ptr(coef), _stream())
 
@@ -101,6 +101,16 @@ class PeerExchange:
         """In-place sum over ranks of a contiguous fp32 vector of at most 2112 elements."""
         assert vec.is_contiguous() and vec.dtype == torch.float32
         self._call(vec, vec.numel())
+        return vec
+
+    def all_reduce_split_(self, vec, between=None):
+        """all_reduce_ as a send launch and a receive launch with `between()` (kernels that do not depend on the result)
+        enqueued in the middle: the NVLink round trip and the wait for the slowest rank hide behind them."""
+        assert vec.is_contiguous() and vec.dtype == torch.float32
+        self._call(vec, vec.numel(), phase=1)
+        if between is not None:
+            between()
+        self._call(vec, vec.numel(), phase=2)
         return vec
 
     def reduce_and_finalize(self, stats, count, c, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps):
@@ -134,14 +144,20 @@ def graph_safe(group=None):
     return not is_parallel(group) or peer_exchange(group) is not None
 
 
-def all_reduce_stats(stats, group=None):
-    """Sum a small fp32 statistics tensor over ranks, in place, in stream order.  Returns the number of ranks."""
+def all_reduce_stats(stats, group=None, between=None):
+    """Sum a small fp32 statistics tensor over ranks, in place, in stream order.  Returns the number of ranks.
+    between: optional callable enqueuing independent kernels; over NVLink peer memory it runs between the send and the
+    receive launch of the exchange (PeerExchange.all_reduce_split_), otherwise before the collective."""
     if not is_parallel(group):
+        if between is not None:
+            between()
         return 1
     px = peer_exchange(group) if stats.is_cuda else None
     if px is not None and stats.numel() <= 2112 and stats.is_contiguous():
-        px.all_reduce_(stats)
+        px.all_reduce_split_(stats, between) if between is not None else px.all_reduce_(stats)
     else:
+        if between is not None:
+            between()
         dist.all_reduce(stats, group=group)
     return dist.get_world_size(group)
 
@@ -207,11 +223,14 @@ class GradBucketReducer:
         if self._pending[b] == 0 and not self._launched[b]:
             self._launch(b)
 
-    def _launch(self, b):
+    def _launch(self, b, overlap=True):
         start, end, _ = self.buckets[b]
         view = self.arena[start:end]
         self._launched[b] = True
-        if self._stream is not None:
+        if not overlap:
+            # called from finish(): nothing left to overlap with, stay on the caller's stream
+            dist.all_reduce(view, group=self.group)
+        elif self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
                 dist.all_reduce(view, group=self.group)
@@ -224,7 +243,7 @@ class GradBucketReducer:
             return 1.0
         for b in range(len(self.buckets)):
             if not self._launched[b]:
-                self._launch(b)
+                self._launch(b, overlap=False)
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
         for w in self._works:

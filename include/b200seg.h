@@ -281,8 +281,9 @@ int b200seg_p2p_close(void* dev_ptr, int opened);
  * finalize_channels = C > 0: vec = {sum[C], sumsq[C], count} (the kernel stores local_count into vec[2C] first, so the
  * element count travels with the sums like sum_size in batchnorm.py:58-62); after the reduction the same launch writes
  * coef[4][C] = {mean, inv_std, scale, shift} and updates the running statistics exactly like b200seg_norm_finalize
- * (this is _compute_mean_std, batchnorm.py:113-125, executed identically on every rank instead of on a master). */
-int b200seg_p2p_allreduce(float* vec, int n, const void* const* mailboxes, int rank, int world, uint32_t* seq,
+ * (this is _compute_mean_std, batchnorm.py:113-125, executed identically on every rank instead of on a master).  * phase: 0 = the whole exchange in one launch; 1 = send only (store + publish), 2 = receive only (wait + sum
+ * [+ finalize]): a 1 ... 2 pair with unrelated kernels in between hides the NVLink round trip behind them. */
+int b200seg_p2p_allreduce(float* vec, int n, const void* const* mailboxes, int rank, int world, uint32_t* seq, int phase,
                           int finalize_channels, double local_count, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float momentum, float eps, int clamp_eps, float* coef, void* stream);
 

@@ -70,15 +70,16 @@ def main():
     results = []
     # (eager, NCCL bucket reducer) is the yardstick; (graph, NCCL after the replay) and (graph / eager, NVLink peer-memory
     # exchange inside the stream) must follow it
-    for use_graph, peer in ((False, False), (True, False), (True, True), (False, True)):
+    for use_graph, peer, reducer in ((False, False, False), (True, False, False), (True, True, False), (False, True, False),
+                                     (False, False, True)):
         net = UNet3D(1, 2, 16).to(dev)
         net.load_state_dict(sd)
         convert_model(net)
         net.train()
         opt = FusedAdam(net.parameters(), lr=1e-3, peer_grads=peer)
         assert opt.peer_grads == peer
-        if not peer:
-            opt.attach_reducer()
+        if reducer:
+            opt.attach_reducer()          # bucketed NCCL all-reduce launched from autograd hooks (eager mode only)
         step = TrainStep(net, DiceCELoss(2), opt, use_graph=use_graph, warmup=2)
         losses = [float(step(xb, yb)[0]) for xb, yb in data]
         assert (step.graph is not None) == use_graph
@@ -90,12 +91,12 @@ def main():
         flat = torch.cat([v.flatten().float() for v in net.parameters()])
         other = flat.clone()
         dist.broadcast(other, 0)
-        assert torch.equal(flat, other), "ranks diverged (graph=%s peer=%s): max diff %g" % (use_graph, peer,
-                                                                                             float((flat - other).abs().max()))
+        assert torch.equal(flat, other), "ranks diverged (graph=%s peer=%s reducer=%s): max diff %g" % (
+            use_graph, peer, reducer, float((flat - other).abs().max()))
         if hasattr(opt, "reducer"):
             opt.reducer.remove()
     l0, p0 = results[0]
-    for (l1, p1), what in zip(results[1:], ("graph+nccl", "graph+peer", "eager+peer")):
+    for (l1, p1), what in zip(results[1:], ("graph+nccl", "graph+peer", "eager+peer", "eager+bucket-reducer")):
         assert max(abs(a - b) for a, b in zip(l0, l1)) < 6e-3, (what, l0, l1)
         for k, tol in (("encoder1.enc1conv1.weight", 2e-2), ("decoder1.dec1conv2.weight", 2e-2), ("conv.weight", 2e-2),
                        ("upconv1.weight", 2e-2), ("encoder2.enc2norm1.running_var", 2e-2)):
