@@ -646,7 +646,8 @@ class _ConvNormAct(torch.autograd.Function):
                 _publish_colsum(dx, colsum[:split])
         if need[2]:
             if (_SCRATCH["active"] and spec.kind == "batch" and spec.sync and spec.training and is_parallel(spec.process_group)
-                    and _arena_managed(weight) and getattr(weight, "_b200_direct_grad", False) and not _use_padded(g)):
+                    and _arena_managed(weight) and getattr(weight, "_b200_direct_grad", False) and not _use_padded(g)
+                    and not getattr(weight, "_b200_hooked", False)):
                 # postponed to the middle of the next layer's statistics exchange (see _DEFERRED)
                 _DEFERRED.append(lambda g=g, xin=xin, dy=dy, weight=weight: conv3d_wgrad_raw(g, xin, dy, weight.shape, weight))
             else:

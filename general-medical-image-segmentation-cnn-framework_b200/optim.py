@@ -193,9 +193,32 @@ class FusedAdam:
 
     def attach_reducer(self, group=None, bucket_bytes=32 << 20):
         """Overlap the data-parallel gradient all-reduce with backward (parallel.GradBucketReducer)."""
+        import struct
         from .parallel import GradBucketReducer
-        self.reducer = GradBucketReducer(self.grad_arena, self.params, self.offsets, bucket_bytes, group)
+        self.reducer = GradBucketReducer(self.grad_arena, self.params, self.offsets, bucket_bytes, group,
+                                         pre_launch=self._unpack_bucket)
+        # per-bucket transposition tables: a bucket's packed conv weight gradients are moved into the gradient arena right
+        # before that bucket is all-reduced (from the autograd hook of its last parameter, overlapping the rest of backward)
+        self._bucket_unpack = []
+        dev = self.param_arena.device
+        for start, end, _ in self.reducer.buckets:
+            recs, tiles = [], 0
+            for p, off in zip(self.params, self.offsets):
+                if start <= off < end and any(p is q for q, _, _ in self._packed):
+                    a, b, k3 = p.shape[0], p.shape[1], p.shape[2] ** 3
+                    recs.append(struct.pack("<qqiiii", off, off, a, b, k3, 0))
+                    tiles += ((a + 31) // 32) * ((b + 7) // 8)
+            desc = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev) if recs else None
+            self._bucket_unpack.append((desc, len(recs), tiles))
+        for p in self.params:
+            p._b200_hooked = True       # functional: no postponed weight gradients, the hook order must mean "gradient final"
         return self.reducer
+
+    def _unpack_bucket(self, b, start, end):
+        desc, n, tiles = self._bucket_unpack[b]
+        if desc is not None and self._pending[0]:
+            _call("b200seg_unpack_wgrads_batched", _ptr(self.dw_arena), _ptr(self.grad_arena), _ptr(desc), n, self._max_k3,
+                  tiles, _stream())
 
     def all_reduce_grads(self, group=None):
         """Data-parallel gradient averaging (what DDP does inside accelerator.backward, train.py:211).  Returns the
@@ -219,9 +242,11 @@ class FusedAdam:
                 self.peer.detections += 1
             self.peer.all_reduce_()
             return 1.0 / dist.get_world_size(group)
-        self.finalize_grads()
         if getattr(self, "reducer", None) is not None and self.reducer.enabled:
-            return self.reducer.finish()
+            scale = self.reducer.finish()      # every bucket transposes its own packed gradients before its all-reduce
+            self._pending[0] = False
+            return scale
+        self.finalize_grads()
         dist.all_reduce(self.grad_arena, group=group)
         return 1.0 / dist.get_world_size(group)
 

@@ -177,8 +177,12 @@ class GradBucketReducer:
     Buckets are contiguous arena ranges of at least `bucket_bytes`, cut from the last parameter backwards.
     """
 
-    def __init__(self, arena, params, offsets, bucket_bytes=32 << 20, group=None):
-        self.arena, self.group = arena, group
+    def __init__(self, arena, params, offsets, bucket_bytes=32 << 20, group=None, pre_launch=None):
+        """pre_launch(bucket index, start, end): called on the caller's stream right before a bucket is all-reduced
+        (optim.FusedAdam transposes that bucket's packed conv weight gradients into the arena there).
+        NOTE: torch fires post-accumulate-grad hooks for a parameter also when its backward returned None, i.e. for the
+        conv weights whose gradient is accumulated outside autograd -- every parameter counts, every step."""
+        self.arena, self.group, self.pre_launch = arena, group, pre_launch
         self.params = list(params)
         self.offsets = list(offsets)
         self.enabled = is_parallel(group)
@@ -227,6 +231,8 @@ class GradBucketReducer:
         start, end, _ = self.buckets[b]
         view = self.arena[start:end]
         self._launched[b] = True
+        if self.pre_launch is not None:
+            self.pre_launch(b, start, end)
         if not overlap:
             # called from finish(): nothing left to overlap with, stay on the caller's stream
             dist.all_reduce(view, group=self.group)

@@ -13,7 +13,7 @@ dev = torch.device("cuda", local)
 sd = ounet.init_state_dict(1, 2, 16, seed=3)
 torch.manual_seed(100 + rank)
 data = [(torch.randn(2, 1, 32, 32, 32, device=dev), (torch.rand(2, 32, 32, 32, device=dev) > 0.8).to(torch.uint8)) for _ in range(3)]
-for reducer in (True, False):
+for reducer in (False, True, False, True):
     net = UNet3D(1, 2, 16).to(dev); net.load_state_dict(sd); convert_model(net); net.train()
     opt = FusedAdam(net.parameters(), lr=1e-3)
     if reducer: opt.attach_reducer()
