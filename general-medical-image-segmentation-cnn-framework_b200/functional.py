@@ -371,6 +371,7 @@ def _grad_target(param):
     if param is None or not getattr(param, "_b200_direct_grad", False) or param.grad is None:
         return None
     param._b200_pending[0] = True
+    param._b200_dw_used = True       # optim.PeerGradExchange: this weight's gradient lives in the packed arena
     return param._b200_dwp
 
 

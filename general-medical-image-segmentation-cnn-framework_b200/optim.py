@@ -257,7 +257,13 @@ class FusedAdam:
         z = self._zeroed
         n = (z.numel() + 63) // 64 * 64
         buf = self.peer.arena[:n] if self.peer is not None else torch.nn.functional.pad(z, (0, n - z.numel()))
-        return buf.view(-1, 64).ne(0).any(dim=1)
+        mask = buf.view(-1, 64).ne(0).any(dim=1)        # what the data shows in this step ...
+        # ... plus what the structure says (a gradient that happens to be all-zero today -- dead ReLU channels of a tiny
+        # bottleneck -- must still be exchanged tomorrow): every parameter's slot in the arena its gradient is written to
+        for p, off in zip(self.params, self.offsets):
+            base = self._padded + off if getattr(p, "_b200_dw_used", False) else off
+            mask[base // 64:(base + p.numel() + 63) // 64] = True
+        return mask
 
     @property
     def peer_grads(self):
