@@ -116,15 +116,14 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(float* __restrict__ 
 // live in cudaMalloc'ed memory that all peers map through CUDA IPC.  Only the 64-float chunks that ever receive a gradient
 // are exchanged (`live`: sorted chunk indices, identical on every rank).  Four launches, all stream-ordered:
 //   1. signal A: "my gradients of exchange `seq` are complete" -> every peer's flag block (release, system scope);
-//   2. reduce-scatter: wait for A from everybody; rank r sums ITS share of the live chunks over all ranks' buffers in rank
-//      order (peer loads over NVLink; the same order everywhere) into its staging buffer;
-//   3. signal B: "my share is reduced";
-//   4. all-gather: wait for B from everybody; copy every share from its owner's staging buffer into the local gradient
-//      buffer.  All ranks end with bit-identical sums.
-// Hazards: a peer's buffer is only overwritten (by its own all-gather, or by the next step's backward) after it has seen B
-// from every rank, i.e. after every rank has finished reading it; staging buffers are rewritten only after A of the next
-// exchange, which every rank sends after its all-gather.  `seq` lives in device memory and is advanced by launch 1, so a
-// captured sequence replays correctly.
+//   2. reduce + push: wait for A from everybody; rank r sums ITS share of the live chunks over all ranks' buffers in rank
+//      order (peer loads over NVLink; the same order everywhere) and stores the sum into EVERY rank's buffer;
+//   3. signal B: "my share has been pushed" (system-scope release after the pushes);
+//   4. wait for B from everybody.  All ranks end with bit-identical sums.
+// Hazards: during an exchange the chunks of rank r's share are read and written by rank r only, in all buffers; a buffer is
+// next overwritten by its owner's following backward pass, which starts after its launch 4, i.e. after every rank has
+// finished reading and pushing.  `seq` lives in device memory and is advanced by launch 1, so a captured sequence replays
+// correctly.  (`reds`, a staging buffer, is no longer used by the kernels; the ABI keeps the argument.)
 constexpr int kGradChunk = 64;   // floats
 
 struct GradPeers {
@@ -155,42 +154,41 @@ __device__ __forceinline__ void grad_wait(const unsigned int* mine, int which, i
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) p2p_grad_reduce_scatter_kernel(GradPeers peers, const int* __restrict__ live, int n_live,
-                                                                      int rank, int world, const unsigned int* __restrict__ seq_ptr) {
-  grad_wait(peers.flags[rank], 0, world, *seq_ptr);
-  const int per = (n_live + world - 1) / world;
+// Reduce + broadcast: rank r sums its share of the live chunks over all ranks' buffers (W peer loads in flight per thread,
+// rank order) and PUSHES the sum into every rank's buffer.  Nobody else touches those chunks during the exchange (each
+// rank reads / writes only its own share, in everybody's buffer), so the pushes need no staging copy; stores over NVLink
+// are fire-and-forget, the all-gather half costs no round trip.
+template <int W>
+__global__ void __launch_bounds__(256) p2p_grad_reduce_push_kernel(GradPeers peers, const int* __restrict__ live, int n_live,
+                                                                   int rank, const unsigned int* __restrict__ seq_ptr) {
+  grad_wait(peers.flags[rank], 0, W, *seq_ptr);
+  const int per = (n_live + W - 1) / W;
   const int lo = rank * per, hi = min(n_live, lo + per);
-  float* out = peers.red[rank];
   const long long items = static_cast<long long>(max(hi - lo, 0)) * (kGradChunk / 4);
   for (long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; w < items;
        w += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int li = lo + static_cast<int>(w / (kGradChunk / 4)), q = static_cast<int>(w % (kGradChunk / 4));
     const long long off = static_cast<long long>(live[li]) * kGradChunk + q * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {
-      const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.buf[r] + off));
-      acc.x += v.x;
-      acc.y += v.y;
-      acc.z += v.z;
-      acc.w += v.w;
+    float4 v[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r) v[r] = __ldcv(reinterpret_cast<const float4*>(peers.buf[r] + off));
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < W; ++r) {
+      acc.x += v[r].x;
+      acc.y += v[r].y;
+      acc.z += v[r].z;
+      acc.w += v[r].w;
     }
-    *reinterpret_cast<float4*>(out + static_cast<long long>(li - lo) * kGradChunk + q * 4) = acc;
+#pragma unroll
+    for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(peers.buf[r] + off) = acc;
   }
+  __threadfence_system();     // the pushes are performed system-wide before this thread retires (flag B follows the kernel)
 }
 
-__global__ void __launch_bounds__(256) p2p_grad_all_gather_kernel(GradPeers peers, const int* __restrict__ live, int n_live, int rank,
-                                                                  int world, const unsigned int* __restrict__ seq_ptr) {
+// Completion: everybody's pushes have landed (flag B from every rank, sent after its reduce+push kernel drained).
+__global__ void p2p_grad_wait_kernel(GradPeers peers, int rank, int world, const unsigned int* __restrict__ seq_ptr) {
   grad_wait(peers.flags[rank], 1, world, *seq_ptr);
-  const int per = (n_live + world - 1) / world;
-  float* dst = peers.buf[rank];
-  const long long items = static_cast<long long>(n_live) * (kGradChunk / 4);
-  for (long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; w < items;
-       w += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int li = static_cast<int>(w / (kGradChunk / 4)), q = static_cast<int>(w % (kGradChunk / 4));
-    const int owner = li / per;
-    const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.red[owner] + static_cast<long long>(li - owner * per) * kGradChunk + q * 4));
-    *reinterpret_cast<float4*>(dst + static_cast<long long>(live[li]) * kGradChunk + q * 4) = v;
-  }
 }
 
 }  // namespace b200
@@ -249,11 +247,19 @@ int b200seg_p2p_grad_allreduce(const void* const* bufs, const void* const* reds,
   auto st = static_cast<cudaStream_t>(stream);
   const int per = (n_live + world - 1) / world;
   const int g_rs = grid_for(static_cast<int64_t>(per) * (kGradChunk / 4), 256, kNumSMs * 4);
-  const int g_ag = grid_for(static_cast<int64_t>(n_live) * (kGradChunk / 4), 256, kNumSMs * 4);
   p2p_grad_signal_kernel<<<1, 32, 0, st>>>(peers, 0, rank, world, seq, 1);
-  p2p_grad_reduce_scatter_kernel<<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, world, seq);
+  switch (world) {
+    case 1: p2p_grad_reduce_push_kernel<1><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+    case 2: p2p_grad_reduce_push_kernel<2><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+    case 3: p2p_grad_reduce_push_kernel<3><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+    case 4: p2p_grad_reduce_push_kernel<4><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+    case 5: p2p_grad_reduce_push_kernel<5><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+    case 6: p2p_grad_reduce_push_kernel<6><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+    case 7: p2p_grad_reduce_push_kernel<7><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+    default: p2p_grad_reduce_push_kernel<8><<<g_rs, 256, 0, st>>>(peers, live, n_live, rank, seq); break;
+  }
   p2p_grad_signal_kernel<<<1, 32, 0, st>>>(peers, 1, rank, world, seq, 0);
-  p2p_grad_all_gather_kernel<<<g_ag, 256, 0, st>>>(peers, live, n_live, rank, world, seq);
+  p2p_grad_wait_kernel<<<1, 32, 0, st>>>(peers, rank, world, seq);
   B200_CHECK_LAUNCH("p2p_grad_allreduce");
   return 0;
 }
