@@ -24,15 +24,26 @@ constexpr int kP2PSlots = 4;
 constexpr int kP2PMaxWorld = 8;
 constexpr int kP2PMaxFloats = 2112;   // 2 * 1024 channels + count, padded
 
+// Every float travels as one 8-byte word {value bits, sequence number}: the receiver polls the word itself, so no
+// separate flag, no system fence between data and flag and no second NVLink transaction are needed (the idea of NCCL's LL
+// protocol; an aligned 8-byte store is a single transaction).  A slot written in exchange `seq` is reused in exchange
+// seq + kP2PSlots, whose tag differs, so stale words are never mistaken for fresh ones.
 struct P2PMailbox {
-  float data[kP2PSlots][kP2PMaxWorld][kP2PMaxFloats];
-  unsigned int flags[kP2PSlots][kP2PMaxWorld];
+  uint2 data[kP2PSlots][kP2PMaxWorld][kP2PMaxFloats];
 };
 
 struct P2PPeers {
   P2PMailbox* box[kP2PMaxWorld];
 };
 
+__device__ __forceinline__ void st_ll(uint2* p, float v, unsigned int tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -59,29 +70,28 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(float* __restrict__ 
       if (threadIdx.x == 0) vec[2 * C] = local_count;
       __syncthreads();
     }
-    // 1. scatter my vector into every rank's mailbox (my own included)
-    for (int r = 0; r < world; ++r) {
-      float* dst = peers.box[r]->data[slot][rank];
-      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vec[i];
+    // 1 + 2. scatter my vector, tagged word by word, into every rank's mailbox (my own included)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = vec[i];
+      for (int r = 0; r < world; ++r) st_ll(&peers.box[r]->data[slot][rank][i], v, seq);
     }
-    __threadfence_system();
-    __syncthreads();
-    // 2. publish
-    if (threadIdx.x < world) st_release_sys(&peers.box[threadIdx.x]->flags[slot][rank], seq);
     if (phase == 1) return;
+    __syncthreads();     // (phase 0: vec is overwritten below by other threads' sums only at their own indices: no hazard,
+                         //  but keep the block together so that the spin starts after all stores were issued)
   }
-  // 3. wait for everybody
+  // 3. wait for everybody's words and sum them in rank order -- the same order everywhere: bit-identical results
   P2PMailbox* mine = peers.box[rank];
-  if (threadIdx.x < world) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(&mine->flags[slot][threadIdx.x]) < seq) {
-      if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a peer never arrived (mismatched call sequence)
-    }
-  }
-  __syncthreads();
+  const long long t0 = clock64();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float s = 0.f;
-    for (int r = 0; r < world; ++r) s += __ldcv(&mine->data[slot][r][i]);
+    for (int r = 0; r < world; ++r) {
+      uint2 w = ld_ll(&mine->data[slot][r][i]);
+      while (w.y != seq) {
+        if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a peer never arrived (mismatched call sequence)
+        w = ld_ll(&mine->data[slot][r][i]);
+      }
+      s += __uint_as_float(w.x);
+    }
     vec[i] = s;
   }
   __syncthreads();
