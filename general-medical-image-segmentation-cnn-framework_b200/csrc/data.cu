@@ -66,6 +66,83 @@ __global__ void __launch_bounds__(256) crop_patch_kernel(const T* __restrict__ v
   }
 }
 
+// ---- Pad3d 'reflect' / 'replicate' (utils/convolution.py:78-86 = F.pad(x, 6*[pad], mode)) on NDHWC bf16 rows ----------
+// source index of padded position o along an axis of n voxels (pad p on both sides)
+__device__ __forceinline__ int pad_src(int o, int n, int p, int mode) {
+  int i = o - p;
+  if (mode == 1) {            // reflect (no edge repeat): -1 -> 1, n -> n-2
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+  } else {                    // replicate
+    i = i < 0 ? 0 : (i >= n ? n - 1 : i);
+  }
+  return i;
+}
+
+__global__ void __launch_bounds__(256) pad3d_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp, __nv_bfloat16* __restrict__ y,
+                                                        int64_t yp, int n, int d, int h, int w, int c, int p, int mode) {
+  const int od = d + 2 * p, oh = h + 2 * p, ow = w + 2 * p;
+  const int64_t total = static_cast<int64_t>(n) * od * oh * ow * c;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    int64_t v = i / c;
+    const int xo = static_cast<int>(v % ow);
+    v /= ow;
+    const int yo = static_cast<int>(v % oh);
+    v /= oh;
+    const int zo = static_cast<int>(v % od);
+    const int nn = static_cast<int>(v / od);
+    const int64_t src = ((static_cast<int64_t>(nn) * d + pad_src(zo, d, p, mode)) * h + pad_src(yo, h, p, mode)) * w +
+                        pad_src(xo, w, p, mode);
+    y[(i / c) * yp + ch] = x[src * xp + ch];
+  }
+}
+
+// Adjoint: dx[i] = sum of dy over every padded position that reads i.  Along one axis those are: the centre i + p, and
+// reflect: p - i (1 <= i <= p) and 2(n-1) + p - i (n-1-p <= i <= n-2); replicate: 0..p-1 for i = 0, n+p..n+2p-1 for i = n-1.
+__device__ __forceinline__ int pad_sources(int i, int n, int p, int mode, int* out) {
+  int k = 0;
+  out[k++] = i + p;
+  if (mode == 1) {
+    if (i >= 1 && i <= p) out[k++] = p - i;
+    if (i >= n - 1 - p && i <= n - 2) out[k++] = 2 * (n - 1) + p - i;
+  } else {
+    if (i == 0)
+      for (int o = 0; o < p; ++o) out[k++] = o;
+    if (i == n - 1)
+      for (int o = n + p; o < n + 2 * p; ++o) out[k++] = o;
+  }
+  return k;
+}
+
+constexpr int kMaxPad = 8;
+
+__global__ void __launch_bounds__(256) pad3d_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dyp, __nv_bfloat16* __restrict__ dx,
+                                                        int64_t dxp, int n, int d, int h, int w, int c, int p, int mode) {
+  const int oh = h + 2 * p, ow = w + 2 * p, od = d + 2 * p;
+  const int64_t total = static_cast<int64_t>(n) * d * h * w * c;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    int64_t v = i / c;
+    const int xi = static_cast<int>(v % w);
+    v /= w;
+    const int yi = static_cast<int>(v % h);
+    v /= h;
+    const int zi = static_cast<int>(v % d);
+    const int nn = static_cast<int>(v / d);
+    int zs[2 * kMaxPad + 1], ys[2 * kMaxPad + 1], xs[2 * kMaxPad + 1];
+    const int nz = pad_sources(zi, d, p, mode, zs), ny = pad_sources(yi, h, p, mode, ys), nx = pad_sources(xi, w, p, mode, xs);
+    float acc = 0.f;
+    for (int a = 0; a < nz; ++a)
+      for (int b = 0; b < ny; ++b)
+        for (int e = 0; e < nx; ++e)
+          acc += __bfloat162float(dy[(((static_cast<int64_t>(nn) * od + zs[a]) * oh + ys[b]) * ow + xs[e]) * dyp + ch]);
+    dx[(i / c) * dxp + ch] = __float2bfloat16(acc);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -100,6 +177,35 @@ int b200seg_crop_patch(const void* vol, int is_label, int c, int w, int h, int d
     crop_patch_kernel<float><<<grid_for(total, 256, kNumSMs * 8), 256, 0, st>>>(static_cast<const float*>(vol), c, w, h, d, x0, y0, z0,
                                                                             pw, ph, pd, mean_inv_std, static_cast<float*>(out));
   B200_CHECK_LAUNCH("crop_patch");
+  return 0;
+}
+
+static int check_pad3d(int n, int d, int h, int w, int c, int pad, int mode, const char* who) {
+  B200_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && pad >= 0 && pad <= kMaxPad, "%s: bad extents (pad <= %d)", who, kMaxPad);
+  B200_CHECK_ARG(mode == 1 || mode == 2, "%s: mode must be 1 (reflect) or 2 (replicate); 'constant' is folded into the convolutions", who);
+  B200_CHECK_ARG(mode != 1 || (pad < d && pad < h && pad < w), "%s: reflect padding must be smaller than every extent", who);
+  return 0;
+}
+
+int b200seg_pad3d_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int n, int d, int h, int w, int c, int pad, int mode,
+                      void* stream) {
+  B200_CHECK_ARG(x && y && x_pitch >= c && y_pitch >= c, "pad3d_fwd: bad buffers");
+  if (int rc = check_pad3d(n, d, h, w, c, pad, mode, "pad3d_fwd")) return rc;
+  const int64_t total = static_cast<int64_t>(n) * (d + 2 * pad) * (h + 2 * pad) * (w + 2 * pad) * c;
+  pad3d_fwd_kernel<<<grid_for(total, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, n, d, h, w, c, pad, mode);
+  B200_CHECK_LAUNCH("pad3d_fwd");
+  return 0;
+}
+
+int b200seg_pad3d_bwd(const void* dy, int64_t dy_pitch, void* dx, int64_t dx_pitch, int n, int d, int h, int w, int c, int pad,
+                      int mode, void* stream) {
+  B200_CHECK_ARG(dy && dx && dy_pitch >= c && dx_pitch >= c, "pad3d_bwd: bad buffers");
+  if (int rc = check_pad3d(n, d, h, w, c, pad, mode, "pad3d_bwd")) return rc;
+  const int64_t total = static_cast<int64_t>(n) * d * h * w * c;
+  pad3d_bwd_kernel<<<grid_for(total, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), dy_pitch, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c, pad, mode);
+  B200_CHECK_LAUNCH("pad3d_bwd");
   return 0;
 }
 

@@ -1156,6 +1156,34 @@ def dropout(x, p, training=True, channel=False, out=None):
     return _Dropout.apply(x, (p, channel, _SALT[0], out))
 
 
+class _Pad3d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg):
+        pad, mode = cfg
+        x, xp = _as_rows(x)
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, d + 2 * pad, h + 2 * pad, w + 2 * pad, c), dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_pad3d_fwd", _ptr(x), xp, _ptr(y), c, n, d, h, w, c, pad, mode, _stream())
+        ctx.cfg = (pad, mode, (n, d, h, w, c))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        pad, mode, (n, d, h, w, c) = ctx.cfg
+        dy, dyp = _as_rows(dy)
+        dx = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=dy.device)
+        _call("b200seg_pad3d_bwd", _ptr(dy), dyp, _ptr(dx), c, n, d, h, w, c, pad, mode, _stream())
+        return dx, None
+
+
+def pad3d(x, pad, mode):
+    """F.pad(x, 6*[pad], mode) for mode in {'reflect', 'replicate'} (utils/convolution.py:78-86); 'constant' padding never
+    materialises (it is the TMA out-of-bounds fill of the convolution kernels)."""
+    if pad == 0:
+        return x
+    return _Pad3d.apply(x, (int(pad), {"reflect": 1, "replicate": 2}[mode]))
+
+
 class _AddSlice(torch.autograd.Function):
     """out[..., off:off+c_x] += x, in place (residual.py:74-83: the shortcut zero-padded to the wider channel count)."""
 

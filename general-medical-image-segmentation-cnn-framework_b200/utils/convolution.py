@@ -2,7 +2,7 @@
 
 [norm -> ReLU ->] pad(dilation) -> Conv(k, dilation, bias = not norm) [-> norm -> ReLU].  The explicit `Pad3d` of the
 reference is folded into the convolution (TMA out-of-bounds fill), which is exact for the default 'constant' mode;
-'reflect' / 'replicate' are not on any in-scope model's path and raise.
+'reflect' / 'replicate' run an explicit pad kernel (b200seg_pad3d_fwd / _bwd) followed by an unpadded convolution.
 """
 import torch.nn as nn
 
@@ -37,8 +37,7 @@ class ConvolutionalBlock(nn.Module, OpsMixin):
         super().__init__()
         if dimensions != 3:
             raise NotImplementedError("b200seg implements the volumetric (dimensions=3) path")
-        if padding_mode != 'constant' and kernel_size > 1:
-            raise NotImplementedError("only padding_mode='constant' is folded into the convolution kernels")
+        self.padding_mode = padding_mode
         norm_class = nn.BatchNorm3d if batch_norm else (nn.InstanceNorm3d if instance_norm else None)
         layers = nn.ModuleList()
         pre_norm = post_norm = None
@@ -86,11 +85,16 @@ class ConvolutionalBlock(nn.Module, OpsMixin):
         F = self.kernels
         act = "relu" if self.activation else "none"
         pad = self.dilation * (self.kernel_size - 1) // 2 if self.kernel_size > 1 else 0
-        geom = dict(k=self.kernel_size, stride=1, pad=pad, dil=self.dilation)
+        explicit = self.padding_mode != 'constant' and pad > 0     # reflect / replicate: pad kernel + 'valid' convolution
+        geom = dict(k=self.kernel_size, stride=1, pad=0 if explicit else pad, dil=self.dilation)
         conv = self._conv
         if self.preactivation:
             if self._pre_norm is not None or self.activation:
                 x = F.norm_act(x, norm_spec(F, self._pre_norm, act, 0.0, self.training), **norm_args(self._pre_norm))
+            if explicit:
+                x = F.pad3d(x, pad, self.padding_mode)
             return F.conv_norm_act(x, conv.weight, conv.bias, **geom)
+        if explicit:
+            x = F.pad3d(x, pad, self.padding_mode)
         return F.conv_norm_act(x, conv.weight, conv.bias, spec=norm_spec(F, self._post_norm, act, 0.0, self.training),
                                **geom, **norm_args(self._post_norm))

@@ -232,6 +232,14 @@ int b200seg_znorm_finalize(const double* sums, int64_t n, float* mean_inv_std, v
 int b200seg_crop_patch(const void* vol, int is_label, int c, int w, int h, int d, int x0, int y0, int z0, int pw, int ph, int pd,
                        const float* mean_inv_std, void* out, void* stream);
 
+/* ---- Pad3d (utils/convolution.py:78-86: F.pad(x, 6*[pad], mode)) ------------------------------------------------- */
+/* mode 1 = 'reflect', 2 = 'replicate' ('constant' is folded into the convolution kernels).  x: NDHWC bf16 [n,d,h,w,c],
+ * y: [n, d+2p, h+2p, w+2p, c].  bwd is the adjoint: dx[i] = sum of dy over the padded positions that read voxel i. */
+int b200seg_pad3d_fwd(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int n, int d, int h, int w, int c, int pad, int mode,
+                      void* stream);
+int b200seg_pad3d_bwd(const void* dy, int64_t dy_pitch, void* dx, int64_t dx_pitch, int n, int d, int h, int w, int c, int pad,
+                      int mode, void* stream);
+
 /* ---- metric (metric.py:20-75) ---------------------------------------------------------------------------------- */
 /* counts: uint64[4] += {sum gt, sum pred, |gt & pred| nonzero, |gt | pred| nonzero} over uint8 label volumes. */
 int b200seg_seg_counts(const uint8_t* gt, const uint8_t* pred, int64_t numel, unsigned long long* counts,

@@ -163,6 +163,10 @@ def upsample_nearest2(x):
     return TF.interpolate(x, scale_factor=2, mode="nearest")
 
 
+def pad3d(x, pad, mode):
+    return TF.pad(x, 6 * [pad], mode) if pad else x
+
+
 def add(a, b, out=None):
     return _ra(a + b)
 

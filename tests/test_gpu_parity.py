@@ -299,6 +299,31 @@ def test_conv_transpose_k4s4(F):
         close(bd.grad.cpu(), dy.sum((0, 2, 3, 4)), 8e-3, "convT k4s4 bias grad")
 
 
+@pytest.mark.parametrize("mode", ["reflect", "replicate"])
+def test_pad3d_reflect_replicate(F, mode):
+    """Pad3d (utils/convolution.py:78-86) forward and adjoint against torch.nn.functional.pad, bit-exact forward."""
+    g = torch.Generator().manual_seed(12)
+    for pad, shape in ((1, (2, 16, 5, 6, 7)), (2, (1, 12, 6, 5, 9)), (4, (1, 8, 6, 7, 5))):
+        x = bf(torch.randn(*shape, generator=g))
+        xr = x.clone().requires_grad_(True)
+        ref = torch.nn.functional.pad(xr, 6 * [pad], mode)
+        dy = bf(torch.randn(ref.shape, generator=g))
+        ref.backward(dy)
+        xd = ndhwc(x).requires_grad_(True)
+        y = F.pad3d(xd, pad, mode)
+        assert torch.equal(ncdhw(y), ref.detach())
+        y.backward(ndhwc(dy))
+        close(ncdhw(xd.grad), xr.grad, 6e-3, "pad3d adjoint (bf16 sums of up to (pad+1)^3 terms)")
+    # through ConvolutionalBlock (HighResNet's building block) on the CUDA kernels
+    from b200seg.utils.convolution import ConvolutionalBlock
+    blk = ConvolutionalBlock(16, 16, 2, 3, padding_mode=mode, batch_norm=False).to(DEV)
+    x = bf(torch.randn(1, 16, 10, 12, 16, generator=g))
+    conv = blk.convolutional_block[-1]
+    want = torch.nn.functional.conv3d(torch.nn.functional.pad(torch.relu(x), 6 * [2], mode), bf(conv.weight.detach().cpu()),
+                                      conv.bias.detach().cpu(), dilation=2)
+    close(ncdhw(blk(ndhwc(x))), want.detach(), 1e-2, "ConvolutionalBlock " + mode)
+
+
 def test_concat_free_decoder_input_equals_torch_cat(F):
     g = torch.Generator().manual_seed(9)
     a = bf(torch.randn(1, 16, 4, 8, 8, generator=g))

@@ -73,8 +73,13 @@ def test_constructor_contracts():
         ConvolutionalBlock(4, 4, 1, 3, batch_norm=True, instance_norm=True)
     with pytest.raises(AssertionError):
         ResidualBlock(4, 4, 2, 1, 3, residual_type="concat")
-    with pytest.raises(NotImplementedError):
-        ConvolutionalBlock(4, 4, 1, 3, padding_mode="reflect")
+    # reflect / replicate padding: the mirror's graph (pad op + 'valid' conv) equals torch's F.pad + conv on the CPU backend
+    for mode in ("reflect", "replicate"):
+        blk = ConvolutionalBlock(4, 6, 2, 3, padding_mode=mode, batch_norm=False).set_kernels(backend_torch)
+        x = torch.randn(1, 4, 7, 8, 9)
+        conv = blk.convolutional_block[-1]
+        want = conv(torch.nn.functional.pad(torch.relu(x), 6 * [2], mode))
+        assert torch.allclose(blk(x), want, atol=1e-5)
     net = HighRes3DNet(1, 2)
     assert int(net.receptive_field) == 87 and net.num_parameters == 803636
     with pytest.raises(ValueError):
