@@ -57,6 +57,8 @@ SIGNATURES = {
     "b200seg_dice_sums": "ppp" + "iil" + "if" + "pp",
     "b200seg_dice_grad": "ppp" + "iil" + "if" + "ppp" + "pp",
     "b200seg_seg_counts": "ppl" + "pp",
+    "b200seg_mask_edge_points": "piii" + "fff" + "pQpp",
+    "b200seg_min_distances": "plplpp",
     "b200seg_pad3d_fwd": "plpl" + "iiiii" + "ii" + "p",
     "b200seg_pad3d_bwd": "plpl" + "iiiii" + "ii" + "p",
     "b200seg_volume_stats": "plpp",

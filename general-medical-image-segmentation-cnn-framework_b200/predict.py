@@ -1,8 +1,9 @@
 """Prediction entry point with the reference's command line (`python predict.py config=unet config.ckpt=/abs/path.pt`,
 predict.py:217-289) and flow (predict.py:62-183): load checkpoint["model"], sliding-window inference per volume
 (GridSampler -> batched eval forward -> argmax -> GridAggregator), Dice/IoU per volume, metrics.csv.  The volumes are
-synthetic unless `config.data` points at a directory of `<name>.npy` / `<name>_gt.npy` pairs; NIfTI / MHD writers are
-outside the path."""
+synthetic unless `config.data` points at a directory of `<name>.npy` / `<name>_gt.npy` pairs.  `config.save_format=nii.gz`
+writes `pred_file/pred-%04d.nii.gz` like predict.py:209-214 (utils/nifti.py), `config.hd95=True` adds the reference's
+precision / recall / HD95 columns and the mean row to metrics.csv (predict.py:154-201; utils/metric.py on the GPU)."""
 import csv
 import glob
 import os
@@ -16,6 +17,7 @@ from .config import build_model, compose
 from .data import synthetic_volume
 from .inference import sliding_window_predict
 from .utils.metric import metric
+from .utils.nifti import save_nifti
 
 
 def volumes(config):
@@ -42,23 +44,38 @@ def predict(config, model, log=print):
         model.load_state_dict(ckpt["model"])
     model = model.to(dev).eval()
     os.makedirs(config.hydra_path, exist_ok=True)
-    rows = []
-    for name, vol, gt in volumes(config):
+    rows, full = [], []
+    want_hd95 = str(config.get("hd95", False)).lower() in ("true", "1")
+    fmt = str(config.get("save_format", "npy"))
+    spacing = tuple(float(v) for v in str(config.get("spacing", "1,1,1")).replace(" ", "").split(","))
+    for i, (name, vol, gt) in enumerate(volumes(config)):
         labels = sliding_window_predict(model, vol, config.patch_size, config.patch_overlap,
                                         batch_size=config.batch_size, overlap_mode=config.overlap_mode)
-        if gt is not None:
+        if gt is not None and want_hd95:
+            precision, recall, jaccard, dice, hs95 = metric(gt.to(dev), labels, spacing)       # predict.py:154
+            full.append((precision, recall, jaccard, dice, hs95))
+        elif gt is not None:
             jaccard, dice = metric(gt.to(dev), labels)
         else:
             jaccard = dice = float("nan")
         rows.append((name, jaccard, dice))
         if rank == 0:
-            np.save(os.path.join(config.hydra_path, "pred-%s.npy" % name), labels.cpu().numpy())
+            if fmt in ("nii", "nii.gz"):                                                       # predict.py:209-214
+                os.makedirs(os.path.join(config.hydra_path, "pred_file"), exist_ok=True)
+                save_nifti(os.path.join(config.hydra_path, "pred_file", "pred-%04d.%s" % (i, fmt)), labels.cpu().numpy())
+            else:
+                np.save(os.path.join(config.hydra_path, "pred-%s.npy" % name), labels.cpu().numpy())
             log("%s: jaccard %.4f dice %.4f" % (name, jaccard, dice))
     if rank == 0:
-        with open(os.path.join(config.hydra_path, "metrics.csv"), "w", newline="") as f:   # predict.py:149-183
+        with open(os.path.join(config.hydra_path, "metrics.csv"), "w", newline="") as f:   # predict.py:186-201
             w = csv.writer(f)
-            w.writerow(["name", "jaccard", "dice"])
-            w.writerows(rows)
+            if want_hd95 and full:
+                w.writerow(["precision", "recall", "jaccard", "dice", "hs95"])
+                w.writerows(full)
+                w.writerow([float(np.mean([r[j] for r in full])) for j in range(5)])           # the mean row of save_csv
+            else:
+                w.writerow(["name", "jaccard", "dice"])
+                w.writerows(rows)
     return rows
 
 

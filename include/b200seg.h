@@ -232,6 +232,16 @@ int b200seg_znorm_finalize(const double* sums, int64_t n, float* mean_inv_std, v
 int b200seg_crop_patch(const void* vol, int is_label, int c, int w, int h, int d, int x0, int y0, int z0, int pw, int ph, int pd,
                        const float* mean_inv_std, void* out, void* stream);
 
+/* ---- 95th-percentile Hausdorff distance (metric.py:29-32 -> monai.metrics.compute_hausdorff_distance) ------------- */
+/* Edge voxels of a binary mask [w][h][d] (uint8, nonzero = foreground): seg ^ binary_erosion(seg), 6-neighbourhood, zero
+ * border -- as physical coordinates (index * spacing).  count (device uint64, caller zeroes) receives the number of edge
+ * voxels; points (float[capacity][3], may be NULL for a counting pass) the first `capacity` of them, in no particular order. */
+int b200seg_mask_edge_points(const uint8_t* mask, int w, int h, int d, float sx, float sy, float sz, float* points,
+                             unsigned long long capacity, unsigned long long* count, void* stream);
+/* out[i] = min_j |a_i - b_j| (Euclidean) for point sets a[na][3], b[nb][3]: the distance transform of b's complement sampled
+ * at a.  Both sets must be non-empty. */
+int b200seg_min_distances(const float* a, int64_t na, const float* b, int64_t nb, float* out, void* stream);
+
 /* ---- Pad3d (utils/convolution.py:78-86: F.pad(x, 6*[pad], mode)) ------------------------------------------------- */
 /* mode 1 = 'reflect', 2 = 'replicate' ('constant' is folded into the convolution kernels).  x: NDHWC bf16 [n,d,h,w,c],
  * y: [n, d+2p, h+2p, w+2p, c].  bwd is the adjoint: dx[i] = sum of dy over the padded positions that read voxel i. */
