@@ -90,7 +90,7 @@ def train(config, model, log=print):
     if str(config.get("data", "synthetic")) == "volumes":
         # device-resident volumes: z-normalisation + uniform patch crop on the GPU (dataloader.py:52-67)
         vols = [synthetic_volume(config.volume_size, config.in_classes, seed=config.seed + 17 * rank + i)
-                for i in range(int(config.get("num_volumes", 2)))]
+                for i in range(int(config.get("train_volumes", 2)))]
         loader = GpuPatchSampler([v for v, _ in vols], [g for _, g in vols], config.patch_size, config.batch_size,
                                  int(config.get("samples_per_volume", 10)), device=dev, seed=config.seed + rank)
     else:

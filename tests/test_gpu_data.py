@@ -59,7 +59,7 @@ def test_train_entry_runs_on_device_resident_volumes(tmp_path):
     """config.data=volumes: the training loop of train.py fed by GpuPatchSampler instead of the synthetic host generator."""
     from b200seg import train as T
     args = ["config=unet", "config.batch_size=2", "config.patch_size=32,32,32", "config.epochs=2", "config.data=volumes",
-            "config.volume_size=48,64,40", "config.num_volumes=2", "config.samples_per_volume=4",
+            "config.volume_size=48,64,40", "config.train_volumes=2", "config.samples_per_volume=4",
             "config.output_dir=%s" % tmp_path, "config.criterion=dice_ce", "config.init_lr=0.002"]
     hist = T.main(args)
     assert len(hist) == 2 and hist[-1][1] < hist[0][1], hist
