@@ -145,3 +145,39 @@ def test_window_sampler_counts_and_roundtrip():
         patches = np.stack([vol[:, a:d, b:e, c:f] for a, b, c, d, e, f in locs])
         agg.add_batch(patches, locs)
         assert np.array_equal(agg.get_output_tensor(), vol)
+
+
+def test_hd95_restatement_equals_brute_force():
+    """oracle/metric.py: hausdorff_distance (MONAI's edge + distance-transform algorithm restated with scipy; parity unpinned
+    against MONAI itself) against its definition evaluated by brute force: percentile over edge voxels of the distance to the
+    nearest edge voxel of the other mask."""
+    rng = np.random.default_rng(4)
+    for shape, spacing in (((9, 8, 11), None), ((12, 10, 7), (0.5, 2.0, 1.25))):
+        a = rng.random(shape) > 0.55
+        b = rng.random(shape) > 0.6
+        sp = np.array(spacing if spacing else (1, 1, 1), dtype=np.float64)
+
+        def edges(m):
+            pad = np.pad(m, 1)
+            core = pad[1:-1, 1:-1, 1:-1]
+            er = core & pad[:-2, 1:-1, 1:-1] & pad[2:, 1:-1, 1:-1] & pad[1:-1, :-2, 1:-1] & pad[1:-1, 2:, 1:-1] & \
+                pad[1:-1, 1:-1, :-2] & pad[1:-1, 1:-1, 2:]
+            return np.argwhere(core & ~er) * sp
+
+        ea, eb = edges(a), edges(b)
+
+        def directed(p, q):
+            d = np.sqrt(((p[:, None, :] - q[None, :, :]) ** 2).sum(-1)).min(1)
+            return np.percentile(d, 95)
+        want = max(directed(ea, eb), directed(eb, ea))
+        assert abs(metric.hausdorff_distance(a, b, 95, spacing) - want) < 1e-9
+    assert np.isnan(metric.hausdorff_distance(np.zeros((4, 4, 4)), np.zeros((4, 4, 4))))
+
+
+def test_data_oracle_znorm_and_crop():
+    from oracle import data as odata
+    rng = np.random.default_rng(0)
+    v = (rng.random((1, 6, 7, 8)) * 50 + 3).astype(np.float32)
+    z = odata.znormalize(v)
+    assert abs(z.mean()) < 1e-5 and abs(z.std(ddof=1) - 1) < 1e-5            # torch.std semantics: unbiased
+    assert np.array_equal(odata.crop(v, (1, 2, 3), (4, 3, 2)), v[:, 1:5, 2:5, 3:5])
