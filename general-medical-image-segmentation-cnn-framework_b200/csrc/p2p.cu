@@ -1,16 +1,16 @@
 // Small all-reduce over NVLink peer memory, fused with the batch-norm statistics finalisation.
 //
 // SynchronizedBatchNorm needs, per layer and per step, the sum over ranks of 2*C+1 floats (sum, sum of squares, element
-// count) in the forward pass and of 2*C floats in the backward pass: 72 latency-bound exchanges per U-Net step, on the
+// count) in the forward pass and of 2*C floats in the backward pass: 36 latency-bound exchanges per U-Net step (18 forward, 18 backward), on the
 // critical path (the reference does them with Python threads, queues and two coalesced device copies per layer:
 // models/sync_batchnorm/batchnorm.py:90-111, comm.py:56-137).  An NCCL call per exchange costs a launch plus a
 // protocol round trip, and NCCL collectives cannot be captured into the training step's CUDA graph on this stack.
 // Here every rank owns a mailbox in its own HBM that its peers map through CUDA IPC.  One single-CTA kernel
-//   1. stores its vector into slot [seq % SLOTS][rank] of EVERY peer's mailbox (plain st.global over NVLink),
-//   2. fences system-wide and publishes flag[slot][rank] = seq in every peer's mailbox,
-//   3. spins (bounded) until its own mailbox shows seq from every rank, sums the world vectors in rank order -- the
+//   1. stores its vector into slot [seq % SLOTS][rank] of EVERY peer's mailbox over NVLink, every float as one 8-byte
+//      {value, seq} word (no separate flag and no fence: the receiver polls the words themselves),
+//   2. spins (bounded) until its own mailbox shows seq-tagged words from every rank, sums them in rank order -- the
 //      same order everywhere, so all ranks obtain bit-identical results -- and
-//   4. optionally finalises the statistics in the same launch (mean, inv_std, fused scale / shift, running stats).
+//   3. optionally finalises the statistics in the same launch (mean, inv_std, fused scale / shift, running stats).
 // `seq` lives in device memory and is advanced by the kernel, so a captured launch replays correctly.  A rank can be at
 // most one exchange ahead of the slowest one (it cannot finish exchange k+1 before everybody has written it, which they
 // do only after finishing k), hence SLOTS >= 2 makes slot reuse safe; 4 are used.
