@@ -66,7 +66,10 @@ bool conv_umma_roll_supported(const UmmaConvArgs& a);
 int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st);
 // persistent plane-mode kernel (conv_umma_p.cu); conv_umma_run dispatches to it when the geometry allows
 bool conv_umma_plane_supported(const UmmaConvArgs& a);
-bool conv_umma_plane_relaxed_supported(const UmmaConvArgs& a);   // short planes (masked tile rows): last resort
+bool conv_umma_plane_relaxed_supported(const UmmaConvArgs& a);
+// CTA-pair (cta_group::2) variant for the K-heavy deep layers (conv_umma_p2.cu): two SMs share one copy of the weight tile
+bool conv_umma_pair_supported(const UmmaConvArgs& a);
+int conv_umma_pair_run(const UmmaConvArgs& a, cudaStream_t st);   // short planes (masked tile rows): last resort
 int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st);
 
 struct UmmaWgradArgs {
