@@ -11,8 +11,8 @@
 //
 // Protocol (rank 0 = leader):
 //   * both CTAs run the input-plane and weight producers for their own tile / their half of the weight rows; every TMA is
-//     the .cta_group::2 form whose completion bytes land on the LEADER's full barrier (count 2: the leader's
-//     arrive.expect_tx for both CTAs' bytes + the peer's remote arrive);
+//     the .cta_group::2 form whose completion bytes land on the LEADER's full barrier (count 1: the leader's
+//     arrive.expect_tx armed with both CTAs' bytes; the peer's slot reuse is ordered by the multicast slot release);
 //   * only the leader's MMA warp issues; every tcgen05.commit is multicast to the barrier at the same offset in both CTAs
 //     (slot release for both producers, accumulator-full for both epilogues);
 //   * both CTAs' epilogue warps drain their own TMEM half and arrive on the leader's accumulator-empty barrier.
@@ -49,6 +49,7 @@ struct PairParams {
   const float* scale;
   int act;
   float slope;
+  long long* dbg;     // B200SEG_PAIR_TIMELINE: cycles the leader's MMA warp of cluster 0 spent waiting, by barrier kind
 };
 
 constexpr int kEpiWarps2 = 8;
@@ -114,11 +115,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
 
   if (tid == 0) {
     for (int i = 0; i < p.S; ++i) {
-      mbar_init(&fullA[i], 2);      // leader: its own arrive.expect_tx + the peer's remote arrive
+      mbar_init(&fullA[i], 1);      // the leader's arrive.expect_tx, armed with BOTH CTAs' bytes (the peer only issues its TMA)
       mbar_init(&emptyA[i], 1);     // one multicast tcgen05.commit per release
     }
     for (int i = 0; i < p.NB; ++i) {
-      mbar_init(&fullB[i], 2);
+      mbar_init(&fullB[i], 1);
       mbar_init(&emptyB[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -152,8 +153,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
         for (int c = 0; c < p.nchunks; ++c) {
           for (int u = 0; u < p.U; ++u) {
             mbar_wait(&emptyA[s], ph ^ 1);
+            // (no per-load remote arrive from the peer: measured ~880 cycles each on the producer thread, which made the
+            //  weight stream 4x slower than the single-CTA kernel's)
             if (is_leader) mbar_arrive_expect_tx(&fullA[s], 2 * p.bytesA);
-            else mbar_arrive_remote(&fullA[s], 0);
             tma_load_5d_2sm(sA + static_cast<size_t>(s) * p.slotA, &tmA, &fullA[s], c * p.KC, tc.w0 - p.pad, tc.h0 - p.pad,
                             tc.d0 - p.pad + u, tc.nn);
             if (++s == p.S) {
@@ -177,7 +179,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
           for (int tap = 0; tap < k3; ++tap) {
             mbar_wait(&emptyB[s], ph ^ 1);
             if (is_leader) mbar_arrive_expect_tx(&fullB[s], 2 * p.bytesB);
-            else mbar_arrive_remote(&fullB[s], 0);
             tma_load_3d_2sm(sB + static_cast<size_t>(s) * p.slotB, &tmB, &fullB[s], c * p.KC, nt * p.NT + static_cast<int>(rank) * half,
                             tap);
             if (++s == p.NB) {
@@ -204,9 +205,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
       int unit0 = 0;
       uint32_t unit0_phase = 0;
       uint32_t it = 0;
+      const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+      long long wA = 0, wB = 0, wE = 0, t_begin = clock64();
       for (long long t = first; t < p.tiles; t += step, ++it) {
         const uint32_t stage = it & 1, use = it >> 1;
+        long long c0 = dbg ? clock64() : 0;
         mbar_wait(&accEmpty[stage], (use & 1) ^ 1);
+        if (dbg) wE += clock64() - c0;
         tc_fence_after();
         const uint32_t d_base = tbase + stage * kStageCols2;
         for (int c = 0; c < p.nchunks; ++c) {
@@ -214,6 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
           uint32_t wphase = unit0_phase;
           for (int a = 0; a < k; ++a) {
             const int need = min(p.U, P + a * p.dil);
+            c0 = dbg ? clock64() : 0;
             for (; waited < need; ++waited) {
               mbar_wait(&fullA[wslot], wphase);
               if (++wslot == p.S) {
@@ -221,6 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
                 wphase ^= 1;
               }
             }
+            if (dbg) wA += clock64() - c0;
             tc_fence_after();
             uint32_t a_lo[P];
             {
@@ -236,7 +243,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
             for (int b = 0; b < k; ++b) {
               uint32_t tap16 = tap16_row;
               for (int e = 0; e < k; ++e) {
+                c0 = dbg ? clock64() : 0;
                 mbar_wait(&fullB[bs], bphase);
+                if (dbg) wB += clock64() - c0;
                 tc_fence_after();
                 const uint32_t b_lo = __shfl_sync(0xffffffffu, ((sB16 + bs * slotB16) & 0x3FFF) | lo_fixed, 0);
                 const uint32_t fresh = (c | a | b | e) == 0 ? 0u : 1u;
@@ -272,6 +281,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
           }
         }
         umma_commit_2sm_pred(&accFull[stage], leader);
+      }
+      if (dbg && lane == 0) {
+        p.dbg[0] = clock64() - t_begin;
+        p.dbg[1] = wA;
+        p.dbg[2] = wB;
+        p.dbg[3] = wE;
+        p.dbg[4] = it;
       }
     }
   } else if (warp >= 4) {
@@ -485,8 +501,23 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Pai
     }
     attr_set = true;
   }
-  conv_umma_pair_kernel<P, KS><<<ctas, kThreadsP2, smem, st>>>(tmA, tmB, p);   // __cluster_dims__(2,1,1): ctas is even
+  PairParams q = p;
+  q.dbg = nullptr;
+  if (getenv("B200SEG_PAIR_TIMELINE")) {
+    cudaMalloc(&q.dbg, 8 * sizeof(long long));
+    cudaMemset(q.dbg, 0, 8 * sizeof(long long));
+  }
+  conv_umma_pair_kernel<P, KS><<<ctas, kThreadsP2, smem, st>>>(tmA, tmB, q);   // __cluster_dims__(2,1,1): ctas is even
   B200_CHECK_LAUNCH("conv_umma_pair");
+  if (q.dbg) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(q.dbg);
+    fprintf(stderr, "[pair timeline] P %d KS %d NT %d KC %d chunks %d S %d U %d NB %d tiles %lld ctas %d | issuer total %lld cycles: "
+            "wait A %lld, wait B %lld, wait accEmpty %lld over %lld tiles\n", P, KS, p.NT, p.KC, p.nchunks, p.S, p.U, p.NB, p.tiles,
+            ctas, h[0], h[1], h[2], h[3], h[4]);
+  }
   return 0;
 }
 
