@@ -402,14 +402,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
 static bool plan_pair_kc(const UmmaConvArgs& a, PairParams& p, int& P, int& KS, size_t& smem_bytes, int kc_cap) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_PERSISTENT") || getenv("B200SEG_DISABLE_PAIR")) return false;
   if (a.tapmode || a.scatter_cout || a.gather2 || a.in_sub || a.out_sub) return false;
-  if (a.cin % 16 || a.cout % 32) return false;
+  if (a.cin % 16 || a.cout % 16) return false;
   if (a.in_pitch % 8 || a.out_pitch % 8) return false;
   if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
   const int halo = (a.k - 1) * a.dil;
   if (a.od != a.d + 2 * a.pad - halo || a.oh != a.h + 2 * a.pad - halo || a.ow != a.w + 2 * a.pad - halo) return false;
   if (!(a.oh >= 16 && a.ow >= 16 && a.ow % 16 == 0)) return false;          // pairs of 8-wide column blocks
-  // K-heavy layers only: that is where the weight stream, not the tensor pipe, is the bound
-  if (static_cast<long long>(a.cin) * a.k * a.k * a.k < 27 * 64 || a.cout < 64) return false;
+  // K-heavy layers: that is where the weight stream, not the tensor pipe, is the bound.  Narrow outputs (C_out 16 / 32) only
+  // for 5x5x5 kernels (vnet3d.py:25), which the kd-stacking roll kernel does not take: an M = 128 MMA costs ~48 cycles
+  // however small N is, so one M = 256 instruction per SM pair halves the issue-bound time of those layers.
+  if (static_cast<long long>(a.cin) * a.k * a.k * a.k < 27 * 64) return false;
+  if (a.cout < 64 && a.k != 5) return false;
   p = PairParams{};
   p.n = a.n; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.out_pitch = a.out_pitch;
   p.k = a.k; p.pad = a.pad; p.dil = a.dil;
@@ -421,7 +424,8 @@ static bool plan_pair_kc(const UmmaConvArgs& a, PairParams& p, int& P, int& KS, 
   if (a.cout <= 128) p.NT = a.cout;
   else if (a.cout % 128 == 0) p.NT = 128;
   else if (a.cout % 64 == 0) p.NT = 64;
-  else p.NT = 32;
+  else if (a.cout % 32 == 0) p.NT = 32;
+  else return false;
   p.n_ntiles = a.cout / p.NT;
   p.WB = 8 + halo;
   p.HB = 16 + halo;
@@ -431,7 +435,7 @@ static bool plan_pair_kc(const UmmaConvArgs& a, PairParams& p, int& P, int& KS, 
   p.bytesB = (p.NT / 2) * p.rowbytes;
   p.slotB = (p.bytesB + 1023) & ~1023u;
   const size_t fixed_small = 2048 + static_cast<size_t>(a.cout) * sizeof(float) * (a.stats ? 3 : 1) + 1024;
-  int pmax = std::min(8, kStageCols2 / p.NT);
+  int pmax = std::min(4, kStageCols2 / p.NT);     // kernel instances exist for P = 4, 2, 1
   while (pmax & (pmax - 1)) pmax &= pmax - 1;
   while (pmax > 1 && pmax / 2 >= a.od) pmax /= 2;
   {
