@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200seg_ncdhw_f32_to_ndhwc_bf16": "ppiilp",
     "b200seg_ndhwc_bf16_to_ncdhw_f32": "ppiilp",
     "b200seg_pack_conv_weight": "ppiiiiiip",
+    "b200seg_pack_conv_weight_padded": "ppiiiiiip",
     "b200seg_pack_weights_batched": "pppiiip",
     "b200seg_unpack_wgrads_batched": "pppiiip",
     "b200seg_pad_channels": "plipilp",
@@ -47,6 +48,7 @@ SIGNATURES = {
     "b200seg_upsample2_bwd": "plpl" + "iiiii" + "p",
     "b200seg_add": "plplpl" + "li" + "p",
     "b200seg_dropout": "plpl" + "ll" + "if" + "pQ" + "i" + "p",
+    "b200seg_dropout2": "plpl" + "ll" + "iif" + "pQQ" + "i" + "p",
     "b200seg_classmap_up2_add": "ppp" + "liii" + "p",
     "b200seg_classmap_down2_sum": "pp" + "liii" + "p",
     "b200seg_head_conv1x1_fwd": "plppp" + "ilii" + "p",

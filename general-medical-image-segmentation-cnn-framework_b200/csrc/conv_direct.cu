@@ -32,6 +32,27 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
   }
 }
 
+// The same packs with both channel counts padded (zero rows / columns): p[t][cout_p][cin_p] or p[k3-1-t][cin_p][cout_p].
+__global__ void pack_conv_weight_padded_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int cout,
+                                               int cin, int k3, int cout_p, int cin_p, int dgrad) {
+  const int64_t total = static_cast<int64_t>(k3) * cout_p * cin_p;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int t, co, ci;
+    if (!dgrad) {
+      ci = static_cast<int>(i % cin_p);
+      co = static_cast<int>((i / cin_p) % cout_p);
+    } else {
+      co = static_cast<int>(i % cout_p);
+      ci = static_cast<int>((i / cout_p) % cin_p);
+    }
+    t = static_cast<int>(i / (static_cast<int64_t>(cin_p) * cout_p));
+    if (dgrad) t = k3 - 1 - t;
+    p[i] = (co < cout && ci < cin) ? __float2bfloat16(w[(static_cast<int64_t>(co) * cin + ci) * k3 + t])
+                                   : __float2bfloat16(0.f);
+  }
+}
+
 // y[row][0:c] = x[row][0:c], y[row][c:cpad] = 0 (cpad a multiple of 8): widens a 1-4 channel tensor so that it can feed
 // the tensor-core kernels, whose K dimension comes in chunks of 16 channels.
 // C = 1 -> 16 (the U-Net stem input): one thread per voxel, one 256-bit store
@@ -881,6 +902,18 @@ int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, in
   pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<__nv_bfloat16*>(packed), cout, cin, k3, cin_off, cin_cnt, dgrad);
   B200_CHECK_LAUNCH("pack_conv_weight");
+  return 0;
+}
+
+int b200seg_pack_conv_weight_padded(const float* w, void* packed, int cout, int cin, int k, int cout_pad, int cin_pad,
+                                    int dgrad, void* stream) {
+  B200_CHECK_ARG(w && packed && cout > 0 && cin > 0 && k > 0 && cout_pad >= cout && cin_pad >= cin,
+                 "pack_conv_weight_padded: bad arguments");
+  const int k3 = k * k * k;
+  const int64_t total = static_cast<int64_t>(k3) * cout_pad * cin_pad;
+  pack_conv_weight_padded_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(packed), cout, cin, k3, cout_pad, cin_pad, dgrad);
+  B200_CHECK_LAUNCH("pack_conv_weight_padded");
   return 0;
 }
 

@@ -441,7 +441,7 @@ static constexpr size_t kSmemBudget = 200 * 1024;
 
 // Chooses the tiling; returns false when the geometry is not handled by this path.
 static bool plan(const UmmaConvArgs& a, UmmaConvParams& p, size_t& smem_bytes) {
-  if (getenv("B200SEG_DISABLE_UMMA")) return false;
+  if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_FLAT")) return false;
   if (a.cin % 16 || a.cout % 16) return false;
   if (!(a.k == 1 || a.k == 3 || a.k == 5) || a.dil < 1 || a.pad < 0) return false;
   if (a.in_pitch % 8 || a.out_pitch % 8) return false;
@@ -601,7 +601,10 @@ int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
   if (conv_umma_plane_supported(a)) return conv_umma_plane_run(a, st);   // persistent kernel (conv_umma_p.cu)
   UmmaConvParams p;
   size_t smem;
-  if (a.scale || !plan(a, p, smem)) {
+  // measured on B200 (probes/flat_vs_plane.py): for K-heavy 3x3x3 layers on 8^3 grids the short-plane kernel (N = 128
+  // tiles, half of the M rows idle) is ~10 % faster than the flat kernel's N = 32 tiles over whole haloed boxes
+  const bool prefer_plane = a.k == 3 && a.oh <= 8 && a.cin >= 256 && !a.gather2 && conv_umma_plane_relaxed_supported(a);
+  if (prefer_plane || a.scale || !plan(a, p, smem)) {
     // small planes with a halo too large for the flat kernel's whole-box slot (5x5x5 at 8^3, vnet3d.py:25)
     if (conv_umma_plane_relaxed_supported(a)) return conv_umma_plane_run(a, st);
     set_error("conv_umma_run: unsupported geometry");

@@ -816,22 +816,34 @@ __device__ __forceinline__ uint32_t mix_hash(uint64_t x) {
 }
 
 // channel_mode = 0: nn.Dropout (one draw per element); 1: nn.Dropout3d (one draw per (sample, channel)).
+// salt2 != 0 applies a second, independent mask in the same pass (densevoxelnet3d.py:25-32 runs its dropout twice);
+// channels [C, c_out) of y are written as zeros (a gradient widened for the 16-channel tensor-core tiles).
 __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, __nv_bfloat16* __restrict__ y,
-                               int64_t y_pitch, int64_t rows, int64_t rows_per_sample, int C, float p,
-                               const unsigned long long* __restrict__ seed, unsigned long long salt, int channel_mode) {
-  const unsigned long long s = (seed ? *seed : 0ULL) * 0x9E3779B97F4A7C15ULL + salt * 0xD1B54A32D192ED03ULL;
+                               int64_t y_pitch, int64_t rows, int64_t rows_per_sample, int C, int c_out, float p,
+                               const unsigned long long* __restrict__ seed, unsigned long long salt,
+                               unsigned long long salt2, int channel_mode) {
+  const unsigned long long sd = (seed ? *seed : 0ULL) * 0x9E3779B97F4A7C15ULL;
+  const unsigned long long s = sd + salt * 0xD1B54A32D192ED03ULL, s2 = sd + salt2 * 0xD1B54A32D192ED03ULL;
   const uint32_t thresh = p >= 1.f ? 0xFFFFFFFFu : static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
   const float scale = p >= 1.f ? 0.f : 1.f / (1.f - p);
-  const int64_t total = rows * C;
+  const int64_t total = rows * c_out;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const int64_t row = i / C;
+    const int c = static_cast<int>(i % c_out);
+    const int64_t row = i / c_out;
+    if (c >= C) {
+      y[row * y_pitch + c] = __float2bfloat16(0.f);
+      continue;
+    }
     const unsigned long long idx = channel_mode ? static_cast<unsigned long long>((row / rows_per_sample) * C + c)
-                                                : static_cast<unsigned long long>(i);
-    const bool keep = mix_hash(s + idx) >= thresh;
-    const float v = __bfloat162float(x[row * x_pitch + c]);
-    y[row * y_pitch + c] = __float2bfloat16(keep ? v * scale : 0.f);
+                                                : static_cast<unsigned long long>(row * C + c);
+    float v = __bfloat162float(x[row * x_pitch + c]);
+    v = mix_hash(s + idx) >= thresh ? v * scale : 0.f;
+    if (salt2) {   // the reference rounds to the storage type between the two modules; so does this
+      v = __bfloat162float(__float2bfloat16(v));
+      v = mix_hash(s2 + idx) >= thresh ? v * scale : 0.f;
+    }
+    y[row * y_pitch + c] = __float2bfloat16(v);
   }
 }
 
@@ -1200,15 +1212,22 @@ int b200seg_add(const void* a, int64_t a_pitch, const void* b, int64_t b_pitch, 
 }
 
 
+int b200seg_dropout2(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int64_t rows, int64_t rows_per_sample,
+                     int c, int c_out, float p, const unsigned long long* seed, unsigned long long salt,
+                     unsigned long long salt2, int channel_mode, void* stream) {
+  B200_CHECK_ARG(x && y && rows > 0 && rows_per_sample > 0 && c > 0 && c_out >= c && y_pitch >= c_out && p >= 0.f && p <= 1.f,
+                 "dropout: bad arguments");
+  dropout_kernel<<<grid_for(rows * c_out, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, rows, rows_per_sample, c,
+      c_out, p, seed, salt, salt2, channel_mode);
+  B200_CHECK_LAUNCH("dropout");
+  return 0;
+}
+
 int b200seg_dropout(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int64_t rows, int64_t rows_per_sample,
                     int c, float p, const unsigned long long* seed, unsigned long long salt, int channel_mode,
                     void* stream) {
-  B200_CHECK_ARG(x && y && rows > 0 && rows_per_sample > 0 && c > 0 && p >= 0.f && p <= 1.f, "dropout: bad arguments");
-  dropout_kernel<<<grid_for(rows * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), y_pitch, rows, rows_per_sample, c, p,
-      seed, salt, channel_mode);
-  B200_CHECK_LAUNCH("dropout");
-  return 0;
+  return b200seg_dropout2(x, x_pitch, y, y_pitch, rows, rows_per_sample, c, c, p, seed, salt, 0ULL, channel_mode, stream);
 }
 
 int b200seg_classmap_up2_add(const float* coarse, const float* fine, float* out, int64_t planes, int d, int h, int w,

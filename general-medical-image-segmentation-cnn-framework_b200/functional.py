@@ -72,12 +72,14 @@ def begin_step(device, nbytes=4 << 20):
     _SCRATCH["buf"].zero_()
     _SCRATCH["pos"], _SCRATCH["active"] = 0, True
     _COLSUMS.clear()
+    _ZERO_TAIL.clear()
 
 
 def end_step():
     flush_deferred()
     _SCRATCH["active"] = False
     _COLSUMS.clear()
+    _ZERO_TAIL.clear()
     flush_counters()
 
 
@@ -233,8 +235,24 @@ def _use_padded(g):
     return conv_uses_tensor_cores(_padded_geom(g))
 
 
+# Tensors that are channel slices [..., :C] of a wider contiguous buffer whose remaining channels are known to be zero
+# (written so by the producing kernel, see _Dropout.backward): _pad_channels hands out the wide buffer instead of copying.
+# Entries hold the wide tensor, so its memory cannot be recycled under the key (same scheme as _COLSUMS below).
+_ZERO_TAIL = {}
+
+
+def _publish_zero_tail(view, wide):
+    if len(_ZERO_TAIL) >= 16:
+        _ZERO_TAIL.clear()
+    _ZERO_TAIL[(view.data_ptr(), tuple(view.shape), tuple(view.stride()))] = wide
+
+
 def _pad_channels(x, c_pad):
     """[N,D,H,W,C] -> contiguous [N,D,H,W,c_pad] with zero-filled extra channels."""
+    if x.dim() == 5 and _ZERO_TAIL:
+        wide = _ZERO_TAIL.pop((x.data_ptr(), tuple(x.shape), tuple(x.stride())), None)
+        if wide is not None and wide.shape[4] == c_pad:
+            return wide
     x, xp = _as_rows(x) if (x.dim() == 5 and x.stride(4) == 1 and _pitched(x)) else (x.contiguous(), x.shape[4])
     n, d, h, w, c = x.shape
     if c == c_pad and xp == c:
@@ -254,6 +272,15 @@ def _padded_weight(weight, cin_p, cout_p):
     return wp
 
 
+def _pack_padded(weight, cin_p, cout_p, dgrad):
+    """bf16 fprop / dgrad pack of `weight` widened with zero rows / columns to cout_p x cin_p, one launch."""
+    w = weight.detach()
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    packed = torch.empty(k ** 3 * cout_p * cin_p, dtype=torch.bfloat16, device=w.device)
+    _call("b200seg_pack_conv_weight_padded", _ptr(w), _ptr(packed), cout, cin, k, cout_p, cin_p, int(dgrad), _stream())
+    return packed
+
+
 def _pack_fresh(w, dgrad):
     cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
     packed = torch.empty(k ** 3 * cout * cin, dtype=torch.bfloat16, device=w.device)
@@ -270,6 +297,9 @@ def _unpad_stats(stats_p, c, c_pad, spare):
     return torch.cat(parts)
 
 
+_LAST_PADDED_INPUT = [None]
+
+
 def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=None):
     x, xp = _as_rows(x)
     cout, cin = weight.shape[0], weight.shape[1]
@@ -283,7 +313,7 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
             wp = torch.empty(k ** 3 * cout * gp.cin, dtype=torch.bfloat16, device=x.device)
             _call("b200seg_pack_conv_weight", _ptr(weight.detach()), _ptr(wp), cout, cin, k, 0, gp.cin, 0, _stream())
         else:
-            wp = _pack_fresh(_padded_weight(weight, gp.cin, gp.cout), False)
+            wp = _pack_padded(weight, gp.cin, gp.cout, False)
         b_p = b
         if b is not None and gp.cout != cout:
             b_p = b.new_zeros(gp.cout)
@@ -293,6 +323,7 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
         _call("b200seg_conv3d_fprop", ctypes.byref(gp), _ptr(x_p), gp.cin, _ptr(wp), _ptr(b_p), _ptr(y_p), gp.cout,
               _ptr(stats_p), None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_padded_tc")
         y = y_p[..., :cout] if gp.cout != cout else y_p
+        _LAST_PADDED_INPUT[0] = x_p      # _ConvNormAct keeps the widened input for the weight gradient
         return y, (_unpad_stats(stats_p, cout, gp.cout, 1) if want_stats else None), g
     if y_out is not None and _pitched(y_out) and tuple(y_out.shape) == (g.n, g.od, g.oh, g.ow, cout) \
             and y_out.data_ptr() % 16 == 0 and y_out.stride(3) % 8 == 0:
@@ -313,7 +344,7 @@ def conv3d_dgrad_raw(g, dy, weight, colsum=False):
     if _use_padded(g):
         gp = _padded_geom(g)
         dy_p = _pad_channels(dy, gp.cout)
-        wd = _pack_fresh(_padded_weight(weight, gp.cin, gp.cout), True)
+        wd = _pack_padded(weight, gp.cin, gp.cout, True)
         dx_p = torch.empty((g.n, g.d, g.h, g.w, gp.cin), dtype=torch.bfloat16, device=dy.device)
         stats_p = _zeros_f32(2 * gp.cin, dy.device) if colsum else None
         _call("b200seg_conv3d_dgrad", ctypes.byref(gp), _ptr(dy_p), gp.cout, _ptr(wd), _ptr(dx_p), gp.cin, _ptr(stats_p),
@@ -338,6 +369,7 @@ _COLSUMS = {}
 def _publish_colsum(t, sums):
     if len(_COLSUMS) >= 16:    # nobody took them (the producers were not up-convolutions): do not pin their memory
         _COLSUMS.clear()
+    _ZERO_TAIL.clear()
     _COLSUMS[(t.data_ptr(), tuple(t.shape), tuple(t.stride()))] = (t, sums)
 
 
@@ -505,7 +537,14 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
         else:
             coef = _eval_coef(gamma, beta, running_mean, running_var, spec.eps, c, y.device)
     if out is None:
-        out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device)
+        if c > 16 and c % 16 and n * d * h * w >= 65536:
+            # channel counts like DenseVoxelNet's 16 + 12 i (densevoxelnet3d.py:36-42): the consumer is a convolution on
+            # the padded tensor-core path, which takes the zero-tailed wide buffer as it is (see _pad_channels)
+            wide = torch.zeros((n, d, h, w, _pad16(c)), dtype=torch.bfloat16, device=y.device)
+            out = wide[..., :c]
+            _publish_zero_tail(out, wide)
+        else:
+            out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device)
     assert _pitched(out) and out.shape == y.shape
     res, resp = (None, 0)
     if residual is not None:
@@ -605,7 +644,12 @@ class _ConvNormAct(torch.autograd.Function):
                 return z
         fused_stats = spec.kind == "batch" and spec.training
         plain = spec.kind is None and spec.act == 0 and residual is None
+        _LAST_PADDED_INPUT[0] = None
         y, stats, g = conv3d_fprop_raw(xin, weight, bias, k, stride, pad, dil, fused_stats, y_out=out if plain else None)
+        if _LAST_PADDED_INPUT[0] is not None and not (g.cin == 1 and g.k == 3):   # (that stem has its own weight gradient)
+            # the padded tensor-core path widened the input (zero channels): save that copy, so that the weight gradient
+            # does not widen it a second time (the extra channels only produce weight-gradient columns that are dropped)
+            xin, _LAST_PADDED_INPUT[0] = _LAST_PADDED_INPUT[0], None
         if plain:
             z, coef, count, groups = y, None, 0.0, 1
             if out is not None and y is not out:
@@ -638,6 +682,10 @@ class _ConvNormAct(torch.autograd.Function):
             if prelu_w is not None:
                 dprelu = sums[0, 2]
         dx = dx2 = dw = db = None
+        if _use_padded(g) and dy.shape[4] != _pad16(g.cout):
+            dy_full, dy = dy, _pad_channels(dy, _pad16(g.cout))     # once, for both the data and the weight gradient
+        else:
+            dy_full = dy
         if need[0] or (split is not None and need[1]):
             if split is None:
                 dx = conv3d_dgrad_raw(g, dy, weight)
@@ -659,7 +707,7 @@ class _ConvNormAct(torch.autograd.Function):
                 # slot of the gradient arena alone instead of accumulating zeros into it
                 db = None if _arena_managed(ctx.bias_ref) else _zeros_f32(g.cout, dz.device)
             else:
-                db = channel_stats(dy, 1)[0, 0]
+                db = channel_stats(dy_full, 1)[0, 0]
         return dx, dx2, dw, db, dgamma, dbeta, dprelu, dres, None, None, None
 
 
@@ -1120,40 +1168,49 @@ def advance_dropout_seed(device):
 class _Dropout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, cfg):
-        p, channel_mode, salt, out = cfg
+        p, channel_mode, salt, salt2, out = cfg
         x, xp = _as_rows(x)
         n, d, h, w, c = x.shape
         if out is None:
             out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device)
         assert _pitched(out) and out.shape == x.shape
         seed = dropout_seed(x.device)
-        _call("b200seg_dropout", _ptr(x), xp, _ptr(out), out.stride(3), n * d * h * w, d * h * w, c, float(p), _ptr(seed),
-              salt, int(channel_mode), _stream())
-        ctx.cfg = (p, channel_mode, salt)
+        _call("b200seg_dropout2", _ptr(x), xp, _ptr(out), out.stride(3), n * d * h * w, d * h * w, c, c, float(p),
+              _ptr(seed), salt, salt2, int(channel_mode), _stream())
+        ctx.cfg = (p, channel_mode, salt, salt2)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        p, channel_mode, salt = ctx.cfg
+        p, channel_mode, salt, salt2 = ctx.cfg
         g, gp = _as_rows(g)
         n, d, h, w, c = g.shape
-        dx = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=g.device)
+        # the gradient is written with its channels widened (zeros) to the next multiple of 16: when the producer of x
+        # was a convolution on the padded tensor-core path, its backward takes the wide buffer as it is
+        c_wide = _pad16(c)
+        wide = torch.empty((n, d, h, w, c_wide), dtype=torch.bfloat16, device=g.device)
         seed = dropout_seed(g.device)
-        _call("b200seg_dropout", _ptr(g), gp, _ptr(dx), c, n * d * h * w, d * h * w, c, float(p), _ptr(seed), salt,
-              int(channel_mode), _stream())
+        _call("b200seg_dropout2", _ptr(g), gp, _ptr(wide), c_wide, n * d * h * w, d * h * w, c, c_wide, float(p),
+              _ptr(seed), salt2 or salt, salt if salt2 else 0, int(channel_mode), _stream())
+        if c_wide == c:
+            return wide, None
+        dx = wide[..., :c]
+        _publish_zero_tail(dx, wide)
         return dx, None
 
 
-def dropout(x, p, training=True, channel=False, out=None):
+def dropout(x, p, training=True, channel=False, out=None, times=1):
     """nn.Dropout (channel=False) / nn.Dropout3d (channel=True).  Identity when not training or p == 0 (how the parity
-    tests run: torch's Philox stream cannot be reproduced)."""
+    tests run: torch's Philox stream cannot be reproduced).  times=2 applies two independent masks in one pass
+    (densevoxelnet3d.py:25-32 calls its dropout twice in train mode)."""
+    assert times in (1, 2)
     if not training or p == 0.0:
         if out is not None:
             out.copy_(x)
             return out
         return x
-    _SALT[0] += 1
-    return _Dropout.apply(x, (p, channel, _SALT[0], out))
+    _SALT[0] += times
+    return _Dropout.apply(x, (p, channel, _SALT[0], _SALT[0] - 1 if times == 2 else 0, out))
 
 
 class _Pad3d(torch.autograd.Function):

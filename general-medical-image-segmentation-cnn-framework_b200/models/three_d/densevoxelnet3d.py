@@ -30,8 +30,8 @@ class _DenseLayer(nn.Sequential, OpsMixin):
         plain_out = out if (self.drop_rate == 0 or not self.training) else None
         new = F.conv_norm_act(h, self.conv1.weight, None, k=3, stride=1, pad=1, dil=1, out=plain_out)
         if self.drop_rate > 0 and self.training:
-            new = F.dropout(new, self.drop_rate, training=True)            # inside nn.Sequential.forward (:30)
-            new = F.dropout(new, self.drop_rate, training=True, out=out)   # the explicit second call (:31-32)
+            # once inside nn.Sequential.forward (:30), once more by the explicit call (:31-32): two masks, one pass
+            new = F.dropout(new, self.drop_rate, training=True, out=out, times=2)
         return new
 
 

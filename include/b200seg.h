@@ -57,6 +57,10 @@ int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, i
 int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
                              int dgrad, void* stream);
 /* (cin_off + cin_cnt may exceed cin: the excess input channels are packed as zeros -- K-dimension padding.) */
+/* The same two packs with BOTH channel counts widened to cout_pad x cin_pad (zero rows / columns): layers whose channel
+ * counts are not multiples of 16 run on the tensor-core kernels this way (densevoxelnet3d.py:22, growth rate 12). */
+int b200seg_pack_conv_weight_padded(const float* w, void* packed, int cout, int cin, int k, int cout_pad, int cin_pad,
+                                    int dgrad, void* stream);
 /* y[rows][cpad] (contiguous) = x[rows][0:c] followed by zeros; cpad a multiple of 8.  Used to widen the 1-channel network
  * input to 16 channels so that the stem convolution (unet3d.py:80, C_in = 1) runs on the tensor-core path. */
 int b200seg_pad_channels(const void* x, int64_t x_pitch, int c, void* y, int cpad, int64_t rows, void* stream);
@@ -180,6 +184,12 @@ int b200seg_add(const void* a, int64_t a_pitch, const void* b, int64_t b_pitch, 
 int b200seg_dropout(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int64_t rows, int64_t rows_per_sample,
                     int c, float p, const unsigned long long* seed, unsigned long long salt, int channel_mode,
                     void* stream);
+/* The same with (a) a second independent mask salt2 (0 = none) applied in the same pass, the value rounded to bf16 in
+ * between -- _DenseLayer runs its dropout twice in train mode (densevoxelnet3d.py:25-32) -- and (b) channels [c, c_out) of
+ * y written as zeros (y_pitch >= c_out): a gradient handed to the 16-channel tensor-core tiles needs no extra pad pass. */
+int b200seg_dropout2(const void* x, int64_t x_pitch, void* y, int64_t y_pitch, int64_t rows, int64_t rows_per_sample,
+                     int c, int c_out, float p, const unsigned long long* seed, unsigned long long salt,
+                     unsigned long long salt2, int channel_mode, void* stream);
 
 /* ---- fp32 NCDHW class-score maps: deep-supervision sum (residual_unet3d.py:196-202) ----------------------------- */
 /* out[planes][2d][2h][2w] = nearest_x2(coarse[planes][d][h][w]) + fine (fine may be NULL); planes = n * classes. */

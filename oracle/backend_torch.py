@@ -179,10 +179,12 @@ def add_channel_padded(out, x):
     return _ra(x + out)
 
 
-def dropout(x, p, training=True, channel=False, out=None):
+def dropout(x, p, training=True, channel=False, out=None, times=1):
     if not training or p == 0.0:
         return x
-    return TF.dropout3d(x, p, True) if channel else TF.dropout(x, p, True)
+    for _ in range(times):
+        x = TF.dropout3d(x, p, True) if channel else TF.dropout(x, p, True)
+    return x
 
 
 def head_conv1x1(x, weight, bias=None):

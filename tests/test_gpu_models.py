@@ -81,3 +81,39 @@ def test_dropout_kernels_statistics_and_backward():
         (gx,) = torch.autograd.grad(y.float().sum(), x)
         assert torch.equal(gx != 0, y != 0)       # backward regenerates the same mask
     assert F.dropout(x, 0.3, training=False) is x
+
+
+def test_double_dropout_in_one_pass_and_widened_gradient():
+    """_DenseLayer's two dropout calls (densevoxelnet3d.py:25-32) as one kernel: two independent masks, the same masks in
+    the backward, and a 12-channel gradient that arrives at the padded tensor-core convolution without a pad pass."""
+    import b200seg.functional as F
+    dev = torch.device("cuda")
+    p = 0.2
+    x = torch.ones(2, 8, 16, 16, 12, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    y = F.dropout(x, p, training=True, times=2)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - (1 - p) ** 2) < 0.02, keep
+    s1 = float(torch.tensor(1 / (1 - p)).bfloat16())
+    s2 = float((torch.tensor(s1).bfloat16().float() / (1 - p)).bfloat16())
+    assert set(torch.unique(y.float()).tolist()) <= {0.0, s2}
+    (gx,) = torch.autograd.grad(y.float().sum(), x)
+    assert torch.equal(gx != 0, y != 0)
+    # conv (C_out = 12, padded path) -> double dropout: gradients equal those of the two-step composition with the same masks
+    torch.manual_seed(0)
+    h = torch.randn(2, 48, 48, 48, 32, device=dev).bfloat16().requires_grad_()
+    w = (torch.randn(12, 32, 3, 3, 3, device=dev) * 0.05).requires_grad_()
+    from b200seg.functional import _geom, _use_padded
+    assert _use_padded(_geom(h.shape, 32, 12, 3, 1, 1, 1))
+    F._SALT[0] = 100
+    out = F.dropout(F.conv_norm_act(h, w, None, k=3, stride=1, pad=1, dil=1), p, training=True, times=2)
+    gy = torch.randn_like(out)
+    F.profile_begin()
+    gh, gw = torch.autograd.grad(out, (h, w), gy)
+    prof = F.profile_end()
+    assert prof["conv_dgrad_padded"]["launches"] == 1 and prof["conv_wgrad_padded"]["launches"] == 1
+    assert "b200seg_pad_channels" not in prof, sorted(prof)      # the dropout backward already wrote the wide gradient
+    mask = (out != 0)
+    conv = F.conv_norm_act(h, w, None, k=3, stride=1, pad=1, dil=1)
+    gh2, gw2 = torch.autograd.grad(conv, (h, w), (gy.float() * mask * s2).bfloat16())
+    assert float((gh.float() - gh2.float()).norm() / gh2.float().norm()) < 1e-2
+    assert float((gw - gw2).norm() / gw2.norm()) < 1e-2
