@@ -39,7 +39,9 @@ bool encode_bf16_map(CUtensorMap* tm, const void* base, int rank, const uint64_t
                      const uint32_t* box, int kc);
 
 constexpr int kRollThreads = 384;
-constexpr int kRollRing = 5;       // accumulators in TMEM
+// accumulators in TMEM: KD of them feed the output plane being assembled, the rest are being filled (KD * C_out columns
+// each: 5 * 96 = 480 for the 3x3x3 layers, 6 * 80 = 480 for 5x5x5 with 16 output channels per CTA)
+__host__ __device__ constexpr int roll_ring(int kd) { return kd == 3 ? 5 : 6; }
 constexpr int kRollEpiWarps = 8;
 
 struct RollParams {
@@ -79,16 +81,18 @@ __device__ __forceinline__ RollItem roll_decode(const RollParams& p, long long i
   return r;
 }
 
-// KS = K steps of 16 channels (C_in / 16), CO = C_out per CTA, HV = halves of the output tensor (compile-time: the
-// single-half kernel must not pay for the generality -- a run-time `halves` cost the 128^3 layers 20 %)
-template <int KS, int CO, int HV, bool AFF>
+// KD = kernel size (3, or 5: the V-Net stem and its 32 -> 2 output convolution, vnet3d.py:25,111), KS = K steps of 16
+// channels (C_in / 16), CO = C_out per CTA, HV = halves of the output tensor (compile-time: the single-half kernel must
+// not pay for the generality -- a run-time `halves` cost the 128^3 layers 20 %)
+template <int KD, int KS, int CO, int HV, bool AFF>
 __global__ void __launch_bounds__(kRollThreads, 1)
     conv_umma_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const RollParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sW = smem;                                          // [9 (kh,kw)][3 (kd)][CO rows][KC]
-  uint8_t* sA = smem + 9u * p.wtile_bytes;                     // [S] plane boxes
+  constexpr int kRollRing = roll_ring(KD);
+  uint8_t* sW = smem;                                          // [KD*KD (kh,kw)][KD (kd)][CO rows][KC]
+  uint8_t* sA = smem + static_cast<unsigned>(KD * KD) * p.wtile_bytes;   // [S] plane boxes
   uint64_t* fullA = reinterpret_cast<uint64_t*>(sA + static_cast<size_t>(p.S) * p.slotA);
   uint64_t* emptyA = fullA + p.S;
   uint64_t* accFull = emptyA + p.S;        // [R]
@@ -125,22 +129,22 @@ __global__ void __launch_bounds__(kRollThreads, 1)
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr;
   const long long first = blockIdx.x, stride = gridDim.x;
-  constexpr int NTOT = 3 * CO;
+  constexpr int NTOT = KD * CO;
 
   if (warp == 0) {
     // =========================== producer: resident weights once, then one plane box per step ====================
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
-      mbar_arrive_expect_tx(wFull, 27u * p.wblock_bytes);
-      for (int be = 0; be < 9; ++be)
-        for (int a = 0; a < 3; ++a)    // packed weights are [tap = (a*3+kh)*3+kw][C_out][C_in]
-          tma_load_3d(sW + be * p.wtile_bytes + a * p.wblock_bytes, &tmB, wFull, 0, co_base, a * 9 + be);
+      mbar_arrive_expect_tx(wFull, static_cast<unsigned>(KD * KD * KD) * p.wblock_bytes);
+      for (int be = 0; be < KD * KD; ++be)
+        for (int a = 0; a < KD; ++a)    // packed weights are [tap = (a*KD+kh)*KD+kw][C_out][C_in]
+          tma_load_3d(sW + be * p.wtile_bytes + a * p.wblock_bytes, &tmB, wFull, 0, co_base, a * KD * KD + be);
       int s = 0;
       uint32_t ph = 0;
       for (long long it = first; it < p.items; it += stride) {
         const RollItem r = roll_decode<HV>(p, it);
-        for (int t = 0; t < r.lq + 2; ++t) {
+        for (int t = 0; t < r.lq + KD - 1; ++t) {
           mbar_wait(&emptyA[s], ph ^ 1);
           mbar_arrive_expect_tx(&fullA[s], p.bytesA);
           tma_load_5d(sA + static_cast<size_t>(s) * p.slotA, &tmA, &fullA[s], 0, r.w0 - p.pad, r.h0 - p.pad,
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(kRollThreads, 1)
     uint32_t ph = 0, accph = 0;
     for (long long it = first; it < p.items; it += stride) {
       const RollItem r = roll_decode<HV>(p, it);
-      for (int t = 0; t < r.lq + 2; ++t) {
+      for (int t = 0; t < r.lq + KD - 1; ++t) {
         mbar_wait(&accEmpty[acc], accph ^ 1);
         mbar_wait(&fullA[s], ph);
         tc_fence_after();
@@ -183,11 +187,11 @@ __global__ void __launch_bounds__(kRollThreads, 1)
 #endif
         const uint32_t d_tmem = tbase + acc * NTOT;
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
+        for (int b = 0; b < KD; ++b) {
 #pragma unroll
-          for (int e = 0; e < 3; ++e) {
+          for (int e = 0; e < KD; ++e) {
             const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(b * p.WB + e) * row16;
-            const uint32_t b_lo = ((sW16 + (b * 3 + e) * wtile16) & 0x3FFF) | lo_fixed;
+            const uint32_t b_lo = ((sW16 + (b * KD + e) * wtile16) & 0x3FFF) | lo_fixed;
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
 #if B200_ROLL_UNIFORM
@@ -234,34 +238,32 @@ __global__ void __launch_bounds__(kRollThreads, 1)
       const RollItem r = roll_decode<HV>(p, it);
       const int oh_ = r.h0 + (m >> 3), ow_ = r.w0 + (m & 7);
       const bool hw_ok = oh_ < p.oh && ow_ < p.ow;
-      for (int t = 0; t < r.lq + 2; ++t) {
+      for (int t = 0; t < r.lq + KD - 1; ++t) {
         mbar_wait(&accFull[acc], accph);
         tc_fence_after();
-        if (t >= 2) {
-          // output plane u = t - 2: block 0 of plane t-2, block 1 of plane t-1, block 2 of plane t
-          const int s2slot = acc, s1slot = (acc + kRollRing - 1) % kRollRing, s0slot = (acc + kRollRing - 2) % kRollRing;
-          uint32_t r0[CH], r1[CH], r2[CH];
-          if constexpr (CH == 16) {
-            tmem_ld_32x16(t_lane + s0slot * NTOT + 0 * CO, r0);
-            tmem_ld_32x16(t_lane + s1slot * NTOT + 1 * CO, r1);
-            tmem_ld_32x16(t_lane + s2slot * NTOT + 2 * CO, r2);
-          } else {
-            tmem_ld_32x8(t_lane + s0slot * NTOT + 0 * CO, r0);
-            tmem_ld_32x8(t_lane + s1slot * NTOT + 1 * CO, r1);
-            tmem_ld_32x8(t_lane + s2slot * NTOT + 2 * CO, r2);
+        if (t >= KD - 1) {
+          // output plane u = t - (KD-1): block j of input plane u + j, j = 0 .. KD-1 (the newest one is in slot `acc`)
+          uint32_t rr[KD][CH];
+#pragma unroll
+          for (int j = 0; j < KD; ++j) {
+            const int slot = (acc + kRollRing - (KD - 1) + j) % kRollRing;
+            if constexpr (CH == 16) tmem_ld_32x16(t_lane + slot * NTOT + j * CO, rr[j]);
+            else tmem_ld_32x8(t_lane + slot * NTOT + j * CO, rr[j]);
           }
           tmem_ld_wait();
-          const int od_ = r.d0 + t - 2;
+          const int od_ = r.d0 + t - (KD - 1);
           if (hw_ok) {
             float v[CH];
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
+              float head = __uint_as_float(rr[0][j]) + __uint_as_float(rr[1][j]);   // (same order as the 3-tap sum)
+#pragma unroll
+              for (int a = 2; a < KD - 1; ++a) head += __uint_as_float(rr[a][j]);
               if constexpr (AFF) {
-                const float acc3 = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
-                const float z = fmaf(acc3, scale_r[j], bias_r[j]);
+                const float z = fmaf(head + __uint_as_float(rr[KD - 1][j]), scale_r[j], bias_r[j]);
                 v[j] = p.act == B200SEG_ACT_NONE ? z : (z > 0.f ? z : (p.act == B200SEG_ACT_RELU ? 0.f : p.slope * z));
               } else {
-                v[j] = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + (__uint_as_float(r2[j]) + bias_r[j]);
+                v[j] = head + (__uint_as_float(rr[KD - 1][j]) + bias_r[j]);
               }
               if (want_stats) {
                 s1[j] += v[j];
@@ -289,13 +291,13 @@ __global__ void __launch_bounds__(kRollThreads, 1)
             }
           }
         }
-        // plane t-2 has now fed all three of its outputs (or lies outside the segment): free its accumulator
+        // plane t-(KD-1) has now fed all KD of its outputs (or lies outside the segment): free its accumulator
         tc_fence_before();
         __syncwarp();
-        if (t >= 2 && lane == 0) mbar_arrive(&accEmpty[(acc + kRollRing - 2) % kRollRing]);
-        if (t == r.lq + 1 && lane == 0) {     // segment end: the last two planes have no further consumers
-          mbar_arrive(&accEmpty[(acc + kRollRing - 1) % kRollRing]);
-          mbar_arrive(&accEmpty[acc]);
+        if (t >= KD - 1 && lane == 0) mbar_arrive(&accEmpty[(acc + kRollRing - (KD - 1)) % kRollRing]);
+        if (t == r.lq + KD - 2 && lane == 0) {     // segment end: the last KD-1 planes have no further consumers
+#pragma unroll
+          for (int j = 0; j < KD - 1; ++j) mbar_arrive(&accEmpty[(acc + kRollRing - j) % kRollRing]);
         }
         if (++acc == kRollRing) {
           acc = 0;
@@ -327,30 +329,39 @@ __global__ void __launch_bounds__(kRollThreads, 1)
 // ------------------------------------------------------------------------------------------------ host side
 static bool plan_roll(const UmmaConvArgs& a, RollParams& p, size_t& smem_bytes) {
   if (getenv("B200SEG_DISABLE_UMMA") || getenv("B200SEG_DISABLE_ROLL")) return false;
-  if (a.k != 3 || a.dil != 1 || a.pad < 0 || a.scatter_cout || a.gather2) return false;
-  if (!(a.cout == 16 || a.cout == 32 || a.cout == 64) || (getenv("B200SEG_DISABLE_ROLL_HALVES") && a.cout == 64)) return false;
-  if (!(a.cin == 16 || a.cin == 32 || a.cin == 64)) return false;
-  const int halves = a.cout == 64 ? 2 : 1;   // two N = 96 instructions beat three N = 64 ones (61 vs 54.6 cycles each)
+  if (!(a.k == 3 || a.k == 5) || a.dil != 1 || a.pad < 0 || a.scatter_cout || a.gather2 || a.tapmode) return false;
+  const int KD = a.k;
+  int halves;
+  if (KD == 3) {
+    if (!(a.cout == 16 || a.cout == 32 || a.cout == 64) || (getenv("B200SEG_DISABLE_ROLL_HALVES") && a.cout == 64)) return false;
+    if (!(a.cin == 16 || a.cin == 32 || a.cin == 64)) return false;
+    halves = a.cout == 64 ? 2 : 1;   // two N = 96 instructions beat three N = 64 ones (61 vs 54.6 cycles each)
+  } else {
+    // 5x5x5 with (padded) 16-channel sides: N = 5 * 16 = 80 per instruction, 25 instead of 125 of them per K step
+    if (getenv("B200SEG_DISABLE_ROLL5") || !(a.cout == 16 || a.cout == 32) || !(a.cin == 16 || a.cin == 32)) return false;
+    halves = a.cout / 16;
+  }
   const int CO = a.cout / halves;
   if (a.in_pitch % 8 || a.out_pitch % 8) return false;
-  if (a.od != a.d + 2 * a.pad - 2 || a.oh != a.h + 2 * a.pad - 2 || a.ow != a.w + 2 * a.pad - 2) return false;
+  if (a.od != a.d + 2 * a.pad - (KD - 1) || a.oh != a.h + 2 * a.pad - (KD - 1) || a.ow != a.w + 2 * a.pad - (KD - 1)) return false;
   if (!(a.oh >= 16 && a.ow >= 8) || a.od < 4) return false;
   p = RollParams{};
   p.n = a.n; p.d = a.d; p.od = a.od; p.oh = a.oh; p.ow = a.ow; p.cout = a.cout; p.pad = a.pad;
   p.out_pitch = a.out_pitch;
   p.halves = halves;
   p.KC = a.cin;
-  p.NTOT = 3 * CO;
+  p.NTOT = KD * CO;
   p.rowbytes = p.KC * 2;
   p.swz = p.KC == 64 ? SWZ_128B : (p.KC == 32 ? SWZ_64B : SWZ_32B);
-  p.WB = 10;
-  p.HB = 18;
+  p.WB = 8 + KD - 1;
+  p.HB = 16 + KD - 1;
   p.bytesA = static_cast<unsigned>(p.WB * p.HB) * p.rowbytes;
   p.slotA = (p.bytesA + 1023) & ~1023u;
   p.wblock_bytes = static_cast<unsigned>(CO) * p.rowbytes;          // one kd tap: C_out rows (of this half)
-  p.wtile_bytes = 3u * p.wblock_bytes;                              // one (kh, kw): 3 * C_out rows, contiguous
-  if (p.wblock_bytes % 1024) return false;                          // blocks must start on a swizzle-atom boundary
-  const size_t fixed = 9u * p.wtile_bytes + 2048 + 1024;
+  p.wtile_bytes = static_cast<unsigned>(KD) * p.wblock_bytes;       // one (kh, kw): KD * C_out rows, contiguous
+  if (p.wblock_bytes % (8u * p.rowbytes)) return false;             // blocks must start on a swizzle-atom boundary
+  if (KD == 3 && p.wblock_bytes % 1024) return false;
+  const size_t fixed = static_cast<size_t>(KD * KD) * p.wtile_bytes + 2048 + 1024;
   const size_t budget = 220 * 1024;
   p.S = static_cast<int>(std::min<size_t>(8, (budget - fixed) / p.slotA));
   if (p.S < 3) return false;
@@ -364,7 +375,7 @@ static bool plan_roll(const UmmaConvArgs& a, RollParams& p, size_t& smem_bytes) 
   for (int segs = 1; segs <= std::max(1, a.od / 4); ++segs) {
     const int cand = (a.od + segs - 1) / segs;
     const long long items = cols * ((a.od + cand - 1) / cand);
-    const long long cost = ((items + kNumSMs - 1) / kNumSMs) * (cand + 3);
+    const long long cost = ((items + kNumSMs - 1) / kNumSMs) * (cand + KD);
     if (best_cost < 0 || cost < best_cost) best_cost = cost, L = cand;
   }
   p.L = L;
@@ -380,27 +391,27 @@ bool conv_umma_roll_supported(const UmmaConvArgs& a) {
   return plan_roll(a, p, smem);
 }
 
-template <int KS, int CO, int HV, bool AFF>
+template <int KD, int KS, int CO, int HV, bool AFF>
 static int launch_roll_(const CUtensorMap& tmA, const CUtensorMap& tmB, const RollParams& p, size_t smem, int ctas,
                        cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_roll_kernel<KS, CO, HV, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+    if (cudaFuncSetAttribute(conv_umma_roll_kernel<KD, KS, CO, HV, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
       set_error("conv_umma_roll: cannot raise the dynamic shared memory limit");
       return B200SEG_ERR_CUDA;
     }
     attr_set = true;
   }
-  conv_umma_roll_kernel<KS, CO, HV, AFF><<<ctas, kRollThreads, smem, st>>>(tmA, tmB, p);
+  conv_umma_roll_kernel<KD, KS, CO, HV, AFF><<<ctas, kRollThreads, smem, st>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv_umma_roll");
   return 0;
 }
-template <int KS, int CO, int HV>
+template <int KD, int KS, int CO, int HV>
 static int launch_roll(const CUtensorMap& tmA, const CUtensorMap& tmB, const RollParams& p, size_t smem, int ctas,
                        cudaStream_t st) {
-  return p.scale ? launch_roll_<KS, CO, HV, true>(tmA, tmB, p, smem, ctas, st)
-                 : launch_roll_<KS, CO, HV, false>(tmA, tmB, p, smem, ctas, st);
+  return p.scale ? launch_roll_<KD, KS, CO, HV, true>(tmA, tmB, p, smem, ctas, st)
+                 : launch_roll_<KD, KS, CO, HV, false>(tmA, tmB, p, smem, ctas, st);
 }
 
 int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
@@ -431,7 +442,8 @@ int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
     if (!encode_bf16_map(&tmA, a.in, 5, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
   }
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.cout), 27ull};
+    const uint64_t dims[3] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.cout),
+                              static_cast<uint64_t>(a.k * a.k * a.k)};
     const uint64_t str[2] = {static_cast<uint64_t>(a.cin) * 2, static_cast<uint64_t>(a.cin) * a.cout * 2};
     const uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(a.cout / p.halves), 1u};
     if (!encode_bf16_map(&tmB, a.wpack, 3, dims, str, box, p.KC)) return B200SEG_ERR_CUDA;
@@ -441,16 +453,21 @@ int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st) {
   const int KS = a.cin / 16;
   const int co = a.cout / p.halves;
   int rc = B200SEG_ERR_INVALID;
-  if (p.halves == 2) {
-    if (KS == 1) rc = launch_roll<1, 32, 2>(tmA, tmB, p, smem, ctas, st);
-    else if (KS == 2) rc = launch_roll<2, 32, 2>(tmA, tmB, p, smem, ctas, st);
-    else if (KS == 4) rc = launch_roll<4, 32, 2>(tmA, tmB, p, smem, ctas, st);
-  } else if (co == 32 && KS == 1) rc = launch_roll<1, 32, 1>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 32 && KS == 2) rc = launch_roll<2, 32, 1>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 32 && KS == 4) rc = launch_roll<4, 32, 1>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 16 && KS == 1) rc = launch_roll<1, 16, 1>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 16 && KS == 2) rc = launch_roll<2, 16, 1>(tmA, tmB, p, smem, ctas, st);
-  else if (co == 16 && KS == 4) rc = launch_roll<4, 16, 1>(tmA, tmB, p, smem, ctas, st);
+  if (a.k == 5) {
+    if (p.halves == 2 && KS == 1) rc = launch_roll<5, 1, 16, 2>(tmA, tmB, p, smem, ctas, st);
+    else if (p.halves == 2 && KS == 2) rc = launch_roll<5, 2, 16, 2>(tmA, tmB, p, smem, ctas, st);
+    else if (p.halves == 1 && KS == 1) rc = launch_roll<5, 1, 16, 1>(tmA, tmB, p, smem, ctas, st);
+    else if (p.halves == 1 && KS == 2) rc = launch_roll<5, 2, 16, 1>(tmA, tmB, p, smem, ctas, st);
+  } else if (p.halves == 2) {
+    if (KS == 1) rc = launch_roll<3, 1, 32, 2>(tmA, tmB, p, smem, ctas, st);
+    else if (KS == 2) rc = launch_roll<3, 2, 32, 2>(tmA, tmB, p, smem, ctas, st);
+    else if (KS == 4) rc = launch_roll<3, 4, 32, 2>(tmA, tmB, p, smem, ctas, st);
+  } else if (co == 32 && KS == 1) rc = launch_roll<3, 1, 32, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 32 && KS == 2) rc = launch_roll<3, 2, 32, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 32 && KS == 4) rc = launch_roll<3, 4, 32, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 1) rc = launch_roll<3, 1, 16, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 2) rc = launch_roll<3, 2, 16, 1>(tmA, tmB, p, smem, ctas, st);
+  else if (co == 16 && KS == 4) rc = launch_roll<3, 4, 16, 1>(tmA, tmB, p, smem, ctas, st);
   if (rc == 0) ++g_umma_launches;
   return rc;
 }

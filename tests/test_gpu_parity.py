@@ -84,6 +84,8 @@ CONV_CASES = [
     (32, 64, 3, 1, 4, 4, (10, 16, 24), 2),
     (64, 64, 5, 1, 2, 1, (8, 8, 8), 1),       # V-Net 5x5x5 at 8^3: short planes (masked tile rows)
     (128, 128, 5, 1, 2, 1, (4, 4, 4), 2),
+    (32, 32, 5, 1, 2, 1, (12, 24, 20), 2),    # V-Net full-resolution 5x5x5: kd taps stacked in N, two 16-channel halves
+    (32, 16, 5, 1, 2, 1, (21, 17, 9), 1),     # ... ragged tiles
     # channel counts that are not multiples of 16, zero-padded onto the tensor cores (>= 65536 voxels)
     (28, 12, 3, 1, 1, 1, (40, 40, 44), 1),    # DenseVoxelNet growth conv
     (32, 2, 5, 1, 2, 1, (40, 40, 44), 1),     # V-Net output conv 5x5x5 to 2 classes
@@ -133,12 +135,13 @@ def test_conv3d_fprop_dgrad_wgrad(F, case):
     close(bd.grad.cpu(), dy.sum((0, 2, 3, 4)), 8e-3, "bias grad")
 
 
-def test_conv_stats_epilogue_matches_separate_reduction(F):
+@pytest.mark.parametrize("k", [3, 5])
+def test_conv_stats_epilogue_matches_separate_reduction(F, k):
     g = torch.Generator().manual_seed(3)
     x = bf(torch.randn(2, 32, 8, 16, 8, generator=g))
-    w = torch.randn(32, 32, 3, 3, 3, generator=g) * 0.05
-    y, stats, _ = F.conv3d_fprop_raw(ndhwc(x), w.to(DEV), None, 3, 1, 1, 1, True)
-    ref = oops.conv3d(x, bf(w), None, 1, 1, 1)
+    w = torch.randn(32, 32, k, k, k, generator=g) * 0.05 * (3.0 / k) ** 1.5
+    y, stats, _ = F.conv3d_fprop_raw(ndhwc(x), w.to(DEV), None, k, 1, k // 2, 1, True)
+    ref = oops.conv3d(x, bf(w), None, 1, k // 2, 1)
     s = torch.stack((ref.sum((0, 2, 3, 4)), (ref ** 2).sum((0, 2, 3, 4))))
     close(stats[:2 * w.shape[0]].view(2, -1).cpu(), s, 5e-3, "fused stats")   # flat {sum[C], sumsq[C], spare}
     close(F.channel_stats(y)[0].cpu(), s, 1e-2, "stand-alone stats")
