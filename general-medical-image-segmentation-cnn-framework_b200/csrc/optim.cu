@@ -54,17 +54,19 @@ __device__ __forceinline__ float adam_one(float pi, float grad, float& mi, float
   return pi - c.lr_bc1 * (mi / denom);
 }
 
-// K3 > 0: compile-time tap count (27, 8); K3 == 0: run-time.  FULL: the brick is 32 x 32 (all index arithmetic is shifts).
-template <int K3, bool FULL>
-__device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_ci, float* __restrict__ tile,
+// K3 > 0: compile-time tap count (27, 8, 125); K3 == 0: run-time.  TCI: C_in extent of a brick (32, or 8 when 5x5x5 weights
+// are present).  FULL: the brick is complete, 32 x TCI (all index arithmetic is shifts / constant divisions).
+template <int K3, int TCI, bool FULL>
+__device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, float* __restrict__ tile,
                                            float* __restrict__ p, const float* __restrict__ g,
                                            const float* __restrict__ dw, float* __restrict__ m, float* __restrict__ v,
                                            __nv_bfloat16* __restrict__ packs, const AdamCoef& c, bool use_dw) {
   const int k3 = K3 ? K3 : d.k3;
   const int cout = d.cout, cin = d.cin;
+  constexpr int tile_ci = TCI;
   const int tiles_ci = (cin + tile_ci - 1) / tile_ci;
   const int co0 = (tix / tiles_ci) * kBrickCo, ci0 = (tix % tiles_ci) * tile_ci;
-  const int nco = FULL ? 32 : min(kBrickCo, cout - co0), nci = FULL ? 32 : min(tile_ci, cin - ci0);
+  const int nco = FULL ? 32 : min(kBrickCo, cout - co0), nci = FULL ? TCI : min(tile_ci, cin - ci0);
   const int row = tile_ci * k3 + 1;     // odd: column walks through the brick are bank-conflict free
   const int run = nci * k3;             // consecutive floats per output channel in torch layout
   const int nthr = blockDim.x, tid = threadIdx.x;
@@ -77,8 +79,8 @@ __device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_
       // 128-bit loads along C_out (8 per (tap, ci) row of the brick); the four values go to four tile rows
 #pragma unroll 4
       for (int i = tid; i < total / 4; i += nthr) {
-        const int co4 = (i & 7) << 2, r = i >> 3;     // r = t * 32 + ci
-        const int ci = r & 31, t = r >> 5;
+        const int co4 = (i & 7) << 2, r = i >> 3;     // r = t * TCI + ci
+        const int ci = r % TCI, t = r / TCI;
         const float4 q = *reinterpret_cast<const float4*>(src + (static_cast<long long>(t) * cin + ci0 + ci) * cout + co0 + co4);
         float* tl = tile + co4 * row + ci * k3 + t;
         tl[0] = q.x;
@@ -163,7 +165,24 @@ __device__ __forceinline__ void adam_brick(const AdamDesc& d, int tix, int tile_
   // bf16 packs from the tile
   __nv_bfloat16* pf = packs + d.dst;                                             // [t][co][ci]
   __nv_bfloat16* pd = pf + static_cast<long long>(cout) * cin * k3;              // [k3-1-t][ci][co]
-  if (FULL) {
+  if (FULL && TCI != 32) {
+    // two bf16 per store: pairs along ci (fprop pack), then pairs along co (dgrad pack)
+#pragma unroll 4
+    for (int i = tid; i < k3 * 32 * (TCI / 2); i += nthr) {
+      const int j = (i % (TCI / 2)) << 1, o = (i / (TCI / 2)) & 31, t = i / (TCI / 2 * 32);
+      const float a = tile[o * row + j * k3 + t], b = tile[o * row + (j + 1) * k3 + t];
+      *reinterpret_cast<__nv_bfloat162*>(pf + (static_cast<long long>(t) * cout + co0 + o) * cin + ci0 + j) =
+          __floats2bfloat162_rn(a, b);
+    }
+#pragma unroll 4
+    for (int i = tid; i < k3 * TCI * 16; i += nthr) {
+      const int j = (i & 15) << 1, o = (i >> 4) % TCI, t = (i >> 4) / TCI;
+      const int tt = k3 - 1 - t;
+      const float a = tile[j * row + o * k3 + tt], b = tile[(j + 1) * row + o * k3 + tt];
+      *reinterpret_cast<__nv_bfloat162*>(pd + (static_cast<long long>(t) * cin + ci0 + o) * cout + co0 + j) =
+          __floats2bfloat162_rn(a, b);
+    }
+  } else if (FULL) {
     // two bf16 per store: pairs along ci (fprop pack) / along co (dgrad pack)
 #pragma unroll 4
     for (int i = tid; i < k3 * 32 * 16; i += nthr) {
@@ -238,18 +257,23 @@ __global__ void __launch_bounds__(256, 2)
     }
     const int tiles_ci = (d.cin + tile_ci - 1) / tile_ci;
     const int co0 = (tix / tiles_ci) * kBrickCo, ci0 = (tix % tiles_ci) * tile_ci;
-    const bool full = tile_ci == 32 && d.cout - co0 >= 32 && d.cin - ci0 >= 32 && ((d.cout | d.cin | d.dst) & 1) == 0;
+    const bool full = d.cout - co0 >= 32 && d.cin - ci0 >= tile_ci && ((d.cout | d.cin | d.dst) & 1) == 0;
     const bool udw = use_dw != 0;
-    if (d.k3 == 27) {
-      if (full) adam_brick<27, true>(d, tix, tile_ci, tile, p, g, dw, m, v, packs, c, udw);
-      else adam_brick<27, false>(d, tix, tile_ci, tile, p, g, dw, m, v, packs, c, udw);
-    } else if (d.k3 == 8) {
-      if (full) adam_brick<8, true>(d, tix, tile_ci, tile, p, g, dw, m, v, packs, c, udw);
-      else adam_brick<8, false>(d, tix, tile_ci, tile, p, g, dw, m, v, packs, c, udw);
-    } else {
-      if (full) adam_brick<0, true>(d, tix, tile_ci, tile, p, g, dw, m, v, packs, c, udw);
-      else adam_brick<0, false>(d, tix, tile_ci, tile, p, g, dw, m, v, packs, c, udw);
+#define B200_BRICK(K3_, TCI_)                                                                     \
+  do {                                                                                            \
+    if (full) adam_brick<K3_, TCI_, true>(d, tix, tile, p, g, dw, m, v, packs, c, udw);            \
+    else adam_brick<K3_, TCI_, false>(d, tix, tile, p, g, dw, m, v, packs, c, udw);                \
+  } while (0)
+    if (tile_ci == 32) {
+      if (d.k3 == 27) B200_BRICK(27, 32);
+      else if (d.k3 == 8) B200_BRICK(8, 32);
+      else B200_BRICK(0, 32);
+    } else {   // networks with 5x5x5 weights (vnet3d.py:25): 32 x 8 bricks for every record of the launch
+      if (d.k3 == 125) B200_BRICK(125, 8);
+      else if (d.k3 == 8) B200_BRICK(8, 8);
+      else B200_BRICK(0, 8);
     }
+#undef B200_BRICK
   }
   __syncthreads();
   if (threadIdx.x == 0) {

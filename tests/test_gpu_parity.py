@@ -646,7 +646,8 @@ def test_fused_optimizer_step_is_bit_identical_to_the_three_kernel_path():
     dev = torch.device("cuda")
     for shapes in ([(64, 32, 3, 3, 3), (64,), (32, 1, 3, 3, 3), (48, 40, 3, 3, 3), (48,), (64, 32, 2, 2, 2), (2, 32, 1, 1, 1),
                     (2,), (96, 64, 3, 3, 3), (7,)],
-                   [(16, 16, 5, 5, 5), (16,), (32, 16, 2, 2, 2), (33, 9, 3, 3, 3)]):
+                   [(16, 16, 5, 5, 5), (16,), (32, 16, 2, 2, 2), (33, 9, 3, 3, 3), (64, 32, 5, 5, 5), (40, 24, 5, 5, 5),
+                    (64, 16, 3, 3, 3)]):
         runs = []
         for fused in (True, False):
             g = torch.Generator(device=dev).manual_seed(11)
