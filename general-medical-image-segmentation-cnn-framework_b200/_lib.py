@@ -20,6 +20,8 @@ SIGNATURES = {
     "b200seg_conv3d_uses_tensor_cores": "g",
     "b200seg_ncdhw_f32_to_ndhwc_bf16": "ppiilp",
     "b200seg_ndhwc_bf16_to_ncdhw_f32": "ppiilp",
+    "b200seg_ncdhw_f32_to_ndhwc_bf16_pitched": "pplii" + "l" + "p",
+    "b200seg_ndhwc_bf16_to_ncdhw_f32_pitched": "plpii" + "l" + "p",
     "b200seg_pack_conv_weight": "ppiiiiiip",
     "b200seg_pack_conv_weight_padded": "ppiiiiiip",
     "b200seg_pack_weights_batched": "pppiiip",
@@ -48,6 +50,15 @@ SIGNATURES = {
     "b200seg_upsample2_bwd": "plpl" + "iiiii" + "p",
     "b200seg_add": "plplpl" + "li" + "p",
     "b200seg_dropout": "plpl" + "ll" + "if" + "pQ" + "i" + "p",
+    "b200seg_convt1_k2s2_fwd": "pppp" + "liii" + "p",
+    "b200seg_convt1_k2s2_bwd": "ppppp" + "liii" + "p",
+    "b200seg_reverse_gate_fwd": "plp" + "pl" + "li" + "p",
+    "b200seg_reverse_gate_bwd": "plplp" + "plp" + "li" + "p",
+    "b200seg_channel_blend_fwd": "plp" + "plp" + "pl" + "lii" + "p",
+    "b200seg_channel_blend_bwd_reduce": "plplpl" + "pp" + "lii" + "p",
+    "b200seg_channel_blend_bwd_apply": "pl" + "ppp" + "plpl" + "lii" + "p",
+    "b200seg_f32_sigmoid_fwd": "ppl" + "p",
+    "b200seg_f32_sigmoid_bwd": "pppl" + "p",
     "b200seg_dropout2": "plpl" + "ll" + "iif" + "pQQ" + "i" + "p",
     "b200seg_classmap_up2_add": "ppp" + "liii" + "p",
     "b200seg_classmap_down2_sum": "pp" + "liii" + "p",

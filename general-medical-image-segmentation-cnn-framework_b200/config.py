@@ -83,8 +83,17 @@ def build_model(config):
     if net == "csrnet":       # train.py:366-369 (init_features defaults to 64 there)
         from .models.three_d.csrnet import CSRNet
         return CSRNet(in_channels=config.in_classes, out_channels=config.out_classes)
+    if net == "er_net":       # train.py:332-335
+        from .models.three_d.ER_net import ER_Net
+        return ER_Net(classes=config.out_classes, channels=config.in_classes)
+    if net == "re_net":       # train.py:336-339
+        from .models.three_d.RE_net import RE_Net
+        return RE_Net()
+    if net == "dunet":  # train.py:370-373
+        from .models.three_d.Double_Unet import Double_Unet
+        return Double_Unet(in_channels=config.in_classes, out_channels=config.out_classes)
     raise ValueError("network %r is not on the b200seg path (supported: unet, res_unet, vnet, densevoxelnet, "
-                     "highresnet, csrnet)" % net)
+                     "highresnet, csrnet, er_net, re_net, dunet)" % net)
 
 
 def weights_init_normal(init_type):

@@ -21,7 +21,7 @@ const char* get_error() { return g_err; }
 
 // ------------------------------------------------------------------------------------------------ layout
 __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int c,
-                                      int64_t spatial) {
+                                      int64_t spatial, int64_t pitch) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t s0 = static_cast<int64_t>(blockIdx.x) * 32;
@@ -35,7 +35,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int64_t s = s0 + i;
     const int cc = c0 + threadIdx.x;
-    if (cc < c && s < spatial) dst[(static_cast<int64_t>(n) * spatial + s) * c + cc] = __float2bfloat16(tile[threadIdx.x][i]);
+    if (cc < c && s < spatial) dst[(static_cast<int64_t>(n) * spatial + s) * pitch + cc] = __float2bfloat16(tile[threadIdx.x][i]);
   }
 }
 
@@ -55,7 +55,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 
 __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int c,
-                                      int64_t spatial) {
+                                      int64_t spatial, int64_t pitch) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t s0 = static_cast<int64_t>(blockIdx.x) * 32;
@@ -63,7 +63,7 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, flo
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int64_t s = s0 + i;
     const int cc = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (cc < c && s < spatial) ? __bfloat162float(src[(static_cast<int64_t>(n) * spatial + s) * c + cc]) : 0.f;
+    tile[i][threadIdx.x] = (cc < c && s < spatial) ? __bfloat162float(src[(static_cast<int64_t>(n) * spatial + s) * pitch + cc]) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -942,9 +942,10 @@ extern "C" {
 const char* b200seg_version(void) { return "b200seg 0.1 (sm_100a)"; }
 const char* b200seg_last_error(void) { return b200::get_error(); }
 
-int b200seg_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int n, int c, int64_t spatial, void* stream) {
-  B200_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "ncdhw_to_ndhwc: bad arguments");
-  if (c == 1 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+int b200seg_ncdhw_f32_to_ndhwc_bf16_pitched(const float* src, void* dst, int64_t dst_pitch, int n, int c, int64_t spatial,
+                                            void* stream) {
+  B200_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0 && dst_pitch >= c, "ncdhw_to_ndhwc: bad arguments");
+  if (c == 1 && dst_pitch == 1 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const int64_t numel = static_cast<int64_t>(n) * spatial;
     f32_to_bf16_kernel<<<grid_for(numel / 8 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, static_cast<__nv_bfloat16*>(dst), numel);
@@ -953,17 +954,24 @@ int b200seg_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int n, int c, i
   }
   dim3 grid(static_cast<unsigned>((spatial + 31) / 32), (c + 31) / 32, n), block(32, 8);
   ncdhw_to_ndhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), c, spatial);
+      src, static_cast<__nv_bfloat16*>(dst), c, spatial, dst_pitch);
   B200_CHECK_LAUNCH("ncdhw_to_ndhwc");
   return 0;
 }
-int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, int64_t spatial, void* stream) {
-  B200_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0, "ndhwc_to_ncdhw: bad arguments");
+int b200seg_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int n, int c, int64_t spatial, void* stream) {
+  return b200seg_ncdhw_f32_to_ndhwc_bf16_pitched(src, dst, c, n, c, spatial, stream);
+}
+int b200seg_ndhwc_bf16_to_ncdhw_f32_pitched(const void* src, int64_t src_pitch, float* dst, int n, int c, int64_t spatial,
+                                            void* stream) {
+  B200_CHECK_ARG(src && dst && n > 0 && c > 0 && spatial > 0 && src_pitch >= c, "ndhwc_to_ncdhw: bad arguments");
   dim3 grid(static_cast<unsigned>((spatial + 31) / 32), (c + 31) / 32, n), block(32, 8);
   ndhwc_to_ncdhw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src), dst, c, spatial);
+      static_cast<const __nv_bfloat16*>(src), dst, c, spatial, src_pitch);
   B200_CHECK_LAUNCH("ndhwc_to_ncdhw");
   return 0;
+}
+int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, int64_t spatial, void* stream) {
+  return b200seg_ndhwc_bf16_to_ncdhw_f32_pitched(src, c, dst, n, c, spatial, stream);
 }
 
 // ACT is a template parameter so every instantiation carries only its own activation code (the runtime switch made the

@@ -610,6 +610,43 @@ def to_ndhwc(x):
     return _ToNDHWC.apply(x)
 
 
+class _ConcatInput(torch.autograd.Function):
+    """torch.cat((x, maps), dim=1) of two fp32 NCDHW tensors, delivered as one bf16 NDHWC activation (Double_Unet.py:90)."""
+
+    @staticmethod
+    def forward(ctx, x, maps):
+        n, c1, c2 = x.shape[0], x.shape[1], maps.shape[1]
+        spatial = x[0, 0].numel()
+        assert maps.shape[0] == n and maps.shape[2:] == x.shape[2:]
+        x, maps = x.contiguous().float(), maps.contiguous().float()
+        out = torch.empty((n,) + tuple(x.shape[2:]) + (c1 + c2,), dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_ncdhw_f32_to_ndhwc_bf16_pitched", _ptr(x), _ptr(out), c1 + c2, n, c1, spatial, _stream())
+        _call("b200seg_ncdhw_f32_to_ndhwc_bf16_pitched", _ptr(maps), out.data_ptr() + 2 * c1, c1 + c2, n, c2, spatial,
+              _stream())
+        ctx.split = (c1, c2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        c1, c2 = ctx.split
+        g = g.contiguous()
+        n = g.shape[0]
+        spatial = g[0, ..., 0].numel()
+        outs = []
+        for need, off, c in ((ctx.needs_input_grad[0], 0, c1), (ctx.needs_input_grad[1], c1, c2)):
+            if not need:
+                outs.append(None)
+                continue
+            o = torch.empty((n, c) + tuple(g.shape[1:4]), dtype=torch.float32, device=g.device)
+            _call("b200seg_ndhwc_bf16_to_ncdhw_f32_pitched", g.data_ptr() + 2 * off, c1 + c2, _ptr(o), n, c, spatial, _stream())
+            outs.append(o)
+        return tuple(outs)
+
+
+def concat_input(x, maps):
+    return _ConcatInput.apply(x, maps)
+
+
 class _FromNDHWC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -1294,6 +1331,160 @@ class _ClassmapUp2Add(torch.autograd.Function):
 def classmap_up2_add(coarse, fine=None):
     """nearest x2 up-sampling of an fp32 NCDHW class-score map, plus `fine` (residual_unet3d.py:196-202)."""
     return _ClassmapUp2Add.apply(coarse, fine)
+
+
+# ---- attention gates of ER-Net / RE-Net / Double-UNet (csrc/gates.cu) -------------------------------------------------
+class _ConvTMap(torch.autograd.Function):
+    """ConvTranspose3d(1, 1, kernel 2, stride 2) on an fp32 single-channel NCDHW map (ER_net.py:166-168)."""
+
+    @staticmethod
+    def forward(ctx, gmap, weight, bias):
+        assert tuple(weight.shape) == (1, 1, 2, 2, 2) and gmap.shape[1] == 1, "single-channel k2s2 transposed convolution"
+        gmap = gmap.contiguous().float()
+        n, _, d, h, w = gmap.shape
+        w8 = weight.detach().reshape(8).float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        out = torch.empty((n, 1, 2 * d, 2 * h, 2 * w), dtype=torch.float32, device=gmap.device)
+        _call("b200seg_convt1_k2s2_fwd", _ptr(gmap), _ptr(w8), _ptr(b), _ptr(out), n, d, h, w, _stream())
+        ctx.save_for_backward(gmap, w8)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gmap, w8 = ctx.saved_tensors
+        n, _, d, h, w = gmap.shape
+        dout = dout.contiguous().float()
+        din = torch.empty_like(gmap)
+        sums = _zeros_f32(9, gmap.device)
+        _call("b200seg_convt1_k2s2_bwd", _ptr(dout), _ptr(gmap), _ptr(w8), _ptr(din), _ptr(sums), n, d, h, w, _stream())
+        return din, sums[:8].view(1, 1, 2, 2, 2), (sums[8:9] if ctx.has_bias else None)
+
+
+def convt_map_k2s2(gmap, weight, bias=None):
+    return _ConvTMap.apply(gmap, weight, bias)
+
+
+class _ReverseGate(torch.autograd.Function):
+    """fine * (1 - sigmoid(g)) + fine with a single-channel fp32 gate map g (ER_net.py:184-187, RE_net.py:118-121)."""
+
+    @staticmethod
+    def forward(ctx, fine, g, out):
+        fine, fp = _as_rows(fine)
+        n, d, h, w, c = fine.shape
+        g = g.contiguous().float()
+        assert g.numel() == n * d * h * w, "gate map and features differ in extent"
+        if out is None:
+            out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=fine.device)
+        assert _pitched(out) and out.shape == fine.shape
+        _call("b200seg_reverse_gate_fwd", _ptr(fine), fp, _ptr(g), _ptr(out), out.stride(3), n * d * h * w, c, _stream())
+        ctx.save_for_backward(fine, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        fine, g = ctx.saved_tensors
+        fine, fp = _as_rows(fine)
+        dout, dp = _as_rows(dout)
+        n, d, h, w, c = fine.shape
+        dfine = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=fine.device)
+        dg = torch.empty_like(g)
+        _call("b200seg_reverse_gate_bwd", _ptr(dout), dp, _ptr(fine), fp, _ptr(g), _ptr(dfine), c, _ptr(dg), n * d * h * w, c,
+              _stream())
+        return dfine, dg, None
+
+
+def reverse_gate(fine, g, out=None):
+    return _ReverseGate.apply(fine, g, out)
+
+
+class _GatedBlend(torch.autograd.Function):
+    """out = x1 * w1[n, c] (+ x2 * w2[n, c]) with (w1, w2) = gate_fn(mean_voxels(x1 (+ x2)), *params).
+
+    The pooled mean (b200seg_channel_stats per sample), the blend and both backward passes are kernels; gate_fn itself --
+    two or three Linear layers on an [N, C] tensor (SE.py:32-37, ER_net.py:80-101: <= 2 x 256 x 64 multiply-adds) -- runs
+    as torch ops inside, and is differentiated by torch on that tiny graph."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, gate_fn, out, *params):
+        x1, p1 = _as_rows(x1)
+        n, d, h, w, c = x1.shape
+        vox = d * h * w
+        pooled = channel_stats(x1, n)[:, 0, :]
+        if x2 is not None:
+            x2, p2 = _as_rows(x2)
+            assert x2.shape == x1.shape
+            pooled = pooled + channel_stats(x2, n)[:, 0, :]
+        with torch.enable_grad():
+            s = (pooled / vox).detach().requires_grad_(True)
+            ps = [p.detach().requires_grad_(True) for p in params]
+            w1, w2 = gate_fn(s, *ps)
+            w1 = w1.float().contiguous()
+            w2 = w2.float().contiguous() if w2 is not None else None
+        assert (w2 is not None) == (x2 is not None)
+        if out is None:
+            out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x1.device)
+        assert _pitched(out) and out.shape == x1.shape
+        _call("b200seg_channel_blend_fwd", _ptr(x1), p1, _ptr(w1.detach()), _ptr(x2), p2 if x2 is not None else 0,
+              _ptr(w2.detach() if w2 is not None else None), _ptr(out), out.stride(3), vox, n, c, _stream())
+        ctx.x1, ctx.x2, ctx.graph = x1, x2, (s, ps, w1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x1, x2 = ctx.x1, ctx.x2
+        s, ps, w1, w2 = ctx.graph
+        x1, p1 = _as_rows(x1)
+        dout, dp = _as_rows(dout)
+        n, d, h, w, c = x1.shape
+        vox = d * h * w
+        dots = _zeros_f32(2 * n * c, x1.device).view(2, n, c)
+        x2p = 0
+        if x2 is not None:
+            x2, x2p = _as_rows(x2)
+        _call("b200seg_channel_blend_bwd_reduce", _ptr(dout), dp, _ptr(x1), p1, _ptr(x2), x2p, _ptr(dots[0]),
+              _ptr(dots[1] if x2 is not None else None), vox, n, c, _stream())
+        outs, gouts = [w1], [dots[0]]
+        if w2 is not None:
+            outs.append(w2)
+            gouts.append(dots[1])
+        grads = torch.autograd.grad(outs, [s] + ps, gouts, allow_unused=True)
+        add = (grads[0] / vox).float().contiguous() if grads[0] is not None else None
+        dx1 = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x1.device)
+        dx2 = torch.empty_like(dx1) if x2 is not None else None
+        _call("b200seg_channel_blend_bwd_apply", _ptr(dout), dp, _ptr(w1.detach()), _ptr(w2.detach() if w2 is not None else None),
+              _ptr(add), _ptr(dx1), c, _ptr(dx2), c, vox, n, c, _stream())
+        ctx.graph = None
+        return (dx1, dx2, None, None) + tuple(grads[1:])
+
+
+def gated_blend(x1, x2, gate_fn, params, out=None):
+    """Squeeze-and-excitation / selective-fusion gates: see _GatedBlend.  gate_fn(pooled_mean [N, C], *params) returns the
+    per-(sample, channel) weights (w1, w2); w2 is None when there is no second input."""
+    return _GatedBlend.apply(x1, x2, gate_fn, out, *params)
+
+
+class _SigmoidMap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        y = torch.empty_like(x)
+        _call("b200seg_f32_sigmoid_fwd", _ptr(x), _ptr(y), x.numel(), _stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        _call("b200seg_f32_sigmoid_bwd", _ptr(dy), _ptr(y), _ptr(dx), y.numel(), _stream())
+        return dx
+
+
+def sigmoid_map(x):
+    """torch.sigmoid on an fp32 class-score map (RE_net.py:158)."""
+    return _SigmoidMap.apply(x)
 
 
 def zeros_ndhwc(n, d, h, w, c, device):

@@ -52,6 +52,12 @@ int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g);
 /* fp32 NCDHW -> bf16 NDHWC (model input, train.py:195) and back (logits handed to the caller as NCDHW fp32). */
 int b200seg_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int n, int c, int64_t spatial, void* stream);
 int b200seg_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int n, int c, int64_t spatial, void* stream);
+/* The same with a row pitch (elements) on the channels-last side, so that `dst` / `src` can be a channel slice of a wider
+ * buffer: Double_Unet.py:90 concatenates the image with the coarse network's class scores without a separate cat pass. */
+int b200seg_ncdhw_f32_to_ndhwc_bf16_pitched(const float* src, void* dst, int64_t dst_pitch, int n, int c, int64_t spatial,
+                                            void* stream);
+int b200seg_ndhwc_bf16_to_ncdhw_f32_pitched(const void* src, int64_t src_pitch, float* dst, int n, int c, int64_t spatial,
+                                            void* stream);
 /* Conv3d weight [cout][cin][k^3] fp32 -> fprop pack [k^3][cout][cin] bf16 (flip=0) or dgrad pack
  * [k^3 flipped][cin][cout] bf16 (flip=1).  cin_off/cin_cnt select an input-channel slice (concat-free decoders). */
 int b200seg_pack_conv_weight(const float* w, void* packed, int cout, int cin, int k, int cin_off, int cin_cnt,
@@ -197,6 +203,39 @@ int b200seg_classmap_up2_add(const float* coarse, const float* fine, float* out,
                              void* stream);
 /* backward of the up-sampling: dcoarse = sum over each 2x2x2 cell of dfine. */
 int b200seg_classmap_down2_sum(const float* dfine, float* dcoarse, int64_t planes, int d, int h, int w, void* stream);
+
+/* ---- attention gates of ER-Net / RE-Net / Double-UNet (models/three_d/ER_net.py, RE_net.py, Double_Unet.py, SE.py) --- */
+/* ConvTranspose3d(1, 1, kernel 2, stride 2) on fp32 single-channel maps [planes][d][h][w] -> [planes][2d][2h][2w]
+ * (ER_net.py:166-168: the reverse-attention map is projected to one channel, then up-sampled).  w: 8 floats, bias: 1. */
+int b200seg_convt1_k2s2_fwd(const float* in, const float* w, const float* bias, float* out, int64_t planes, int d, int h,
+                            int wd, void* stream);
+/* din (may be NULL) and sums[9] += {dw[8], dbias} (caller zeroes sums). */
+int b200seg_convt1_k2s2_bwd(const float* dout, const float* in, const float* w, float* din, float* sums, int64_t planes,
+                            int d, int h, int wd, void* stream);
+/* out[v][c] = fine[v][c] * (2 - sigmoid(g[v])): `x = -1 * sigmoid(g) + 1; x = x.expand(..).mul(enc); x = x + enc`
+ * (ER_net.py:184-187).  fine / out bf16 NDHWC rows, g fp32 [rows]. */
+int b200seg_reverse_gate_fwd(const void* fine, int64_t fine_pitch, const float* g, void* out, int64_t out_pitch,
+                             int64_t rows, int c, void* stream);
+/* dfine = dout * (2 - s), dg[v] = -s (1 - s) sum_c dout[v][c] fine[v][c] with s = sigmoid(g[v]).  C: power of two. */
+int b200seg_reverse_gate_bwd(const void* dout, int64_t dout_pitch, const void* fine, int64_t fine_pitch, const float* g,
+                             void* dfine, int64_t dfine_pitch, float* dg, int64_t rows, int c, void* stream);
+/* out[v][c] = x1[v][c] * w1[n][c] (+ x2[v][c] * w2[n][c]); w fp32 [n][c].  Squeeze-and-excitation `x + x * y`
+ * (SE.py:41-49, w1 = 1 + y) and the selective fusion of two branches (ER_net.py:86-105, w = softmax over the branches). */
+int b200seg_channel_blend_fwd(const void* x1, int64_t x1_pitch, const float* w1, const void* x2, int64_t x2_pitch,
+                              const float* w2, void* out, int64_t out_pitch, int64_t rows_per_sample, int n, int c,
+                              void* stream);
+/* dots1[n][c] += sum_v dout * x1, dots2[n][c] += sum_v dout * x2 (caller zeroes them): the gradients of w1 / w2. */
+int b200seg_channel_blend_bwd_reduce(const void* dout, int64_t dout_pitch, const void* x1, int64_t x1_pitch, const void* x2,
+                                     int64_t x2_pitch, float* dots1, float* dots2, int64_t rows_per_sample, int n, int c,
+                                     void* stream);
+/* dx1 = dout * w1 + add, dx2 = dout * w2 + add; add[n][c] (may be NULL) = gradient reaching the inputs through the global
+ * average pool that produced the weights, already divided by the voxel count. */
+int b200seg_channel_blend_bwd_apply(const void* dout, int64_t dout_pitch, const float* w1, const float* w2, const float* add,
+                                    void* dx1, int64_t dx1_pitch, void* dx2, int64_t dx2_pitch, int64_t rows_per_sample,
+                                    int n, int c, void* stream);
+/* y = sigmoid(x) on fp32 maps (RE_net.py:158 `F.sigmoid(final)`), dx = dy * y * (1 - y). */
+int b200seg_f32_sigmoid_fwd(const float* x, float* y, int64_t numel, void* stream);
+int b200seg_f32_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t numel, void* stream);
 
 /* ---- head + loss (unet3d.py:46-48,70; loss_function.py:8-16,102-130,148-185; train.py:115,204) ---------------- */
 /* logits[n][classes][spatial] fp32 (NCDHW, what the module returns) = 1x1x1 conv of NDHWC bf16 features. */

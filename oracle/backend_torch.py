@@ -194,3 +194,30 @@ def head_conv1x1(x, weight, bias=None):
 def classmap_up2_add(coarse, fine=None):
     up = TF.interpolate(coarse, scale_factor=2, mode="nearest")
     return up if fine is None else up + fine
+
+
+# ---- attention gates (ER_net.py, RE_net.py, Double_Unet.py + SE.py) ----------------------------------------------------
+def convt_map_k2s2(gmap, weight, bias=None):
+    return TF.conv_transpose3d(gmap, weight, bias, stride=2)
+
+
+def reverse_gate(fine, g, out=None):
+    x = -1 * torch.sigmoid(g) + 1
+    return _ra(x.expand(-1, fine.shape[1], -1, -1, -1).mul(fine) + fine)
+
+
+def gated_blend(x1, x2, gate_fn, params, out=None):
+    pooled = x1.mean((2, 3, 4)) if x2 is None else (x1 + x2).mean((2, 3, 4))
+    w1, w2 = gate_fn(pooled, *params)
+    y = x1 * w1[:, :, None, None, None]
+    if x2 is not None:
+        y = y + x2 * w2[:, :, None, None, None]
+    return _ra(y)
+
+
+def sigmoid_map(x):
+    return torch.sigmoid(x)
+
+
+def concat_input(x, maps):
+    return _ra(torch.cat((x.float(), maps), dim=1))

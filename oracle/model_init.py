@@ -15,6 +15,8 @@ def init_module_(module, seed=0):
             if p.dim() >= 3:                          # conv / conv-transpose weights
                 fan_in = p[0].numel() if p.dim() == 5 else p.numel()
                 p.copy_(torch.randn(p.shape, generator=g) * math.sqrt(2.0 / max(fan_in, 1)))
+            elif p.dim() == 2:                        # Linear weights (squeeze-and-excitation / selective-fusion gates)
+                p.copy_(torch.randn(p.shape, generator=g) * math.sqrt(1.0 / p.shape[1]))
             elif name.endswith("weight") and p.numel() > 1 and ("bn" in name or "norm" in name or ".0.weight" in name):
                 p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g))
             elif name.endswith("weight"):             # PReLU slopes, other 1-D weights
@@ -42,6 +44,10 @@ MODEL_CASES = {
     "highres3d": ("models.three_d.highresnet", "HighRes3DNet", dict(in_channels=1, out_channels=2), 24, 1),
     "densevoxel": ("models.three_d.densevoxelnet3d", "DenseVoxelNet", dict(in_channels=1, classes=2), 32, 2),
     "csrnet": ("models.three_d.csrnet", "CSRNet", dict(in_channels=1, out_channels=2, init_features=8), 32, 2),
+    "re_net": ("models.three_d.RE_net", "RE_Net", dict(), 32, 2),
+    "er_net": ("models.three_d.ER_net", "ER_Net", dict(classes=2, channels=1), 32, 2),
+    "double_unet": ("models.three_d.Double_Unet", "Double_Unet",
+                    dict(in_channels=1, out_channels=2, unet_init_features=16), 32, 2),
 }
 
 

@@ -1,4 +1,4 @@
-"""Golden vectors for the V-Net / residual U-Net / HighRes3DNet / DenseVoxelNet mirrors, produced by the UNMODIFIED
+"""Golden vectors for the V-Net / residual U-Net / HighRes3DNet / DenseVoxelNet / CSRNet / RE-Net / ER-Net / Double-UNet mirrors, produced by the UNMODIFIED
 reference modules (run in the build container only):
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_models.py
@@ -20,6 +20,15 @@ ROOT = os.path.dirname(os.path.dirname(OUT))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 sys.dont_write_bytecode = True
+
+import types  # noqa: E402
+
+for _name in ("thop", "torchvision"):      # imported (not used) by Double_Unet.py; absent from this image
+    try:
+        importlib.import_module(_name)
+    except Exception:
+        sys.modules[_name] = types.ModuleType(_name)
+        sys.modules[_name].profile = None
 
 from oracle.model_init import MODEL_CASES, case_inputs, disable_dropout_, init_module_  # noqa: E402
 from utils.loss_function import DiceLossss, cross_entropy_3D  # noqa: E402  (reference)

@@ -23,6 +23,10 @@ def test_config_compose_and_overrides():
                          ("highresnet", 803636)):
         m = build_model(compose(["config=" + name]))
         assert sum(p.numel() for p in m.parameters()) == params
+    # the extra config.network values of train.py:332-339,366-373 (parameter counts of the reference's constructors)
+    for name, params in (("er_net", 5110176), ("re_net", 5646560), ("csrnet", None), ("dunet", None)):
+        m = build_model(compose(["config=unet", "config.network=" + name]))
+        assert params is None or sum(p.numel() for p in m.parameters()) == params
     m = build_model(compose(["config=unet"]))
     m.apply(weights_init_normal("kaiming"))
     assert float(m.encoder1[0].bias.abs().max()) == 0.0 and float(m.upconv1.bias.abs().max()) == 0.0

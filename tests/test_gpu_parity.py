@@ -689,3 +689,90 @@ def test_fused_optimizer_step_is_bit_identical_to_the_three_kernel_path():
         for x, y in zip(runs[0][:4], runs[1][:4]):
             assert torch.equal(x, y)
         assert runs[0][4] == runs[1][4] == 3
+
+
+# ---- attention gates of ER-Net / RE-Net / Double-UNet (csrc/gates.cu) against the torch restatement -------------------
+def test_reverse_attention_gate_forward_backward(F):
+    """`-1 * sigmoid(up(proj(coarse))) + 1` expanded over the channels, times the skip, plus the skip (ER_net.py:184-187)."""
+    from oracle import backend_torch as B
+    g = torch.Generator().manual_seed(21)
+    for c, cc, size in ((32, 64, (4, 6, 8)), (64, 128, (3, 4, 4)), (128, 256, (2, 2, 4))):
+        fine = bf(torch.randn(2, c, 2 * size[0], 2 * size[1], 2 * size[2], generator=g))
+        coarse = bf(torch.randn(2, cc, *size, generator=g))
+        wp = torch.randn(1, cc, 1, 1, 1, generator=g) * 0.2
+        bp = torch.randn(1, generator=g) * 0.1
+        wt = torch.randn(1, 1, 2, 2, 2, generator=g)
+        bt = torch.randn(1, generator=g) * 0.1
+        dy = bf(torch.randn(fine.shape, generator=g))
+        # reference arithmetic
+        r = [t.clone().requires_grad_(True) for t in (fine, coarse, wp, bp, wt, bt)]
+        gmap = B.convt_map_k2s2(torch.nn.functional.conv3d(r[1], r[2], r[3]), r[4], r[5])
+        ref = B.reverse_gate(r[0], gmap)
+        ref.backward(dy)
+        # kernels
+        d = [ndhwc(fine).requires_grad_(True), ndhwc(coarse).requires_grad_(True)] + \
+            [t.to(DEV).requires_grad_(True) for t in (wp, bp, wt, bt)]
+        gm = F.convt_map_k2s2(F.head_conv1x1(d[1], d[2], d[3]), d[4], d[5])
+        close(gm.detach().cpu(), gmap.detach(), 5e-3, "gate map")
+        out = F.reverse_gate(d[0], gm)
+        close(ncdhw(out), ref.detach(), 6e-3, "reverse gate")
+        out.backward(ndhwc(dy))
+        close(ncdhw(d[0].grad), r[0].grad, 8e-3, "d fine")
+        close(ncdhw(d[1].grad), r[1].grad, 1.5e-2, "d coarse")
+        for i, what in ((2, "d proj weight"), (3, "d proj bias"), (4, "d up weight"), (5, "d up bias")):
+            close(d[i].grad.cpu(), r[i].grad, 1.5e-2, what)
+
+
+@pytest.mark.parametrize("kind", ["se_residual", "se_inception", "selective_fusion"])
+def test_gated_blend_forward_backward(F, kind):
+    """SE.py:4-49 (x * y, x + x * y) and SFConv (ER_net.py:57-105) through the mirrors' own modules, bound once to the
+    kernels and once to the torch restatement."""
+    from oracle import backend_torch as B
+    from b200seg.models.three_d.ER_net import SFConv
+    from b200seg.models.three_d.SE import SE_Inception, SE_Residual
+    g = torch.Generator().manual_seed(22)
+    c, shape = 64, (2, 64, 6, 5, 8)
+    torch.manual_seed(5)
+    mod = {"se_residual": lambda: SE_Residual(c), "se_inception": lambda: SE_Inception(c),
+           "selective_fusion": lambda: SFConv(c)}[kind]()
+    x1 = bf(torch.randn(*shape, generator=g) + 0.3)
+    x2 = bf(torch.randn(*shape, generator=g))
+    dy = bf(torch.randn(*shape, generator=g))
+    two = kind == "selective_fusion"
+    mod.set_kernels(B)
+    a1, a2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    ref = mod(a1, a2) if two else mod(a1)
+    ref.backward(dy)
+    ref_grads = {k: p.grad.clone() for k, p in mod.named_parameters()}
+    mod.zero_grad()
+    mod.set_kernels(None)
+    mod = mod.to(DEV)
+    d1, d2 = ndhwc(x1).requires_grad_(True), ndhwc(x2).requires_grad_(True)
+    out = mod(d1, d2) if two else mod(d1)
+    close(ncdhw(out), ref.detach(), 6e-3, kind)
+    out.backward(ndhwc(dy))
+    close(ncdhw(d1.grad), a1.grad, 8e-3, "dx1")
+    if two:
+        close(ncdhw(d2.grad), a2.grad, 8e-3, "dx2")
+    for k, p in mod.named_parameters():
+        close(p.grad.cpu(), ref_grads[k], 2e-2, "d " + k)
+
+
+def test_sigmoid_map_and_concat_input(F):
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(2, 2, 5, 6, 7, generator=g) * 3
+    xd = x.to(DEV).requires_grad_(True)
+    y = F.sigmoid_map(xd)
+    assert float((y.cpu() - torch.sigmoid(x)).abs().max()) < 1e-6
+    dy = torch.randn(x.shape, generator=g)
+    y.backward(dy.to(DEV))
+    s = torch.sigmoid(x)
+    assert float((xd.grad.cpu() - dy * s * (1 - s)).abs().max()) < 1e-6
+    # torch.cat((image, class scores), 1) -> channels-last bf16 (Double_Unet.py:90), gradient back to the class scores
+    img = torch.randn(2, 1, 5, 6, 7, generator=g)
+    maps = torch.randn(2, 2, 5, 6, 7, generator=g).to(DEV).requires_grad_(True)
+    cat = F.concat_input(img.to(DEV), maps)
+    assert torch.equal(ncdhw(cat), bf(torch.cat((img, maps.detach().cpu()), 1)))
+    gcat = bf(torch.randn(2, 3, 5, 6, 7, generator=g))
+    cat.backward(ndhwc(gcat))
+    assert torch.equal(maps.grad.cpu(), gcat[:, 1:])

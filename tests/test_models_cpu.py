@@ -16,12 +16,15 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def build(name):
     from b200seg.models.three_d.csrnet import CSRNet
+    from b200seg.models.three_d.Double_Unet import Double_Unet
+    from b200seg.models.three_d.ER_net import ER_Net
+    from b200seg.models.three_d.RE_net import RE_Net
     from b200seg.models.three_d.densevoxelnet3d import DenseVoxelNet
     from b200seg.models.three_d.highresnet import HighRes3DNet
     from b200seg.models.three_d.residual_unet3d import UNet
     from b200seg.models.three_d.vnet3d import VNet
     cls = {"VNet": VNet, "UNet": UNet, "HighRes3DNet": HighRes3DNet, "DenseVoxelNet": DenseVoxelNet,
-           "CSRNet": CSRNet}[MODEL_CASES[name][1]]
+           "CSRNet": CSRNet, "RE_Net": RE_Net, "ER_Net": ER_Net, "Double_Unet": Double_Unet}[MODEL_CASES[name][1]]
     net = cls(**MODEL_CASES[name][2])
     init_module_(net, seed=11)
     disable_dropout_(net)
