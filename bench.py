@@ -476,7 +476,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": patches, "parallelism": "dp%d" % world,
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
-                       "gradient_exchange": None if world == 1 else ("NVLink peer-memory reduce-scatter + all-gather inside the "
+                       "gradient_exchange": None if world == 1 else ("NVLink peer-memory reduce + push inside the "
                                                                      "graph" if opt.peer_grads else "NCCL all-reduce after the graph"),
                        "l2": "no flush needed: each step streams >10 GB of activations, far larger than the 126 MB L2"},
             "voxels_per_s": value * vox,
