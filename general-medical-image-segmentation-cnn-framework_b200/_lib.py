@@ -50,6 +50,8 @@ SIGNATURES = {
     "b200seg_upsample2_bwd": "plpl" + "iiiii" + "p",
     "b200seg_add": "plplpl" + "li" + "p",
     "b200seg_dropout": "plpl" + "ll" + "if" + "pQ" + "i" + "p",
+    "b200seg_space_to_depth": "plp" + "iiiiiiiiii" + "p",
+    "b200seg_depth_to_space": "ppl" + "iiiiiiiiii" + "p",
     "b200seg_convt1_k2s2_fwd": "pppp" + "liii" + "p",
     "b200seg_convt1_k2s2_bwd": "ppppp" + "liii" + "p",
     "b200seg_reverse_gate_fwd": "plp" + "pl" + "li" + "p",

@@ -143,6 +143,71 @@ __global__ void __launch_bounds__(256) pad3d_bwd_kernel(const __nv_bfloat16* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ space <-> depth
+// Non-overlapping strided convolutions (kernel k <= stride s, no padding: csrnet.py:115-154 uses Conv3d(k3, s4) and
+// ConvTranspose3d(k4, s4)) are plain GEMMs once the k^3 taps of every s^3 cell sit next to each other in the channel
+// dimension: y[n, oz, oy, ox, ((a*k + b)*k + e)*C + c] = x[n, oz*s + a, oy*s + b, ox*s + e, c].  V = channels per thread.
+template <int V>
+__global__ void space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_pitch, __nv_bfloat16* __restrict__ y,
+                                      int n, int d, int h, int w, int C, int k, int s, int od, int oh, int ow) {
+  const int cv = C / V;
+  const int k3 = k * k * k;
+  const int64_t total = static_cast<int64_t>(n) * od * oh * ow * k3 * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    int64_t r = i / cv;
+    const int t = static_cast<int>(r % k3);
+    r /= k3;
+    const int ox = static_cast<int>(r % ow);
+    r /= ow;
+    const int oy = static_cast<int>(r % oh);
+    r /= oh;
+    const int oz = static_cast<int>(r % od);
+    const int nn = static_cast<int>(r / od);
+    const int e = t % k, b = (t / k) % k, a = t / (k * k);
+    const int64_t src = ((static_cast<int64_t>(nn) * d + oz * s + a) * h + oy * s + b) * w + ox * s + e;
+    if constexpr (V == 8) st8(y + i * 8, ld8(x + src * x_pitch + ch * 8));
+    else y[i] = x[src * x_pitch + ch];
+  }
+}
+
+// The adjoint / inverse: x[n, z, yy, xx, c] = y[n, z/s, yy/s, xx/s, tap(z%s, yy%s, xx%s), c], zero where the position is not
+// covered (index >= k inside its cell, or a cell beyond the last output).
+template <int V>
+__global__ void depth_to_space_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ x, int64_t x_pitch,
+                                      int n, int d, int h, int w, int C, int k, int s, int od, int oh, int ow) {
+  const int cv = C / V;
+  const int k3 = k * k * k;
+  const int64_t total = static_cast<int64_t>(n) * d * h * w * cv;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % cv);
+    int64_t r = i / cv;
+    const int64_t row = r;
+    const int xx = static_cast<int>(r % w);
+    r /= w;
+    const int yy = static_cast<int>(r % h);
+    r /= h;
+    const int z = static_cast<int>(r % d);
+    const int nn = static_cast<int>(r / d);
+    const int oz = z / s, a = z % s, oy = yy / s, b = yy % s, ox = xx / s, e = xx % s;
+    const bool ok = a < k && b < k && e < k && oz < od && oy < oh && ox < ow;
+    const int64_t src = ((((static_cast<int64_t>(nn) * od + oz) * oh + oy) * ow + ox) * k3 + (a * k + b) * k + e) * cv + ch;
+    if constexpr (V == 8) {
+      bf16x8 v;
+      if (ok) v = ld8(y + src * 8);
+      else {
+        const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        v = pack8(z8);
+      }
+      st8(x + row * x_pitch + ch * 8, v);
+    } else {
+      x[row * x_pitch + ch] = ok ? y[src] : __float2bfloat16(0.f);
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -206,6 +271,47 @@ int b200seg_pad3d_bwd(const void* dy, int64_t dy_pitch, void* dx, int64_t dx_pit
   pad3d_bwd_kernel<<<grid_for(total, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), dy_pitch, static_cast<__nv_bfloat16*>(dx), dx_pitch, n, d, h, w, c, pad, mode);
   B200_CHECK_LAUNCH("pad3d_bwd");
+  return 0;
+}
+
+static int check_s2d(int n, int d, int h, int w, int c, int k, int s, int od, int oh, int ow, const char* who) {
+  B200_CHECK_ARG(n > 0 && c > 0 && k >= 1 && k <= s && s >= 1 && d >= k && h >= k && w >= k, "%s: bad geometry (needs k <= s)", who);
+  B200_CHECK_ARG(od >= 1 && oh >= 1 && ow >= 1 && (od - 1) * s + k <= d && (oh - 1) * s + k <= h && (ow - 1) * s + k <= w,
+                 "%s: output extent does not fit the input", who);
+  return 0;
+}
+
+int b200seg_space_to_depth(const void* x, int64_t x_pitch, void* y, int n, int d, int h, int w, int c, int k, int s, int od,
+                           int oh, int ow, void* stream) {
+  B200_CHECK_ARG(x && y && x_pitch >= c, "space_to_depth: bad buffers");
+  if (int rc = check_s2d(n, d, h, w, c, k, s, od, oh, ow, "space_to_depth")) return rc;
+  const bool vec = c % 8 == 0 && x_pitch % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const int64_t total = static_cast<int64_t>(n) * od * oh * ow * k * k * k * (vec ? c / 8 : c);
+  const int grid = grid_for(total, 256, kNumSMs * 8);
+  if (vec)
+    space_to_depth_kernel<8><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), n, d, h, w, c, k, s, od, oh, ow);
+  else
+    space_to_depth_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(y), n, d, h, w, c, k, s, od, oh, ow);
+  B200_CHECK_LAUNCH("space_to_depth");
+  return 0;
+}
+
+int b200seg_depth_to_space(const void* y, void* x, int64_t x_pitch, int n, int d, int h, int w, int c, int k, int s, int od,
+                           int oh, int ow, void* stream) {
+  B200_CHECK_ARG(x && y && x_pitch >= c, "depth_to_space: bad buffers");
+  if (int rc = check_s2d(n, d, h, w, c, k, s, od, oh, ow, "depth_to_space")) return rc;
+  const bool vec = c % 8 == 0 && x_pitch % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const int64_t total = static_cast<int64_t>(n) * d * h * w * (vec ? c / 8 : c);
+  const int grid = grid_for(total, 256, kNumSMs * 8);
+  if (vec)
+    depth_to_space_kernel<8><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(x), x_pitch, n, d, h, w, c, k, s, od, oh, ow);
+  else
+    depth_to_space_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(x), x_pitch, n, d, h, w, c, k, s, od, oh, ow);
+  B200_CHECK_LAUNCH("depth_to_space");
   return 0;
 }
 

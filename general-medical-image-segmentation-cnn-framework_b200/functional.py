@@ -6,6 +6,7 @@ wider buffer (that is how the U-Net skip concatenation is made copy-free).  Para
 gradients are fp32.  PyTorch supplies memory, streams and the autograd tape; all arithmetic is in the kernels.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -748,9 +749,66 @@ class _ConvNormAct(torch.autograd.Function):
         return dx, dx2, dw, db, dgamma, dbeta, dprelu, dres, None, None, None
 
 
+class _SpaceToDepth(torch.autograd.Function):
+    """[n, d, h, w, c] -> [n, od, oh, ow, k^3 * c]: the taps of every s^3 cell side by side (k <= s, no padding)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg):
+        k, s = cfg
+        x, xp = _as_rows(x)
+        n, d, h, w, c = x.shape
+        od, oh, ow = (d - k) // s + 1, (h - k) // s + 1, (w - k) // s + 1
+        y = torch.empty((n, od, oh, ow, k ** 3 * c), dtype=torch.bfloat16, device=x.device)
+        _call("b200seg_space_to_depth", _ptr(x), xp, _ptr(y), n, d, h, w, c, k, s, od, oh, ow, _stream())
+        ctx.cfg = (k, s, (n, d, h, w, c))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k, s, (n, d, h, w, c) = ctx.cfg
+        dy = dy.contiguous()
+        od, oh, ow = dy.shape[1:4]
+        dx = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=dy.device)
+        _call("b200seg_depth_to_space", _ptr(dy), _ptr(dx), c, n, d, h, w, c, k, s, od, oh, ow, _stream())
+        return dx, None
+
+
+class _DepthToSpace(torch.autograd.Function):
+    """[n, d, h, w, s^3 * c] -> [n, s d, s h, s w, c] (pixel shuffle, the k == s inverse of _SpaceToDepth)."""
+
+    @staticmethod
+    def forward(ctx, y, cfg):
+        s, out = cfg
+        y = y.contiguous()
+        n, d, h, w, cc = y.shape
+        c = cc // s ** 3
+        if out is None:
+            out = torch.empty((n, s * d, s * h, s * w, c), dtype=torch.bfloat16, device=y.device)
+        assert _pitched(out) and tuple(out.shape) == (n, s * d, s * h, s * w, c)
+        _call("b200seg_depth_to_space", _ptr(y), _ptr(out), out.stride(3), n, s * d, s * h, s * w, c, s, s, d, h, w, _stream())
+        ctx.cfg = (s, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        s, c = ctx.cfg
+        dout, dp = _as_rows(dout)
+        n, D, H, W, _ = dout.shape
+        dy = torch.empty((n, D // s, H // s, W // s, s ** 3 * c), dtype=torch.bfloat16, device=dout.device)
+        _call("b200seg_space_to_depth", _ptr(dout), dp, _ptr(dy), n, D, H, W, c, s, s, D // s, H // s, W // s, _stream())
+        return dy, None
+
+
 def conv_norm_act(x, weight, bias=None, *, x2=None, k=3, stride=1, pad=1, dil=1, spec=None, gamma=None, beta=None,
                   prelu_weight=None, residual=None, running_mean=None, running_var=None, out=None):
     spec = spec or NormSpec()
+    if stride > 2 and k <= stride and pad == 0 and dil == 1 and x2 is None:
+        # non-overlapping windows (csrnet.py:115-133: Conv3d(k3, s4)): gather the taps into the channel dimension and run a
+        # 1x1x1 convolution (a plain GEMM on the tensor cores) with the weight in the same (tap, channel) order
+        xs = _SpaceToDepth.apply(x, (int(k), int(stride)))
+        w2 = weight.permute(0, 2, 3, 4, 1).reshape(weight.shape[0], -1, 1, 1, 1)
+        return _ConvNormAct.apply(xs, None, w2, bias, gamma, beta, prelu_weight, residual, running_mean, running_var,
+                                  (1, 1, 0, 1, spec, out))
     return _ConvNormAct.apply(x, x2, weight, bias, gamma, beta, prelu_weight, residual, running_mean, running_var,
                               (k, stride, pad, dil, spec, out))
 
@@ -957,7 +1015,14 @@ def conv_transpose_kxsx(x, weight, bias=None, stride=2, out=None):
     """nn.ConvTranspose3d(kernel_size = stride).  stride 2 takes the dedicated tensor-core path (conv_transpose_k2s2)."""
     if stride == 2:
         return _ConvT2.apply(x, weight, bias, out)
-    return _ConvTS.apply(x, weight, bias, (int(stride), out))
+    s, cin, cout = int(stride), weight.shape[0], weight.shape[1]
+    if tuple(weight.shape[2:]) == (s, s, s) and cin % 16 == 0 and (s ** 3 * cout) % 16 == 0 and not os.environ.get("B200SEG_CONVT_DIRECT"):
+        # a 1x1x1 convolution to s^3 * C_out channels (tap-major) on the tensor cores, then the pixel shuffle
+        w2 = weight.permute(2, 3, 4, 1, 0).reshape(s ** 3 * cout, cin, 1, 1, 1)
+        b2 = bias.repeat(s ** 3) if bias is not None else None
+        y = _ConvNormAct.apply(x, None, w2, b2, None, None, None, None, None, None, (1, 1, 0, 1, NormSpec(), None))
+        return _DepthToSpace.apply(y, (s, out))
+    return _ConvTS.apply(x, weight, bias, (s, out))
 
 
 class _Head(torch.autograd.Function):

@@ -204,6 +204,16 @@ int b200seg_classmap_up2_add(const float* coarse, const float* fine, float* out,
 /* backward of the up-sampling: dcoarse = sum over each 2x2x2 cell of dfine. */
 int b200seg_classmap_down2_sum(const float* dfine, float* dcoarse, int64_t planes, int d, int h, int w, void* stream);
 
+/* ---- non-overlapping strided convolutions as GEMMs (csrnet.py:115-154: Conv3d(k3, s4), ConvTranspose3d(k4, s4)) -------- */
+/* y[n][od][oh][ow][k^3 * c] (contiguous) = the k^3 taps of every s^3 cell of x [n][d][h][w][c] side by side in the channel
+ * dimension, tap-major (k <= s, no padding): the strided convolution becomes a 1x1x1 convolution with k^3 * c inputs. */
+int b200seg_space_to_depth(const void* x, int64_t x_pitch, void* y, int n, int d, int h, int w, int c, int k, int s, int od,
+                           int oh, int ow, void* stream);
+/* The inverse / adjoint: x[n][d][h][w][c] from y, zero at positions no tap covers.  With k == s it is the pixel shuffle that
+ * turns a 1x1x1 convolution with s^3 * c outputs into ConvTranspose3d(kernel = stride = s). */
+int b200seg_depth_to_space(const void* y, void* x, int64_t x_pitch, int n, int d, int h, int w, int c, int k, int s, int od,
+                           int oh, int ow, void* stream);
+
 /* ---- attention gates of ER-Net / RE-Net / Double-UNet (models/three_d/ER_net.py, RE_net.py, Double_Unet.py, SE.py) --- */
 /* ConvTranspose3d(1, 1, kernel 2, stride 2) on fp32 single-channel maps [planes][d][h][w] -> [planes][2d][2h][2w]
  * (ER_net.py:166-168: the reverse-attention map is projected to one channel, then up-sampled).  w: 8 floats, bias: 1. */

@@ -21,7 +21,7 @@ REF_DST = os.path.join(HERE, "_ref")
 FILES = [
     "models/three_d/unet3d.py", "models/three_d/vnet3d.py", "models/three_d/residual_unet3d.py",
     "models/three_d/densevoxelnet3d.py", "models/three_d/highresnet.py", "models/three_d/csrnet.py",
-    "models/three_d/Double_Unet.py", "models/three_d/ER_net.py", "models/three_d/RE_net.py",
+    "models/three_d/Double_Unet.py", "models/three_d/SE.py", "models/three_d/ER_net.py", "models/three_d/RE_net.py",
     "models/sync_batchnorm/batchnorm.py", "models/sync_batchnorm/comm.py", "models/sync_batchnorm/replicate.py",
     "models/sync_batchnorm/batchnorm_reimpl.py",
     "utils/convolution.py", "utils/residual.py", "utils/dilation.py", "utils/loss_function.py", "utils/metric.py",
@@ -61,6 +61,12 @@ def import_ref():
     sys.dont_write_bytecode = True
     for name in ("torchio", "monai", "monai.metrics"):
         sys.modules.setdefault(name, types.ModuleType(name))
+    for name in ("thop", "torchvision"):       # imported, never used, by Double_Unet.py
+        try:
+            __import__(name)
+        except Exception:
+            sys.modules[name] = types.ModuleType(name)
+            sys.modules[name].profile = None
     if not hasattr(sys.modules["monai.metrics"], "compute_hausdorff_distance"):
         sys.modules["monai.metrics"].compute_hausdorff_distance = None
     return True

@@ -39,6 +39,18 @@ def ref_model(name):
     if name == "densevoxel":
         from models.three_d.densevoxelnet3d import DenseVoxelNet
         return DenseVoxelNet(1, 2)
+    if name == "csrnet":
+        from models.three_d.csrnet import CSRNet
+        return CSRNet(1, 2, 32)
+    if name == "er_net":
+        from models.three_d.ER_net import ER_Net
+        return ER_Net(classes=2, channels=1)
+    if name == "re_net":
+        from models.three_d.RE_net import RE_Net
+        return RE_Net()
+    if name == "dunet":
+        from models.three_d.Double_Unet import Double_Unet
+        return Double_Unet(1, 2)
     raise KeyError(name)
 
 
@@ -46,12 +58,15 @@ def our_model(name):
     import importlib
     mod, cls, args = {"unet": ("unet3d", "UNet3D", (1, 2, 32)), "vnet": ("vnet3d", "VNet", (True, 1, 2)),
                       "res_unet": ("residual_unet3d", "UNet", (1, 2, 32)), "highres": ("highresnet", "HighRes3DNet", (1, 2)),
-                      "densevoxel": ("densevoxelnet3d", "DenseVoxelNet", (1, 2))}[name]
+                      "densevoxel": ("densevoxelnet3d", "DenseVoxelNet", (1, 2)), "csrnet": ("csrnet", "CSRNet", (1, 2, 32)),
+                      "er_net": ("ER_net", "ER_Net", (2, 1)), "re_net": ("RE_net", "RE_Net", ()),
+                      "dunet": ("Double_Unet", "Double_Unet", (1, 2))}[name]
     return getattr(importlib.import_module("b200seg.models.three_d." + mod), cls)(*args)
 
 
-SIZES = {"unet": 128, "vnet": 128, "res_unet": 128, "highres": 96, "densevoxel": 96}
-GFLOP_FWD = {"unet": 951.3, "vnet": 1463.1, "res_unet": 1820.7, "highres": 1419.7, "densevoxel": 144.7}
+SIZES = {"unet": 128, "vnet": 128, "res_unet": 128, "highres": 96, "densevoxel": 96, "csrnet": 128, "er_net": 128, "re_net": 128,
+         "dunet": 96}
+GFLOP_FWD = {"unet": 951.3, "vnet": 1463.1, "res_unet": 1820.7, "highres": 1419.7, "densevoxel": 144.7}   # others: not counted
 
 
 def timed(fn, iters):
@@ -132,7 +147,7 @@ if __name__ == "__main__":
         try:
             ms, mem = ours(name)
             rec["b200seg"] = {"ms_per_step": round(ms, 2), "patches_per_s": round(2e3 / ms, 2), "peak_mem_GB": round(mem, 1),
-                              "train_tflops": round(3 * GFLOP_FWD[name] * 2 / ms, 1)}
+                              "train_tflops": round(3 * GFLOP_FWD[name] * 2 / ms, 1) if name in GFLOP_FWD else None}
             best = min((rec[m]["ms_per_step"] for m in ("tf32", "bf16_cl") if "ms_per_step" in rec[m]), default=None)
             if best:
                 rec["speedup_vs_best_library"] = round(best / ms, 2)

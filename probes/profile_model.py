@@ -12,6 +12,10 @@ from bench_models import CASES
 dev = torch.device("cuda")
 CASES = dict(CASES)
 CASES["unet"] = (lambda: __import__("b200seg.models.three_d.unet3d", fromlist=["UNet3D"]).UNet3D(1, 2, 32), 128, 2, 951.3)
+CASES["er_net"] = (lambda: __import__("b200seg.models.three_d.ER_net", fromlist=["ER_Net"]).ER_Net(2, 1), 128, 2, 0.0)
+CASES["dunet"] = (lambda: __import__("b200seg.models.three_d.Double_Unet", fromlist=["Double_Unet"]).Double_Unet(1, 2), 96, 2, 0.0)
+CASES["re_net"] = (lambda: __import__("b200seg.models.three_d.RE_net", fromlist=["RE_Net"]).RE_Net(), 128, 2, 0.0)
+CASES["csrnet"] = (lambda: __import__("b200seg.models.three_d.csrnet", fromlist=["CSRNet"]).CSRNet(1, 2, 32), 128, 2, 0.0)
 
 _orig_call = F._call
 

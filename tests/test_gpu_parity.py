@@ -92,7 +92,8 @@ CONV_CASES = [
     (1, 16, 5, 1, 2, 1, (40, 40, 44), 1),     # V-Net stem 5x5x5
     (64, 2, 1, 1, 0, 1, (40, 40, 44), 1),     # HighRes3DNet classifier
     (24, 40, 3, 2, 1, 1, (64, 64, 64), 1),    # stride 2 with padded channels
-    (32, 64, 3, 4, 0, 1, (16, 16, 20), 2),    # CSRNet cross-scale branch: stride 4, no padding (generic strided kernels)
+    (32, 64, 3, 4, 0, 1, (16, 16, 20), 2),    # CSRNet cross-scale branch: stride 4, no padding (space-to-depth + 1x1x1 GEMM)
+    (32, 128, 3, 4, 0, 1, (33, 34, 35), 1),   # ... extents that leave uncovered planes at the far end (zero gradient there)
 ]
 
 
@@ -121,6 +122,9 @@ def test_conv3d_fprop_dgrad_wgrad(F, case):
     # which path ran: tcgen05 for stride-1 k in {1,3,5} with 16-aligned channels
     if stride == 1 and k in (1, 3, 5) and cin % 16 == 0 and cout % 16 == 0:
         assert F.umma_launch_count() - n0 == 3, "tensor-core path was not taken"
+    elif stride > 2 and k <= stride and pad == 0 and (cin * k ** 3) % 16 == 0 and cout % 16 == 0:
+        # non-overlapping windows: space-to-depth + a 1x1x1 convolution with k^3 * C_in inputs, all three passes on tcgen05
+        assert F.umma_launch_count() - n0 == 3, "space-to-depth GEMM path was not taken"
     elif stride == 2 and cin % 16 == 0 and cout % 16 == 0 and min(size) >= 8:
         # k3s2: 1 forward + 8 data-gradient + 8 weight-gradient class launches; k2s2: one launch per pass
         assert F.umma_launch_count() - n0 == (17 if k == 3 else 3), "strided tensor-core path was not taken"
@@ -283,9 +287,10 @@ def test_conv_transpose_k2s2(F):
 
 
 def test_conv_transpose_k4s4(F):
-    """nn.ConvTranspose3d(kernel 4, stride 4) (csrnet.py:137-149) through the strided convolution's three passes."""
+    """nn.ConvTranspose3d(kernel 4, stride 4) (csrnet.py:137-149): a 1x1x1 convolution to 64 * C_out channels on the tensor
+    cores followed by the pixel shuffle (C_in % 16 == 0), else the strided convolution's three passes."""
     g = torch.Generator().manual_seed(6)
-    for cin, cout, size in [(32, 16, (2, 3, 4)), (64, 8, (2, 2, 2))]:
+    for cin, cout, size in [(32, 16, (2, 3, 4)), (64, 8, (2, 2, 2)), (128, 32, (4, 5, 6)), (24, 8, (2, 2, 3))]:
         x = bf(torch.randn(2, cin, *size, generator=g))
         w = torch.randn(cin, cout, 4, 4, 4, generator=g) * 0.1
         b = torch.randn(cout, generator=g) * 0.1
