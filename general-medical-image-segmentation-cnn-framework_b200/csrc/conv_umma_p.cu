@@ -478,10 +478,17 @@ static bool plan_plane_kc(const UmmaConvArgs& a, PlaneParams& p, int& P, int& KS
   p.rowbytes = p.KC * 2;
   p.swz = p.KC == 64 ? SWZ_128B : (p.KC == 32 ? SWZ_64B : SWZ_32B);
   if (a.cout <= 128 && !a.scatter_cout) p.NT = a.cout;
+  // pixel-shuffle GEMMs (ConvTranspose k2s2 forward) are bound by their scattered output writes; the widest N tile reads
+  // the input once instead of twice and halves the tile count (probes/convt_knobs.py: 0.126 -> 0.115 ms at 2 x 64^3)
+  else if (a.scatter_cout && a.cout % 256 == 0 && !getenv("B200SEG_SCATTER_NT")) p.NT = 256;
   else if (a.cout % 128 == 0) p.NT = 128;
   else if (a.cout % 64 == 0) p.NT = 64;
   else if (a.cout % 32 == 0) p.NT = 32;
   else p.NT = 16;
+  if (a.scatter_cout && getenv("B200SEG_SCATTER_NT")) {     // experiment knob (probes/convt_knobs.py)
+    const int v = atoi(getenv("B200SEG_SCATTER_NT"));
+    if (v >= 16 && v <= 256 && a.cout % v == 0) p.NT = v;
+  }
   if (p.NT % 16) return false;
   p.n_ntiles = a.cout / p.NT;
   p.WB = 8 + halo;

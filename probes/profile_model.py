@@ -49,7 +49,7 @@ for name in (sys.argv[1:] or ["highres"]):
     rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
     total = sum(v["ms"] for v in prof.values())
     print("== %s: %.2f ms of kernel time in %d launches" % (name, total, sum(v["launches"] for v in prof.values())))
-    for k, v in rows[:28]:
+    for k, v in rows[:int(os.environ.get("ROWS", "28"))]:
         tf = v["work"] / (v["ms"] * 1e-3) / 1e12 if v["work"] and v["ms"] else 0.0
         print("  %-58s %4d x  %9.3f ms  %5.1f %%  %s" % (k, v["launches"], v["ms"], 100 * v["ms"] / total,
                                                        ("%.0f TFLOP/s" % tf) if tf else ""))
