@@ -263,29 +263,12 @@ def _pad_channels(x, c_pad):
     return out
 
 
-def _padded_weight(weight, cin_p, cout_p):
-    w = weight.detach()
-    cout, cin = w.shape[0], w.shape[1]
-    if (cout, cin) == (cout_p, cin_p):
-        return w
-    wp = w.new_zeros((cout_p, cin_p) + tuple(w.shape[2:]))
-    wp[:cout, :cin] = w
-    return wp
-
-
 def _pack_padded(weight, cin_p, cout_p, dgrad):
     """bf16 fprop / dgrad pack of `weight` widened with zero rows / columns to cout_p x cin_p, one launch."""
     w = weight.detach()
     cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
     packed = torch.empty(k ** 3 * cout_p * cin_p, dtype=torch.bfloat16, device=w.device)
     _call("b200seg_pack_conv_weight_padded", _ptr(w), _ptr(packed), cout, cin, k, cout_p, cin_p, int(dgrad), _stream())
-    return packed
-
-
-def _pack_fresh(w, dgrad):
-    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
-    packed = torch.empty(k ** 3 * cout * cin, dtype=torch.bfloat16, device=w.device)
-    _call("b200seg_pack_conv_weight", _ptr(w), _ptr(packed), cout, cin, k, 0, cin, int(dgrad), _stream())
     return packed
 
 

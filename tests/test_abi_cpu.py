@@ -85,3 +85,39 @@ def test_grid_sampler_matches_oracle():
         GridSampler((8, 8, 8), (16, 16, 16), (0, 0, 0))
     with pytest.raises(ValueError):
         GridSampler((32, 32, 32), (16, 16, 16), (3, 4, 4))
+
+
+def test_build_outputs_are_renamed_into_place_and_builds_are_serialised(tmp_path):
+    """The ranks of one torchrun launch all call build(): outputs appear atomically and only one build runs at a time
+    (a rank once loaded a half-written library while seven others were linking it)."""
+    import multiprocessing as mp
+    import time
+    import __graft_entry__ as ge
+    target = tmp_path / "out.bin"
+    src = tmp_path / "in.bin"
+    src.write_bytes(b"x" * 1000)
+    ge._run_atomic(["cp", str(src), str(target)], str(target))
+    assert target.read_bytes() == src.read_bytes() and not list(tmp_path.glob("out.bin.tmp.*"))
+    with pytest.raises(Exception):
+        ge._run_atomic(["cp", str(tmp_path / "missing"), str(target)], str(target))
+    assert target.read_bytes() == src.read_bytes() and not list(tmp_path.glob("out.bin.tmp.*"))   # old file intact
+    # two processes inside _BuildLock never overlap
+    log = tmp_path / "log.txt"
+
+    def worker(path):
+        import __graft_entry__ as g
+        with g._BuildLock():
+            with open(path, "a") as f:
+                f.write("enter\n")
+            time.sleep(0.3)
+            with open(path, "a") as f:
+                f.write("exit\n")
+
+    ctx = mp.get_context("fork")
+    procs = [ctx.Process(target=worker, args=(str(log),)) for _ in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert log.read_text().split() == ["enter", "exit"] * 3
