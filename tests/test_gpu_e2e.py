@@ -258,3 +258,50 @@ def test_full_size_config2_step_against_fp32_reference():
     for k, v in ref_stats.items():
         if "running" in k and "num_batches" not in k:
             assert rel(my_stats[k].float(), v.float()) < 1e-2, k
+
+
+@pytest.mark.parametrize("name", ["vnet", "er_net"])
+def test_full_size_other_networks_against_fp32_reference(name):
+    """BASELINE configs[2] (V-Net) and an extra config.network (ER-Net) at FULL size -- batch 2 x 1 x 128^3, Dice+CE, one
+    forward + backward -- against the reference's own modules in strict fp32 on the same GPU.  Exercises at full extent what
+    the small parity cases cannot: the kd-stacked 5x5x5 kernel over 128 planes, the zero-padded stem / output layers, the
+    reverse-attention and selective-fusion gates."""
+    if not build_ref.import_ref():
+        pytest.skip("oracle/_ref (vendored reference modules) is not on this box")
+    import importlib
+    from b200seg.utils.loss_function import DiceCELoss
+    from oracle.model_init import disable_dropout_, init_module_
+    mod, cls, args = {"vnet": ("vnet3d", "VNet", (True, 1, 2)), "er_net": ("ER_net", "ER_Net", (2, 1))}[name]
+    x, lab = structured_batch(2, 128, seed=11, device=DEV)
+    mine_net = getattr(importlib.import_module("b200seg.models.three_d." + mod), cls)(*args)
+    disable_dropout_(init_module_(mine_net, seed=5))
+    sd = {k: v.clone() for k, v in mine_net.state_dict().items()}
+    mine_net = mine_net.to(DEV).train()
+    out = mine_net(x)
+    loss = DiceCELoss(2)(out, lab)
+    loss.backward()
+    torch.cuda.synchronize()
+    mine = {k: p.grad.detach().float() for k, p in mine_net.named_parameters() if p.grad is not None}
+    my_out, my_loss = out.detach().clone(), loss.item()
+    del mine_net, out, loss
+    torch.cuda.empty_cache()
+    with strict_fp32():
+        ref = getattr(importlib.import_module("models.three_d." + mod), cls)(*args)
+        ref.load_state_dict(sd)
+        disable_dropout_(ref)
+        ref = ref.to(DEV).train()
+        rout = ref(x)
+        rloss = _ref_loss(rout, lab)
+        rloss.backward()
+        theirs = {k: p.grad.detach() for k, p in ref.named_parameters() if p.grad is not None}
+    e_out = rel(my_out, rout.detach())
+    # parameters whose gradient is analytically zero (a conv bias in front of batch statistics) carry only round-off
+    live = [k for k in theirs if k in mine and float(theirs[k].norm()) > 1e-4 * float(max(t.norm() for t in theirs.values()))]
+    cos = cosine(torch.cat([mine[k].flatten() for k in live]), torch.cat([theirs[k].flatten() for k in live]))
+    errs = {k: rel(mine[k], theirs[k]) for k in live}
+    print("\n%s full size: logits rel-fro %.4f  loss %.5f vs %.5f  gradient cosine %.5f  per-parameter median %.3f" %
+          (name, e_out, my_loss, float(rloss), cos, float(np.median(list(errs.values())))))
+    assert e_out < 6e-2, e_out
+    assert abs(my_loss - float(rloss)) < 5e-3 * max(1.0, abs(float(rloss)))
+    assert cos >= 0.99, cos
+    assert float(np.median(list(errs.values()))) < 0.1

@@ -175,3 +175,39 @@ def test_config5_sliding_window_round_trip():
             agg.add_batch(data if mode == "crop" else data.float(), locs)
         out = agg.get_output_tensor()
         assert torch.equal(out.to(torch.uint8), vol), mode
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (32, 2), (1, 16)])
+def test_full_resolution_5x5x5_kernels_agree(cin, cout):
+    """V-Net's 5x5x5 layers at 2 x 128^3 (vnet3d.py:25,47,111): the kd-stacked rolling-accumulator kernel (five taps in N,
+    ring of six accumulators over all 128 planes, two 16-channel halves) against the plane kernel that issues one instruction
+    per tap -- forward with fused statistics, data gradient -- and the weight gradient's linearity."""
+    import b200seg.functional as F
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(2, 128, 128, 128, cin, device=DEV, generator=g).bfloat16()
+    w = torch.randn(cout, cin, 5, 5, 5, device=DEV, generator=g) * (2.0 / (125 * cin)) ** 0.5
+    b = torch.randn(cout, device=DEV, generator=g) * 0.1
+    dy = torch.randn(2, 128, 128, 128, cout, device=DEV, generator=g).bfloat16()
+    n0 = F.umma_launch_count()
+    y_roll, st_roll, geom = F.conv3d_fprop_raw(x, w, b, 5, 1, 2, 1, True)
+    dx_roll = F.conv3d_dgrad_raw(geom, dy, w) if cin > 1 else None
+    assert F.umma_launch_count() - n0 == (2 if cin > 1 else 1)
+    with env(B200SEG_DISABLE_ROLL5="1"):
+        y_plane, st_plane, _ = F.conv3d_fprop_raw(x, w, b, 5, 1, 2, 1, True)
+        dx_plane = F.conv3d_dgrad_raw(geom, dy, w) if cin > 1 else None
+    assert rel(y_roll, y_plane) < 3e-3
+    assert float((y_roll.float() - y_plane.float()).abs().max()) <= 2 ** -6 * float(y_plane.float().abs().max())
+    if cin > 1:
+        assert rel(dx_roll, dx_plane) < 3e-3
+    sep = F.channel_stats(y_roll.contiguous())[0]
+    assert rel(st_roll[:cout], sep[0]) < 2e-3 and rel(st_roll[cout:2 * cout], sep[1]) < 2e-3
+    assert rel(st_roll[:2 * cout], st_plane[:2 * cout]) < 1e-4
+    # the first and last planes see the zero padding: compare one border plane with cuDNN in strict fp32
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xs = x[:1, :6].permute(0, 4, 1, 2, 3).float()
+        ref = torch.nn.functional.conv3d(xs, w.bfloat16().float(), b, padding=2)[:, :, :4]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel(y_roll[:1, :4].permute(0, 4, 1, 2, 3), ref) < 6e-3
