@@ -462,15 +462,21 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_fast_kernel(
   };
   const int64_t stride = static_cast<int64_t>(gridDim.x) * TY;
   int64_t r = static_cast<int64_t>(blockIdx.x) * TY + threadIdx.y;
-  for (; r + 3 * stride < rows; r += 4 * stride) {
-    bf16x8 ry[4], rd[4];
+#ifndef B200_REDUCE_ROWS
+#define B200_REDUCE_ROWS 4
+#endif
+  // rows in flight per thread (2 * UR 128-bit loads).  6 and 8 were measured (probes/norm_bw.py, -DB200_REDUCE_ROWS): no
+  // gain -- at 5.1 TB/s of reads the kernel is bound by its ~10 instructions per element, not by bytes in flight
+  constexpr int UR = B200_REDUCE_ROWS;
+  for (; r + (UR - 1) * stride < rows; r += UR * stride) {
+    bf16x8 ry[UR], rd[UR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UR; ++u) {
       ry[u] = ld8(y + (base + r + u * stride) * y_pitch + ch * V);
       rd[u] = ld8(dz + (base + r + u * stride) * dz_pitch + ch * V);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) fold(ry[u], rd[u]);
+    for (int u = 0; u < UR; ++u) fold(ry[u], rd[u]);
   }
   for (; r < rows; r += stride) fold(ld8(y + (base + r) * y_pitch + ch * V), ld8(dz + (base + r) * dz_pitch + ch * V));
   float* mine = red + (static_cast<size_t>(threadIdx.y) * TX + threadIdx.x) * (2 * V);
