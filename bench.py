@@ -488,7 +488,7 @@ def run_b200(args):
             # dominant kernel family: the tcgen05 implicit-GEMM convolutions (conv_umma_roll / conv_umma_plane), the 17 fprop +
             # 17 dgrad launches of the step; achieved = their algorithmic FLOPs / their CUDA-event time in a burst (eager)
             # pass, so the peak is the BURST cuBLAS figure; frac_of_sustained_peak is given beside it.
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_plane_kernel (the fprop + dgrad "
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_pair_kernel + conv_umma_plane_kernel (the fprop + dgrad "
                                                       "launches of the step)",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst (bf16_tflops)",
@@ -595,8 +595,10 @@ def run_predict(args):
             "e2e": {"value": 1e3 / ms_e2e, "unit": "volumes/s", "h2d_bytes_per_step": vol_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel()},
             "gpu_launches": launches, "tcgen05_launches": umma_launches,
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_plane_kernel (the forward conv launches "
-                                                      "of one volume, eval-mode BatchNorm + ReLU in the epilogue)",
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_roll_kernel + conv_umma_pair_kernel + conv_umma_plane_kernel (the 17 "
+                                                      "forward conv launches per batch with C_in >= 32, eval-mode BatchNorm + ReLU in "
+                                                      "the epilogue; the K-padded C_in = 1 stem, bound by its 2.1 GB of output "
+                                                      "writes, is per_kernel.conv_fprop_padded_tc; `traffic` covers all 18)",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst (bf16_tflops)",
                          "traffic": traffic, "traffic_source": traffic_src,

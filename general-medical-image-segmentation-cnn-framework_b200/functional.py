@@ -5,6 +5,7 @@ dimension is contiguous and consecutive voxels are `pitch` elements apart, so a 
 wider buffer (that is how the U-Net skip concatenation is made copy-free).  Parameters, statistics and parameter
 gradients are fp32.  PyTorch supplies memory, streams and the autograd tape; all arithmetic is in the kernels.
 """
+import contextlib
 import ctypes
 import os
 
@@ -203,6 +204,34 @@ def _cached_pack(weight, variant):
     return None
 
 
+# Inference over many batches with fixed parameters (sliding-window prediction: 10 batches per volume, predict.py:112-139):
+# inside `frozen_parameters()` the bf16 weight packs and the eval-mode normalisation constants are computed once and reused,
+# instead of once per batch (18 pack + 18 constant launches per U-Net forward).  Keys are object ids; the entries hold the
+# objects, so an id cannot be recycled while the cache lives.
+_FROZEN = [None]
+
+
+@contextlib.contextmanager
+def frozen_parameters():
+    prev = _FROZEN[0]
+    if prev is None:
+        _FROZEN[0] = {}
+    try:
+        yield
+    finally:
+        _FROZEN[0] = prev
+
+
+def _frozen_get(key, keep, make):
+    cache = _FROZEN[0]
+    if cache is None or torch.is_grad_enabled():
+        return make()
+    hit = cache.get(key)
+    if hit is None:
+        hit = cache[key] = (keep, make())
+    return hit[1]
+
+
 def pack_conv_weight(weight, cin_off=0, cin_cnt=None, dgrad=False):
     cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
     cin_cnt = cin if cin_cnt is None else cin_cnt
@@ -210,10 +239,13 @@ def pack_conv_weight(weight, cin_off=0, cin_cnt=None, dgrad=False):
         cached = _cached_pack(weight, 1 if dgrad else 0)
         if cached is not None:
             return cached
-    weight = weight.detach()
-    packed = torch.empty(k ** 3 * cout * cin_cnt, dtype=torch.bfloat16, device=weight.device)
-    _call("b200seg_pack_conv_weight", _ptr(weight), _ptr(packed), cout, cin, k, cin_off, cin_cnt, int(dgrad), _stream())
-    return packed
+
+    def make():
+        w = weight.detach()
+        packed = torch.empty(k ** 3 * cout * cin_cnt, dtype=torch.bfloat16, device=w.device)
+        _call("b200seg_pack_conv_weight", _ptr(w), _ptr(packed), cout, cin, k, cin_off, cin_cnt, int(dgrad), _stream())
+        return packed
+    return _frozen_get(("pack", id(weight), cin_off, cin_cnt, bool(dgrad)), weight, make)
 
 
 # ------------------------------------------------------------------------------------------------ raw op helpers
@@ -449,11 +481,14 @@ def _norm_coef(stats, count, groups, c, gamma, beta, running_mean, running_var, 
 def _eval_coef(gamma, beta, running_mean, running_var, eps, c, device, conv_bias=None):
     """Inference-mode normalisation constants [1][4][C] = {mean, inv_std, scale, shift} from the running statistics;
     a convolution bias in front of the norm is folded into the shift (for the fused conv epilogue)."""
-    coef = torch.empty((1, 4, c), dtype=torch.float32, device=device)
-    f32 = lambda t: None if t is None else t.detach().float().contiguous()   # noqa: E731
-    g_, b_, rm, rv, cb = f32(gamma), f32(beta), f32(running_mean), f32(running_var), f32(conv_bias)
-    _call("b200seg_norm_eval_coef", _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), _ptr(cb), float(eps), c, _ptr(coef), _stream())
-    return coef
+    def make():
+        coef = torch.empty((1, 4, c), dtype=torch.float32, device=device)
+        f32 = lambda t: None if t is None else t.detach().float().contiguous()   # noqa: E731
+        g_, b_, rm, rv, cb = f32(gamma), f32(beta), f32(running_mean), f32(running_var), f32(conv_bias)
+        _call("b200seg_norm_eval_coef", _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), _ptr(cb), float(eps), c, _ptr(coef), _stream())
+        return coef
+    keep = (gamma, beta, running_mean, running_var, conv_bias)
+    return _frozen_get(("coef",) + tuple(id(t) for t in keep) + (float(eps), c), keep, make)
 
 
 def conv_fused_eval_supported(g):
@@ -467,7 +502,19 @@ def conv3d_fprop_eval_fused(x, weight, bias, k, pad, dil, spec, gamma, beta, run
     x, xp = _as_rows(x)
     cout, cin = weight.shape[0], weight.shape[1]
     g = _geom(x.shape, cin, cout, k, 1, pad, dil)
-    if cin % 16 or cout % 16 or not conv_fused_eval_supported(g):
+    wp = None
+    if cin % 16 and cout % 16 == 0 and _use_padded(g) and conv_fused_eval_supported(_padded_geom(g)):
+        # C_in = 1 stems (unet3d.py:80, vnet3d.py:47): K zero-padded to 16 channels, the same fused epilogue
+        g = _padded_geom(g)
+        x = _pad_channels(x, g.cin)
+        xp = g.cin
+
+        def make():
+            packed = torch.empty(k ** 3 * cout * g.cin, dtype=torch.bfloat16, device=x.device)
+            _call("b200seg_pack_conv_weight", _ptr(weight.detach()), _ptr(packed), cout, cin, k, 0, g.cin, 0, _stream())
+            return packed
+        wp = _frozen_get(("packk", id(weight), g.cin), weight, make)
+    elif cin % 16 or cout % 16 or not conv_fused_eval_supported(g):
         return None
     coef = _eval_coef(gamma, beta, running_mean, running_var, spec.eps, cout, x.device, conv_bias=bias)
     if out is not None and _pitched(out) and tuple(out.shape) == (g.n, g.od, g.oh, g.ow, cout) and out.data_ptr() % 16 == 0 \
@@ -475,8 +522,9 @@ def conv3d_fprop_eval_fused(x, weight, bias, k, pad, dil, spec, gamma, beta, run
         z = out
     else:
         z = torch.empty((g.n, g.od, g.oh, g.ow, cout), dtype=torch.bfloat16, device=x.device)
-    _call("b200seg_conv3d_fprop_act", ctypes.byref(g), _ptr(x), xp, _ptr(pack_conv_weight(weight)), _ptr(coef[0, 2]),
-          _ptr(coef[0, 3]), spec.act, spec.act_param, _ptr(z), z.stride(3), _stream(), work=_conv_flops(g), tag="conv_fprop_tc")
+    _call("b200seg_conv3d_fprop_act", ctypes.byref(g), _ptr(x), xp, _ptr(wp if wp is not None else pack_conv_weight(weight)), _ptr(coef[0, 2]),
+          _ptr(coef[0, 3]), spec.act, spec.act_param, _ptr(z), z.stride(3), _stream(), work=_conv_flops(g),
+          tag="conv_fprop_tc" if wp is None else "conv_fprop_padded_tc")
     if out is not None and z is not out:
         out.copy_(z)
         z = out

@@ -151,15 +151,16 @@ def sliding_window_predict(model, volume, patch_size, patch_overlap, batch_size=
     vol = volume.to(dev, non_blocking=True)
     was_training = model.training
     model.eval()
-    for s in range(0, len(mine), batch_size):
-        ids = torch.tensor(mine[s:s + batch_size], dtype=torch.int64)
-        locs = sampler.locations[ids]
-        x = torch.stack([vol[..., a:d, b:e, c:f] for a, b, c, d, e, f in locs.tolist()]).float()
-        logits = model(x)
-        if overlap_mode == "crop":
-            agg.add_batch(F.argmax_labels(logits), locs, patch_ids=ids)
-        else:
-            agg.add_batch(logits, locs)
+    with F.frozen_parameters():     # weight packs and eval-mode normalisation constants: once per volume, not per batch
+        for s in range(0, len(mine), batch_size):
+            ids = torch.tensor(mine[s:s + batch_size], dtype=torch.int64)
+            locs = sampler.locations[ids]
+            x = torch.stack([vol[..., a:d, b:e, c:f] for a, b, c, d, e, f in locs.tolist()]).float()
+            logits = model(x)
+            if overlap_mode == "crop":
+                agg.add_batch(F.argmax_labels(logits), locs, patch_ids=ids)
+            else:
+                agg.add_batch(logits, locs)
     agg.all_reduce(group, channels=getattr(model, "out_channels", None) or _out_channels(model))
     model.train(was_training)
     if overlap_mode == "crop":

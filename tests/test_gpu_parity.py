@@ -217,7 +217,7 @@ def test_batchnorm_eval_mode(F):
 
 @pytest.mark.parametrize("cin,cout,size,act", [(32, 32, (8, 16, 8), "relu"), (64, 128, (4, 16, 16), "leaky_relu"),
                                                (32, 64, (8, 16, 16), "none"), (256, 256, (4, 4, 4), "relu"),
-                                               (16, 16, (6, 32, 24), "relu")])
+                                               (16, 16, (6, 32, 24), "relu"), (1, 32, (24, 48, 32), "relu")])
 def test_eval_mode_conv_bn_act_fused_epilogue(F, cin, cout, size, act):
     """Inference: conv -> BatchNorm(eval) -> activation as ONE launch (scale / shift / activation in the conv epilogue) against
     the oracle's three separate ops, and against our own unfused two-pass path."""
@@ -238,7 +238,8 @@ def test_eval_mode_conv_bn_act_fused_epilogue(F, cin, cout, size, act):
         k0, u0 = F.launches(), F.umma_launch_count()
         z = F.conv_norm_act(ndhwc(x), w.to(DEV), b.to(DEV), **args)
         fused_launches = F.launches() - k0
-        assert F.umma_launch_count() - u0 == 1 and fused_launches <= 3, fused_launches   # (pack +) coefficients + conv
+        # (pack +) coefficients + conv; the C_in = 1 stem also widens its input to 16 channels first
+        assert F.umma_launch_count() - u0 == 1 and fused_launches <= (4 if cin == 1 else 3), fused_launches
     close(ncdhw(z), ref, 1e-2, "fused eval conv+bn+act")
     z2 = F.conv_norm_act(ndhwc(x).requires_grad_(True), w.to(DEV), b.to(DEV), **args)   # grad mode: the unfused passes
     close(ncdhw(z2), ref, 1.2e-2, "unfused eval path")
@@ -781,3 +782,31 @@ def test_sigmoid_map_and_concat_input(F):
     gcat = bf(torch.randn(2, 3, 5, 6, 7, generator=g))
     cat.backward(ndhwc(gcat))
     assert torch.equal(maps.grad.cpu(), gcat[:, 1:])
+
+
+def test_frozen_parameters_reuse_packs_and_constants(F):
+    """Inside functional.frozen_parameters() (sliding-window inference: many batches, fixed weights) a layer's weight pack and
+    eval-mode constants are computed once; results are identical, and nothing is cached outside the context or in grad mode."""
+    g = torch.Generator().manual_seed(31)
+    x = ndhwc(bf(torch.randn(2, 32, 8, 16, 8, generator=g)))
+    w = (torch.randn(32, 32, 3, 3, 3, generator=g) * 0.05).to(DEV)
+    b = (torch.randn(32, generator=g) * 0.1).to(DEV)
+    gamma, beta = (torch.rand(32, generator=g) + 0.5).to(DEV), (torch.randn(32, generator=g) * 0.3).to(DEV)
+    rm, rv = (torch.randn(32, generator=g) * 0.2).to(DEV), (torch.rand(32, generator=g) + 0.5).to(DEV)
+    args = dict(k=3, stride=1, pad=1, dil=1, spec=F.NormSpec("batch", "relu", training=False), gamma=gamma, beta=beta,
+                running_mean=rm, running_var=rv)
+    with torch.no_grad():
+        k0 = F.launches()
+        ref = F.conv_norm_act(x, w, b, **args)
+        plain = F.launches() - k0
+        with F.frozen_parameters():
+            first = F.conv_norm_act(x, w, b, **args)
+            k1 = F.launches()
+            second = F.conv_norm_act(x, w, b, **args)
+            cached = F.launches() - k1
+        k2 = F.launches()
+        after = F.conv_norm_act(x, w, b, **args)
+        assert F.launches() - k2 == plain
+    assert plain == 3 and cached == 1, (plain, cached)
+    assert torch.equal(ref, first) and torch.equal(ref, second) and torch.equal(ref, after)
+    assert F._FROZEN[0] is None
