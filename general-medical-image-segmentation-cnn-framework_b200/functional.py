@@ -82,6 +82,7 @@ def end_step():
     _SCRATCH["active"] = False
     _COLSUMS.clear()
     _ZERO_TAIL.clear()
+    _LAST_PADDED_INPUT[0] = None
     flush_counters()
 
 
