@@ -51,12 +51,10 @@ class _DenseBlock(nn.Sequential, OpsMixin):
 
 class _Transition(nn.Module, OpsMixin):
     def __init__(self, num_input_features, num_output_features):
-        super(_Transition, self).__init__()
-        norm = nn.BatchNorm3d(num_input_features)
-        relu = nn.ReLU(inplace=True)
-        conv3d = nn.Conv3d(num_input_features, num_output_features, kernel_size=1, padding=0, stride=1)
-        self.conv = nn.Sequential(norm, relu, conv3d)
-        self.max_pool = nn.MaxPool3d(kernel_size=2, stride=2)
+        super().__init__()
+        self.conv = nn.Sequential(nn.BatchNorm3d(num_input_features), nn.ReLU(inplace=True),
+                                  nn.Conv3d(num_input_features, num_output_features, 1))
+        self.max_pool = nn.MaxPool3d(2, 2)
 
     def forward(self, x):
         F = self.kernels
@@ -68,17 +66,14 @@ class _Transition(nn.Module, OpsMixin):
 
 class _Upsampling(nn.Sequential, OpsMixin):
     def __init__(self, input_features, out_features):
-        super(_Upsampling, self).__init__()
-        self.tr_conv1_features = 128
-        self.tr_conv2_features = out_features
-        self.add_module('norm', nn.BatchNorm3d(input_features))
-        self.add_module('relu', nn.ReLU(inplace=True))
-        self.add_module('conv', nn.Conv3d(input_features, input_features, kernel_size=1, stride=1, padding=0,
-                                          bias=False))
-        self.add_module('transp_conv_1', nn.ConvTranspose3d(input_features, self.tr_conv1_features, kernel_size=2,
-                                                            padding=0, output_padding=0, stride=2))
-        self.add_module('transp_conv_2', nn.ConvTranspose3d(self.tr_conv1_features, self.tr_conv2_features,
-                                                            kernel_size=2, padding=0, output_padding=0, stride=2))
+        super().__init__()
+        self.tr_conv1_features, self.tr_conv2_features = 128, out_features
+        widths = (input_features, self.tr_conv1_features, self.tr_conv2_features)
+        children = [('norm', nn.BatchNorm3d(input_features)), ('relu', nn.ReLU(inplace=True)),
+                    ('conv', nn.Conv3d(input_features, input_features, 1, bias=False))]
+        children += [('transp_conv_%d' % (i + 1), nn.ConvTranspose3d(widths[i], widths[i + 1], 2, stride=2)) for i in (0, 1)]
+        for name, child in children:          # names and order of the reference (:63-76): they are the state_dict keys
+            self.add_module(name, child)
 
     def forward(self, x):
         F = self.kernels
@@ -92,22 +87,19 @@ class DenseVoxelNet(nn.Module, OpsMixin):
     """Implementation based on https://arxiv.org/abs/1708.00573 (reference densevoxelnet3d.py:90-128)."""
 
     def __init__(self, in_channels=1, classes=2):
-        super(DenseVoxelNet, self).__init__()
-        num_input_features = 16
-        self.dense_1_out_features = 160
-        self.dense_2_out_features = 304
-        self.up_out_features = 64
-        self.classes = classes
-        self.in_channels = in_channels
-        self.conv_init = nn.Conv3d(in_channels, num_input_features, kernel_size=1, stride=2, padding=0, bias=False)
-        self.dense_1 = _DenseBlock(num_layers=12, num_input_features=num_input_features, bn_size=1, growth_rate=12)
-        self.trans = _Transition(self.dense_1_out_features, self.dense_1_out_features)
-        self.dense_2 = _DenseBlock(num_layers=12, num_input_features=self.dense_1_out_features, bn_size=1,
-                                   growth_rate=12)
-        self.up_block = _Upsampling(self.dense_2_out_features, self.up_out_features)
-        self.conv_final = nn.Conv3d(self.up_out_features, classes, kernel_size=1, padding=0, bias=False)
-        self.transpose = nn.ConvTranspose3d(self.dense_1_out_features, self.up_out_features, kernel_size=2, padding=0,
-                                            output_padding=0, stride=2)
+        super().__init__()
+        stem, growth, layers = 16, 12, 12
+        d1 = stem + layers * growth                 # 160 channels after the first dense block
+        d2 = d1 + layers * growth                   # 304 after the second
+        self.dense_1_out_features, self.dense_2_out_features, self.up_out_features = d1, d2, 64
+        self.classes, self.in_channels = classes, in_channels
+        self.conv_init = nn.Conv3d(in_channels, stem, 1, stride=2, bias=False)
+        self.dense_1 = _DenseBlock(layers, stem, bn_size=1, growth_rate=growth)
+        self.trans = _Transition(d1, d1)
+        self.dense_2 = _DenseBlock(layers, d1, bn_size=1, growth_rate=growth)
+        self.up_block = _Upsampling(d2, self.up_out_features)
+        self.conv_final = nn.Conv3d(self.up_out_features, classes, 1, bias=False)
+        self.transpose = nn.ConvTranspose3d(d1, self.up_out_features, 2, stride=2)
 
     def forward(self, x):
         if x.dim() != 5:

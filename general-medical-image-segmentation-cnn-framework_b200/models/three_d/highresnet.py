@@ -18,41 +18,29 @@ class HighResNet(nn.Module, OpsMixin):
                  instance_norm=False, residual=True, padding_mode='constant', add_dropout_layer=False):
         assert dimensions in (2, 3)
         super().__init__()
-        self.in_channels = in_channels
-        self.out_channels = out_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
         self.layers_per_residual_block = layers_per_residual_block
         self.residual_blocks_per_dilation = residual_blocks_per_dilation
         self.dilations = dilations
-        blocks = nn.ModuleList()
-        initial_out_channels = 2 ** initial_out_channels_power
-        blocks.append(ConvolutionalBlock(in_channels=self.in_channels, out_channels=initial_out_channels, dilation=1,
-                                         dimensions=dimensions, batch_norm=batch_norm, instance_norm=instance_norm,
-                                         preactivation=False, padding_mode=padding_mode))
-        in_channels = out_channels = initial_out_channels
-        dilation_block = None
-        for dilation_idx in range(dilations):
-            if dilation_idx >= 1:
-                in_channels = dilation_block.out_channels
-            dilation_block = DilationBlock(in_channels, out_channels, 2 ** dilation_idx, dimensions,
-                                           layers_per_block=layers_per_residual_block,
-                                           num_residual_blocks=residual_blocks_per_dilation, batch_norm=batch_norm,
-                                           instance_norm=instance_norm, residual=residual, padding_mode=padding_mode)
-            blocks.append(dilation_block)
-            out_channels *= 2
-        out_channels = out_channels // 2
+        norm = dict(dimensions=dimensions, batch_norm=batch_norm, instance_norm=instance_norm)
+
+        def plain(cin, cout, **kw):      # a post-activation conv block at dilation 1 (highresnet.py:39-49, 81-105)
+            return ConvolutionalBlock(in_channels=cin, out_channels=cout, dilation=1, preactivation=False, **norm, **kw)
+
+        width = 2 ** initial_out_channels_power
+        stages = [plain(in_channels, width, padding_mode=padding_mode)]
+        cin = width
+        for idx in range(dilations):     # dilation 1, 2, 4, ... at width, 2 width, 4 width, ... (highresnet.py:52-72)
+            stages.append(DilationBlock(cin, width << idx, 2 ** idx, dimensions, layers_per_block=layers_per_residual_block,
+                                        num_residual_blocks=residual_blocks_per_dilation, batch_norm=batch_norm,
+                                        instance_norm=instance_norm, residual=residual, padding_mode=padding_mode))
+            cin = width << idx
         self._dropout = None
         if add_dropout_layer:
-            in_channels = out_channels
-            out_channels = 80
-            blocks.append(ConvolutionalBlock(in_channels=in_channels, out_channels=out_channels, dilation=1,
-                                             dimensions=dimensions, batch_norm=batch_norm,
-                                             instance_norm=instance_norm, preactivation=False, kernel_size=1))
-            blocks.append(nn.Dropout3d())
-        blocks.append(ConvolutionalBlock(in_channels=out_channels, out_channels=self.out_channels, dilation=1,
-                                         dimensions=dimensions, batch_norm=batch_norm, instance_norm=instance_norm,
-                                         preactivation=False, kernel_size=1, activation=False,
-                                         padding_mode=padding_mode))
-        self.block = nn.Sequential(*blocks)
+            stages += [plain(cin, 80, kernel_size=1), nn.Dropout3d()]
+            cin = 80
+        stages.append(plain(cin, self.out_channels, kernel_size=1, activation=False, padding_mode=padding_mode))
+        self.block = nn.Sequential(*stages)
 
     def forward(self, x):
         if x.dim() != 5:

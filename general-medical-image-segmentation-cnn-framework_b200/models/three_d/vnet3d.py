@@ -4,7 +4,6 @@ Each (Conv3d k5 -> BatchNorm3d -> ELU/PReLU) triple is one conv (+ fused statist
 the residual sums in front of an activation (`relu(add(out, x))`, vnet3d.py:58,79,103) ride in that same pass; the
 decoder's `torch.cat((out, skipxdo), 1)` (vnet3d.py:100) is two producers writing the halves of one buffer.
 """
-import torch
 import torch.nn as nn
 
 from .._common import OpsMixin, act_of, conv_args, norm_args, norm_spec
@@ -15,9 +14,18 @@ def passthrough(x, **kwargs):
 
 
 def ELUCons(elu, nchan):
-    if elu:
-        return nn.ELU(inplace=True)
-    return nn.PReLU(nchan)
+    """ELU, or a per-channel PReLU (vnet3d.py:14-18)."""
+    return nn.ELU(inplace=True) if elu else nn.PReLU(nchan)
+
+
+def _conv5(cin, cout):
+    return nn.Conv3d(cin, cout, 5, padding=2)
+
+
+def _register(module, **children):
+    """Assign sub-modules in the given order (= the reference's registration order, hence its state_dict key order)."""
+    for name, child in children.items():
+        setattr(module, name, child)
 
 
 def _conv_bn_act(mod, F, conv, bn, act_mod, x, x2=None, residual=None, out=None):
@@ -37,10 +45,8 @@ def _drop(mod, F, do, x, out=None):
 
 class LUConv(nn.Module, OpsMixin):
     def __init__(self, nchan, elu):
-        super(LUConv, self).__init__()
-        self.relu1 = ELUCons(elu, nchan)
-        self.conv1 = nn.Conv3d(nchan, nchan, kernel_size=5, padding=2)
-        self.bn1 = torch.nn.BatchNorm3d(nchan)
+        super().__init__()
+        _register(self, relu1=ELUCons(elu, nchan), conv1=_conv5(nchan, nchan), bn1=nn.BatchNorm3d(nchan))
 
     def forward(self, x, x2=None):
         return _conv_bn_act(self, self.kernels, self.conv1, self.bn1, self.relu1, x, x2=x2)
@@ -52,12 +58,9 @@ def _make_nConv(nchan, depth, elu):
 
 class InputTransition(nn.Module, OpsMixin):
     def __init__(self, in_channels, elu):
-        super(InputTransition, self).__init__()
-        self.num_features = 16
-        self.in_channels = in_channels
-        self.conv1 = nn.Conv3d(self.in_channels, self.num_features, kernel_size=5, padding=2)
-        self.bn1 = torch.nn.BatchNorm3d(self.num_features)
-        self.relu1 = ELUCons(elu, self.num_features)
+        super().__init__()
+        self.num_features, self.in_channels = 16, in_channels
+        _register(self, conv1=_conv5(in_channels, 16), bn1=nn.BatchNorm3d(16), relu1=ELUCons(elu, 16))
 
     def forward(self, x):
         F = self.kernels
@@ -67,16 +70,12 @@ class InputTransition(nn.Module, OpsMixin):
 
 class DownTransition(nn.Module, OpsMixin):
     def __init__(self, inChans, nConvs, elu, dropout=False):
-        super(DownTransition, self).__init__()
-        outChans = 2 * inChans
-        self.down_conv = nn.Conv3d(inChans, outChans, kernel_size=2, stride=2)
-        self.bn1 = torch.nn.BatchNorm3d(outChans)
-        self.do1 = passthrough
-        self.relu1 = ELUCons(elu, outChans)
-        self.relu2 = ELUCons(elu, outChans)
-        if dropout:
-            self.do1 = nn.Dropout3d()
-        self.ops = _make_nConv(outChans, nConvs, elu)
+        super().__init__()
+        wide = 2 * inChans
+        _register(self, down_conv=nn.Conv3d(inChans, wide, 2, stride=2), bn1=nn.BatchNorm3d(wide),
+                  relu1=ELUCons(elu, wide), relu2=ELUCons(elu, wide))
+        self.do1 = nn.Dropout3d() if dropout else passthrough
+        self.ops = _make_nConv(wide, nConvs, elu)
 
     def forward(self, x, out=None):
         F = self.kernels
@@ -90,15 +89,11 @@ class DownTransition(nn.Module, OpsMixin):
 
 class UpTransition(nn.Module, OpsMixin):
     def __init__(self, inChans, outChans, nConvs, elu, dropout=False):
-        super(UpTransition, self).__init__()
-        self.up_conv = nn.ConvTranspose3d(inChans, outChans // 2, kernel_size=2, stride=2)
-        self.bn1 = torch.nn.BatchNorm3d(outChans // 2)
-        self.do1 = passthrough
-        self.do2 = nn.Dropout3d()
-        self.relu1 = ELUCons(elu, outChans // 2)
-        self.relu2 = ELUCons(elu, outChans)
-        if dropout:
-            self.do1 = nn.Dropout3d()
+        super().__init__()
+        half = outChans // 2
+        _register(self, up_conv=nn.ConvTranspose3d(inChans, half, 2, stride=2), bn1=nn.BatchNorm3d(half),
+                  do2=nn.Dropout3d(), relu1=ELUCons(elu, half), relu2=ELUCons(elu, outChans))
+        self.do1 = nn.Dropout3d() if dropout else passthrough
         self.ops = _make_nConv(outChans, nConvs, elu)
 
     def forward(self, x, skipx):
@@ -122,12 +117,10 @@ class UpTransition(nn.Module, OpsMixin):
 
 class OutputTransition(nn.Module, OpsMixin):
     def __init__(self, in_channels, classes, elu):
-        super(OutputTransition, self).__init__()
+        super().__init__()
         self.classes = classes
-        self.conv1 = nn.Conv3d(in_channels, classes, kernel_size=5, padding=2)
-        self.bn1 = torch.nn.BatchNorm3d(classes)
-        self.conv2 = nn.Conv3d(classes, classes, kernel_size=1)
-        self.relu1 = ELUCons(elu, classes)
+        _register(self, conv1=_conv5(in_channels, classes), bn1=nn.BatchNorm3d(classes), conv2=nn.Conv3d(classes, classes, 1),
+                  relu1=ELUCons(elu, classes))
 
     def forward(self, x):
         F = self.kernels
@@ -139,32 +132,24 @@ class VNet(nn.Module, OpsMixin):
     """Implementations based on the Vnet paper: https://arxiv.org/abs/1606.04797 (reference vnet3d.py:124-157)."""
 
     def __init__(self, elu=True, in_channels=1, classes=2):
-        super(VNet, self).__init__()
-        self.classes = classes
-        self.in_channels = in_channels
+        super().__init__()
+        self.classes, self.in_channels = classes, in_channels
         self.in_tr = InputTransition(in_channels, elu=elu)
-        self.down_tr32 = DownTransition(16, 1, elu)
-        self.down_tr64 = DownTransition(32, 2, elu)
-        self.down_tr128 = DownTransition(64, 3, elu, dropout=False)
-        self.down_tr256 = DownTransition(128, 2, elu, dropout=False)
-        self.up_tr256 = UpTransition(256, 256, 2, elu, dropout=False)
-        self.up_tr128 = UpTransition(256, 128, 2, elu, dropout=False)
-        self.up_tr64 = UpTransition(128, 64, 1, elu)
-        self.up_tr32 = UpTransition(64, 32, 1, elu)
+        # (input channels, LUConv count) of the four encoder stages, then (in, out, LUConv count) of the decoder stages
+        for cin, depth in ((16, 1), (32, 2), (64, 3), (128, 2)):
+            setattr(self, "down_tr%d" % (2 * cin), DownTransition(cin, depth, elu, dropout=False))
+        for cin, cout, depth in ((256, 256, 2), (256, 128, 2), (128, 64, 1), (64, 32, 1)):
+            setattr(self, "up_tr%d" % cout, UpTransition(cin, cout, depth, elu, dropout=False))
         self.out_tr = OutputTransition(32, classes, elu)
 
     def forward(self, x):
         if x.dim() != 5:
             raise ValueError("expected 5D input (got {}D input)".format(x.dim()))
         F = self.kernels
-        h = F.to_ndhwc(x)
-        out16 = self.in_tr(h)
-        out32 = self.down_tr32(out16)
-        out64 = self.down_tr64(out32)
-        out128 = self.down_tr128(out64)
-        out256 = self.down_tr256(out128)
-        out = self.up_tr256(out256, out128)
-        out = self.up_tr128(out, out64)
-        out = self.up_tr64(out, out32)
-        out = self.up_tr32(out, out16)
+        skips = [self.in_tr(F.to_ndhwc(x))]                      # 16 channels at full resolution
+        for stage in (self.down_tr32, self.down_tr64, self.down_tr128, self.down_tr256):
+            skips.append(stage(skips[-1]))
+        out = skips.pop()
+        for stage in (self.up_tr256, self.up_tr128, self.up_tr64, self.up_tr32):
+            out = stage(out, skips.pop())
         return self.out_tr(out)

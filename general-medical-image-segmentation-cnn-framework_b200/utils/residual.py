@@ -13,19 +13,14 @@ class ResidualBlock(nn.Module, OpsMixin):
                  instance_norm=False, residual=True, residual_type='pad', padding_mode='constant'):
         assert residual_type in ('pad', 'project')
         super().__init__()
-        self.residual = residual
+        self.residual, self.residual_type, self.dimensions = residual, residual_type, dimensions
         self.change_dimension = in_channels != out_channels
-        self.residual_type = residual_type
-        self.dimensions = dimensions
-        if self.change_dimension and residual_type == 'project':
+        if self.change_dimension and residual_type == 'project':      # 1x1x1 projection of the shortcut (residual.py:36-43)
             self.change_dim_layer = nn.Conv3d(in_channels, out_channels, kernel_size=1, dilation=dilation, bias=False)
-        conv_blocks = nn.ModuleList()
-        for _ in range(num_layers):
-            conv_blocks.append(ConvolutionalBlock(in_channels, out_channels, dilation, dimensions,
-                                                  batch_norm=batch_norm, instance_norm=instance_norm,
-                                                  padding_mode=padding_mode))
-            in_channels = out_channels
-        self.residual_block = nn.Sequential(*conv_blocks)
+        norm = dict(batch_norm=batch_norm, instance_norm=instance_norm, padding_mode=padding_mode)
+        widths = [in_channels] + [out_channels] * num_layers
+        self.residual_block = nn.Sequential(*(ConvolutionalBlock(cin, cout, dilation, dimensions, **norm)
+                                              for cin, cout in zip(widths[:-1], widths[1:])))
 
     def forward(self, x):
         F = self.kernels
