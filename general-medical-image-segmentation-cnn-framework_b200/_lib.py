@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200seg_norm_finalize": "pdii" + "pppp" + "ffi" + "pp",
     "b200seg_norm_eval_coef": "ppppp" + "fi" + "pp",
     "b200seg_norm_act_fwd": "plp" + "lii" + "if" + "p" + "pl" + "pl" + "p",
+    "b200seg_norm_act_fwd_stats": "plp" + "d" + "pppp" + "ffi" + "p" + "li" + "if" + "p" + "pl" + "pl" + "p",
     "b200seg_norm_act_bwd_reduce": "plpl" + "p" + "lii" + "if" + "p" + "pl" + "ppp" + "p",
     "b200seg_norm_act_bwd_apply": "plpl" + "pp" + "d" + "lii" + "if" + "p" + "pl" + "pl" + "pl" + "p",
     "b200seg_maxpool2_fwd": "plplp" + "iiiii" + "p",

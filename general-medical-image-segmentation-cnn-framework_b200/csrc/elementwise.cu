@@ -220,6 +220,34 @@ __global__ void __launch_bounds__(256, 4) channel_stats_kernel(const __nv_bfloat
       });
 }
 
+// {sum, sum of squares} of one channel -> {mean, inv_std, scale, shift} (and the running statistics when `update`).
+// One definition for the stand-alone finalisation kernel and for the prologue of the fused normalise kernel: bit-identical.
+struct NormCoef {
+  float mean, inv_std, scale, shift;
+};
+__device__ __forceinline__ NormCoef norm_finalize_channel(double s, double q, double count, int c,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                          float momentum, float eps, int clamp_eps, bool update) {
+  const double mean = s / count;
+  double var = (q - s * mean) / count;  // batchnorm.py:116-120: sumvar = ssum - sum*mean
+  if (var < 0) var = 0;
+  const double inv_std = clamp_eps ? 1.0 / sqrt(var < eps ? static_cast<double>(eps) : var) : 1.0 / sqrt(var + eps);
+  if (update && running_mean != nullptr) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
+    running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+  const double ga = gamma ? gamma[c] : 1.0;
+  const double be = beta ? beta[c] : 0.0;
+  NormCoef r;
+  r.mean = static_cast<float>(mean);
+  r.inv_std = static_cast<float>(inv_std);
+  r.scale = static_cast<float>(ga * inv_std);
+  r.shift = static_cast<float>(be - mean * ga * inv_std);
+  return r;
+}
+
 __global__ void norm_finalize_kernel(const float* __restrict__ stats, double count, int groups, int C,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
@@ -229,23 +257,30 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, double cou
   const int g = i / C, c = i % C;
   const double s = stats[(static_cast<size_t>(g) * 2 + 0) * C + c];
   const double q = stats[(static_cast<size_t>(g) * 2 + 1) * C + c];
-  const double mean = s / count;
-  double var = (q - s * mean) / count;  // batchnorm.py:116-120: sumvar = ssum - sum*mean
-  if (var < 0) var = 0;
-  const double inv_std = clamp_eps ? 1.0 / sqrt(var < eps ? static_cast<double>(eps) : var) : 1.0 / sqrt(var + eps);
-  if (running_mean != nullptr && groups == 1) {
-    const double unbiased = count > 1 ? var * count / (count - 1) : var;
-    running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
-    running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
-  }
-  const double ga = gamma ? gamma[c] : 1.0;
-  const double be = beta ? beta[c] : 0.0;
+  const NormCoef r = norm_finalize_channel(s, q, count, c, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps,
+                                           groups == 1);
   float* o = out + static_cast<size_t>(g) * 4 * C;
-  o[0 * C + c] = static_cast<float>(mean);
-  o[1 * C + c] = static_cast<float>(inv_std);
-  o[2 * C + c] = static_cast<float>(ga * inv_std);
-  o[3 * C + c] = static_cast<float>(be - mean * ga * inv_std);
+  o[0 * C + c] = r.mean;
+  o[1 * C + c] = r.inv_std;
+  o[2 * C + c] = r.scale;
+  o[3 * C + c] = r.shift;
 }
+
+// Training-mode BatchNorm without a separate finalisation launch: every block of the normalise kernel derives the
+// constants of all C <= kFusedNormMaxC channels from the {sum, sumsq} vector in its prologue (shared memory); block 0 also
+// stores them for the backward pass and updates the running statistics.
+constexpr int kFusedNormMaxC = 512;
+struct NormFinalizeArgs {
+  const float* stats;     // {sum[C], sumsq[C]}; nullptr: `coef` holds finished constants (the unfused form)
+  double count;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float momentum, eps;
+  int clamp_eps;
+  float* coef_out;        // [4][C]
+};
 
 // Inference-mode BatchNorm constants from the running statistics (F.batch_norm(training=False)): rows {mean, inv_std,
 // scale = gamma * inv_std, shift = beta - mean * scale [+ scale * conv_bias]} -- the optional conv bias is folded into the
@@ -271,9 +306,26 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat1
                                     const float* __restrict__ coef, int64_t rows_per_group, int groups, int C, int act_rt,
                                     float act_param, const float* __restrict__ prelu_w,
                                     const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
-                                    __nv_bfloat16* __restrict__ z, int64_t z_pitch) {
+                                    __nv_bfloat16* __restrict__ z, int64_t z_pitch, const NormFinalizeArgs fin) {
   constexpr int act = ACT;
   (void)act_rt;
+  __shared__ float s_fin[2][kFusedNormMaxC];     // scale, shift (fused finalisation only)
+  if (fin.stats != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const NormCoef r = norm_finalize_channel(fin.stats[c], fin.stats[C + c], fin.count, c, fin.gamma, fin.beta,
+                                               fin.running_mean, fin.running_var, fin.momentum, fin.eps, fin.clamp_eps,
+                                               blockIdx.x == 0);
+      s_fin[0][c] = r.scale;
+      s_fin[1][c] = r.shift;
+      if (blockIdx.x == 0) {
+        fin.coef_out[0 * C + c] = r.mean;
+        fin.coef_out[1 * C + c] = r.inv_std;
+        fin.coef_out[2 * C + c] = r.scale;
+        fin.coef_out[3 * C + c] = r.shift;
+      }
+    }
+    __syncthreads();
+  }
   // Host guarantees (gridDim.x * blockDim.x) % (C / V) == 0: a thread keeps one channel chunk for its whole life,
   // so scale / shift / slope live in registers; rows are walked 4 at a time to keep 4 loads in flight.
   const int cv = C / V;
@@ -291,6 +343,16 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(const __nv_bfloat1
     sl[j] = (act == B200SEG_ACT_PRELU) ? prelu_w[ch * V + j] : act_param;
   }
   auto load_coef = [&](int g) {
+    if (fin.stats != nullptr) {      // groups == 1: the prologue's constants
+      if (cur_g == 0) return;
+      cur_g = 0;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        sc[j] = s_fin[0][ch * V + j];
+        sh[j] = s_fin[1][ch * V + j];
+      }
+      return;
+    }
     if (coef == nullptr || g == cur_g) return;
     cur_g = g;
 #pragma unroll
@@ -1057,9 +1119,32 @@ int b200seg_norm_eval_coef(const float* gamma, const float* beta, const float* r
   return 0;
 }
 
+static int norm_act_fwd_launch(const void* y, int64_t y_pitch, const float* coef, int64_t rows_per_group, int groups, int c,
+                               int act, float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                               void* z, int64_t z_pitch, const b200::NormFinalizeArgs& fin, void* stream);
+
 int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int64_t rows_per_group, int groups, int c,
                          int act, float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
                          void* z, int64_t z_pitch, void* stream) {
+  return norm_act_fwd_launch(y, y_pitch, coef, rows_per_group, groups, c, act, act_param, prelu_w, residual, res_pitch, z,
+                             z_pitch, b200::NormFinalizeArgs{}, stream);
+}
+
+int b200seg_norm_act_fwd_stats(const void* y, int64_t y_pitch, const float* stats, double count, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                               int clamp_eps, float* coef_out, int64_t rows, int c, int act, float act_param,
+                               const float* prelu_w, const void* residual, int64_t res_pitch, void* z, int64_t z_pitch,
+                               void* stream) {
+  B200_CHECK_ARG(stats && coef_out && count > 0 && c > 0 && c <= b200::kFusedNormMaxC,
+                 "norm_act_fwd_stats: needs statistics, a coefficient buffer and C <= %d", b200::kFusedNormMaxC);
+  b200::NormFinalizeArgs fin{stats, count, gamma, beta, running_mean, running_var, momentum, eps, clamp_eps, coef_out};
+  return norm_act_fwd_launch(y, y_pitch, nullptr, rows, 1, c, act, act_param, prelu_w, residual, res_pitch, z, z_pitch, fin,
+                             stream);
+}
+
+static int norm_act_fwd_launch(const void* y, int64_t y_pitch, const float* coef, int64_t rows_per_group, int groups, int c,
+                               int act, float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                               void* z, int64_t z_pitch, const b200::NormFinalizeArgs& fin, void* stream) {
   B200_CHECK_ARG(y && z && rows_per_group > 0 && groups > 0 && c > 0, "norm_act_fwd: bad arguments");
   B200_CHECK_ARG(act != B200SEG_ACT_PRELU || prelu_w, "norm_act_fwd: PReLU needs a slope vector");
   auto st = static_cast<cudaStream_t>(stream);
@@ -1069,11 +1154,11 @@ int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int6
   if (vec_ok(c, y_pitch, z_pitch, residual ? res_pitch : 0)) {
     const int64_t total = rows_per_group * groups * (c / 8);
     B200_ACT_DISPATCH(act, norm_act_fwd_kernel<8, A_><<<ew_grid(total, c / 8), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
-                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch));
+                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch, fin));
   } else {
     const int64_t total = rows_per_group * groups * c;
     B200_ACT_DISPATCH(act, norm_act_fwd_kernel<1, A_><<<ew_grid(total, c), 256, 0, st>>>(yp, y_pitch, coef, rows_per_group, groups, c, act,
-                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch));
+                                                                 act_param, prelu_w, rp, res_pitch, zp, z_pitch, fin));
   }
   B200_CHECK_LAUNCH("norm_act_fwd");
   return 0;

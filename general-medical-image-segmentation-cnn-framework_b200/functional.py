@@ -548,6 +548,7 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
     y, yp = _as_rows(y)
     n, d, h, w, c = y.shape
     groups, count, coef = 1, float(n * d * h * w), None
+    fused_stats = None
     if spec.kind == "instance":
         groups, count = n, float(d * h * w)
         coef = _norm_coef(channel_stats(y, groups), count, groups, c, None, None, None, None, 0.0, spec.eps, False,
@@ -565,8 +566,11 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
             else:
                 if spec.sync:
                     count *= all_reduce_stats(stats[:2 * c], spec.process_group)
-                coef = _norm_coef(stats, count, 1, c, gamma, beta, running_mean, running_var, spec.momentum,
-                                  spec.eps, spec.clamp_eps, y.device)
+                if c <= 512 and not os.environ.get("B200SEG_SEPARATE_FINALIZE"):
+                    fused_stats = stats       # finalised in the prologue of the normalise kernel below (no extra launch)
+                else:
+                    coef = _norm_coef(stats, count, 1, c, gamma, beta, running_mean, running_var, spec.momentum,
+                                      spec.eps, spec.clamp_eps, y.device)
         else:
             coef = _eval_coef(gamma, beta, running_mean, running_var, spec.eps, c, y.device)
     if out is None:
@@ -583,6 +587,13 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
     if residual is not None:
         res, resp = _as_rows(residual)
     rows = n * d * h * w // groups
+    if fused_stats is not None:
+        coef = torch.empty((1, 4, c), dtype=torch.float32, device=y.device)
+        _call("b200seg_norm_act_fwd_stats", _ptr(y), yp, _ptr(fused_stats), float(count), _ptr(gamma), _ptr(beta),
+              _ptr(running_mean), _ptr(running_var), float(spec.momentum), float(spec.eps), int(spec.clamp_eps), _ptr(coef),
+              rows, c, spec.act, spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(out), out.stride(3), _stream(),
+              tag="b200seg_norm_act_fwd")
+        return out, coef, count, groups
     _call("b200seg_norm_act_fwd", _ptr(y), yp, _ptr(coef), rows, groups, c, spec.act, spec.act_param, _ptr(prelu_w),
           _ptr(res), resp, _ptr(out), out.stride(3), _stream())
     return out, coef, count, groups

@@ -148,6 +148,14 @@ int b200seg_norm_eval_coef(const float* gamma, const float* beta, const float* r
 int b200seg_norm_act_fwd(const void* y, int64_t y_pitch, const float* coef, int64_t rows_per_group, int groups,
                          int c, int act, float act_param, const float* prelu_w, const void* residual,
                          int64_t res_pitch, void* z, int64_t z_pitch, void* stream);
+/* Training-mode BatchNorm3d + activation WITHOUT the separate b200seg_norm_finalize launch: every block derives the
+ * constants of all c <= 512 channels from stats = {sum[c], sumsq[c]} in its prologue (same arithmetic, bit-identical);
+ * block 0 stores them to coef_out [4][c] for the backward pass and updates running_mean / running_var (may be NULL). */
+int b200seg_norm_act_fwd_stats(const void* y, int64_t y_pitch, const float* stats, double count, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                               int clamp_eps, float* coef_out, int64_t rows, int c, int act, float act_param,
+                               const float* prelu_w, const void* residual, int64_t res_pitch, void* z, int64_t z_pitch,
+                               void* stream);
 /* Backward, pass 1: sums[g][2][c] += {sum(dpre), sum(dpre * xhat)}, dpre = dz * act'(pre).  Also accumulates the
  * PReLU slope gradient when dprelu != NULL, and -- when grad_affine != NULL -- adds the same two sums (over all groups)
  * to grad_affine[0..c) = d(gamma) and grad_affine[c..2c) = d(beta): the affine parameter gradients of the norm layer

@@ -810,3 +810,28 @@ def test_frozen_parameters_reuse_packs_and_constants(F):
     assert plain == 3 and cached == 1, (plain, cached)
     assert torch.equal(ref, first) and torch.equal(ref, second) and torch.equal(ref, after)
     assert F._FROZEN[0] is None
+
+
+def test_finalisation_in_the_normalise_prologue_is_bit_identical(F, monkeypatch):
+    """Training-mode BatchNorm: the constants derived in the prologue of the normalise kernel (b200seg_norm_act_fwd_stats)
+    equal the separate b200seg_norm_finalize launch bit for bit -- output, saved constants, running statistics."""
+    g = torch.Generator().manual_seed(41)
+    for c, shape in ((32, (2, 8, 16, 8)), (512, (2, 4, 4, 4)), (24, (1, 6, 10, 8))):
+        y = ndhwc(bf(torch.randn(shape[0], c, *shape[1:], generator=g) * 2 + 0.5))
+        gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.randn(c, generator=g) * 0.3).to(DEV)
+        outs = []
+        stats = F.channel_stats(y, 1, spare=1)       # one statistics vector for both runs (its atomics are not ordered)
+        for separate in (False, True):
+            if separate:
+                monkeypatch.setenv("B200SEG_SEPARATE_FINALIZE", "1")
+            else:
+                monkeypatch.delenv("B200SEG_SEPARATE_FINALIZE", raising=False)
+            rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+            k0 = F.launches()
+            z, coef, count, groups = F._norm_forward(y, stats.clone(), F.NormSpec("batch", "relu", training=True), gamma, beta,
+                                                     rm, rv, None, None, None)
+            outs.append((z.clone(), coef.clone(), rm.clone(), rv.clone(), F.launches() - k0))
+        monkeypatch.delenv("B200SEG_SEPARATE_FINALIZE", raising=False)
+        for a, b in zip(outs[0][:4], outs[1][:4]):
+            assert torch.equal(a, b)
+        assert outs[0][4] == outs[1][4] - 1      # one launch fewer
