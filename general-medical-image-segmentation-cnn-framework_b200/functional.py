@@ -492,6 +492,20 @@ def _eval_coef(gamma, beta, running_mean, running_var, eps, c, device, conv_bias
     return _frozen_get(("coef",) + tuple(id(t) for t in keep) + (float(eps), c), keep, make)
 
 
+def _copy_into(out, y):
+    """out[...] = y by kernel (the identity form of the normalise pass).  `out` is usually a channel slice of a buffer of
+    which autograd-visible views exist (concat-free decoders, dense blocks); a torch in-place op on it would be refused."""
+    y, yp = _as_rows(y)
+    n, d, h, w, c = y.shape
+    assert _pitched(out) and tuple(out.shape) == tuple(y.shape)
+    if out.data_ptr() % 16 and c % 8 == 0 and out.stride(3) % 8 == 0:      # the 128-bit path would be misaligned
+        out.copy_(y)
+        return out
+    _call("b200seg_norm_act_fwd", _ptr(y), yp, None, n * d * h * w, 1, c, 0, 0.0, None, None, 0, _ptr(out), out.stride(3),
+          _stream())
+    return out
+
+
 def conv_fused_eval_supported(g):
     from ._lib import load
     return bool(load().b200seg_conv3d_fprop_act_supported(ctypes.byref(g)))
@@ -527,8 +541,7 @@ def conv3d_fprop_eval_fused(x, weight, bias, k, pad, dil, spec, gamma, beta, run
           _ptr(coef[0, 3]), spec.act, spec.act_param, _ptr(z), z.stride(3), _stream(), work=_conv_flops(g),
           tag="conv_fprop_tc" if wp is None else "conv_fprop_padded_tc")
     if out is not None and z is not out:
-        out.copy_(z)
-        z = out
+        z = _copy_into(out, z)
     return z
 
 
@@ -734,8 +747,7 @@ class _ConvNormAct(torch.autograd.Function):
         if plain:
             z, coef, count, groups = y, None, 0.0, 1
             if out is not None and y is not out:
-                out.copy_(y)
-                z = out
+                z = _copy_into(out, y)
         else:
             z, coef, count, groups = _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_w,
                                                    residual, out)
@@ -1351,8 +1363,7 @@ def dropout(x, p, training=True, channel=False, out=None, times=1):
     assert times in (1, 2)
     if not training or p == 0.0:
         if out is not None:
-            out.copy_(x)
-            return out
+            return activation(x, "none", out=out)      # a differentiable copy by kernel
         return x
     _SALT[0] += times
     return _Dropout.apply(x, (p, channel, _SALT[0], _SALT[0] - 1 if times == 2 else 0, out))
@@ -1593,6 +1604,12 @@ class _SigmoidMap(torch.autograd.Function):
 def sigmoid_map(x):
     """torch.sigmoid on an fp32 class-score map (RE_net.py:158)."""
     return _SigmoidMap.apply(x)
+
+
+def alloc_channels(n, d, h, w, c, device):
+    """Uninitialised [n, d, h, w, c] activation buffer whose channel slices are filled by `out=` of the producing ops
+    (DenseVoxelNet's dense blocks, densevoxelnet3d.py:36-42)."""
+    return torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=device)
 
 
 def zeros_ndhwc(n, d, h, w, c, device):

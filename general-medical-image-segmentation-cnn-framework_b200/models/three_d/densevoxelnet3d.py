@@ -44,9 +44,23 @@ class _DenseBlock(nn.Sequential, OpsMixin):
 
     def forward(self, x):
         F = self.kernels
-        for layer in self:
-            x = F.concat_channels(x, layer(x))
-        return x
+        alloc = getattr(F, "alloc_channels", None)
+        if alloc is None:                    # reference arithmetic (oracle backend): torch.cat per layer (:41)
+            for layer in self:
+                x = F.concat_channels(x, layer(x))
+            return x
+        # one channels-last buffer for the whole block: the input is copied to its head once, every layer writes its
+        # `growth` new channels straight behind what exists, and the "concatenation" is a wider view of the same memory
+        layers = list(self)
+        growth = layers[0].conv1.out_channels
+        n, d, h, w = F.spatial(x)
+        c = F.channels(x)
+        buf = alloc(n, d, h, w, c + len(layers) * growth, F.device_of(x))
+        cur = F.activation(x, "none", out=buf[..., :c])
+        for layer in layers:
+            cur = F.concat_channels(cur, layer(cur, out=buf[..., c:c + growth]))
+            c += growth
+        return cur
 
 
 class _Transition(nn.Module, OpsMixin):

@@ -38,8 +38,7 @@ def _drop(mod, F, do, x, out=None):
     if isinstance(do, nn.Dropout3d):
         return F.dropout(x, do.p, training=mod.training, channel=True, out=out)
     if out is not None:
-        out.copy_(x)
-        return out
+        return F.activation(x, "none", out=out)        # differentiable copy into the concatenation buffer
     return x
 
 
