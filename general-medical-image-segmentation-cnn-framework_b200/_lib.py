@@ -95,7 +95,7 @@ SIGNATURES = {
     "b200seg_adam_step_fused": "ppppp" + "pp" + "iii" + "pp" + "i" + "p",
 }
 STRING_FUNCS = ("b200seg_version", "b200seg_last_error")
-SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g", "b200seg_p2p_mailbox_bytes": ""}
+SIZE_FUNCS = {"b200seg_conv3d_workspace_bytes": "g", "b200seg_conv3d_ws_bytes": "gi", "b200seg_p2p_mailbox_bytes": ""}
 INT64_FUNCS = {"b200seg_umma_launch_count": ""}
 
 

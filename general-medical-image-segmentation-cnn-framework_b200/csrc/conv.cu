@@ -188,6 +188,14 @@ int b200seg_conv3d_uses_tensor_cores(const b200seg_conv_geom* g) {
   return conv_umma_supported(a) ? 1 : 0;
 }
 
+size_t b200seg_conv3d_ws_bytes(const b200seg_conv_geom* g, int dgrad) {
+  if (!g || g->stride != 1) return 0;
+  if (dgrad && g->dil * (g->k - 1) - g->pad < 0) return 0;
+  const UmmaConvArgs a = dgrad ? dgrad_args(g, nullptr, g->cout, nullptr, nullptr, g->cin, nullptr)
+                               : fprop_args(g, nullptr, g->cin, nullptr, nullptr, nullptr, g->cout, nullptr);
+  return conv_umma_ws_bytes(a);
+}
+
 size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g) {
   // only the weight gradient uses scratch memory: split-K partial tiles (0 = not needed / atomics path), or the
   // taps-as-channels copy of a single-channel input (stem_plan)
@@ -204,12 +212,13 @@ size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g) {
 int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
                          const float* bias, void* y, int64_t y_pitch, float* stats, void* workspace,
                          size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (int rc = check_geom(g, "conv3d_fprop")) return rc;
   B200_CHECK_ARG(x && w_packed && y && x_pitch >= g->cin && y_pitch >= g->cout, "conv3d_fprop: bad buffers");
   auto st = static_cast<cudaStream_t>(stream);
   if (g->stride == 1) {
     UmmaConvArgs a = fprop_args(g, x, x_pitch, w_packed, bias, y, y_pitch, stats);
+    a.ws = workspace;
+    a.ws_bytes = workspace_bytes;
     if (conv_umma_supported(a)) return conv_umma_run(a, st);
   } else if (is_k2s2(g)) {
     UmmaConvArgs a = k2s2_fprop_args(g, x, x_pitch, w_packed, bias, y, y_pitch, stats);
@@ -251,12 +260,13 @@ int b200seg_conv3d_fprop_act(const b200seg_conv_geom* g, const void* x, int64_t 
 int b200seg_conv3d_dgrad(const b200seg_conv_geom* g, const void* dy, int64_t dy_pitch, const void* w_packed_dgrad,
                          void* dx, int64_t dx_pitch, float* stats, void* workspace, size_t workspace_bytes,
                          void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (int rc = check_geom(g, "conv3d_dgrad")) return rc;
   B200_CHECK_ARG(dy && w_packed_dgrad && dx && dy_pitch >= g->cout && dx_pitch >= g->cin, "conv3d_dgrad: bad buffers");
   auto st = static_cast<cudaStream_t>(stream);
   if (g->stride == 1 && g->dil * (g->k - 1) - g->pad >= 0) {
     UmmaConvArgs a = dgrad_args(g, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch, stats);
+    a.ws = workspace;
+    a.ws_bytes = workspace_bytes;
     if (conv_umma_supported(a)) return conv_umma_run(a, st);
   } else if (is_k2s2(g)) {
     UmmaConvArgs a = k2s2_dgrad_args(g, dy, dy_pitch, w_packed_dgrad, dx, dx_pitch);

@@ -57,6 +57,10 @@ struct UmmaConvArgs {
   int tapmode, in_sub, out_sub, cls, wtaps;
   int fd, fh, fw;
   unsigned char tapw[8][8];
+  // caller-provided scratch (b200seg_conv3d_ws_bytes): the weights-stationary kernel for K-heavy layers on 8 x 8 planes
+  // accumulates the partial sums of its tap rows in an fp32 copy of the output (conv_umma_ws.cu).  null: not available.
+  void* ws;
+  size_t ws_bytes;
 };
 extern long long g_umma_launches;
 bool conv_umma_supported(const UmmaConvArgs& a);
@@ -68,6 +72,10 @@ int conv_umma_roll_run(const UmmaConvArgs& a, cudaStream_t st);
 bool conv_umma_plane_supported(const UmmaConvArgs& a);
 bool conv_umma_plane_relaxed_supported(const UmmaConvArgs& a);
 // CTA-pair (cta_group::2) variant for the K-heavy deep layers (conv_umma_p2.cu): two SMs share one copy of the weight tile
+// weights-stationary kernel for K-heavy layers on tiny grids (conv_umma_ws.cu): units = (kd, kh) tap row x N tile
+size_t conv_umma_ws_bytes(const UmmaConvArgs& a);     // scratch it needs for this geometry, 0 = not applicable
+bool conv_umma_ws_supported(const UmmaConvArgs& a);
+int conv_umma_ws_run(const UmmaConvArgs& a, cudaStream_t st);
 bool conv_umma_pair_supported(const UmmaConvArgs& a);
 int conv_umma_pair_run(const UmmaConvArgs& a, cudaStream_t st);   // short planes (masked tile rows): last resort
 int conv_umma_plane_run(const UmmaConvArgs& a, cudaStream_t st);

@@ -596,6 +596,7 @@ bool conv_umma_supported(const UmmaConvArgs& a) {
 }
 
 int conv_umma_run(const UmmaConvArgs& a, cudaStream_t st) {
+  if (conv_umma_ws_supported(a)) return conv_umma_ws_run(a, st);          // K-heavy layers on 8 x 8 planes: weights stationary
   if (conv_umma_roll_supported(a)) return conv_umma_roll_run(a, st);     // narrow outputs: kd taps in N (conv_umma_roll.cu)
   if (conv_umma_pair_supported(a)) return conv_umma_pair_run(a, st);     // K-heavy deep layers: CTA pairs share the weights
   if (conv_umma_plane_supported(a)) return conv_umma_plane_run(a, st);   // persistent kernel (conv_umma_p.cu)

@@ -317,6 +317,16 @@ def _unpad_stats(stats_p, c, c_pad, spare):
 _LAST_PADDED_INPUT = [None]
 
 
+def _conv_scratch(g, dgrad, device):
+    """Scratch for the weights-stationary kernel of the K-heavy layers on 8 x 8 planes (b200seg_conv3d_ws_bytes): an fp32
+    copy of the output in which the partial sums of the tap rows meet.  (None, 0) for every other geometry."""
+    from ._lib import load
+    nbytes = int(load().b200seg_conv3d_ws_bytes(ctypes.byref(g), int(dgrad)))
+    if not nbytes:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
 def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=None):
     x, xp = _as_rows(x)
     cout, cin = weight.shape[0], weight.shape[1]
@@ -350,8 +360,10 @@ def conv3d_fprop_raw(x, weight, bias, k, stride, pad, dil, want_stats, y_out=Non
     # flat {sum[C], sumsq[C], (count)}: the spare float lets the cross-GPU exchange carry the element count
     stats = _zeros_f32(2 * cout + 1, x.device) if want_stats else None
     wp = pack_conv_weight(weight)
+    ws, ws_bytes = _conv_scratch(g, 0, x.device)
     _call("b200seg_conv3d_fprop", ctypes.byref(g), _ptr(x), xp, _ptr(wp), _ptr(b), _ptr(y), y.stride(3), _ptr(stats),
-          None, 0, _stream(), work=_conv_flops(g), tag="conv_fprop_tc" if conv_uses_tensor_cores(g) else "conv_fprop_direct")
+          _ptr(ws), ws_bytes, _stream(), work=_conv_flops(g),
+          tag="conv_fprop_tc" if conv_uses_tensor_cores(g) else "conv_fprop_direct")
     return y, stats, g
 
 
@@ -372,7 +384,8 @@ def conv3d_dgrad_raw(g, dy, weight, colsum=False):
     wd = pack_conv_weight(weight, dgrad=True)
     dx = torch.empty((g.n, g.d, g.h, g.w, g.cin), dtype=torch.bfloat16, device=dy.device)
     stats = _zeros_f32(2 * g.cin, dy.device) if colsum else None
-    _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, _ptr(stats), None, 0,
+    ws, ws_bytes = _conv_scratch(g, 1, dy.device)
+    _call("b200seg_conv3d_dgrad", ctypes.byref(g), _ptr(dy), dyp, _ptr(wd), _ptr(dx), g.cin, _ptr(stats), _ptr(ws), ws_bytes,
           _stream(), work=_conv_flops(g), tag="conv_dgrad")
     return (dx, stats) if colsum else dx
 

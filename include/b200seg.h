@@ -91,6 +91,11 @@ int b200seg_unpack_conv_wgrad(const float* dw_packed, float* grad_w, int cout, i
  * fused into the epilogue, unet3d.py:88,100).  w_packed from b200seg_pack_conv_weight(dgrad=0).
  * stats (may be NULL): float[2*cout] = {sum, sumsq}, accumulated into (caller zeroes). */
 size_t b200seg_conv3d_workspace_bytes(const b200seg_conv_geom* g);
+/* Scratch bytes b200seg_conv3d_fprop (dgrad = 0) / b200seg_conv3d_dgrad (dgrad = 1) can use for this geometry, 0 = none.
+ * Only the K-heavy layers on 8 x 8 planes (the U-Net bottleneck at 8^3, unet3d.py:28; V-Net's deepest 5x5x5 layers) have
+ * one: with it they run weights-stationary, split over tap rows, and meet in an fp32 copy of the output (the library
+ * clears it); without it they take the voxel-tiled kernels.  Pass it as `workspace`, `workspace_bytes`. */
+size_t b200seg_conv3d_ws_bytes(const b200seg_conv_geom* g, int dgrad);
 int b200seg_conv3d_fprop(const b200seg_conv_geom* g, const void* x, int64_t x_pitch, const void* w_packed,
                          const float* bias, void* y, int64_t y_pitch, float* stats, void* workspace,
                          size_t workspace_bytes, void* stream);

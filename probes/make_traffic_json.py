@@ -35,8 +35,8 @@ def parse(path):
 
 
 def family(launches):
-    conv = [l for l in launches if l["name"].startswith("conv_umma")]
-    other = [l for l in launches if not l["name"].startswith("conv_umma")]
+    conv = [l for l in launches if l["name"].startswith(("conv_umma", "conv_ws"))]
+    other = [l for l in launches if not l["name"].startswith(("conv_umma", "conv_ws"))]
     return {"launches": len(conv), "dram_bytes_per_step": sum(l["rd"] + l["wr"] for l in conv),
             "dram_read_bytes": sum(l["rd"] for l in conv), "dram_write_bytes": sum(l["wr"] for l in conv),
             "ncu_ms_cold_serialised": round(sum(l["ms"] for l in conv), 4),

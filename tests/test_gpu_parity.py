@@ -92,6 +92,11 @@ CONV_CASES = [
     (1, 16, 5, 1, 2, 1, (40, 40, 44), 1),     # V-Net stem 5x5x5
     (64, 2, 1, 1, 0, 1, (40, 40, 44), 1),     # HighRes3DNet classifier
     (24, 40, 3, 2, 1, 1, (64, 64, 64), 1),    # stride 2 with padded channels
+    # K-heavy layers on 8 x 8 planes: weights-stationary kernel, partial sums of the tap rows meet in an fp32 workspace
+    (256, 512, 3, 1, 1, 1, (8, 8, 8), 2),     # U-Net bottleneck conv1 (unet3d.py:28)
+    (512, 256, 3, 1, 1, 1, (8, 8, 8), 2),     # ... the geometry of its data gradient's twin
+    (256, 256, 5, 1, 2, 1, (8, 8, 8), 2),     # V-Net's deepest 5x5x5 layers (vnet3d.py:25)
+    (256, 320, 3, 1, 1, 1, (4, 8, 8), 1),     # four planes, an N tile count that does not divide the SM count
     (32, 64, 3, 4, 0, 1, (16, 16, 20), 2),    # CSRNet cross-scale branch: stride 4, no padding (space-to-depth + 1x1x1 GEMM)
     (32, 128, 3, 4, 0, 1, (33, 34, 35), 1),   # ... extents that leave uncovered planes at the far end (zero gradient there)
 ]
