@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200seg_norm_act_fwd_stats": "plp" + "d" + "pppp" + "ffi" + "p" + "li" + "if" + "p" + "pl" + "pl" + "p",
     "b200seg_norm_act_bwd_reduce": "plpl" + "p" + "lii" + "if" + "p" + "pl" + "ppp" + "p",
     "b200seg_norm_act_bwd_apply": "plpl" + "pp" + "d" + "lii" + "if" + "p" + "pl" + "pl" + "pl" + "p",
+    "b200seg_norm_act_bwd_apply_acc": "plpl" + "pp" + "d" + "lii" + "if" + "p" + "pl" + "pl" + "pl" + "pl" + "p",
     "b200seg_maxpool2_fwd": "plplp" + "iiiii" + "p",
     "b200seg_maxpool2_bwd": "plp" + "pl" + "pl" + "iiiii" + "p",
     "b200seg_maxpool2_idx_to_torch": "pp" + "iiiii" + "p",

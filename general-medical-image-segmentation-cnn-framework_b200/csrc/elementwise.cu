@@ -583,9 +583,12 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_b
                                           int act_rt, float act_param, const float* __restrict__ prelu_w,
                                           const __nv_bfloat16* __restrict__ res, int64_t res_pitch,
                                           __nv_bfloat16* __restrict__ dy, int64_t dy_pitch,
-                                          __nv_bfloat16* __restrict__ dres, int64_t dres_pitch) {
+                                          __nv_bfloat16* __restrict__ dres, int64_t dres_pitch,
+                                          const __nv_bfloat16* acc, int64_t acc_pitch) {
   constexpr int act = ACT;
   (void)act_rt;
+  // acc != nullptr: dy = acc + (the gradient below); acc may alias dy (every thread reads its own elements before it
+  // writes them) -- a tensor that also feeds a concatenation accumulates both gradients in one buffer (dense blocks).
   // dy = scale * (dpre - m1 - xhat * m2), xhat = (y - mean) * inv_std, m1 = sum(dpre)/n, m2 = sum(dpre*xhat)/n.
   // Same thread -> channel-chunk binding as the forward kernel (host guarantees divisibility).
   const int cv = C / V;
@@ -637,6 +640,12 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_kernel(const __nv_b
       const float dpre = fd[j] * act_bwd(pre, act, sl[j]);
       dr[j] = dpre;
       o[j] = dpre * sc[j] - (ca[j] + fy[j] * cb[j]);
+    }
+    if (acc != nullptr) {
+      float fa[V];
+      load_vec<V>(acc + row * acc_pitch + ch * V, fa);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] += fa[j];
     }
     store_vec<V>(dy + row * dy_pitch + ch * V, o);
     if (dres) store_vec<V>(dres + row * dres_pitch + ch * V, dr);
@@ -1201,7 +1210,17 @@ int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, 
                                const float* sums, double count, int64_t rows_per_group, int groups, int c, int act,
                                float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
                                void* dy, int64_t dy_pitch, void* dres, int64_t dres_pitch, void* stream) {
+  return b200seg_norm_act_bwd_apply_acc(dz, dz_pitch, y, y_pitch, coef, sums, count, rows_per_group, groups, c, act, act_param,
+                                        prelu_w, residual, res_pitch, dy, dy_pitch, dres, dres_pitch, nullptr, 0, stream);
+}
+
+int b200seg_norm_act_bwd_apply_acc(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch, const float* coef,
+                                   const float* sums, double count, int64_t rows_per_group, int groups, int c, int act,
+                                   float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                                   void* dy, int64_t dy_pitch, void* dres, int64_t dres_pitch, const void* acc,
+                                   int64_t acc_pitch, void* stream) {
   B200_CHECK_ARG(dz && y && dy && rows_per_group > 0 && groups > 0 && c > 0, "norm_act_bwd_apply: bad arguments");
+  const auto* ap = static_cast<const __nv_bfloat16*>(acc);
   auto st = static_cast<cudaStream_t>(stream);
   const auto* dzp = static_cast<const __nv_bfloat16*>(dz);
   const auto* yp = static_cast<const __nv_bfloat16*>(y);
@@ -1210,16 +1229,16 @@ int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, 
   auto* drp = static_cast<__nv_bfloat16*>(dres);
   const float inv_count = sums ? static_cast<float>(1.0 / count) : 0.f;
   const int sums_stride = (act == B200SEG_ACT_PRELU) ? 3 : 2;
-  if (vec_ok(c, dz_pitch, y_pitch, dy_pitch, (residual ? res_pitch : 0) | (dres ? dres_pitch : 0))) {
+  if (vec_ok(c, dz_pitch, y_pitch, dy_pitch, (residual ? res_pitch : 0) | (dres ? dres_pitch : 0) | (acc ? acc_pitch : 0))) {
     const int64_t total = rows_per_group * groups * (c / 8);
     B200_ACT_DISPATCH(act, norm_act_bwd_apply_kernel<8, A_><<<ew_grid(total, c / 8), 256, 0, st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
-        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch));
+        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch, ap, acc_pitch));
   } else {
     const int64_t total = rows_per_group * groups * c;
     B200_ACT_DISPATCH(act, norm_act_bwd_apply_kernel<1, A_><<<ew_grid(total, c), 256, 0, st>>>(
         dzp, dz_pitch, yp, y_pitch, coef, sums, sums_stride, inv_count, rows_per_group, groups, c, act, act_param,
-        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch));
+        prelu_w, rp, res_pitch, dyp, dy_pitch, drp, dres_pitch, ap, acc_pitch));
   }
   B200_CHECK_LAUNCH("norm_act_bwd_apply");
   return 0;

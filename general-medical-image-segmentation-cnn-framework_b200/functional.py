@@ -75,6 +75,7 @@ def begin_step(device, nbytes=4 << 20):
     _SCRATCH["pos"], _SCRATCH["active"] = 0, True
     _COLSUMS.clear()
     _ZERO_TAIL.clear()
+    _GRAD_STASH.clear()
 
 
 def end_step():
@@ -82,6 +83,7 @@ def end_step():
     _SCRATCH["active"] = False
     _COLSUMS.clear()
     _ZERO_TAIL.clear()
+    _GRAD_STASH.clear()
     _LAST_PADDED_INPUT[0] = None
     flush_counters()
 
@@ -399,7 +401,6 @@ _COLSUMS = {}
 def _publish_colsum(t, sums):
     if len(_COLSUMS) >= 16:    # nobody took them (the producers were not up-convolutions): do not pin their memory
         _COLSUMS.clear()
-    _ZERO_TAIL.clear()
     _COLSUMS[(t.data_ptr(), tuple(t.shape), tuple(t.stride()))] = (t, sums)
 
 
@@ -625,8 +626,10 @@ def _norm_forward(y, stats, spec, gamma, beta, running_mean, running_var, prelu_
     return out, coef, count, groups
 
 
-def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dres, grad_affine=None):
-    """Returns dy (bf16, contiguous), dres, sums ([groups][2 or 3][C] fp32: sum dpre, sum dpre*xhat[, dPReLU])."""
+def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dres, grad_affine=None, acc_into=None):
+    """Returns dy (bf16, contiguous), dres, sums ([groups][2 or 3][C] fp32: sum dpre, sum dpre*xhat[, dPReLU]).
+    acc_into: a gradient buffer (view) that already holds what y received through another consumer; the result is added
+    to it in place and it is returned as dy."""
     dz, dzp = _as_rows(dz)
     y, yp = _as_rows(y)
     n, d, h, w, c = y.shape
@@ -646,8 +649,16 @@ def _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual, want_dre
     if use_batch_stats and spec.kind == "batch" and spec.sync and is_parallel(spec.process_group):
         red = sums.clone()
         all_reduce_stats(red, spec.process_group, between=flush_deferred if _DEFERRED else None)
+    dres = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device) if want_dres else None
+    if acc_into is not None:
+        assert _pitched(acc_into) and tuple(acc_into.shape) == (n, d, h, w, c)
+        dy = acc_into
+        _call("b200seg_norm_act_bwd_apply_acc", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef),
+              _ptr(red if use_batch_stats else None), float(count), rows, groups, c, spec.act, spec.act_param, _ptr(prelu_w),
+              _ptr(res), resp, _ptr(dy), dy.stride(3), _ptr(dres), c, _ptr(dy), dy.stride(3), _stream(),
+              tag="b200seg_norm_act_bwd_apply")
+        return dy, dres, sums
     dy = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=y.device)
-    dres = torch.empty_like(dy) if want_dres else None
     _call("b200seg_norm_act_bwd_apply", _ptr(dz), dzp, _ptr(y), yp, _ptr(coef), _ptr(red if use_batch_stats else None),
           float(count), rows, groups, c, spec.act, spec.act_param, _ptr(prelu_w), _ptr(res), resp, _ptr(dy), c,
           _ptr(dres), c, _stream())
@@ -886,19 +897,24 @@ class _NormAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, gamma, beta, prelu_w, residual, running_mean, running_var, cfg):
-        spec, out = cfg
+        spec, out = cfg[0], cfg[1]
         z, coef, count, groups = _norm_forward(y, None, spec, gamma, beta, running_mean, running_var, prelu_w, residual,
                                                out)
         ctx.save_for_backward(y, coef, gamma, prelu_w, residual)
         ctx.cfg = (spec, count, groups)
+        ctx.shared_grad = len(cfg) > 2 and bool(cfg[2])
         return z
 
     @staticmethod
     def backward(ctx, dz):
         y, coef, gamma, prelu_w, residual = ctx.saved_tensors
         spec, count, groups = ctx.cfg
+        acc = None
+        if ctx.shared_grad:      # y is also the head of a dense-block concatenation: its gradient buffer already exists
+            hit = _GRAD_STASH.pop((y.data_ptr(), tuple(y.shape), tuple(y.stride())), None)
+            acc = hit[1] if hit is not None else None
         dy, dres, sums = _norm_backward(dz, y, coef, count, groups, spec, prelu_w, residual,
-                                        residual is not None and ctx.needs_input_grad[4])
+                                        residual is not None and ctx.needs_input_grad[4], acc_into=acc)
         dgamma = dbeta = dprelu = None
         if gamma is not None:
             dgamma, dbeta = (sums[0, 1], sums[0, 0]) if groups == 1 else (sums[:, 1].sum(0), sums[:, 0].sum(0))
@@ -908,8 +924,10 @@ class _NormAct(torch.autograd.Function):
 
 
 def norm_act(y, spec, gamma=None, beta=None, prelu_weight=None, residual=None, running_mean=None, running_var=None,
-             out=None):
-    return _NormAct.apply(y, gamma, beta, prelu_weight, residual, running_mean, running_var, (spec, out))
+             out=None, shared_grad=False):
+    """shared_grad: y was produced by concat_channels_shared (dense blocks): the backward adds this op's input gradient
+    into the buffer that already holds the gradient y received as the head of the next concatenation."""
+    return _NormAct.apply(y, gamma, beta, prelu_weight, residual, running_mean, running_var, (spec, out, shared_grad))
 
 
 class _MaxPool2(torch.autograd.Function):
@@ -1666,3 +1684,35 @@ class _Concat(torch.autograd.Function):
 
 def concat_channels(a, b):
     return _Concat.apply(a, b)
+
+
+# Dense blocks (densevoxelnet3d.py:36-42): the tensor `a` of cat((a, new)) is also the input of the layer that produced
+# `new`, so its gradient has two parts -- the head slice of the concatenation's gradient and what comes back through that
+# layer.  Instead of letting autograd sum a strided slice and a dense tensor (a non-vectorised ATen add per layer), the
+# concatenation's backward leaves the head slice here, keyed by `a`, and returns nothing for it; the layer's normalise
+# backward (norm_act(..., shared_grad=True) on the same `a`) adds its result INTO that slice and returns it.  Entries hold
+# the tensors, so an address cannot be recycled under a key; begin_step / end_step clear the table.
+_GRAD_STASH = {}
+
+
+class _ConcatShared(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[4]
+        ctx.key = (a.data_ptr(), tuple(a.shape), tuple(a.stride()))
+        ctx.keep = a
+        return merge_channels(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        head = g[..., :ctx.ca]
+        if _pitched(head) and head.data_ptr() % 16 == 0 and ctx.needs_input_grad[0]:
+            _GRAD_STASH[ctx.key] = (ctx.keep, head)
+            ctx.keep = None
+            return None, g[..., ctx.ca:]
+        return head, g[..., ctx.ca:]
+
+
+def concat_channels_shared(a, b):
+    """concat_channels for a tensor `a` that is ALSO consumed by norm_act(a, ..., shared_grad=True): see _GRAD_STASH."""
+    return _ConcatShared.apply(a, b)

@@ -23,10 +23,11 @@ class _DenseLayer(nn.Sequential, OpsMixin):
         if self.drop_rate > 0:
             self.drop_layer = nn.Dropout(p=self.drop_rate)
 
-    def forward(self, x, out=None):
+    def forward(self, x, out=None, shared_grad=False):
         """Returns only the new features (the caller owns the concatenation buffer)."""
         F = self.kernels
-        h = F.norm_act(x, norm_spec(F, self.norm1, "relu", 0.0, self.training), **norm_args(self.norm1))
+        extra = dict(shared_grad=True) if shared_grad else {}
+        h = F.norm_act(x, norm_spec(F, self.norm1, "relu", 0.0, self.training), **norm_args(self.norm1), **extra)
         plain_out = out if (self.drop_rate == 0 or not self.training) else None
         new = F.conv_norm_act(h, self.conv1.weight, None, k=3, stride=1, pad=1, dil=1, out=plain_out)
         if self.drop_rate > 0 and self.training:
@@ -58,7 +59,8 @@ class _DenseBlock(nn.Sequential, OpsMixin):
         buf = alloc(n, d, h, w, c + len(layers) * growth, F.device_of(x))
         cur = F.activation(x, "none", out=buf[..., :c])
         for layer in layers:
-            cur = F.concat_channels(cur, layer(cur, out=buf[..., c:c + growth]))
+            # `cur` feeds the layer and is the head of the next concatenation: both gradients meet in one buffer
+            cur = F.concat_channels_shared(cur, layer(cur, out=buf[..., c:c + growth], shared_grad=True))
             c += growth
         return cur
 

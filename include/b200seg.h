@@ -175,6 +175,14 @@ int b200seg_norm_act_bwd_apply(const void* dz, int64_t dz_pitch, const void* y, 
                                const float* sums, double count, int64_t rows_per_group, int groups, int c, int act,
                                float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
                                void* dy, int64_t dy_pitch, void* dres, int64_t dres_pitch, void* stream);
+/* The same with dy = acc + (that gradient); acc (bf16 rows, may be NULL, may alias dy) is the gradient the tensor already
+ * received through another consumer -- DenseVoxelNet's dense blocks (densevoxelnet3d.py:36-42): the input of layer i also is
+ * the head of the concatenation, and both gradients are accumulated in one buffer instead of being summed by a third pass. */
+int b200seg_norm_act_bwd_apply_acc(const void* dz, int64_t dz_pitch, const void* y, int64_t y_pitch, const float* coef,
+                                   const float* sums, double count, int64_t rows_per_group, int groups, int c, int act,
+                                   float act_param, const float* prelu_w, const void* residual, int64_t res_pitch,
+                                   void* dy, int64_t dy_pitch, void* dres, int64_t dres_pitch, const void* acc,
+                                   int64_t acc_pitch, void* stream);
 
 /* ---- MaxPool3d(2,2) (unet3d.py:19-25) -------------------------------------------------------------------------- */
 /* idx: uint8 per output element, local argmax 0..7 = (a*2+b)*2+e in (d,h,w) scan order; ties -> first, NaN wins. */
