@@ -360,7 +360,9 @@ static bool plan_roll(const UmmaConvArgs& a, RollParams& p, size_t& smem_bytes) 
   p.wblock_bytes = static_cast<unsigned>(CO) * p.rowbytes;          // one kd tap: C_out rows (of this half)
   p.wtile_bytes = static_cast<unsigned>(KD) * p.wblock_bytes;       // one (kh, kw): KD * C_out rows, contiguous
   if (p.wblock_bytes % (8u * p.rowbytes)) return false;             // blocks must start on a swizzle-atom boundary
-  if (KD == 3 && p.wblock_bytes % 1024) return false;
+  // (16 -> 16 layers, HighRes3DNet's first stage: 512-byte blocks = two 32-byte-swizzle atoms; the 5x5x5 form has run
+  //  with them all along)
+  if (KD == 3 && p.wblock_bytes % 1024 && getenv("B200SEG_ROLL_STRICT_BLOCKS")) return false;
   const size_t fixed = static_cast<size_t>(KD * KD) * p.wtile_bytes + 2048 + 1024;
   const size_t budget = 220 * 1024;
   p.S = static_cast<int>(std::min<size_t>(8, (budget - fixed) / p.slotA));
